@@ -1,0 +1,185 @@
+/*
+ * visde.h -- C ABI of the B200-native variational path-sampling library (libvisde.so).
+ *
+ * The reference (Tom-Ryder/VIforSDEs) has no C ABI / FFI: its operator boundary for this
+ * path is Python.  Each entry point below replaces one reference-side
+ * Python operator and is what a binding for that operator would call (INTEGRATION.md shows
+ * the ctypes stub a maintainer adds to the reference):
+ *
+ *   visde_path_fwd      <- kernels/forward.py:378-563   launch_fwd  (+ sde_fwd_kernel :91-375)
+ *   visde_path_bwd      <- kernels/backward.py:627-784  launch_bwd  (+ sde_bwd_kernel :156-624)
+ *   visde_elbo_fwd/_bwd <- inference/evidence_lower_bound.py:19-83 (path-dependent terms) with
+ *                          inference/state_space.py:20-38, inference/types.py:19-24,
+ *                          core/observations.py:52-74, examples/{ornstein_uhlenbeck,lotka_volterra}.py
+ *   visde_gauss_lp_fwd/_bwd <- evidence_lower_bound.py:77-83 _gaussian_log_prob (generic-SDE path)
+ *   visde_session_*     <- one trainer iteration's path part (inference/trainer.py:176-198) with
+ *                          HOST buffers: H2D, path fwd, ELBO fwd+bwd, path bwd, D2H.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every device buffer is allocated by the caller; the library
+ *     keeps no global mutable state (visde_last_error is thread-local); re-entrant.
+ *   - all kernels are enqueued on the cudaStream_t passed as `stream` (void*; NULL = legacy default).
+ *   - return 0 on success, negative VISDE_E* otherwise; visde_last_error() describes the failure.
+ *   - tensors are fp32, contiguous, row-major unless a stride argument says otherwise.
+ *   - weights use the nn.GRU / nn.Linear native layout (kernels/weights.py:79-196 documents the
+ *     reference's transposed copies; this library reads the native tensors directly):
+ *       w_ih[0] [3H, S+C+P] (input columns: state, context, theta), w_ih[k>0] [3H, H],
+ *       w_hh[k] [3H, H], b_ih[k], b_hh[k] [3H]; gate row blocks r, z, n;
+ *       out_w [S+S(S+1)/2, H] (rows: mu then tril row-major), out_b.
+ *   - limits (kernels/constants.py:13): 1 <= NL <= 4, 1 <= H <= 256, 1 <= S <= 16.
+ */
+#ifndef VISDE_H
+#define VISDE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VISDE_VERSION 1
+#define VISDE_MAX_LAYERS 4
+#define VISDE_MAX_STATE 16
+#define VISDE_MAX_HIDDEN 256
+#define VISDE_DIAG_MIN 1e-2f /* inference/constants.py:6 */
+
+enum {
+  VISDE_OK = 0,
+  VISDE_EINVAL = -1,   /* bad dims / null pointer / unsupported config (Python raises ValueError) */
+  VISDE_ECUDA = -2,    /* CUDA runtime error (Python raises RuntimeError) */
+  VISDE_EWORKSPACE = -3 /* workspace too small */
+};
+
+enum { VISDE_F32 = 0, VISDE_BF16 = 1 };                 /* dtype of context / grad_context */
+enum { VISDE_SDE_GENERIC = 0, VISDE_SDE_OU = 1, VISDE_SDE_LV = 2 };
+enum { VISDE_VARIANT_AUTO = 0, VISDE_VARIANT_GENERIC = 1, VISDE_VARIANT_FAST = 2 };
+
+typedef struct {
+  int64_t B;  /* trajectories on this rank */
+  int64_t T;  /* grid steps */
+  int32_t S;  /* state dim */
+  int32_t C;  /* context dim */
+  int32_t P;  /* sde parameter dim */
+  int32_t H;  /* GRU hidden */
+  int32_t NL; /* GRU layers */
+  int32_t variant; /* VISDE_VARIANT_*: kernel family selector (AUTO in production) */
+} visde_dims;
+
+typedef struct {
+  const float* w_ih[VISDE_MAX_LAYERS];
+  const float* w_hh[VISDE_MAX_LAYERS];
+  const float* b_ih[VISDE_MAX_LAYERS];
+  const float* b_hh[VISDE_MAX_LAYERS];
+  const float* out_w;
+  const float* out_b;
+} visde_weights;
+
+typedef struct {
+  float* w_ih[VISDE_MAX_LAYERS];
+  float* w_hh[VISDE_MAX_LAYERS];
+  float* b_ih[VISDE_MAX_LAYERS];
+  float* b_hh[VISDE_MAX_LAYERS];
+  float* out_w;
+  float* out_b;
+} visde_weight_grads;
+
+/* strided [B,T,C] view (the reference passes context[:, :-1] of a [B,T+1,C] tensor,
+ * inference/diffusion_path_sampler.py:60-61; strides in ELEMENTS, innermost stride 1) */
+typedef struct {
+  const void* ptr;
+  int64_t batch_stride;
+  int64_t time_stride;
+  int32_t dtype; /* VISDE_F32 | VISDE_BF16 */
+} visde_ctx_view;
+
+typedef struct {
+  void* ptr;
+  int64_t batch_stride;
+  int64_t time_stride;
+  int32_t dtype;
+} visde_ctx_grad_view;
+
+/* Gaussian observation model (core/observations.py:41-74) evaluated at grid indices
+ * obs_idx = clamp(round(times/dt), max=T) (evidence_lower_bound.py:52; computed by the host). */
+typedef struct {
+  int32_t n_obs;
+  int32_t obs_dim;
+  const int32_t* idx;      /* device [n_obs] */
+  const float* values;     /* device [n_obs, obs_dim] */
+  const float* obs_matrix; /* device [obs_dim, S] or NULL (identity; requires obs_dim == S) */
+  float variance;
+} visde_obs;
+
+int visde_version(void);
+const char* visde_last_error(void);
+
+/* bytes of the activation stash written by visde_path_fwd (save != 0) and read by _bwd */
+size_t visde_stash_bytes(const visde_dims* d);
+/* scratch bytes for visde_path_fwd (backward=0) / visde_path_bwd (backward=1) */
+size_t visde_workspace_bytes(const visde_dims* d, int backward);
+
+/* launch_fwd (kernels/forward.py:378): x0 [B,S] latent, theta [B,P], eps [B,T,S] ->
+ * paths [B,T+1,S], means [B,T,S], chol [B,T,S,S] (upper triangle written as 0).
+ * stash == NULL -> inference mode (save_activations=False, autograd.py:244-268). */
+int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_ctx_view* ctx,
+                   const float* theta, const float* eps, const visde_weights* w, float* paths,
+                   float* means, float* chol, void* stash, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* launch_bwd (kernels/backward.py:627): cotangents g_paths [B,T+1,S], g_means [B,T,S],
+ * g_chol [B,T,S,S] (lower triangle consumed, backward.py:316-324) ->
+ * grad_x0 [B,S], grad_ctx (strided view, fully overwritten), grad_theta [B,P], weight grads
+ * in native layout (fully overwritten; deterministic two-stage reduction, no atomics). */
+int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const float* g_means,
+                   const float* g_chol, const visde_ctx_view* ctx, const float* theta,
+                   const float* eps, const visde_weights* w, const float* paths, const void* stash,
+                   float* grad_x0, const visde_ctx_grad_view* grad_ctx, float* grad_theta,
+                   const visde_weight_grads* gw, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* Path-dependent ELBO terms per trajectory: terms [B,4] = (obs, sde, gen, jacobian) log-probs
+ * (evidence_lower_bound.py:28-56).  sde_kind OU/LV use built-in drift/diffusion functors
+ * (examples/*.py); GENERIC reads drift [B,T,S] and diffusion [B,T,S,S] evaluated by the caller.
+ * positive_mask bit s set <=> state dim s uses the softplus transform (state_space.py:20-25). */
+int visde_elbo_fwd(const visde_dims* d, float dt, int sde_kind, uint32_t positive_mask,
+                   const float* z, const float* means, const float* chol, const float* theta,
+                   const float* drift, const float* diffusion, const visde_obs* obs, float* terms,
+                   void* stream);
+
+/* Backward of visde_elbo_fwd: g_terms [B,4] -> g_z [B,T+1,S], g_means [B,T,S], g_chol [B,T,S,S]
+ * (all fully overwritten), g_theta [B,P] (OU/LV; zeroed for GENERIC), and for GENERIC
+ * g_drift [B,T,S], g_diffusion [B,T,S,S] (otherwise may be NULL). */
+int visde_elbo_bwd(const visde_dims* d, float dt, int sde_kind, uint32_t positive_mask,
+                   const float* z, const float* means, const float* chol, const float* theta,
+                   const float* drift, const float* diffusion, const visde_obs* obs,
+                   const float* g_terms, float* g_z, float* g_means, float* g_chol,
+                   float* g_theta, float* g_drift, float* g_diffusion, void* stream);
+
+/* ---- host-buffer session: one ELBO iteration of the path through HOST memory ------------- */
+typedef struct visde_session visde_session;
+
+/* Allocates device buffers, pinned staging and a stream for dims d (context is a dense
+ * [B,T+1,C] fp32 host tensor of which rows 0..T-1 are used). */
+int visde_session_create(const visde_dims* d, int sde_kind, uint32_t positive_mask, int32_t n_obs,
+                         int32_t obs_dim, visde_session** out);
+void visde_session_destroy(visde_session* s);
+/* bytes copied host->device / device->host by one visde_session_step */
+size_t visde_session_h2d_bytes(const visde_session* s);
+size_t visde_session_d2h_bytes(const visde_session* s);
+/* number of kernels one visde_session_step launches */
+int visde_session_launches(const visde_session* s);
+
+/* HOST in: x0, context [B,T+1,C], theta, eps, weights (host pointers in visde_weights),
+ * obs (host pointers).  HOST out: terms [B,4], grad_x0 [B,S], grad_theta [B,P], weight grads
+ * (host pointers), and grad_context [B,T+1,C] if non-NULL (row T zero).  The loss is
+ * -(mean_b(obs + sde - gen + jac)); its cotangent 1/B is applied inside. Synchronous. */
+int visde_session_step(visde_session* s, float dt, const float* x0, const float* context,
+                       const float* theta, const float* eps, const visde_weights* w_host,
+                       const visde_obs* obs_host, float* terms, float* grad_x0, float* grad_theta,
+                       const visde_weight_grads* gw_host, float* grad_context);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VISDE_H */

@@ -1,0 +1,104 @@
+"""Shared helpers for the GPU parity tests: run the CUDA path on an oracle Problem."""
+from __future__ import annotations
+
+import torch
+
+from oracle import oracle_torch as O
+
+
+def normwise(a: torch.Tensor, ref: torch.Tensor) -> float:
+    a, ref = a.detach().double().cpu(), ref.detach().double().cpu()
+    den = ref.abs().max().item()
+    return (a - ref).abs().max().item() / (den if den > 0 else 1.0)
+
+
+def assert_close(a, ref, rtol=1e-4, atol_scale=1e-5, name=""):
+    """|a - ref| <= atol_scale * max|ref| + rtol * |ref| elementwise (fp32 parity bar of
+    BASELINE.json: rtol 1e-4, with an absolute floor scaled to the tensor's magnitude)."""
+    a, ref = a.detach().double().cpu(), ref.detach().double().cpu()
+    assert a.shape == ref.shape, f"{name}: shape {tuple(a.shape)} vs {tuple(ref.shape)}"
+    scale = ref.abs().max().item() if ref.numel() else 0.0
+    err = (a - ref).abs()
+    tol = atol_scale * scale + rtol * ref.abs()
+    bad = err > tol
+    assert not bad.any(), (f"{name}: {int(bad.sum())}/{a.numel()} elements off; max abs err "
+                           f"{err.max().item():.3e} (scale {scale:.3e}, normwise {err.max().item() / (scale or 1):.3e})")
+
+
+def build_head(p: O.Problem, device="cuda"):
+    from viforsdes_b200.head import DiffusionTransitionHead, HeadConfig
+
+    w = p.weights
+    head = DiffusionTransitionHead(w.state_dim, w.context_dim, w.param_dim,
+                                   HeadConfig(hidden_dim=w.hidden_dim, num_layers=w.num_layers))
+    with torch.no_grad():
+        for k in range(w.num_layers):
+            getattr(head.gru, f"weight_ih_l{k}").copy_(w.w_ih[k])
+            getattr(head.gru, f"weight_hh_l{k}").copy_(w.w_hh[k])
+            getattr(head.gru, f"bias_ih_l{k}").copy_(w.b_ih[k])
+            getattr(head.gru, f"bias_hh_l{k}").copy_(w.b_hh[k])
+        head.out_proj.weight.copy_(w.out_w)
+        head.out_proj.bias.copy_(w.out_b)
+    return head.to(device).train()
+
+
+def cuda_sde(p: O.Problem):
+    from viforsdes_b200 import sde as vs
+
+    if p.name == "ou":
+        return vs.OrnsteinUhlenbeck()
+    if p.name == "lv":
+        return vs.LotkaVolterra()
+    return p.sde  # user-defined SDE through the protocol (PyTorch drift / diffusion)
+
+
+def head_grads(head) -> dict:
+    g = {}
+    for k in range(head.num_layers):
+        g[f"w_ih_l{k}"] = getattr(head.gru, f"weight_ih_l{k}").grad
+        g[f"w_hh_l{k}"] = getattr(head.gru, f"weight_hh_l{k}").grad
+        g[f"b_ih_l{k}"] = getattr(head.gru, f"bias_ih_l{k}").grad
+        g[f"b_hh_l{k}"] = getattr(head.gru, f"bias_hh_l{k}").grad
+    g["out_w"] = head.out_proj.weight.grad
+    g["out_b"] = head.out_proj.bias.grad
+    return g
+
+
+def cuda_inputs(p: O.Problem, ctx_dtype=torch.float32, strided=True):
+    """x0, context (strided [B,T,C] view of a [B,T+1,C] leaf, like the reference call site), theta, eps."""
+    dev = "cuda"
+    B, T, Cd = p.context.shape
+    x0 = p.x0.to(dev).requires_grad_(True)
+    theta = p.theta.to(dev).requires_grad_(True)
+    eps = p.eps.to(dev)
+    if strided:
+        full = torch.zeros(B, T + 1, Cd, device=dev, dtype=ctx_dtype)
+        full[:, :-1] = p.context.to(dev).to(ctx_dtype)
+        full.requires_grad_(True)
+        view = full[:, :-1]
+    else:
+        full = p.context.to(dev).to(ctx_dtype).contiguous().requires_grad_(True)
+        view = full
+    return x0, full, view, theta, eps
+
+
+def run_cuda_fwd_bwd(p: O.Problem, ctx_dtype=torch.float32, strided=True):
+    """CUDA iteration through the public modules: head.sample_diffusion_paths -> path_elbo_terms ->
+    backward of -mean(obs + sde - gen + jac).  Mirrors oracle.run_fwd_bwd."""
+    from viforsdes_b200.elbo import path_elbo_terms
+    from viforsdes_b200.observations import GaussianObservationLikelihood, Observations
+    from viforsdes_b200.state_space import StateSpace
+    from viforsdes_b200.types import DiffusionPathSample
+
+    head = build_head(p)
+    x0, full, view, theta, eps = cuda_inputs(p, ctx_dtype, strided)
+    paths, means, chol = head.sample_diffusion_paths(x0, view, theta, eps, p.dt)
+    sample = DiffusionPathSample(paths, means, chol, StateSpace(p.weights.state_dim, list(p.positive_dims)))
+    terms = path_elbo_terms(cuda_sde(p), Observations(times=p.obs_times, values=p.obs_values),
+                            GaussianObservationLikelihood(variance=p.obs_variance), theta, sample, p.dt)
+    loss = -(terms[:, 0] + terms[:, 1] - terms[:, 2] + terms[:, 3]).mean()
+    loss.backward()
+    B, T, _ = p.context.shape
+    grads = {"x0": x0.grad, "context": full.grad[:, :T] if strided else full.grad, "theta": theta.grad}
+    grads.update(head_grads(head))
+    return paths.detach(), means.detach(), chol.detach(), terms.detach(), grads

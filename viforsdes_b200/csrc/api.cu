@@ -1,0 +1,574 @@
+// extern "C" surface of libvisde (include/visde.h): validation, workspace carving, kernel
+// sequencing.  No torch types; every buffer is caller-owned except inside visde_session.
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace visde {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+int check_dims(const visde_dims* d) {
+  VISDE_REQUIRE(d != nullptr, "dims is NULL");
+  VISDE_REQUIRE(d->B >= 0 && d->T >= 0, "B and T must be non-negative (got %lld, %lld)", (long long)d->B,
+                (long long)d->T);
+  VISDE_REQUIRE(d->S >= 1 && d->S <= VISDE_MAX_STATE, "state_dim must be in [1, %d], got %d", VISDE_MAX_STATE, d->S);
+  VISDE_REQUIRE(d->NL >= 1 && d->NL <= VISDE_MAX_LAYERS, "num_layers must be in [1, %d], got %d", VISDE_MAX_LAYERS,
+                d->NL);  // models/head.py:33-36
+  VISDE_REQUIRE(d->H >= 1 && d->H <= VISDE_MAX_HIDDEN, "hidden_dim must be in [1, %d], got %d", VISDE_MAX_HIDDEN, d->H);
+  VISDE_REQUIRE(d->C >= 0 && d->P >= 0, "context_dim and sde_param_dim must be non-negative");
+  return VISDE_OK;
+}
+
+struct StashLayout {
+  size_t h_floats, raw_floats;
+};
+StashLayout stash_layout(const visde_dims* d) {
+  size_t bt = (size_t)d->B * d->T;
+  return {bt * d->NL * kStashSlots * d->H, bt * (size_t)(d->S * (d->S + 1) / 2)};
+}
+
+struct BwdWs {
+  size_t dg, dout, sdg, partials, total, partial_floats;
+};
+BwdWs bwd_ws(const visde_dims* d) {
+  BwdWs w{};
+  size_t bt = (size_t)d->B * d->T;
+  int n_out = d->S + d->S * (d->S + 1) / 2;
+  int G = 3 * d->H;
+  size_t off = 0;
+  w.dg = off;
+  off += align_up(sizeof(float) * bt * d->NL * kDgSlots * d->H);
+  w.dout = off;
+  off += align_up(sizeof(float) * bt * n_out);
+  w.sdg = off;
+  off += align_up(sizeof(float) * (size_t)d->B * G);
+  int64_t K = d->B * d->T;
+  size_t pf = gemm_tn_partial_floats(G, d->S + d->C + d->P + 1, K);
+  size_t pf2 = gemm_tn_partial_floats(G, d->H + 1, K);
+  size_t pf3 = gemm_tn_partial_floats(n_out, d->H + 1, K);
+  if (pf2 > pf) pf = pf2;
+  if (pf3 > pf) pf = pf3;
+  w.partial_floats = pf;
+  w.partials = off;
+  off += align_up(sizeof(float) * pf);
+  w.total = off;
+  return w;
+}
+
+void fill_common(PathParams& p, const visde_dims* d, float dt, const visde_weights* w) {
+  memset(&p, 0, sizeof(p));
+  p.B = d->B;
+  p.T = d->T;
+  p.S = d->S;
+  p.C = d->C;
+  p.P = d->P;
+  p.H = d->H;
+  p.NL = d->NL;
+  p.n_tril = d->S * (d->S + 1) / 2;
+  p.n_out = d->S + p.n_tril;
+  p.dt = dt;
+  p.sqrt_dt = sqrtf(dt);
+  for (int k = 0; k < d->NL; ++k) {
+    p.w_ih[k] = w->w_ih[k];
+    p.w_hh[k] = w->w_hh[k];
+    p.b_ih[k] = w->b_ih[k];
+    p.b_hh[k] = w->b_hh[k];
+  }
+  p.out_w = w->out_w;
+  p.out_b = w->out_b;
+}
+
+int check_weights(const visde_dims* d, const visde_weights* w) {
+  VISDE_REQUIRE(w != nullptr, "weights is NULL");
+  for (int k = 0; k < d->NL; ++k)
+    VISDE_REQUIRE(w->w_ih[k] && w->w_hh[k] && w->b_ih[k] && w->b_hh[k], "weights of layer %d are NULL", k);
+  VISDE_REQUIRE(w->out_w && w->out_b, "out_proj weights are NULL");
+  return VISDE_OK;
+}
+
+bool use_fast(const visde_dims* d, const PathParams& p) {
+  if (d->variant == VISDE_VARIANT_GENERIC) return false;
+  return fast_supported(p);
+}
+
+__global__ void fill_loss_cotangent_kernel(float* g_terms, int64_t B) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  // loss = -mean_b(obs + sde - gen + jac)   (evidence_lower_bound.py:64, trainer.py:197)
+  const float s = -1.0f / (float)B;
+  g_terms[b * 4 + 0] = s;
+  g_terms[b * 4 + 1] = s;
+  g_terms[b * 4 + 2] = -s;
+  g_terms[b * 4 + 3] = s;
+}
+
+__global__ void add_inplace_kernel(float* dst, const float* src, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+}  // namespace
+}  // namespace visde
+
+using namespace visde;
+
+extern "C" {
+
+int visde_version(void) { return VISDE_VERSION; }
+const char* visde_last_error(void) { return g_err; }
+
+size_t visde_stash_bytes(const visde_dims* d) {
+  if (check_dims(d) != VISDE_OK) return 0;
+  StashLayout s = stash_layout(d);
+  return align_up(sizeof(float) * s.h_floats) + align_up(sizeof(float) * s.raw_floats) + 256;
+}
+
+size_t visde_workspace_bytes(const visde_dims* d, int backward) {
+  if (check_dims(d) != VISDE_OK) return 0;
+  if (!backward) return align_up(sizeof(float) * (size_t)d->B * d->T * 3 * d->H) + 256;
+  return bwd_ws(d).total + 256;
+}
+
+int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_ctx_view* ctx,
+                   const float* theta, const float* eps, const visde_weights* w, float* paths,
+                   float* means, float* chol, void* stash, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if ((rc = check_weights(d, w))) return rc;
+  VISDE_REQUIRE(dt > 0.f, "time_step must be positive");
+  if (d->B == 0) return VISDE_OK;
+  VISDE_REQUIRE(x0 && paths, "x0 / paths is NULL");
+  VISDE_REQUIRE(d->T == 0 || (ctx && ctx->ptr && eps && means && chol), "NULL tensor argument");
+  VISDE_REQUIRE(d->P == 0 || theta, "theta is NULL");
+  VISDE_REQUIRE(d->variant != VISDE_VARIANT_FAST || (d->H <= 64 && d->NL <= 2 && d->S <= 4),
+                "fast variant requested for an unsupported shape (H=%d NL=%d S=%d)", d->H, d->NL, d->S);
+  if (workspace_bytes < visde_workspace_bytes(d, 0) - 256 || (!workspace && d->T > 0)) {
+    set_error("path_fwd: workspace too small (%zu < %zu)", workspace_bytes, visde_workspace_bytes(d, 0));
+    return VISDE_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  PathParams p;
+  fill_common(p, d, dt, w);
+  p.x0 = x0;
+  p.theta = theta;
+  p.eps = eps;
+  p.paths = paths;
+  p.means = means;
+  p.chol = chol;
+  float* gi = reinterpret_cast<float*>(workspace);
+  p.gi_ctx = gi;
+  if (stash) {
+    StashLayout s = stash_layout(d);
+    p.stash = reinterpret_cast<float*>(stash);
+    p.raw = reinterpret_cast<float*>(reinterpret_cast<char*>(stash) + align_up(sizeof(float) * s.h_floats));
+  }
+  if (d->T > 0) {
+    // K0: context rows of W_ih_l0 as one time-parallel GEMM, b_ih_l0 folded in
+    RowSrc A{ctx->ptr, ctx->batch_stride, ctx->time_stride, 0, d->C, ctx->dtype};
+    rc = launch_gemm_nt(A, d->B, d->T, d->C, w->w_ih[0] + d->S, d->S + d->C + d->P, 3 * d->H, w->b_ih[0], gi,
+                        3 * d->H, st);
+    if (rc) return rc;
+  }
+  return use_fast(d, p) ? launch_path_fwd_fast(p, st) : launch_path_fwd_generic(p, st);
+}
+
+int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const float* g_means,
+                   const float* g_chol, const visde_ctx_view* ctx, const float* theta,
+                   const float* eps, const visde_weights* w, const float* paths, const void* stash,
+                   float* grad_x0, const visde_ctx_grad_view* grad_ctx, float* grad_theta,
+                   const visde_weight_grads* gw, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if ((rc = check_weights(d, w))) return rc;
+  VISDE_REQUIRE(dt > 0.f, "time_step must be positive");
+  VISDE_REQUIRE(gw != nullptr, "weight grads is NULL");
+  if (d->B == 0) return VISDE_OK;
+  VISDE_REQUIRE(g_paths && grad_x0 && paths, "NULL tensor argument");
+  VISDE_REQUIRE(d->T == 0 || (g_means && g_chol && ctx && ctx->ptr && eps && stash && grad_ctx && grad_ctx->ptr),
+                "NULL tensor argument");
+  VISDE_REQUIRE(d->P == 0 || (theta && grad_theta), "theta / grad_theta is NULL");
+  BwdWs ws = bwd_ws(d);
+  if (workspace_bytes < ws.total || !workspace) {
+    set_error("path_bwd: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+    return VISDE_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = d->H, S = d->S, C = d->C, P = d->P, NL = d->NL, G = 3 * d->H;
+  const int ld0 = S + C + P;
+  char* wsb = reinterpret_cast<char*>(workspace);
+  PathParams p;
+  fill_common(p, d, dt, w);
+  p.x0 = nullptr;
+  p.theta = theta;
+  p.eps = eps;
+  p.g_paths = g_paths;
+  p.g_means = g_means;
+  p.g_chol = g_chol;
+  p.grad_x0 = grad_x0;
+  StashLayout sl = stash_layout(d);
+  p.stash = const_cast<float*>(reinterpret_cast<const float*>(stash));
+  p.raw = reinterpret_cast<float*>(const_cast<char*>(reinterpret_cast<const char*>(stash)) +
+                                   align_up(sizeof(float) * sl.h_floats));
+  p.dg = reinterpret_cast<float*>(wsb + ws.dg);
+  p.dout = reinterpret_cast<float*>(wsb + ws.dout);
+  p.sdg = reinterpret_cast<float*>(wsb + ws.sdg);
+  float* partials = reinterpret_cast<float*>(wsb + ws.partials);
+
+  // K2: reverse-time recurrence
+  rc = use_fast(d, p) ? launch_path_bwd_fast(p, st) : launch_path_bwd_generic(p, st);
+  if (rc) return rc;
+  if (d->T == 0) {
+    // no steps: every parameter gradient is zero, grad_x0 = g_paths[:, 0]
+    for (int k = 0; k < NL; ++k) {
+      VISDE_CUDA_CHECK(cudaMemsetAsync(gw->w_ih[k], 0, sizeof(float) * G * (k ? H : ld0), st));
+      VISDE_CUDA_CHECK(cudaMemsetAsync(gw->w_hh[k], 0, sizeof(float) * G * H, st));
+      VISDE_CUDA_CHECK(cudaMemsetAsync(gw->b_ih[k], 0, sizeof(float) * G, st));
+      VISDE_CUDA_CHECK(cudaMemsetAsync(gw->b_hh[k], 0, sizeof(float) * G, st));
+    }
+    VISDE_CUDA_CHECK(cudaMemsetAsync(gw->out_w, 0, sizeof(float) * p.n_out * H, st));
+    VISDE_CUDA_CHECK(cudaMemsetAsync(gw->out_b, 0, sizeof(float) * p.n_out, st));
+    if (P) VISDE_CUDA_CHECK(cudaMemsetAsync(grad_theta, 0, sizeof(float) * d->B * P, st));
+    return VISDE_OK;
+  }
+
+  const int64_t dg_t = (int64_t)NL * kDgSlots * H, dg_b = d->T * dg_t;
+  const int64_t st_t = stash_row_floats(NL, H), st_b = d->T * st_t;
+  auto dg_src = [&](int k) { return RowSrc{p.dg + (int64_t)k * kDgSlots * H, dg_b, dg_t, 0, kDgSlots * H, VISDE_F32}; };
+  auto h_src = [&](int k, int tshift) {
+    return RowSrc{p.stash + ((int64_t)k * kStashSlots + kStashH) * H, st_b, st_t, tshift, H, VISDE_F32};
+  };
+  const RowSrc ones{nullptr, 0, 0, 0, 1, VISDE_F32};
+
+  // K3: grad_context = d_gi_l0 . W_ih_l0[:, S:S+C]
+  if (C > 0) {
+    rc = launch_gemm_nn(dg_src(0), d->B, d->T, G, w->w_ih[0] + S, ld0, C, grad_ctx->ptr, grad_ctx->batch_stride,
+                        grad_ctx->time_stride, grad_ctx->dtype, st);
+    if (rc) return rc;
+  }
+  // grad_theta (through the GRU input) = (sum_t d_gi_l0) . W_ih_l0[:, S+C:]
+  if (P > 0) {
+    RowSrc A{p.sdg, G, 0, 0, G, VISDE_F32};
+    rc = launch_gemm_nn(A, d->B, 1, G, w->w_ih[0] + S + C, ld0, P, grad_theta, P, 0, VISDE_F32, st);
+    if (rc) return rc;
+  }
+  // K4: weight gradients (bias gradients ride along as a column of ones)
+  {
+    RowSrc bs[4];
+    int n = 0;
+    bs[n++] = RowSrc{paths, (int64_t)(d->T + 1) * S, S, 0, S, VISDE_F32};
+    if (C > 0) bs[n++] = RowSrc{ctx->ptr, ctx->batch_stride, ctx->time_stride, 0, C, ctx->dtype};
+    if (P > 0) bs[n++] = RowSrc{theta, P, 0, 0, P, VISDE_F32};
+    bs[n++] = ones;
+    TnOut outs[2] = {{gw->w_ih[0], ld0, 0, ld0}, {gw->b_ih[0], 1, ld0, 1}};
+    rc = launch_gemm_tn(dg_src(0), G, G, 0, bs, n, d->B, d->T, outs, 2, partials, ws.partial_floats, st);
+    if (rc) return rc;
+  }
+  for (int k = 0; k < NL; ++k) {
+    {
+      RowSrc bs[2] = {h_src(k, -1), ones};
+      TnOut outs[2] = {{gw->w_hh[k], H, 0, H}, {gw->b_hh[k], 1, H, 1}};
+      rc = launch_gemm_tn(dg_src(k), G, 2 * H, H, bs, 2, d->B, d->T, outs, 2, partials, ws.partial_floats, st);
+      if (rc) return rc;
+    }
+    if (k > 0) {
+      RowSrc bs[2] = {h_src(k - 1, 0), ones};
+      TnOut outs[2] = {{gw->w_ih[k], H, 0, H}, {gw->b_ih[k], 1, H, 1}};
+      rc = launch_gemm_tn(dg_src(k), G, G, 0, bs, 2, d->B, d->T, outs, 2, partials, ws.partial_floats, st);
+      if (rc) return rc;
+    }
+  }
+  {
+    RowSrc A{p.dout, d->T * (int64_t)p.n_out, p.n_out, 0, p.n_out, VISDE_F32};
+    RowSrc bs[2] = {h_src(NL - 1, 0), ones};
+    TnOut outs[2] = {{gw->out_w, H, 0, H}, {gw->out_b, 1, H, 1}};
+    rc = launch_gemm_tn(A, p.n_out, p.n_out, 0, bs, 2, d->B, d->T, outs, 2, partials, ws.partial_floats, st);
+    if (rc) return rc;
+  }
+  return VISDE_OK;
+}
+
+static int fill_elbo(ElboParams& e, const visde_dims* d, float dt, int sde_kind, uint32_t positive_mask,
+                     const float* z, const float* means, const float* chol, const float* theta,
+                     const float* drift, const float* diffusion, const visde_obs* obs) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  VISDE_REQUIRE(dt > 0.f, "time_step must be positive");
+  VISDE_REQUIRE(sde_kind == VISDE_SDE_GENERIC || sde_kind == VISDE_SDE_OU || sde_kind == VISDE_SDE_LV,
+                "unknown sde_kind %d", sde_kind);
+  VISDE_REQUIRE(sde_kind != VISDE_SDE_OU || (d->S == 1 && d->P == 3), "OU requires state_dim 1, sde_param_dim 3");
+  VISDE_REQUIRE(sde_kind != VISDE_SDE_LV || (d->S == 2 && d->P == 3), "LV requires state_dim 2, sde_param_dim 3");
+  VISDE_REQUIRE(d->B == 0 || z, "z is NULL");
+  VISDE_REQUIRE(d->B == 0 || d->T == 0 || (means && chol), "means / chol is NULL");
+  VISDE_REQUIRE(sde_kind == VISDE_SDE_GENERIC || d->B == 0 || theta, "theta is NULL");
+  VISDE_REQUIRE(sde_kind != VISDE_SDE_GENERIC || d->B == 0 || d->T == 0 || (drift && diffusion),
+                "generic SDE needs drift and diffusion tensors");
+  memset(&e, 0, sizeof(e));
+  e.B = d->B;
+  e.T = d->T;
+  e.S = d->S;
+  e.P = d->P;
+  e.sde_kind = sde_kind;
+  e.pos_mask = positive_mask;
+  e.dt = dt;
+  e.z = z;
+  e.means = means;
+  e.chol = chol;
+  e.theta = theta;
+  e.drift = drift;
+  e.diffusion = diffusion;
+  if (obs) {
+    VISDE_REQUIRE(obs->n_obs >= 0 && obs->obs_dim >= 0, "bad observation sizes");
+    VISDE_REQUIRE(obs->n_obs == 0 || (obs->idx && obs->values), "observation pointers are NULL");
+    VISDE_REQUIRE(obs->n_obs == 0 || obs->variance > 0.f, "variance must be positive");  // observations.py:47-50
+    VISDE_REQUIRE(obs->n_obs == 0 || obs->obs_matrix || obs->obs_dim == d->S,
+                  "observation dim %d does not match state dim %d", obs->obs_dim, d->S);
+    e.obs = *obs;
+  }
+  return VISDE_OK;
+}
+
+int visde_elbo_fwd(const visde_dims* d, float dt, int sde_kind, uint32_t positive_mask,
+                   const float* z, const float* means, const float* chol, const float* theta,
+                   const float* drift, const float* diffusion, const visde_obs* obs, float* terms,
+                   void* stream) {
+  ElboParams e;
+  int rc = fill_elbo(e, d, dt, sde_kind, positive_mask, z, means, chol, theta, drift, diffusion, obs);
+  if (rc) return rc;
+  VISDE_REQUIRE(d->B == 0 || terms, "terms is NULL");
+  e.terms = terms;
+  return launch_elbo_fwd(e, (cudaStream_t)stream);
+}
+
+int visde_elbo_bwd(const visde_dims* d, float dt, int sde_kind, uint32_t positive_mask,
+                   const float* z, const float* means, const float* chol, const float* theta,
+                   const float* drift, const float* diffusion, const visde_obs* obs,
+                   const float* g_terms, float* g_z, float* g_means, float* g_chol,
+                   float* g_theta, float* g_drift, float* g_diffusion, void* stream) {
+  ElboParams e;
+  int rc = fill_elbo(e, d, dt, sde_kind, positive_mask, z, means, chol, theta, drift, diffusion, obs);
+  if (rc) return rc;
+  VISDE_REQUIRE(d->B == 0 || (g_terms && g_z), "g_terms / g_z is NULL");
+  VISDE_REQUIRE(d->B == 0 || d->T == 0 || (g_means && g_chol), "g_means / g_chol is NULL");
+  VISDE_REQUIRE(d->B == 0 || d->P == 0 || g_theta, "g_theta is NULL");
+  VISDE_REQUIRE(sde_kind != VISDE_SDE_GENERIC || d->B == 0 || d->T == 0 || (g_drift && g_diffusion),
+                "generic SDE needs g_drift and g_diffusion");
+  e.g_terms = g_terms;
+  e.g_z = g_z;
+  e.g_means = g_means;
+  e.g_chol = g_chol;
+  e.g_theta = g_theta;
+  e.g_drift = g_drift;
+  e.g_diffusion = g_diffusion;
+  return launch_elbo_bwd(e, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer session
+// ------------------------------------------------------------------------------------------
+struct visde_session {
+  visde_dims d;
+  int sde_kind;
+  uint32_t pos_mask;
+  int n_obs, obs_dim;
+  cudaStream_t st;
+  std::vector<void*> allocs;
+  // device buffers
+  float *x0, *ctx, *theta, *eps, *paths, *means, *chol, *terms, *g_terms;
+  float *g_z, *g_means, *g_chol, *g_theta_elbo, *grad_x0, *grad_theta, *grad_ctx;
+  void *stash, *ws_f, *ws_b;
+  size_t ws_f_bytes, ws_b_bytes;
+  visde_weights w;
+  visde_weight_grads gw;
+  int32_t* obs_idx;
+  float *obs_values, *obs_matrix;
+  size_t h2d, d2h;
+  int launches;
+};
+
+}  // extern "C"
+
+namespace {
+template <typename Tp>
+int dev_alloc(visde_session* s, Tp** p, size_t bytes) {
+  void* q = nullptr;
+  VISDE_CUDA_CHECK(cudaMalloc(&q, bytes ? bytes : 16));
+  s->allocs.push_back(q);
+  *p = reinterpret_cast<Tp*>(q);
+  return VISDE_OK;
+}
+size_t w_ih_floats(const visde_dims& d, int k) { return (size_t)3 * d.H * (k ? d.H : d.S + d.C + d.P); }
+}  // namespace
+
+extern "C" {
+
+int visde_session_create(const visde_dims* d, int sde_kind, uint32_t positive_mask, int32_t n_obs,
+                         int32_t obs_dim, visde_session** out) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  VISDE_REQUIRE(out != nullptr, "out is NULL");
+  VISDE_REQUIRE(sde_kind == VISDE_SDE_OU || sde_kind == VISDE_SDE_LV,
+                "the host session supports the built-in OU / LV functors only");
+  VISDE_REQUIRE(d->B > 0 && d->T > 0, "session needs B > 0 and T > 0");
+  visde_session* s = new visde_session();
+  s->d = *d;
+  s->sde_kind = sde_kind;
+  s->pos_mask = positive_mask;
+  s->n_obs = n_obs;
+  s->obs_dim = obs_dim;
+  const size_t B = d->B, T = d->T, S = d->S, C = d->C, P = d->P, H = d->H, G = 3 * H;
+  const size_t n_out = S + S * (S + 1) / 2;
+#define A_(ptr, n) if ((rc = dev_alloc(s, &s->ptr, sizeof(float) * (n)))) { visde_session_destroy(s); return rc; }
+  if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaStreamCreate failed");
+    delete s;
+    return VISDE_ECUDA;
+  }
+  A_(x0, B * S) A_(ctx, B * (T + 1) * C) A_(theta, B * P) A_(eps, B * T * S)
+  A_(paths, B * (T + 1) * S) A_(means, B * T * S) A_(chol, B * T * S * S) A_(terms, B * 4) A_(g_terms, B * 4)
+  A_(g_z, B * (T + 1) * S) A_(g_means, B * T * S) A_(g_chol, B * T * S * S) A_(g_theta_elbo, B * P)
+  A_(grad_x0, B * S) A_(grad_theta, B * P) A_(grad_ctx, B * (T + 1) * C)
+  A_(obs_values, (size_t)n_obs * obs_dim) A_(obs_matrix, (size_t)obs_dim * S)
+  if ((rc = dev_alloc(s, &s->obs_idx, sizeof(int32_t) * n_obs))) { visde_session_destroy(s); return rc; }
+  if ((rc = dev_alloc(s, &s->stash, visde_stash_bytes(d)))) { visde_session_destroy(s); return rc; }
+  s->ws_f_bytes = visde_workspace_bytes(d, 0);
+  s->ws_b_bytes = visde_workspace_bytes(d, 1);
+  if ((rc = dev_alloc(s, &s->ws_f, s->ws_f_bytes))) { visde_session_destroy(s); return rc; }
+  if ((rc = dev_alloc(s, &s->ws_b, s->ws_b_bytes))) { visde_session_destroy(s); return rc; }
+  size_t wfloats = 0;
+  for (int k = 0; k < d->NL; ++k) {
+    float *a, *b2, *c2, *e2, *ga, *gb, *gc, *ge;
+    if ((rc = dev_alloc(s, &a, sizeof(float) * w_ih_floats(*d, k))) || (rc = dev_alloc(s, &b2, sizeof(float) * G * H)) ||
+        (rc = dev_alloc(s, &c2, sizeof(float) * G)) || (rc = dev_alloc(s, &e2, sizeof(float) * G)) ||
+        (rc = dev_alloc(s, &ga, sizeof(float) * w_ih_floats(*d, k))) || (rc = dev_alloc(s, &gb, sizeof(float) * G * H)) ||
+        (rc = dev_alloc(s, &gc, sizeof(float) * G)) || (rc = dev_alloc(s, &ge, sizeof(float) * G))) {
+      visde_session_destroy(s);
+      return rc;
+    }
+    s->w.w_ih[k] = a; s->w.w_hh[k] = b2; s->w.b_ih[k] = c2; s->w.b_hh[k] = e2;
+    s->gw.w_ih[k] = ga; s->gw.w_hh[k] = gb; s->gw.b_ih[k] = gc; s->gw.b_hh[k] = ge;
+    wfloats += w_ih_floats(*d, k) + G * H + 2 * G;
+  }
+  {
+    float *a, *b2, *ga, *gb;
+    if ((rc = dev_alloc(s, &a, sizeof(float) * n_out * H)) || (rc = dev_alloc(s, &b2, sizeof(float) * n_out)) ||
+        (rc = dev_alloc(s, &ga, sizeof(float) * n_out * H)) || (rc = dev_alloc(s, &gb, sizeof(float) * n_out))) {
+      visde_session_destroy(s);
+      return rc;
+    }
+    s->w.out_w = a; s->w.out_b = b2; s->gw.out_w = ga; s->gw.out_b = gb;
+    wfloats += n_out * H + n_out;
+  }
+#undef A_
+  // grad_ctx row T is never written by the kernels: zero it once
+  cudaMemsetAsync(s->grad_ctx, 0, sizeof(float) * B * (T + 1) * C, s->st);
+  cudaStreamSynchronize(s->st);
+  s->h2d = sizeof(float) * (B * S + B * (T + 1) * C + B * P + B * T * S + wfloats + (size_t)n_obs * obs_dim) +
+           sizeof(int32_t) * n_obs;
+  s->d2h = sizeof(float) * (B * 4 + B * S + B * P + wfloats);
+  // K0, K1, elbo fwd, cotangent fill, elbo bwd, K2, K3, grad_theta gemm, (2 NL + 1) x (tn + reduce), add
+  s->launches = 8 + 2 * (2 * d->NL + 1) + 1;
+  *out = s;
+  return VISDE_OK;
+}
+
+void visde_session_destroy(visde_session* s) {
+  if (!s) return;
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->st) cudaStreamDestroy(s->st);
+  delete s;
+}
+
+size_t visde_session_h2d_bytes(const visde_session* s) { return s ? s->h2d : 0; }
+size_t visde_session_d2h_bytes(const visde_session* s) { return s ? s->d2h : 0; }
+int visde_session_launches(const visde_session* s) { return s ? s->launches : 0; }
+
+int visde_session_step(visde_session* s, float dt, const float* x0, const float* context,
+                       const float* theta, const float* eps, const visde_weights* w_host,
+                       const visde_obs* obs_host, float* terms, float* grad_x0, float* grad_theta,
+                       const visde_weight_grads* gw_host, float* grad_context) {
+  VISDE_REQUIRE(s && x0 && context && theta && eps && w_host && obs_host && terms && grad_x0 && grad_theta && gw_host,
+                "session_step: NULL argument");
+  VISDE_REQUIRE(obs_host->n_obs == s->n_obs && obs_host->obs_dim == s->obs_dim, "session_step: observation shape changed");
+  const visde_dims& d = s->d;
+  const size_t B = d.B, T = d.T, S = d.S, C = d.C, P = d.P, H = d.H, G = 3 * H;
+  const size_t n_out = S + S * (S + 1) / 2;
+  cudaStream_t st = s->st;
+#define H2D(dst, src, n) VISDE_CUDA_CHECK(cudaMemcpyAsync((void*)(dst), (src), sizeof(float) * (n), cudaMemcpyHostToDevice, st))
+#define D2H(dst, src, n) VISDE_CUDA_CHECK(cudaMemcpyAsync((dst), (src), sizeof(float) * (n), cudaMemcpyDeviceToHost, st))
+  H2D(s->x0, x0, B * S);
+  H2D(s->ctx, context, B * (T + 1) * C);
+  H2D(s->theta, theta, B * P);
+  H2D(s->eps, eps, B * T * S);
+  for (int k = 0; k < d.NL; ++k) {
+    H2D(s->w.w_ih[k], w_host->w_ih[k], w_ih_floats(d, k));
+    H2D(s->w.w_hh[k], w_host->w_hh[k], G * H);
+    H2D(s->w.b_ih[k], w_host->b_ih[k], G);
+    H2D(s->w.b_hh[k], w_host->b_hh[k], G);
+  }
+  H2D(s->w.out_w, w_host->out_w, n_out * H);
+  H2D(s->w.out_b, w_host->out_b, n_out);
+  visde_obs od = *obs_host;
+  if (s->n_obs) {
+    H2D(s->obs_values, obs_host->values, (size_t)s->n_obs * s->obs_dim);
+    VISDE_CUDA_CHECK(cudaMemcpyAsync(s->obs_idx, obs_host->idx, sizeof(int32_t) * s->n_obs, cudaMemcpyHostToDevice, st));
+    if (obs_host->obs_matrix) H2D(s->obs_matrix, obs_host->obs_matrix, (size_t)s->obs_dim * S);
+  }
+  od.idx = s->obs_idx;
+  od.values = s->obs_values;
+  od.obs_matrix = obs_host->obs_matrix ? s->obs_matrix : nullptr;
+
+  visde_ctx_view cv{s->ctx, (int64_t)((T + 1) * C), (int64_t)C, VISDE_F32};
+  visde_ctx_grad_view gv{s->grad_ctx, (int64_t)((T + 1) * C), (int64_t)C, VISDE_F32};
+  int rc = visde_path_fwd(&d, dt, s->x0, &cv, s->theta, s->eps, &s->w, s->paths, s->means, s->chol, s->stash, s->ws_f,
+                          s->ws_f_bytes, st);
+  if (rc) return rc;
+  rc = visde_elbo_fwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, s->theta, nullptr, nullptr, &od,
+                      s->terms, st);
+  if (rc) return rc;
+  fill_loss_cotangent_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(s->g_terms, (int64_t)B);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  rc = visde_elbo_bwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, s->theta, nullptr, nullptr, &od,
+                      s->g_terms, s->g_z, s->g_means, s->g_chol, s->g_theta_elbo, nullptr, nullptr, st);
+  if (rc) return rc;
+  rc = visde_path_bwd(&d, dt, s->g_z, s->g_means, s->g_chol, &cv, s->theta, s->eps, &s->w, s->paths, s->stash,
+                      s->grad_x0, &gv, s->grad_theta, &s->gw, s->ws_b, s->ws_b_bytes, st);
+  if (rc) return rc;
+  add_inplace_kernel<<<(unsigned)((B * P + 255) / 256), 256, 0, st>>>(s->grad_theta, s->g_theta_elbo, (int64_t)(B * P));
+  VISDE_CUDA_CHECK(cudaGetLastError());
+
+  D2H(terms, s->terms, B * 4);
+  D2H(grad_x0, s->grad_x0, B * S);
+  D2H(grad_theta, s->grad_theta, B * P);
+  for (int k = 0; k < d.NL; ++k) {
+    D2H(gw_host->w_ih[k], s->gw.w_ih[k], w_ih_floats(d, k));
+    D2H(gw_host->w_hh[k], s->gw.w_hh[k], G * H);
+    D2H(gw_host->b_ih[k], s->gw.b_ih[k], G);
+    D2H(gw_host->b_hh[k], s->gw.b_hh[k], G);
+  }
+  D2H(gw_host->out_w, s->gw.out_w, n_out * H);
+  D2H(gw_host->out_b, s->gw.out_b, n_out);
+  if (grad_context) D2H(grad_context, s->grad_ctx, B * (T + 1) * C);
+#undef H2D
+#undef D2H
+  VISDE_CUDA_CHECK(cudaStreamSynchronize(st));
+  return VISDE_OK;
+}
+
+}  // extern "C"

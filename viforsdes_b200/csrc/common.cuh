@@ -1,0 +1,145 @@
+// Shared declarations for libvisde (sm_100a).  Internal; the public surface is include/visde.h.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/visde.h"
+
+namespace visde {
+
+void set_error(const char* fmt, ...);
+
+#define VISDE_CUDA_CHECK(expr)                                                            \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::visde::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,             \
+                         cudaGetErrorString(_e));                                         \
+      return VISDE_ECUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+#define VISDE_REQUIRE(cond, ...)                                                          \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      ::visde::set_error(__VA_ARGS__);                                                    \
+      return VISDE_EINVAL;                                                                \
+    }                                                                                     \
+  } while (0)
+
+constexpr int kGateR = 0, kGateU = 1, kGateN = 2;  // nn.GRU row-block order r, z(update), n
+// stash slots per (b, t, layer): r, u, n, n_hh (= W_hn h + b_hn), h_new
+constexpr int kStashR = 0, kStashU = 1, kStashN = 2, kStashNhh = 3, kStashH = 4, kStashSlots = 5;
+// backward scratch slots per (b, t, layer): d r_pre, d u_pre, d n_pre, d n_hh (= d n_pre * r)
+constexpr int kDgSlots = 4;
+
+// Everything the recurrence kernels need.  All pointers are device pointers.
+struct PathParams {
+  int64_t B, T;
+  int S, C, P, H, NL;
+  int n_tril, n_out;
+  float dt, sqrt_dt;
+  const float* x0;      // [B,S]
+  const float* theta;   // [B,P]
+  const float* eps;     // [B,T,S]
+  const float* gi_ctx;  // [B*T,3H]  context rows of W_ih_l0 applied to ctx, + b_ih_l0 (K0 output)
+  const float* w_ih[VISDE_MAX_LAYERS];
+  const float* w_hh[VISDE_MAX_LAYERS];
+  const float* b_ih[VISDE_MAX_LAYERS];
+  const float* b_hh[VISDE_MAX_LAYERS];
+  const float* out_w;
+  const float* out_b;
+  // forward outputs
+  float* paths;  // [B,T+1,S]
+  float* means;  // [B,T,S]
+  float* chol;   // [B,T,S,S]
+  float* stash;  // [B,T,NL,5,H] or nullptr
+  float* raw;    // [B,T,n_tril] raw (unfloored) Cholesky params, or nullptr
+  // backward inputs
+  const float* g_paths;  // [B,T+1,S]
+  const float* g_means;  // [B,T,S]
+  const float* g_chol;   // [B,T,S,S]
+  // backward outputs
+  float* grad_x0;  // [B,S]
+  float* dg;       // [B*T,NL,4,H]
+  float* dout;     // [B*T,n_out]
+  float* sdg;      // [B,3H]  sum_t d_gi of layer 0
+};
+
+__host__ __device__ inline int64_t stash_row_floats(int NL, int H) { return (int64_t)NL * kStashSlots * H; }
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// tanh via exp: abs error ~1e-7 (the hidden state only needs absolute accuracy)
+__device__ __forceinline__ float tanh_f(float x) {
+  float e = __expf(2.0f * x);
+  return 1.0f - 2.0f / (e + 1.0f);
+}
+
+// launchers (return 0 / VISDE_E*)
+int launch_path_fwd_generic(const PathParams& p, cudaStream_t st);
+int launch_path_bwd_generic(const PathParams& p, cudaStream_t st);
+bool fast_supported(const PathParams& p);
+int launch_path_fwd_fast(const PathParams& p, cudaStream_t st);
+int launch_path_bwd_fast(const PathParams& p, cudaStream_t st);
+
+// --- SIMT fp32 GEMMs with (b,t) row gathering -------------------------------------------
+// A "row source": row k = (b, t) with b = k / T, t = k % T lives at
+//   base + b*bstride + (t + tshift)*tstride + col; rows with t + tshift < 0 read as zero.
+// base == nullptr means a column of ones (used to fold bias gradients into a GEMM).
+struct RowSrc {
+  const void* base;
+  int64_t bstride, tstride;
+  int tshift;
+  int ncols;
+  int dtype;  // VISDE_F32 / VISDE_BF16
+};
+
+// out[k, n] = bias[n] + sum_c A[k, c] * W[n*ldw + c]          (k over B*T rows, "NT")
+int launch_gemm_nt(const RowSrc& A, int64_t B, int64_t T, int K, const float* W, int ldw, int N,
+                   const float* bias, float* out, int ldo, cudaStream_t st);
+// out[(b,t), c] = sum_n A[k, n] * W[n*ldw + c]   written to a strided fp32/bf16 view ("NN")
+int launch_gemm_nn(const RowSrc& A, int64_t B, int64_t T, int K, const float* W, int ldw, int N,
+                   void* out, int64_t out_bstride, int64_t out_tstride, int out_dtype,
+                   cudaStream_t st);
+// C[m, n] = sum_k A[k, amap(m)] * Bcat[k, n]; Bcat = concatenation of up to 3 row sources.
+// amap: m < a_split -> m, else m + a_skip (selects the (r,u,n_hh) columns of a 4H-wide row).
+// Split-K over CTAs into `partials`, then a fixed-order reduction writes C (ldc) -- deterministic.
+struct TnOut {
+  float* ptr;  // destination for columns [col0, col0+ncols) of the product; row-major, ld
+  int ld;
+  int col0, ncols;
+};
+int launch_gemm_tn(const RowSrc& A, int M, int a_split, int a_skip, const RowSrc* Bsrc, int nsrc,
+                   int64_t B, int64_t T, const TnOut* outs, int nouts, float* partials,
+                   size_t partial_floats, cudaStream_t st);
+size_t gemm_tn_partial_floats(int M, int N, int64_t K);
+
+// --- ELBO ---------------------------------------------------------------------------------
+struct ElboParams {
+  int64_t B, T;
+  int S, P;
+  int sde_kind;
+  uint32_t pos_mask;
+  float dt;
+  const float* z;
+  const float* means;
+  const float* chol;
+  const float* theta;
+  const float* drift;
+  const float* diffusion;
+  visde_obs obs;
+  float* terms;         // fwd out [B,4]
+  const float* g_terms; // bwd in  [B,4]
+  float* g_z;
+  float* g_means;
+  float* g_chol;
+  float* g_theta;
+  float* g_drift;
+  float* g_diffusion;
+};
+int launch_elbo_fwd(const ElboParams& p, cudaStream_t st);
+int launch_elbo_bwd(const ElboParams& p, cudaStream_t st);
+
+}  // namespace visde

@@ -1,0 +1,404 @@
+// Time-parallel ELBO terms (forward and backward) -- K5/K6.
+//
+// Restates, as one pass over (b, tau) with tau in [0, T], the path-dependent terms of
+// inference/evidence_lower_bound.py:28-56:
+//   sde  = sum_t log N(x_{t+1}; x_t + f(x_t,th) dt, D(x_t,th) sqrt(dt))      (:42-44, :77-83)
+//   gen  = sum_t log N(z_{t+1}; z_t + mu_t dt,     L_t sqrt(dt))             (:46-48)
+//   jac  = sum_{t>=1} sum_{pos} logsigmoid(z_t)                              (:50, types.py:23-24)
+//   obs  = sum_k log N(y_k; Hx[idx_k], var)                                  (:52-56, observations.py:52-74)
+// with x = softplus(z) on positive dims (state_space.py:20-25; torch threshold 20), and f, D either
+// the built-in Ornstein-Uhlenbeck / Lotka-Volterra functors (examples/*.py) or caller tensors.
+// The Gaussian terms solve the triangular system in fp32 exactly like
+// MultivariateNormal(scale_tril).log_prob, rather than using the analytic |eps|^2 shortcut, so the
+// partial derivatives w.r.t. (z, mu, L) are the ones the reference's autograd produces.
+// One CTA per trajectory; per-trajectory sums by block reduction (no atomics, deterministic).
+#include "common.cuh"
+
+namespace visde {
+namespace {
+
+constexpr int kElboThreads = 128;
+constexpr float kHalfLog2Pi = 0.91893853320467274178f;
+
+__device__ __forceinline__ float softplus_f(float z) { return z > 20.f ? z : log1pf(expf(z)); }
+__device__ __forceinline__ float softplus_grad_f(float z) { return z > 20.f ? 1.f : 1.f / (1.f + expf(-z)); }
+__device__ __forceinline__ float logsigmoid_f(float z) { return fminf(z, 0.f) - log1pf(expf(-fabsf(z))); }
+
+// y = A^{-1} r (forward substitution), lp = -1/2 |y|^2 - sum log A_ii - S/2 log 2pi,
+// optionally w = A^{-T} y (back substitution).  A lower-triangular [SMAX][SMAX], S <= SMAX.
+template <int SMAX>
+__device__ __forceinline__ float gauss_solve(int S, const float (&A)[SMAX][SMAX], const float (&r)[SMAX],
+                                             float (&y)[SMAX], float (&w)[SMAX], bool want_w) {
+  float lp = 0.f;
+#pragma unroll
+  for (int i = 0; i < SMAX; ++i) {
+    y[i] = 0.f;
+    if (i < S) {
+      float acc = r[i];
+#pragma unroll
+      for (int j = 0; j < i; ++j) acc -= A[i][j] * y[j];
+      y[i] = acc / A[i][i];
+      lp += -0.5f * y[i] * y[i] - logf(A[i][i]) - kHalfLog2Pi;
+    }
+  }
+  if (want_w) {
+#pragma unroll
+    for (int i = SMAX - 1; i >= 0; --i) {
+      w[i] = 0.f;
+      if (i < S) {
+        float acc = y[i];
+#pragma unroll
+        for (int j = i + 1; j < SMAX; ++j)
+          if (j < S) acc -= A[j][i] * w[j];
+        w[i] = acc / A[i][i];
+      }
+    }
+  }
+  return lp;
+}
+
+template <int SMAX>
+__device__ __forceinline__ void load_vec(const float* p, int S, float (&v)[SMAX]) {
+#pragma unroll
+  for (int i = 0; i < SMAX; ++i) v[i] = i < S ? p[i] : 0.f;
+}
+
+template <int SMAX>
+__device__ __forceinline__ void load_tril_scaled(const float* p, int S, float scale, float (&A)[SMAX][SMAX]) {
+#pragma unroll
+  for (int i = 0; i < SMAX; ++i)
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) A[i][j] = (i < S && j <= i) ? p[i * S + j] * scale : 0.f;
+}
+
+template <int SMAX>
+__device__ __forceinline__ void to_state_vec(int S, uint32_t mask, const float (&z)[SMAX], float (&x)[SMAX]) {
+#pragma unroll
+  for (int i = 0; i < SMAX; ++i) x[i] = (i < S && ((mask >> i) & 1u)) ? softplus_f(z[i]) : z[i];
+}
+
+// Lotka-Volterra Cholesky factor of the diffusion matrix (examples/lotka_volterra.py:31-46)
+struct LvDiff {
+  float b11, b12, b22, L00, d00, L10, e, L11;
+};
+__device__ __forceinline__ LvDiff lv_diffusion(float u, float v, float t1, float t2, float t3) {
+  LvDiff d;
+  float uv = u * v;
+  d.b11 = t1 * u + t2 * uv;
+  d.b12 = -t2 * uv;
+  d.b22 = t3 * v + t2 * uv;
+  d.L00 = sqrtf(fmaxf(d.b11, 1e-6f));
+  d.d00 = fmaxf(d.L00, 1e-6f);
+  d.L10 = d.b12 / d.d00;
+  d.e = d.b22 - d.L10 * d.L10;
+  d.L11 = sqrtf(fmaxf(d.e, 1e-6f));
+  return d;
+}
+
+// Builds the SDE transition's mean residual and scaled Cholesky factor for transition t of
+// trajectory b:  r = x_next - (x_t + f dt),  A = D sqrt(dt).
+template <int SMAX>
+__device__ __forceinline__ void sde_transition(const ElboParams& p, int64_t b, int64_t t, const float* th,
+                                               const float (&xt)[SMAX], const float (&xn)[SMAX],
+                                               float (&r)[SMAX], float (&A)[SMAX][SMAX]) {
+  const int S = p.S;
+  const float sq = sqrtf(p.dt);
+#pragma unroll
+  for (int i = 0; i < SMAX; ++i)
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) A[i][j] = 0.f;
+  if (p.sde_kind == VISDE_SDE_OU) {
+    r[0] = xn[0] - (xt[0] + th[0] * (th[1] - xt[0]) * p.dt);
+    A[0][0] = th[2] * sq;
+  } else if (p.sde_kind == VISDE_SDE_LV) {
+    if (SMAX >= 2) {
+      float u = xt[0], v = xt[1 % SMAX];
+      float f0 = th[0] * u - th[1] * u * v;
+      float f1 = th[1] * u * v - th[2] * v;
+      r[0] = xn[0] - (u + f0 * p.dt);
+      r[1 % SMAX] = xn[1 % SMAX] - (v + f1 * p.dt);
+      LvDiff d = lv_diffusion(u, v, th[0], th[1], th[2]);
+      A[0][0] = d.L00 * sq;
+      A[1 % SMAX][0] = d.L10 * sq;
+      A[1 % SMAX][1 % SMAX] = d.L11 * sq;
+    }
+  } else {
+    const float* f = p.drift + (b * p.T + t) * S;
+    const float* D = p.diffusion + (b * p.T + t) * (int64_t)S * S;
+#pragma unroll
+    for (int i = 0; i < SMAX; ++i) r[i] = i < S ? xn[i] - (xt[i] + f[i] * p.dt) : 0.f;
+    load_tril_scaled<SMAX>(D, S, sq, A);
+  }
+}
+
+template <int SMAX>
+__device__ __forceinline__ void gen_transition(const ElboParams& p, int64_t b, int64_t t,
+                                               const float (&zt)[SMAX], const float (&zn)[SMAX],
+                                               float (&r)[SMAX], float (&A)[SMAX][SMAX]) {
+  const int S = p.S;
+  const float* mu = p.means + (b * p.T + t) * S;
+#pragma unroll
+  for (int i = 0; i < SMAX; ++i) r[i] = i < S ? zn[i] - (zt[i] + mu[i] * p.dt) : 0.f;
+  load_tril_scaled<SMAX>(p.chol + (b * p.T + t) * (int64_t)S * S, S, sqrtf(p.dt), A);
+}
+
+// observation log-likelihood at grid index tau (all observations whose idx == tau)
+template <int SMAX>
+__device__ __forceinline__ float obs_term(const ElboParams& p, int64_t tau, const float (&x)[SMAX],
+                                          float g_obs, float (&gx)[SMAX], bool want_grad) {
+  float lp = 0.f;
+  const visde_obs& o = p.obs;
+  for (int k = 0; k < o.n_obs; ++k) {
+    if ((int64_t)o.idx[k] != tau) continue;
+    for (int d = 0; d < o.obs_dim; ++d) {
+      float pred = 0.f;
+      if (o.obs_matrix) {
+#pragma unroll
+        for (int s = 0; s < SMAX; ++s)
+          if (s < p.S) pred += o.obs_matrix[d * p.S + s] * x[s];
+      } else {
+#pragma unroll
+        for (int s = 0; s < SMAX; ++s)
+          if (s == d) pred = x[s];
+      }
+      float diff = o.values[k * o.obs_dim + d] - pred;
+      lp += -0.5f * diff * diff / o.variance - 0.5f * logf(6.283185307179586f * o.variance);
+      if (want_grad) {
+        float gp = g_obs * diff / o.variance;
+        if (o.obs_matrix) {
+#pragma unroll
+          for (int s = 0; s < SMAX; ++s)
+            if (s < p.S) gx[s] += gp * o.obs_matrix[d * p.S + s];
+        } else {
+#pragma unroll
+          for (int s = 0; s < SMAX; ++s)
+            if (s == d) gx[s] += gp;
+        }
+      }
+    }
+  }
+  return lp;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kElboThreads / 32; ++i) s += red[i];
+  return s;
+}
+
+template <int SMAX>
+__global__ void __launch_bounds__(kElboThreads) elbo_fwd_kernel(ElboParams p) {
+  __shared__ float red[kElboThreads / 32];
+  const int S = p.S;
+  for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+    float th[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.sde_kind != VISDE_SDE_GENERIC)
+      for (int q = 0; q < 3; ++q) th[q] = p.theta[b * p.P + q];
+    float s_obs = 0.f, s_sde = 0.f, s_gen = 0.f, s_jac = 0.f;
+    for (int64_t tau = threadIdx.x; tau <= p.T; tau += kElboThreads) {
+      float zt[SMAX], xt[SMAX];
+      load_vec<SMAX>(p.z + (b * (p.T + 1) + tau) * S, S, zt);
+      to_state_vec<SMAX>(S, p.pos_mask, zt, xt);
+      if (tau >= 1) {
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i)
+          if (i < S && ((p.pos_mask >> i) & 1u)) s_jac += logsigmoid_f(zt[i]);
+      }
+      float dummy[SMAX];
+      s_obs += obs_term<SMAX>(p, tau, xt, 0.f, dummy, false);
+      if (tau < p.T) {
+        float zn[SMAX], xn[SMAX], r[SMAX], y[SMAX], w[SMAX], A[SMAX][SMAX];
+        load_vec<SMAX>(p.z + (b * (p.T + 1) + tau + 1) * S, S, zn);
+        to_state_vec<SMAX>(S, p.pos_mask, zn, xn);
+        gen_transition<SMAX>(p, b, tau, zt, zn, r, A);
+        s_gen += gauss_solve<SMAX>(S, A, r, y, w, false);
+        sde_transition<SMAX>(p, b, tau, th, xt, xn, r, A);
+        s_sde += gauss_solve<SMAX>(S, A, r, y, w, false);
+      }
+    }
+    s_obs = block_sum(s_obs, red);
+    s_sde = block_sum(s_sde, red);
+    s_gen = block_sum(s_gen, red);
+    s_jac = block_sum(s_jac, red);
+    if (threadIdx.x == 0) {
+      float* o = p.terms + b * 4;
+      o[0] = s_obs;
+      o[1] = s_sde;
+      o[2] = s_gen;
+      o[3] = s_jac;
+    }
+  }
+}
+
+template <int SMAX>
+__global__ void __launch_bounds__(kElboThreads) elbo_bwd_kernel(ElboParams p) {
+  __shared__ float red[kElboThreads / 32];
+  const int S = p.S;
+  const float sq = sqrtf(p.dt);
+  for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+    float th[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.sde_kind != VISDE_SDE_GENERIC)
+      for (int q = 0; q < 3; ++q) th[q] = p.theta[b * p.P + q];
+    const float g_obs = p.g_terms[b * 4 + 0], g_sde = p.g_terms[b * 4 + 1];
+    const float g_gen = p.g_terms[b * 4 + 2], g_jac = p.g_terms[b * 4 + 3];
+    float gth[3] = {0.f, 0.f, 0.f};
+    for (int64_t tau = threadIdx.x; tau <= p.T; tau += kElboThreads) {
+      float zt[SMAX], xt[SMAX], spg[SMAX], gz[SMAX], gx[SMAX];
+      load_vec<SMAX>(p.z + (b * (p.T + 1) + tau) * S, S, zt);
+      to_state_vec<SMAX>(S, p.pos_mask, zt, xt);
+#pragma unroll
+      for (int i = 0; i < SMAX; ++i) {
+        bool pos = i < S && ((p.pos_mask >> i) & 1u);
+        spg[i] = pos ? softplus_grad_f(zt[i]) : 1.f;
+        gz[i] = 0.f;
+        gx[i] = 0.f;
+        if (pos && tau >= 1) gz[i] += g_jac * (1.f - 1.f / (1.f + expf(-zt[i])));
+      }
+      obs_term<SMAX>(p, tau, xt, g_obs, gx, true);
+      float r[SMAX], y[SMAX], w[SMAX], A[SMAX][SMAX];
+      if (tau >= 1) {
+        // this point is x_next / z_next of transition tau-1: d lp / d next = -w
+        float zp[SMAX], xp[SMAX];
+        load_vec<SMAX>(p.z + (b * (p.T + 1) + tau - 1) * S, S, zp);
+        to_state_vec<SMAX>(S, p.pos_mask, zp, xp);
+        gen_transition<SMAX>(p, b, tau - 1, zp, zt, r, A);
+        gauss_solve<SMAX>(S, A, r, y, w, true);
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i) gz[i] -= g_gen * w[i];
+        sde_transition<SMAX>(p, b, tau - 1, th, xp, xt, r, A);
+        gauss_solve<SMAX>(S, A, r, y, w, true);
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i) gx[i] -= g_sde * w[i];
+      }
+      if (tau < p.T) {
+        const int64_t row = b * p.T + tau;
+        float zn[SMAX], xn[SMAX];
+        load_vec<SMAX>(p.z + (b * (p.T + 1) + tau + 1) * S, S, zn);
+        to_state_vec<SMAX>(S, p.pos_mask, zn, xn);
+        // generative (variational) transition: gradients w.r.t. z_t, mu_t, L_t
+        gen_transition<SMAX>(p, b, tau, zt, zn, r, A);
+        gauss_solve<SMAX>(S, A, r, y, w, true);
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i) {
+          if (i < S) {
+            gz[i] += g_gen * w[i];
+            p.g_means[row * S + i] = g_gen * w[i] * p.dt;
+#pragma unroll
+            for (int j = 0; j < SMAX; ++j)
+              if (j < S) {
+                float g = 0.f;
+                if (j <= i) g = g_gen * sq * (w[i] * y[j] - (i == j ? 1.f / A[i][i] : 0.f));
+                p.g_chol[(row * S + i) * S + j] = g;
+              }
+          }
+        }
+        // SDE transition: gradients w.r.t. x_t (direct + through f, D) and theta
+        sde_transition<SMAX>(p, b, tau, th, xt, xn, r, A);
+        gauss_solve<SMAX>(S, A, r, y, w, true);
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i) gx[i] += g_sde * w[i];  // through the mean's x_t term
+        if (p.sde_kind == VISDE_SDE_OU) {
+          float gf = g_sde * w[0] * p.dt;
+          float gD = g_sde * sq * (w[0] * y[0] - 1.f / A[0][0]);
+          gx[0] += gf * (-th[0]);
+          gth[0] += gf * (th[1] - xt[0]);
+          gth[1] += gf * th[0];
+          gth[2] += gD;
+        } else if (p.sde_kind == VISDE_SDE_LV) {
+          if (SMAX >= 2) {
+            const float u = xt[0], v = xt[1 % SMAX], t1 = th[0], t2 = th[1], t3 = th[2], uv = u * v;
+            const float w0 = w[0], w1 = w[1 % SMAX], y0 = y[0], y1 = y[1 % SMAX];
+            float gf0 = g_sde * w0 * p.dt, gf1 = g_sde * w1 * p.dt;
+            float gL00 = g_sde * sq * (w0 * y0 - 1.f / A[0][0]);
+            float gL10 = g_sde * sq * (w1 * y0);
+            float gL11 = g_sde * sq * (w1 * y1 - 1.f / A[1 % SMAX][1 % SMAX]);
+            LvDiff d = lv_diffusion(u, v, t1, t2, t3);
+            // reverse through the Cholesky with torch.clamp's inclusive pass-through
+            float g_e = (d.e >= 1e-6f) ? gL11 * 0.5f / d.L11 : 0.f;
+            float g_b22 = g_e;
+            float g_L10 = gL10 - 2.f * d.L10 * g_e;
+            float g_b12 = g_L10 / d.d00;
+            float g_d00 = -g_L10 * d.b12 / (d.d00 * d.d00);
+            float g_L00 = gL00 + ((d.L00 >= 1e-6f) ? g_d00 : 0.f);
+            float g_b11 = (d.b11 >= 1e-6f) ? g_L00 * 0.5f / d.L00 : 0.f;
+            float g_t1 = g_b11 * u + gf0 * u;
+            float g_t2 = (g_b11 - g_b12 + g_b22) * uv + (gf1 - gf0) * uv;
+            float g_t3 = g_b22 * v - gf1 * v;
+            float g_uv = (g_b11 - g_b12 + g_b22) * t2 + (gf1 - gf0) * t2;
+            float g_u = g_b11 * t1 + gf0 * t1 + g_uv * v;
+            float g_v = g_b22 * t3 - gf1 * t3 + g_uv * u;
+            gx[0] += g_u;
+            gx[1 % SMAX] += g_v;
+            gth[0] += g_t1;
+            gth[1] += g_t2;
+            gth[2] += g_t3;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < SMAX; ++i) {
+            if (i < S) {
+              p.g_drift[row * S + i] = g_sde * w[i] * p.dt;
+#pragma unroll
+              for (int j = 0; j < SMAX; ++j)
+                if (j < S) {
+                  float g = 0.f;
+                  if (j <= i) g = g_sde * sq * (w[i] * y[j] - (i == j ? 1.f / A[i][i] : 0.f));
+                  p.g_diffusion[(row * S + i) * S + j] = g;
+                }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < SMAX; ++i)
+        if (i < S) p.g_z[(b * (p.T + 1) + tau) * S + i] = gz[i] + gx[i] * spg[i];
+    }
+    float t0 = block_sum(gth[0], red), t1 = block_sum(gth[1], red), t2 = block_sum(gth[2], red);
+    if (threadIdx.x == 0) {
+      for (int q = 0; q < p.P; ++q) p.g_theta[b * p.P + q] = 0.f;
+      if (p.sde_kind != VISDE_SDE_GENERIC) {
+        p.g_theta[b * p.P + 0] = t0;
+        p.g_theta[b * p.P + 1] = t1;
+        p.g_theta[b * p.P + 2] = t2;
+      }
+    }
+  }
+}
+
+int elbo_grid(int64_t B) {
+  int64_t cap = 148 * 16;
+  return (int)(B < cap ? B : cap);
+}
+
+template <int SMAX>
+int launch_both(const ElboParams& p, cudaStream_t st, bool bwd) {
+  if (bwd)
+    elbo_bwd_kernel<SMAX><<<elbo_grid(p.B), kElboThreads, 0, st>>>(p);
+  else
+    elbo_fwd_kernel<SMAX><<<elbo_grid(p.B), kElboThreads, 0, st>>>(p);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  return VISDE_OK;
+}
+
+int dispatch(const ElboParams& p, cudaStream_t st, bool bwd) {
+  if (p.B == 0) return VISDE_OK;
+  if (p.S <= 1) return launch_both<1>(p, st, bwd);
+  if (p.S <= 2) return launch_both<2>(p, st, bwd);
+  if (p.S <= 4) return launch_both<4>(p, st, bwd);
+  if (p.S <= 8) return launch_both<8>(p, st, bwd);
+  return launch_both<16>(p, st, bwd);
+}
+
+}  // namespace
+
+int launch_elbo_fwd(const ElboParams& p, cudaStream_t st) { return dispatch(p, st, false); }
+int launch_elbo_bwd(const ElboParams& p, cudaStream_t st) { return dispatch(p, st, true); }
+
+}  // namespace visde

@@ -1,0 +1,99 @@
+"""``DiffusionTransitionHead`` -- drop-in for src/variational_sde/models/head.py:20-209.
+
+Same constructor, parameter / buffer names (so reference checkpoints load: ``gru.weight_ih_l{k}``,
+``gru.weight_hh_l{k}``, ``gru.bias_ih_l{k}``, ``gru.bias_hh_l{k}``, ``out_proj.weight``,
+``out_proj.bias``, ``_tril_rows``, ``_tril_cols``, ``_diag_mask``) and the same
+``HeadProtocol.sample_diffusion_paths`` signature (inference/diffusion_path_sampler.py:24-32).
+Only the dispatch changes: the Triton ``_SDEFunction`` / ``launch_fwd`` are replaced by the
+``visde::path_fwd`` custom op (sm_100a CUDA kernels); the nn.GRU weights are read in their native
+layout, so the per-call stack / transpose copies of head.py:106-154 and weights.py:176-196 vanish.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+from torch import Tensor, nn
+
+from viforsdes_b200 import ops  # noqa: F401  (registers torch.ops.visde.*)
+
+MAX_LAYERS = 4  # src/variational_sde/kernels/constants.py:13
+DIAG_MIN = 1e-2  # src/variational_sde/inference/constants.py:6
+
+
+@dataclass(frozen=True)
+class HeadConfig:
+    """src/variational_sde/config.py:83-92."""
+
+    hidden_dim: int = 64
+    num_layers: int = 2
+
+    def __post_init__(self) -> None:
+        if self.hidden_dim <= 0 or self.num_layers <= 0:
+            raise ValueError("value must be positive")
+
+
+class DiffusionTransitionHead(nn.Module):
+    _tril_rows: Tensor
+    _tril_cols: Tensor
+    _diag_mask: Tensor
+
+    def __init__(self, state_dim: int, context_dim: int, sde_param_dim: int, config: HeadConfig) -> None:
+        super().__init__()
+        if config.num_layers < 1 or config.num_layers > MAX_LAYERS:
+            raise ValueError(f"num_layers must be in [1, {MAX_LAYERS}], got {config.num_layers}")
+        self.state_dim = state_dim
+        self.context_dim = context_dim
+        self.sde_param_dim = sde_param_dim
+        self.hidden_dim = config.hidden_dim
+        self.num_layers = config.num_layers
+        self.n_tril = state_dim * (state_dim + 1) // 2
+
+        rows, cols = torch.tril_indices(state_dim, state_dim)
+        self.register_buffer("_tril_rows", rows)
+        self.register_buffer("_tril_cols", cols)
+        self.register_buffer("_diag_mask", rows == cols)
+
+        self.gru = nn.GRU(input_size=state_dim + context_dim + sde_param_dim, hidden_size=config.hidden_dim,
+                          num_layers=config.num_layers, batch_first=True)
+        self.out_proj = nn.Linear(config.hidden_dim, state_dim + self.n_tril)
+        self._init_out_proj()
+
+    def _init_out_proj(self) -> None:
+        # head.py:60-66: mu = 0 and L = I at initialisation
+        with torch.no_grad():
+            self.out_proj.weight.zero_()
+            self.out_proj.bias.zero_()
+            for k in range(self.state_dim):
+                self.out_proj.bias[self.state_dim + k * (k + 3) // 2] = 1.0
+
+    def init_hidden(self, batch: int, device: torch.device, dtype: torch.dtype = torch.float32) -> Tensor:
+        return torch.zeros(self.num_layers, batch, self.hidden_dim, device=device, dtype=dtype)
+
+    def _weight_lists(self):
+        nl = self.num_layers
+        g = self.gru
+        return ([getattr(g, f"weight_ih_l{k}") for k in range(nl)], [getattr(g, f"weight_hh_l{k}") for k in range(nl)],
+                [getattr(g, f"bias_ih_l{k}") for k in range(nl)], [getattr(g, f"bias_hh_l{k}") for k in range(nl)])
+
+    def sample_diffusion_paths(self, x0: Tensor, context: Tensor, sde_parameters: Tensor, standard_noise: Tensor,
+                               time_step: float) -> tuple[Tensor, Tensor, Tensor]:
+        """x0 [B,S] latent, context [B,T,C] (fp32/bf16, may be the strided view context[:, :-1]),
+        sde_parameters [B,P], standard_noise [B,T,S] -> paths [B,T+1,S], means [B,T,S], chol [B,T,S,S].
+        Training mode records the autograd graph (head.py:164-199); eval mode is the no-grad,
+        no-stash launch (head.py:200-209)."""
+        if context.shape[-1] != self.context_dim or sde_parameters.shape[-1] != self.sde_param_dim:
+            raise ValueError("context / sde_parameters feature dims do not match the head")
+        w_ih, w_hh, b_ih, b_hh = self._weight_lists()
+        if self.training and torch.is_grad_enabled():
+            paths, means, chol, _ = torch.ops.visde.path_fwd(
+                x0, context, sde_parameters, standard_noise, w_ih, w_hh, b_ih, b_hh, self.out_proj.weight,
+                self.out_proj.bias, float(time_step), True)
+        else:
+            with torch.no_grad():
+                paths, means, chol, _ = torch.ops.visde.path_fwd(
+                    x0, context, sde_parameters, standard_noise, w_ih, w_hh, b_ih, b_hh, self.out_proj.weight,
+                    self.out_proj.bias, float(time_step), False)
+        if x0.dtype != torch.float32:  # autograd.py:117-122
+            return paths.to(x0.dtype), means.to(x0.dtype), chol.to(x0.dtype)
+        return paths, means, chol

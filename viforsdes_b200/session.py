@@ -1,0 +1,109 @@
+"""Host-buffer iteration through the C ABI (``visde_session_*`` in include/visde.h): the call a
+non-PyTorch host (or the reference's trainer, inference/trainer.py:176-198, via ctypes) makes for
+one ELBO iteration of the path: pinned host tensors in, ELBO terms and gradients out."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List
+
+import torch
+from torch import Tensor
+
+from viforsdes_b200 import _lib
+
+
+def _pin(t: Tensor) -> Tensor:
+    t = t.detach().to(torch.float32).contiguous().cpu()
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+class HostSession:
+    def __init__(self, *, x0: Tensor, context_full: Tensor, theta: Tensor, eps: Tensor, w_ih: List[Tensor],
+                 w_hh: List[Tensor], b_ih: List[Tensor], b_hh: List[Tensor], out_w: Tensor, out_b: Tensor, dt: float,
+                 sde_kind: int, positive_mask: int, obs_idx: Tensor, obs_values: Tensor, obs_variance: float,
+                 variant: int = _lib.VARIANT_AUTO, want_grad_context: bool = False) -> None:
+        self.lib = _lib.load()
+        B, S = x0.shape
+        T, Cd = context_full.shape[1] - 1, context_full.shape[2]
+        P, NL, H = theta.shape[1], len(w_hh), w_hh[0].shape[1]
+        self.dims = _lib.Dims(B, T, S, Cd, P, H, NL, variant)
+        self.dt = float(dt)
+        self.x0, self.ctx, self.theta, self.eps = _pin(x0), _pin(context_full), _pin(theta), _pin(eps)
+        self.w = [[_pin(t) for t in ws] for ws in (w_ih, w_hh, b_ih, b_hh)]
+        self.out_w, self.out_b = _pin(out_w), _pin(out_b)
+        self.gw = [[torch.empty_like(t).pin_memory() for t in ws] for ws in self.w]
+        self.g_out_w, self.g_out_b = torch.empty_like(self.out_w).pin_memory(), torch.empty_like(self.out_b).pin_memory()
+        self.terms = torch.empty(B, 4).pin_memory()
+        self.grad_x0 = torch.empty(B, S).pin_memory()
+        self.grad_theta = torch.empty(B, P).pin_memory()
+        self.grad_ctx = torch.empty(B, T + 1, Cd).pin_memory() if want_grad_context else None
+        self.obs_idx = obs_idx.detach().to(torch.int32).contiguous().cpu()
+        self.obs_values = obs_values.detach().to(torch.float32).contiguous().cpu()
+        self.obs = _lib.Obs(self.obs_idx.shape[0], self.obs_values.shape[1], self.obs_idx.data_ptr(),
+                            self.obs_values.data_ptr(), None, float(obs_variance))
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.visde_session_create(C.byref(self.dims), sde_kind, positive_mask, self.obs.n_obs,
+                                                 self.obs.obs_dim, C.byref(self.handle)))
+
+    @classmethod
+    def from_problem(cls, p, **kw) -> "HostSession":
+        """Build from an oracle ``Problem`` (tests / bench only construct the inputs there)."""
+        B, T, Cd = p.context.shape
+        full = torch.zeros(B, T + 1, Cd)
+        full[:, :T] = p.context
+        w = p.weights
+        kind = {"ou": _lib.SDE_OU, "lv": _lib.SDE_LV}[p.name]
+        mask = 0
+        for d in p.positive_dims:
+            mask |= 1 << d
+        idx = torch.clamp(torch.round(p.obs_times / p.dt).long(), max=T)
+        return cls(x0=p.x0, context_full=full, theta=p.theta, eps=p.eps, w_ih=w.w_ih, w_hh=w.w_hh, b_ih=w.b_ih,
+                   b_hh=w.b_hh, out_w=w.out_w, out_b=w.out_b, dt=p.dt, sde_kind=kind, positive_mask=mask,
+                   obs_idx=idx, obs_values=p.obs_values, obs_variance=p.obs_variance, **kw)
+
+    def _wstruct(self, groups, ow, ob) -> _lib.Weights:
+        s = _lib.Weights()
+        for k in range(self.dims.NL):
+            s.w_ih[k], s.w_hh[k] = groups[0][k].data_ptr(), groups[1][k].data_ptr()
+            s.b_ih[k], s.b_hh[k] = groups[2][k].data_ptr(), groups[3][k].data_ptr()
+        s.out_w, s.out_b = ow.data_ptr(), ob.data_ptr()
+        return s
+
+    @property
+    def h2d_bytes(self) -> int:
+        return int(self.lib.visde_session_h2d_bytes(self.handle))
+
+    @property
+    def d2h_bytes(self) -> int:
+        extra = self.grad_ctx.numel() * 4 if self.grad_ctx is not None else 0
+        return int(self.lib.visde_session_d2h_bytes(self.handle)) + extra
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.visde_session_launches(self.handle))
+
+    def step(self) -> Dict[str, object]:
+        w = self._wstruct(self.w, self.out_w, self.out_b)
+        gw = self._wstruct(self.gw, self.g_out_w, self.g_out_b)
+        _lib.check(self.lib.visde_session_step(
+            self.handle, self.dt, self.x0.data_ptr(), self.ctx.data_ptr(), self.theta.data_ptr(), self.eps.data_ptr(),
+            C.byref(w), C.byref(self.obs), self.terms.data_ptr(), self.grad_x0.data_ptr(), self.grad_theta.data_ptr(),
+            C.byref(gw), None if self.grad_ctx is None else self.grad_ctx.data_ptr()))
+        grads = {"x0": self.grad_x0, "theta": self.grad_theta, "out_w": self.g_out_w, "out_b": self.g_out_b}
+        for k in range(self.dims.NL):
+            grads[f"w_ih_l{k}"], grads[f"w_hh_l{k}"] = self.gw[0][k], self.gw[1][k]
+            grads[f"b_ih_l{k}"], grads[f"b_hh_l{k}"] = self.gw[2][k], self.gw[3][k]
+        if self.grad_ctx is not None:
+            grads["context"] = self.grad_ctx[:, : self.dims.T]
+        return {"terms": self.terms, "grads": grads}
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.visde_session_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
