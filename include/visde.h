@@ -11,7 +11,8 @@
  *   visde_elbo_fwd/_bwd <- inference/evidence_lower_bound.py:19-83 (path-dependent terms) with
  *                          inference/state_space.py:20-38, inference/types.py:19-24,
  *                          core/observations.py:52-74, examples/{ornstein_uhlenbeck,lotka_volterra}.py
- *   visde_gauss_lp_fwd/_bwd <- evidence_lower_bound.py:77-83 _gaussian_log_prob (generic-SDE path)
+ *                          (sde_kind GENERIC = user SDE: drift/diffusion tensors evaluated by the caller,
+ *                          evidence_lower_bound.py:37-40, only the Gaussian algebra :77-83 runs here)
  *   visde_session_*     <- one trainer iteration's path part (inference/trainer.py:176-198) with
  *                          HOST buffers: H2D, path fwd, ELBO fwd+bwd, path bwd, D2H.
  *
@@ -54,6 +55,17 @@ enum {
 enum { VISDE_F32 = 0, VISDE_BF16 = 1 };                 /* dtype of context / grad_context */
 enum { VISDE_SDE_GENERIC = 0, VISDE_SDE_OU = 1, VISDE_SDE_LV = 2 };
 enum { VISDE_VARIANT_AUTO = 0, VISDE_VARIANT_GENERIC = 1, VISDE_VARIANT_FAST = 2 };
+/* stages timed by the opt-in profiler (visde_profile_begin / _end) */
+enum {
+  VISDE_STAGE_K0_CTX_GEMM = 0, /* gi_ctx = ctx . W_ctx^T + b_ih_l0                */
+  VISDE_STAGE_K1_PATH_FWD = 1, /* forward recurrence                               */
+  VISDE_STAGE_K5_ELBO_FWD = 2,
+  VISDE_STAGE_K6_ELBO_BWD = 3,
+  VISDE_STAGE_K2_PATH_BWD = 4, /* reverse-time recurrence                          */
+  VISDE_STAGE_K3_GRAD_CTX = 5, /* grad_context and grad_theta GEMMs                */
+  VISDE_STAGE_K4_WGRAD = 6,    /* weight-gradient GEMMs + split-K reductions       */
+  VISDE_NUM_STAGES = 7
+};
 
 typedef struct {
   int64_t B;  /* trajectories on this rank */
@@ -155,6 +167,13 @@ int visde_elbo_bwd(const visde_dims* d, float dt, int sde_kind, uint32_t positiv
                    const float* drift, const float* diffusion, const visde_obs* obs,
                    const float* g_terms, float* g_z, float* g_means, float* g_chol,
                    float* g_theta, float* g_drift, float* g_diffusion, void* stream);
+
+/* Opt-in stage profiler (bench.py's roofline): while enabled, every entry point brackets its
+ * stages with CUDA events on the caller's stream; visde_profile_end synchronises those events and
+ * returns the summed device time (ms) and launch count per stage.  Process-wide, off by default,
+ * the only global state in the library.  max_records bounds the number of bracketed stages. */
+int visde_profile_begin(int max_records);
+int visde_profile_end(double* ms_per_stage, int* launches_per_stage);
 
 /* ---- host-buffer session: one ELBO iteration of the path through HOST memory ------------- */
 typedef struct visde_session visde_session;

@@ -287,7 +287,7 @@ class Lorenz96:
         return (xp1 - xm2) * xm1 - x + p[..., 0:1]
 
     def diffusion(self, x: Tensor, p: Tensor) -> Tensor:
-        eye = torch.eye(self.state_dim, dtype=x.dtype)
+        eye = torch.eye(self.state_dim, dtype=x.dtype, device=x.device)
         return p[..., 1].reshape(-1, 1, 1) * eye
 
 

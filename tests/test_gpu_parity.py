@@ -10,7 +10,8 @@ import pytest
 import torch
 
 from oracle import oracle_torch as O
-from tests._util import assert_close, build_head, cuda_inputs, head_grads, normwise, run_cuda_fwd_bwd
+from tests._util import (assert_close, assert_parity, build_head, check_iteration, cuda_inputs, head_grads, normwise,
+                         oracle_refs, run_cuda_fwd_bwd)
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).parent / "golden"
@@ -73,17 +74,20 @@ def test_backward_matches_oracle_autograd(name):
     g = torch.Generator().manual_seed(7)
     S = p.weights.state_dim
     gP, gM, gL = torch.randn(B, T + 1, S, generator=g), torch.randn(B, T, S, generator=g), torch.randn(B, T, S, S, generator=g)
-    w = p.weights.map(lambda t: t.clone().requires_grad_(True))
-    x0 = p.x0.clone().requires_grad_(True)
-    ctx = p.context.clone().requires_grad_(True)
-    theta = p.theta.clone().requires_grad_(True)
-    outs = O.sample_paths(w, x0, ctx, theta, p.eps, p.dt)
-    leaves = [x0, ctx, theta, *w.tensors()]
-    ref = torch.autograd.grad(list(outs), leaves, [gP, gM, gL])
-    nl = w.num_layers
+    nl = p.weights.num_layers
     names = (["x0", "context", "theta"] + [f"w_ih_l{k}" for k in range(nl)] + [f"w_hh_l{k}" for k in range(nl)]
              + [f"b_ih_l{k}" for k in range(nl)] + [f"b_hh_l{k}" for k in range(nl)] + ["out_w", "out_b"])
-    ref = dict(zip(names, ref))
+
+    def oracle(dtype):
+        w = p.weights.map(lambda t: t.to(dtype).clone().requires_grad_(True))
+        x0 = p.x0.to(dtype).clone().requires_grad_(True)
+        ctx = p.context.to(dtype).clone().requires_grad_(True)
+        theta = p.theta.to(dtype).clone().requires_grad_(True)
+        outs = O.sample_paths(w, x0, ctx, theta, p.eps.to(dtype), p.dt)
+        gr = torch.autograd.grad(list(outs), [x0, ctx, theta, *w.tensors()], [gP.to(dtype), gM.to(dtype), gL.to(dtype)])
+        return dict(zip(names, gr))
+
+    ref, ref64 = oracle(torch.float32), oracle(torch.float64)
     for v in _variants(name):
         ops.set_variant(v)
         head = build_head(p)
@@ -93,7 +97,7 @@ def test_backward_matches_oracle_autograd(name):
         got = {"x0": cx0.grad, "context": full.grad[:, :T], "theta": cth.grad, **head_grads(head)}
         assert torch.all(full.grad[:, T] == 0)
         for nm in names:
-            assert_close(got[nm], ref[nm], name=f"{name}/v{v}/grad_{nm}")
+            assert_parity(got[nm], ref[nm], ref64[nm], name=f"{name}/v{v}/grad_{nm}")
 
 
 @pytest.mark.parametrize("name", ["ou_h64_l2", "lv_h64_l2", "lv_h16_l1", "l96s4_h24_l3", "l96s10_h64_l2"])
@@ -101,15 +105,8 @@ def test_elbo_iteration_matches_oracle(name):
     """paths, ELBO terms and every gradient of -mean(obs + sde - gen + jac): the full hot path."""
     kind, B, T, kw = CASES[name]
     p = O.make_problem(kind, B, T, **kw)
-    r_paths, r_means, r_chol, r_terms, r_grads = O.run_fwd_bwd(p)
-    paths, means, chol, terms, grads = run_cuda_fwd_bwd(p)
-    assert_close(paths, r_paths, name="paths")
-    assert_close(means, r_means, name="means")
-    assert_close(chol, r_chol, name="chol")
-    for j, nm in enumerate(("obs", "sde", "gen", "jac")):
-        assert_close(terms[:, j], getattr(r_terms, nm), rtol=1e-4, atol_scale=2e-5, name=f"term_{nm}")
-    for nm, r in r_grads.items():
-        assert_close(grads[nm], r, rtol=1e-4, atol_scale=2e-5, name=f"grad_{nm}")
+    r32, r64 = oracle_refs(p)
+    check_iteration(run_cuda_fwd_bwd(p), r32, r64, tag=f"{name}/")
 
 
 @pytest.mark.parametrize("name", ["stepwise_ou", "stepwise_lv", "stepwise_l96", "stepwise_ou_h64"])
@@ -118,9 +115,10 @@ def test_matches_reference_golden(name):
     g = torch.load(GOLD / f"{name}.pt")
     p = O.make_problem(g["kind"], g["B"], g["T"], **g["kw"])
     paths, means, chol, terms, grads = run_cuda_fwd_bwd(p)
-    assert_close(paths, g["paths"], name="paths")
-    assert_close(means, g["means"], name="means")
-    assert_close(chol, g["chol"], name="chol")
+    r64 = O.run_fwd_bwd(p, dtype=torch.float64)
+    assert_parity(paths, g["paths"], r64[0], name="paths")
+    assert_parity(means, g["means"], r64[1], name="means")
+    assert_parity(chol, g["chol"], r64[2], name="chol")
     for j, nm in enumerate(("obs", "sde", "gen", "jac")):
         tol = 2e-3 if nm == "jac" else 2e-4  # jac_mean is recovered by subtraction in the golden script
         assert abs(terms[:, j].mean().item() - g[f"{nm}_mean"].item()) <= tol * max(1.0, abs(g[f"{nm}_mean"].item()))
@@ -129,7 +127,7 @@ def test_matches_reference_golden(name):
         ref[f"w_ih_l{k}"], ref[f"w_hh_l{k}"] = g[f"g_weight_ih_l{k}"], g[f"g_weight_hh_l{k}"]
         ref[f"b_ih_l{k}"], ref[f"b_hh_l{k}"] = g[f"g_bias_ih_l{k}"], g[f"g_bias_hh_l{k}"]
     for nm, r in ref.items():
-        assert_close(grads[nm], r, rtol=1e-4, atol_scale=2e-5, name=f"grad_{nm}")
+        assert_parity(grads[nm], r, r64[4][nm], name=f"grad_{nm}")
 
 
 @pytest.mark.parametrize("name", ["triton_lv", "triton_l96"])
@@ -137,26 +135,34 @@ def test_matches_reference_triton_golden(name):
     """Same cotangents as the reference's own fused kernels were run with (interpreter mode)."""
     g = torch.load(GOLD / f"{name}.pt")
     p = O.make_problem(g["kind"], g["B"], g["T"], **g["kw"])
+    nl = p.weights.num_layers
+    d = torch.float64
+    w64 = p.weights.map(lambda t: t.to(d).clone().requires_grad_(True))
+    lx0, lctx, lth = (t.to(d).clone().requires_grad_(True) for t in (p.x0, p.context, p.theta))
+    o64 = O.sample_paths(w64, lx0, lctx, lth, p.eps.to(d), p.dt)
+    g64 = torch.autograd.grad(list(o64), [lx0, lctx, lth, *w64.tensors()], [g["gP"].to(d), g["gM"].to(d), g["gL"].to(d)])
+    w_ih64, w_hh64, b_ih64, b_hh64 = (g64[3 + i * nl:3 + (i + 1) * nl] for i in range(4))
+
     head = build_head(p)
     x0, full, view, theta, eps = cuda_inputs(p)
     out = head.sample_diffusion_paths(x0, view, theta, eps, p.dt)
-    for a, nm in zip(out, ("paths", "means", "chol")):
-        assert_close(a, g[nm], name=nm)
+    for a, r64, nm in zip(out, o64, ("paths", "means", "chol")):
+        assert_parity(a, g[nm], r64, name=nm)
     torch.autograd.backward(list(out), [g["gP"].cuda(), g["gM"].cuda(), g["gL"].cuda()])
     hg = head_grads(head)
-    nl = p.weights.num_layers
-    assert_close(x0.grad, g["g_x0"], name="g_x0")
-    assert_close(full.grad[:, :g["T"]], g["g_context"], name="g_context")
-    assert_close(theta.grad, g["g_theta"], name="g_theta")
-    assert_close(hg["w_ih_l0"], g["g_w_ih_l0"], name="g_w_ih_l0")
-    assert_close(hg["w_hh_l0"], g["g_w_hh_l0"], name="g_w_hh_l0")
-    assert_close(hg["b_ih_l0"], g["g_b_ih_l0"], name="g_b_ih_l0")
-    assert_close(hg["b_hh_l0"], g["g_b_hh_l0"], name="g_b_hh_l0")
+    assert_parity(x0.grad, g["g_x0"], g64[0], name="g_x0")
+    assert_parity(full.grad[:, :g["T"]], g["g_context"], g64[1], name="g_context")
+    assert_parity(theta.grad, g["g_theta"], g64[2], name="g_theta")
+    assert_parity(hg["w_ih_l0"], g["g_w_ih_l0"], w_ih64[0], name="g_w_ih_l0")
+    assert_parity(hg["w_hh_l0"], g["g_w_hh_l0"], w_hh64[0], name="g_w_hh_l0")
+    assert_parity(hg["b_ih_l0"], g["g_b_ih_l0"], b_ih64[0], name="g_b_ih_l0")
+    assert_parity(hg["b_hh_l0"], g["g_b_hh_l0"], b_hh64[0], name="g_b_hh_l0")
     if nl > 1:
-        for nm, key in (("w_ih", "g_w_ih_stack"), ("w_hh", "g_w_hh_stack"), ("b_ih", "g_b_ih_stack"), ("b_hh", "g_b_hh_stack")):
-            assert_close(torch.stack([hg[f"{nm}_l{k}"] for k in range(1, nl)]), g[key], name=key)
-    assert_close(hg["out_w"], g["g_out_w"], name="g_out_w")
-    assert_close(hg["out_b"], g["g_out_b"], name="g_out_b")
+        for nm, key, r in (("w_ih", "g_w_ih_stack", w_ih64), ("w_hh", "g_w_hh_stack", w_hh64),
+                           ("b_ih", "g_b_ih_stack", b_ih64), ("b_hh", "g_b_hh_stack", b_hh64)):
+            assert_parity(torch.stack([hg[f"{nm}_l{k}"] for k in range(1, nl)]), g[key], torch.stack(list(r[1:])), name=key)
+    assert_parity(hg["out_w"], g["g_out_w"], g64[3 + 4 * nl], name="g_out_w")
+    assert_parity(hg["out_b"], g["g_out_b"], g64[4 + 4 * nl], name="g_out_b")
 
 
 def test_diag_floor_branch_and_gradient_rule():
@@ -170,13 +176,10 @@ def test_diag_floor_branch_and_gradient_rule():
         p.weights.out_b[S + d * (d + 3) // 2] = -0.5 if d == 0 else 0.02
     ref = O.sample_paths(p.weights, p.x0, p.context, p.theta, p.eps, p.dt)
     assert (ref[2][:, :, 0, 0] == O.DIAG_MIN).any(), "test must exercise the clamped branch"
-    r_paths, r_means, r_chol, r_terms, r_grads = O.run_fwd_bwd(p)
+    r32, r64 = oracle_refs(p)
     for v in (_lib.VARIANT_GENERIC, _lib.VARIANT_FAST):
         ops.set_variant(v)
-        paths, means, chol, terms, grads = run_cuda_fwd_bwd(p)
-        assert_close(chol, r_chol, name="chol")
-        for nm, r in r_grads.items():
-            assert_close(grads[nm], r, rtol=1e-4, atol_scale=2e-5, name=f"v{v}/grad_{nm}")
+        check_iteration(run_cuda_fwd_bwd(p), r32, r64, tag=f"v{v}/")
 
 
 def test_bf16_and_contiguous_context():
@@ -185,12 +188,13 @@ def test_bf16_and_contiguous_context():
     pb = O.make_problem("ou", 4, 20, context_dim=32, hidden_dim=64, num_layers=2)
     pb.context = p.context.to(torch.bfloat16).to(torch.float32)  # oracle sees the rounded values
     r_paths, _, _, r_terms, r_grads = O.run_fwd_bwd(pb)
+    r64 = O.run_fwd_bwd(pb, dtype=torch.float64)
     paths, _, _, terms, grads = run_cuda_fwd_bwd(p, ctx_dtype=torch.bfloat16)
     assert grads["context"].dtype == torch.bfloat16
     assert_close(paths, r_paths, name="paths")
     assert_close(grads["context"].float(), r_grads["context"], rtol=1e-2, atol_scale=1e-2, name="grad_context(bf16)")
     for nm in ("x0", "theta", "w_ih_l0", "w_hh_l1", "out_w"):
-        assert_close(grads[nm], r_grads[nm], rtol=1e-4, atol_scale=2e-5, name=nm)
+        assert_parity(grads[nm], r_grads[nm], r64[4][nm], name=nm)
     # contiguous [B,T,C] fp32 input gives bit-identical results to the strided view
     a = run_cuda_fwd_bwd(p, strided=True)
     b = run_cuda_fwd_bwd(p, strided=False)
@@ -201,11 +205,8 @@ def test_edge_shapes():
     """B = 1, T = 1, and empty inputs (B = 0 / T = 0) do not crash and match the oracle."""
     for B, T in ((1, 1), (1, 5), (3, 1)):
         p = O.make_problem("lv", B, T, context_dim=8, hidden_dim=16, num_layers=2)
-        r = O.run_fwd_bwd(p)
-        c = run_cuda_fwd_bwd(p)
-        assert_close(c[0], r[0], name=f"paths B{B} T{T}")
-        for nm, g in r[4].items():
-            assert_close(c[4][nm], g, rtol=1e-4, atol_scale=2e-5, name=f"B{B} T{T} grad_{nm}")
+        r32, r64 = oracle_refs(p)
+        check_iteration(run_cuda_fwd_bwd(p), r32, r64, tag=f"B{B} T{T} ")
     p = O.make_problem("ou", 2, 4, context_dim=8, hidden_dim=16, num_layers=1)
     head = build_head(p).eval()
     z = torch.zeros
@@ -235,13 +236,13 @@ def test_session_host_step_matches_oracle():
     from viforsdes_b200.session import HostSession
 
     p = O.make_problem("lv", 6, 30, context_dim=32, hidden_dim=64, num_layers=2)
-    _, _, _, r_terms, r_grads = O.run_fwd_bwd(p)
-    sess = HostSession.from_problem(p)
+    r32, r64 = oracle_refs(p)
+    sess = HostSession.from_problem(p, want_grad_context=True)
     res = sess.step()
     for j, nm in enumerate(("obs", "sde", "gen", "jac")):
-        assert_close(res["terms"][:, j], getattr(r_terms, nm), rtol=1e-4, atol_scale=2e-5, name=nm)
-    for nm, r in r_grads.items():
-        assert_close(res["grads"][nm], r, rtol=1e-4, atol_scale=2e-5, name=f"grad_{nm}")
+        assert_parity(res["terms"][:, j], getattr(r32[3], nm), getattr(r64[3], nm), name=nm)
+    for nm in r64[4]:
+        assert_parity(res["grads"][nm], r32[4][nm], r64[4][nm], name=f"grad_{nm}")
     assert sess.h2d_bytes > 0 and sess.d2h_bytes > 0 and sess.launches > 0
     sess.close()
 

@@ -15,6 +15,7 @@ F32, BF16 = 0, 1
 SDE_GENERIC, SDE_OU, SDE_LV = 0, 1, 2
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_FAST = 0, 1, 2
 OK, EINVAL, ECUDA, EWORKSPACE = 0, -1, -2, -3
+STAGES = ("K0_ctx_gemm", "K1_path_fwd", "K5_elbo_fwd", "K6_elbo_bwd", "K2_path_bwd", "K3_grad_ctx", "K4_wgrad")
 
 _fp = C.c_void_p
 
@@ -53,6 +54,8 @@ PROTOTYPES = {
                                  C.POINTER(Obs), _fp, _fp]),
     "visde_elbo_bwd": (C.c_int, [C.POINTER(Dims), C.c_float, C.c_int, C.c_uint32, _fp, _fp, _fp, _fp, _fp, _fp,
                                  C.POINTER(Obs), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "visde_profile_begin": (C.c_int, [C.c_int]),
+    "visde_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "visde_session_create": (C.c_int, [C.POINTER(Dims), C.c_int, C.c_uint32, C.c_int32, C.c_int32, C.POINTER(_fp)]),
     "visde_session_destroy": (None, [_fp]),
     "visde_session_h2d_bytes": (C.c_size_t, [_fp]),

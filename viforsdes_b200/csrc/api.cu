@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -16,6 +17,31 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ---- opt-in profiler ------------------------------------------------------------------------
+namespace {
+struct ProfRecord {
+  cudaEvent_t beg, end;
+  int stage, launches;
+};
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRecord> g_prof;
+size_t g_prof_used = 0;
+}  // namespace
+
+StageTimer::StageTimer(int stage, int launches, cudaStream_t st) : rec(-1), st_(st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_on || g_prof_used >= g_prof.size()) return;
+  rec = (int)g_prof_used++;
+  g_prof[rec].stage = stage;
+  g_prof[rec].launches = launches;
+  cudaEventRecord(g_prof[rec].beg, st);
+}
+StageTimer::~StageTimer() {
+  if (rec >= 0) cudaEventRecord(g_prof[rec].end, st_);
 }
 
 namespace {
@@ -102,7 +128,7 @@ int check_weights(const visde_dims* d, const visde_weights* w) {
 }
 
 bool use_fast(const visde_dims* d, const PathParams& p) {
-  if (d->variant == VISDE_VARIANT_GENERIC) return false;
+  if ((d->variant & 0xff) == VISDE_VARIANT_GENERIC) return false;
   return fast_supported(p);
 }
 
@@ -156,7 +182,7 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
   VISDE_REQUIRE(x0 && paths, "x0 / paths is NULL");
   VISDE_REQUIRE(d->T == 0 || (ctx && ctx->ptr && eps && means && chol), "NULL tensor argument");
   VISDE_REQUIRE(d->P == 0 || theta, "theta is NULL");
-  VISDE_REQUIRE(d->variant != VISDE_VARIANT_FAST || (d->H <= 64 && d->NL <= 2 && d->S <= 4),
+  VISDE_REQUIRE((d->variant & 0xff) != VISDE_VARIANT_FAST || (d->H <= 64 && d->NL <= 2 && d->S <= 4),
                 "fast variant requested for an unsupported shape (H=%d NL=%d S=%d)", d->H, d->NL, d->S);
   if (workspace_bytes < visde_workspace_bytes(d, 0) - 256 || (!workspace && d->T > 0)) {
     set_error("path_fwd: workspace too small (%zu < %zu)", workspace_bytes, visde_workspace_bytes(d, 0));
@@ -180,11 +206,13 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
   }
   if (d->T > 0) {
     // K0: context rows of W_ih_l0 as one time-parallel GEMM, b_ih_l0 folded in
+    StageTimer tm(VISDE_STAGE_K0_CTX_GEMM, 1, st);
     RowSrc A{ctx->ptr, ctx->batch_stride, ctx->time_stride, 0, d->C, ctx->dtype};
     rc = launch_gemm_nt(A, d->B, d->T, d->C, w->w_ih[0] + d->S, d->S + d->C + d->P, 3 * d->H, w->b_ih[0], gi,
                         3 * d->H, st);
     if (rc) return rc;
   }
+  StageTimer tm(VISDE_STAGE_K1_PATH_FWD, 1, st);
   return use_fast(d, p) ? launch_path_fwd_fast(p, st) : launch_path_fwd_generic(p, st);
 }
 
@@ -232,8 +260,11 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
   float* partials = reinterpret_cast<float*>(wsb + ws.partials);
 
   // K2: reverse-time recurrence
-  rc = use_fast(d, p) ? launch_path_bwd_fast(p, st) : launch_path_bwd_generic(p, st);
-  if (rc) return rc;
+  {
+    StageTimer tm(VISDE_STAGE_K2_PATH_BWD, 1, st);
+    rc = use_fast(d, p) ? launch_path_bwd_fast(p, st) : launch_path_bwd_generic(p, st);
+    if (rc) return rc;
+  }
   if (d->T == 0) {
     // no steps: every parameter gradient is zero, grad_x0 = g_paths[:, 0]
     for (int k = 0; k < NL; ++k) {
@@ -257,6 +288,8 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
   const RowSrc ones{nullptr, 0, 0, 0, 1, VISDE_F32};
 
   // K3: grad_context = d_gi_l0 . W_ih_l0[:, S:S+C]
+  {
+  StageTimer tm3(VISDE_STAGE_K3_GRAD_CTX, (C > 0) + (P > 0), st);
   if (C > 0) {
     rc = launch_gemm_nn(dg_src(0), d->B, d->T, G, w->w_ih[0] + S, ld0, C, grad_ctx->ptr, grad_ctx->batch_stride,
                         grad_ctx->time_stride, grad_ctx->dtype, st);
@@ -269,6 +302,8 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
     if (rc) return rc;
   }
   // K4: weight gradients (bias gradients ride along as a column of ones)
+  }
+  StageTimer tm4(VISDE_STAGE_K4_WGRAD, 2 * (2 * NL + 1), st);
   {
     RowSrc bs[4];
     int n = 0;
@@ -353,6 +388,7 @@ int visde_elbo_fwd(const visde_dims* d, float dt, int sde_kind, uint32_t positiv
   if (rc) return rc;
   VISDE_REQUIRE(d->B == 0 || terms, "terms is NULL");
   e.terms = terms;
+  StageTimer tm(VISDE_STAGE_K5_ELBO_FWD, 1, (cudaStream_t)stream);
   return launch_elbo_fwd(e, (cudaStream_t)stream);
 }
 
@@ -376,7 +412,50 @@ int visde_elbo_bwd(const visde_dims* d, float dt, int sde_kind, uint32_t positiv
   e.g_theta = g_theta;
   e.g_drift = g_drift;
   e.g_diffusion = g_diffusion;
+  StageTimer tm(VISDE_STAGE_K6_ELBO_BWD, 1, (cudaStream_t)stream);
   return launch_elbo_bwd(e, (cudaStream_t)stream);
+}
+
+int visde_profile_begin(int max_records) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  VISDE_REQUIRE(!g_prof_on, "profiler already enabled");
+  VISDE_REQUIRE(max_records > 0 && max_records <= (1 << 20), "bad max_records");
+  g_prof.resize(max_records);
+  for (auto& r : g_prof) {
+    VISDE_CUDA_CHECK(cudaEventCreate(&r.beg));
+    VISDE_CUDA_CHECK(cudaEventCreate(&r.end));
+  }
+  g_prof_used = 0;
+  g_prof_on = true;
+  return VISDE_OK;
+}
+
+int visde_profile_end(double* ms_per_stage, int* launches_per_stage) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  VISDE_REQUIRE(g_prof_on, "profiler not enabled");
+  g_prof_on = false;
+  for (int s = 0; s < VISDE_NUM_STAGES; ++s) {
+    if (ms_per_stage) ms_per_stage[s] = 0.0;
+    if (launches_per_stage) launches_per_stage[s] = 0;
+  }
+  int rc = VISDE_OK;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(g_prof[i].end) != cudaSuccess || cudaEventElapsedTime(&ms, g_prof[i].beg, g_prof[i].end) != cudaSuccess) {
+      set_error("profiler: event query failed");
+      rc = VISDE_ECUDA;
+      continue;
+    }
+    if (ms_per_stage) ms_per_stage[g_prof[i].stage] += ms;
+    if (launches_per_stage) launches_per_stage[g_prof[i].stage] += g_prof[i].launches;
+  }
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.beg);
+    cudaEventDestroy(r.end);
+  }
+  g_prof.clear();
+  g_prof_used = 0;
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------

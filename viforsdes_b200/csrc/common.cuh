@@ -77,6 +77,14 @@ __device__ __forceinline__ float tanh_f(float x) {
   return 1.0f - 2.0f / (e + 1.0f);
 }
 
+// opt-in stage profiler (api.cu)
+struct StageTimer {
+  int rec;
+  StageTimer(int stage, int launches, cudaStream_t st);
+  ~StageTimer();
+  cudaStream_t st_;
+};
+
 // launchers (return 0 / VISDE_E*)
 int launch_path_fwd_generic(const PathParams& p, cudaStream_t st);
 int launch_path_bwd_generic(const PathParams& p, cudaStream_t st);

@@ -1,0 +1,112 @@
+"""Device-resident ELBO iteration of the hot path, straight over the C ABI with buffers allocated
+once (what a training loop does after its first step): K0 -> K1 -> K5 -> K6 -> K2 -> K3 -> K4.
+Used by bench.py (`value` leg: inputs already in HBM) and by the data-parallel wrapper."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List
+
+import torch
+from torch import Tensor
+
+from viforsdes_b200 import _lib
+from viforsdes_b200.dist import FlatBucket
+from viforsdes_b200.synthetic import Inputs
+
+
+class PathIteration:
+    def __init__(self, inp: Inputs, device: torch.device | str = "cuda", variant: int = _lib.VARIANT_AUTO) -> None:
+        if inp.sde_kind == _lib.SDE_GENERIC:
+            raise ValueError("PathIteration covers the built-in OU / LV functors; user SDEs go through "
+                             "viforsdes_b200.elbo.compute_evidence_lower_bound")
+        self.lib = _lib.load()
+        dev = torch.device(device)
+        self.dev = dev
+        f = dict(device=dev, dtype=torch.float32)
+        B, S = inp.x0.shape
+        T, Cd = inp.context_full.shape[1] - 1, inp.context_full.shape[2]
+        P, NL, H = inp.theta.shape[1], len(inp.w_hh), inp.w_hh[0].shape[1]
+        self.B, self.T, self.S, self.C, self.P, self.H, self.NL = B, T, S, Cd, P, H, NL
+        self.dims = _lib.Dims(B, T, S, Cd, P, H, NL, variant)
+        self.dt, self.sde_kind, self.mask = float(inp.dt), inp.sde_kind, inp.positive_mask
+        to = lambda t: t.to(dev).contiguous()  # noqa: E731
+        self.x0, self.ctx, self.theta, self.eps = to(inp.x0), to(inp.context_full), to(inp.theta), to(inp.eps)
+        self.w = [[to(t) for t in ws] for ws in (inp.w_ih, inp.w_hh, inp.b_ih, inp.b_hh)]
+        self.out_w, self.out_b = to(inp.out_w), to(inp.out_b)
+        # all 4*NL+2 weight gradients are views of ONE flat buffer: it is the all-reduce bucket
+        shapes = [tuple(t.shape) for ws in self.w for t in ws] + [tuple(self.out_w.shape), tuple(self.out_b.shape)]
+        self.bucket = FlatBucket(shapes, dev)
+        v = self.bucket.views
+        self.gw = [v[i * NL:(i + 1) * NL] for i in range(4)]
+        self.g_out_w, self.g_out_b = v[4 * NL], v[4 * NL + 1]
+        self.paths = torch.empty(B, T + 1, S, **f)
+        self.means = torch.empty(B, T, S, **f)
+        self.chol = torch.empty(B, T, S, S, **f)
+        self.terms = torch.empty(B, 4, **f)
+        s = -1.0 / B  # loss = -mean_b(obs + sde - gen + jac)
+        self.g_terms = torch.tensor([s, s, -s, s], **f).repeat(B, 1).contiguous()
+        self.g_z, self.g_means, self.g_chol = torch.empty_like(self.paths), torch.empty_like(self.means), torch.empty_like(self.chol)
+        self.g_theta_elbo = torch.empty(B, P, **f)
+        self.grad_x0, self.grad_theta = torch.empty(B, S, **f), torch.empty(B, P, **f)
+        self.grad_ctx = torch.zeros(B, T + 1, Cd, **f)
+        u8 = dict(device=dev, dtype=torch.uint8)
+        self.stash = torch.empty(self.lib.visde_stash_bytes(C.byref(self.dims)), **u8)
+        self.ws_f = torch.empty(self.lib.visde_workspace_bytes(C.byref(self.dims), 0), **u8)
+        self.ws_b = torch.empty(self.lib.visde_workspace_bytes(C.byref(self.dims), 1), **u8)
+        self.obs_idx = inp.obs_idx.to(torch.int32).to(dev)
+        self.obs_values = to(inp.obs_values)
+        self.obs = _lib.Obs(self.obs_idx.shape[0], self.obs_values.shape[1], self.obs_idx.data_ptr(),
+                            self.obs_values.data_ptr(), None, float(inp.obs_variance))
+        self.cv = _lib.CtxView(self.ctx.data_ptr(), (T + 1) * Cd, Cd, _lib.F32)
+        self.gv = _lib.CtxView(self.grad_ctx.data_ptr(), (T + 1) * Cd, Cd, _lib.F32)
+        self.ws_struct = self._wstruct(self.w, self.out_w, self.out_b)
+        self.gw_struct = self._wstruct(self.gw, self.g_out_w, self.g_out_b)
+        # K0, K1, K5, K6, K2, grad_ctx, grad_theta, (2 NL + 1) x (split-K GEMM + reduce), theta-grad add
+        self.launches_per_step = 7 + 2 * (2 * NL + 1) + 1
+
+    def _wstruct(self, groups, ow, ob) -> _lib.Weights:
+        s = _lib.Weights()
+        for k in range(self.NL):
+            s.w_ih[k], s.w_hh[k] = groups[0][k].data_ptr(), groups[1][k].data_ptr()
+            s.b_ih[k], s.b_hh[k] = groups[2][k].data_ptr(), groups[3][k].data_ptr()
+        s.out_w, s.out_b = ow.data_ptr(), ob.data_ptr()
+        return s
+
+    def head_weight_grads(self) -> List[Tensor]:
+        return [*self.gw[0], *self.gw[1], *self.gw[2], *self.gw[3], self.g_out_w, self.g_out_b]
+
+    def forward(self) -> None:
+        lib, d = self.lib, self.dims
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        p = lambda t: t.data_ptr()  # noqa: E731
+        _lib.check(lib.visde_path_fwd(C.byref(d), self.dt, p(self.x0), C.byref(self.cv), p(self.theta), p(self.eps),
+                                      C.byref(self.ws_struct), p(self.paths), p(self.means), p(self.chol), p(self.stash),
+                                      p(self.ws_f), self.ws_f.numel(), st))
+        _lib.check(lib.visde_elbo_fwd(C.byref(d), self.dt, self.sde_kind, self.mask, p(self.paths), p(self.means),
+                                      p(self.chol), p(self.theta), None, None, C.byref(self.obs), p(self.terms), st))
+
+    def backward(self) -> None:
+        lib, d = self.lib, self.dims
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        p = lambda t: t.data_ptr()  # noqa: E731
+        _lib.check(lib.visde_elbo_bwd(C.byref(d), self.dt, self.sde_kind, self.mask, p(self.paths), p(self.means),
+                                      p(self.chol), p(self.theta), None, None, C.byref(self.obs), p(self.g_terms),
+                                      p(self.g_z), p(self.g_means), p(self.g_chol), p(self.g_theta_elbo), None, None, st))
+        _lib.check(lib.visde_path_bwd(C.byref(d), self.dt, p(self.g_z), p(self.g_means), p(self.g_chol),
+                                      C.byref(self.cv), p(self.theta), p(self.eps), C.byref(self.ws_struct),
+                                      p(self.paths), p(self.stash), p(self.grad_x0), C.byref(self.gv), p(self.grad_theta),
+                                      C.byref(self.gw_struct), p(self.ws_b), self.ws_b.numel(), st))
+        self.grad_theta.add_(self.g_theta_elbo)
+
+    def step(self) -> None:
+        with torch.cuda.device(self.dev):
+            self.forward()
+            self.backward()
+
+    def results(self) -> Dict[str, object]:
+        grads = {"x0": self.grad_x0, "context": self.grad_ctx[:, : self.T], "theta": self.grad_theta,
+                 "out_w": self.g_out_w, "out_b": self.g_out_b}
+        for k in range(self.NL):
+            grads[f"w_ih_l{k}"], grads[f"w_hh_l{k}"] = self.gw[0][k], self.gw[1][k]
+            grads[f"b_ih_l{k}"], grads[f"b_hh_l{k}"] = self.gw[2][k], self.gw[3][k]
+        return {"paths": self.paths, "means": self.means, "chol": self.chol, "terms": self.terms, "grads": grads}

@@ -61,6 +61,14 @@ class HostSession:
                    b_hh=w.b_hh, out_w=w.out_w, out_b=w.out_b, dt=p.dt, sde_kind=kind, positive_mask=mask,
                    obs_idx=idx, obs_values=p.obs_values, obs_variance=p.obs_variance, **kw)
 
+    @classmethod
+    def from_inputs(cls, inp, **kw) -> "HostSession":
+        """Build from ``viforsdes_b200.synthetic.Inputs``."""
+        return cls(x0=inp.x0, context_full=inp.context_full, theta=inp.theta, eps=inp.eps, w_ih=inp.w_ih,
+                   w_hh=inp.w_hh, b_ih=inp.b_ih, b_hh=inp.b_hh, out_w=inp.out_w, out_b=inp.out_b, dt=inp.dt,
+                   sde_kind=inp.sde_kind, positive_mask=inp.positive_mask, obs_idx=inp.obs_idx,
+                   obs_values=inp.obs_values, obs_variance=inp.obs_variance, **kw)
+
     def _wstruct(self, groups, ow, ob) -> _lib.Weights:
         s = _lib.Weights()
         for k in range(self.dims.NL):
