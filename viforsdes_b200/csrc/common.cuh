@@ -70,11 +70,29 @@ struct PathParams {
 
 __host__ __device__ inline int64_t stash_row_floats(int NL, int H) { return (int64_t)NL * kStashSlots * H; }
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
-// tanh via exp: abs error ~1e-7 (the hidden state only needs absolute accuracy)
+// MUFU-based gates on the serial critical path: raw ex2.approx / rcp.approx (~1 ulp each, no range
+// guards, no IEEE-division slow path); absolute error ~2e-7, which is what the hidden state needs.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_f(float x) {
-  float e = __expf(2.0f * x);
-  return 1.0f - 2.0f / (e + 1.0f);
+  return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * x)), 1.0f);
+}
+// packed dual-fp32 FMA (sm_100 FFMA2): d.x += a.x * b.x ; d.y += a.y * b.y
+__device__ __forceinline__ void fma2(float2& d, const float2& a, const float2& b) {
+  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(dd)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  d = *reinterpret_cast<float2*>(&dd);
 }
 
 // opt-in stage profiler (api.cu)

@@ -5,19 +5,23 @@
 //   * one persistent CTA per trajectory slot, looping over all T steps; every recurrent weight
 //     matrix (W_hh_l0, W_ih_l1, W_hh_l1 = 147 KB fp32 at H=64) lives in REGISTERS for the whole
 //     launch: thread (i, ks) owns the K-slice ks of the three gate rows of hidden unit i
-//     (forward) or of column i of the transposed matrices (backward);
+//     (forward) or of column i of the transposed matrices (backward); products are issued as
+//     packed FFMA2 (fma.rn.f32x2) with two independent accumulators per dot;
 //   * the hidden state of unit i stays in a register of its KS lanes; the only per-step exchange
-//     is one H-float shared-memory vector per layer (parity double-buffered, one __syncthreads
-//     per layer per step);
+//     is one H-float shared-memory vector per layer (parity double-buffered, bank-padded slices,
+//     one __syncthreads per layer per step);
 //   * the recurrent product W_hh_k h_k(t) needed by step t+1 is issued right after h_k(t) is
 //     published, together with W_ih_{k+1} h_k(t): same operand, and it fills the pipeline while
 //     the critical gate chain of the next layer waits on shuffles and MUFU;
 //   * the context rows of W_ih_l0 (57 % of forward MACs) are hoisted into the time-parallel
 //     GEMM K0 (gi_ctx); the kernel prefetches gi_ctx / eps one step ahead;
-//   * the tiny output projection + Euler-Maruyama update is computed redundantly by every warp
-//     (no extra barrier, z_{t+1} is in every thread's registers when layer 0 of step t+1 starts);
+//   * the tiny output projection is computed by KS-lane groups from the h slice already in
+//     registers (2 shuffle stages + one broadcast stage, redundantly in every warp: no extra
+//     barrier, z_{t+1} is in every thread's registers when layer 0 of step t+1 starts); the
+//     backward's d z_t reduction uses the same grouping;
 //   * backward emits d(pre-activations) [B,T,NL,4,H] and d(out) for the weight-gradient GEMMs
 //     (K4) instead of accumulating weight gradients with atomics.
+// The stall profile that shaped this layout is in profiles/r1_path_kernels.md.
 #include "common.cuh"
 
 namespace visde {
@@ -29,23 +33,34 @@ __device__ __forceinline__ float ks_allreduce(float v) {
   for (int o = KS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float warp_allreduce(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 template <int SL>
-__device__ __forceinline__ void load_slice(const float* __restrict__ src, float (&dst)[SL]) {
+__device__ __forceinline__ void load_slice2(const float* __restrict__ src, float2 (&dst)[SL / 2]) {
   static_assert(SL % 4 == 0, "slice must be float4-divisible");
 #pragma unroll
-  for (int q = 0; q < SL; q += 4) {
-    float4 v = *reinterpret_cast<const float4*>(src + q);
-    dst[q] = v.x;
-    dst[q + 1] = v.y;
-    dst[q + 2] = v.z;
-    dst[q + 3] = v.w;
+  for (int q = 0; q < SL / 4; ++q) {
+    float4 v = *reinterpret_cast<const float4*>(src + 4 * q);
+    dst[2 * q] = make_float2(v.x, v.y);
+    dst[2 * q + 1] = make_float2(v.z, v.w);
   }
+}
+
+// dot of a register-resident weight slice with an operand slice: FFMA2, two independent chains
+template <int SL>
+__device__ __forceinline__ float dot2(const float2 (&w)[SL / 2], const float2 (&x)[SL / 2]) {
+  float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < SL / 2; q += 2) {
+    fma2(a, w[q], x[q]);
+    if (q + 1 < SL / 2) fma2(b, w[q + 1], x[q + 1]);
+  }
+  return (a.x + a.y) + (b.x + b.y);
+}
+
+// bank-padded slice layout of an H-vector in shared memory: slice ks starts at ks * (SL + 4)
+template <int SL>
+__device__ __forceinline__ int padded(int j) {
+  return (j / SL) * (SL + 4) + (j % SL);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -53,18 +68,21 @@ __device__ __forceinline__ void load_slice(const float* __restrict__ src, float 
 // ---------------------------------------------------------------------------------------------
 template <int HP, int KS, int NL, int S>
 __global__ void __launch_bounds__(HP* KS, 1) path_fwd_fast_kernel(PathParams p) {
-  constexpr int SL = HP / KS, NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL, JC = HP / 32;
+  constexpr int SL = HP / KS, NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL;
+  constexpr int HB = KS * (SL + 4);        // padded H-vector length
+  constexpr int RPP = 32 / KS;             // output rows handled per pass by the KS-lane groups of a warp
+  constexpr int NP = (NOUT + RPP - 1) / RPP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int i = tid / KS, ks = tid % KS;
+  const int i = tid / KS, ks = tid % KS, grp = lane / KS;
   const int H = p.H, G = 3 * p.H, ld0 = p.S + p.C + p.P;
   const bool unit_ok = i < H;
   const float lead = ks == 0 ? 1.f : 0.f;  // lane that adds the non-sliced terms before the reduce
 
-  __shared__ __align__(16) float hbuf[2][NL][HP];
+  __shared__ __align__(16) float hbuf[2][NL][HB];
 
   // ---- weights into registers (once per CTA) ----
-  float whh[NL][3][SL];
-  float wih[NL > 1 ? NL - 1 : 1][3][SL];
+  float2 whh[NL][3][SL / 2];
+  float2 wih[NL > 1 ? NL - 1 : 1][3][SL / 2];
 #pragma unroll
   for (int k = 0; k < NL; ++k)
 #pragma unroll
@@ -73,8 +91,10 @@ __global__ void __launch_bounds__(HP* KS, 1) path_fwd_fast_kernel(PathParams p) 
       for (int q = 0; q < SL; ++q) {
         const int kk = ks * SL + q;
         const bool ok = unit_ok && kk < H;
-        whh[k][g][q] = ok ? p.w_hh[k][(int64_t)(g * H + i) * H + kk] : 0.f;
-        if (k > 0) wih[k > 0 ? k - 1 : 0][g][q] = ok ? p.w_ih[k][(int64_t)(g * H + i) * H + kk] : 0.f;
+        const float a = ok ? p.w_hh[k][(int64_t)(g * H + i) * H + kk] : 0.f;
+        const float b = (ok && k > 0) ? p.w_ih[k][(int64_t)(g * H + i) * H + kk] : 0.f;
+        if (q & 1) whh[k][g][q / 2].y = a; else whh[k][g][q / 2].x = a;
+        if (k > 0) { if (q & 1) wih[k > 0 ? k - 1 : 0][g][q / 2].y = b; else wih[k > 0 ? k - 1 : 0][g][q / 2].x = b; }
       }
   float wz[3][S], cb[NL][4];  // cb: constant parts of (r, u, n_i, n_h) pre-activations
 #pragma unroll
@@ -94,16 +114,19 @@ __global__ void __launch_bounds__(HP* KS, 1) path_fwd_fast_kernel(PathParams p) 
     cb[k][2] = bin;
     cb[k][3] = unit_ok ? p.b_hh[k][2 * H + i] : 0.f;
   }
-  float wout[NOUT][JC], bout[NOUT];
+  // output projection: group `grp` of the warp owns row m = pass * RPP + grp, lane ks its K-slice
+  float2 wout[NP][SL / 2];
+  float bout[NOUT];
 #pragma unroll
-  for (int m = 0; m < NOUT; ++m) {
-    bout[m] = p.out_b[m];
+  for (int m = 0; m < NOUT; ++m) bout[m] = p.out_b[m];
 #pragma unroll
-    for (int c = 0; c < JC; ++c) {
-      const int j = lane + 32 * c;
-      wout[m][c] = j < H ? p.out_w[(int64_t)m * H + j] : 0.f;
+  for (int ps = 0; ps < NP; ++ps)
+#pragma unroll
+    for (int q = 0; q < SL; ++q) {
+      const int m = ps * RPP + grp, kk = ks * SL + q;
+      const float a = (m < NOUT && kk < H) ? p.out_w[(int64_t)m * H + kk] : 0.f;
+      if (q & 1) wout[ps][q / 2].y = a; else wout[ps][q / 2].x = a;
     }
-  }
 
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     // theta rows of W_ih_l0 applied once per trajectory (kernels/forward.py:157-175)
@@ -115,6 +138,8 @@ __global__ void __launch_bounds__(HP* KS, 1) path_fwd_fast_kernel(PathParams p) 
         for (int g = 0; g < 3; ++g) gth[g] += p.w_ih[0][(int64_t)(g * H + i) * ld0 + p.S + p.C + q] * th;
       }
     }
+#pragma unroll
+    for (int g = 0; g < 3; ++g) gth[g] += cb[0][g];  // fold the constant part once per trajectory
     float z[S], hreg[NL], acc_hh[NL][3];
 #pragma unroll
     for (int s = 0; s < S; ++s) z[s] = p.x0[b * S + s];
@@ -125,36 +150,45 @@ __global__ void __launch_bounds__(HP* KS, 1) path_fwd_fast_kernel(PathParams p) 
     }
     if (tid < S) p.paths[b * (p.T + 1) * S + tid] = p.x0[b * S + tid];
 
-    const float* gi_base = p.gi_ctx + b * p.T * G;
-    const float* eps_base = p.eps + b * p.T * S;
+    // running per-thread pointers (advanced once per step)
+    const float* gi_p = p.gi_ctx + b * p.T * G + (unit_ok ? i : 0);
+    const float* eps_p = p.eps + b * p.T * S;
     float gi_cur[3] = {0.f, 0.f, 0.f}, eps_cur[S];
     if (unit_ok && p.T > 0) {
 #pragma unroll
-      for (int g = 0; g < 3; ++g) gi_cur[g] = gi_base[g * H + i];
+      for (int g = 0; g < 3; ++g) gi_cur[g] = gi_p[g * H];
     }
 #pragma unroll
-    for (int s = 0; s < S; ++s) eps_cur[s] = p.T > 0 ? eps_base[s] : 0.f;
+    for (int s = 0; s < S; ++s) eps_cur[s] = p.T > 0 ? eps_p[s] : 0.f;
+    // stash: lane ks of unit i writes slot ks (r, u, n, n_hh[, h]); KS == 4: lane 0 also writes h
+    const bool st_on = p.stash != nullptr && unit_ok && ks < kStashSlots;
+    float* st_lane = p.stash ? p.stash + b * p.T * (int64_t)(NL * kStashSlots * H) + (ks < kStashSlots ? ks : 0) * H + (unit_ok ? i : 0) : nullptr;
+    float* paths_o = p.paths + (b * (p.T + 1) + 1) * S;
+    float* means_o = p.means + b * p.T * S;
+    float* chol_o = p.chol + b * p.T * S * S;
+    float* raw_o = p.raw ? p.raw + b * p.T * NTRIL : nullptr;
 
     for (int64_t t = 0; t < p.T; ++t) {
       const int par = (int)(t & 1);
-      const int64_t row = b * p.T + t;
       // prefetch next step's inputs
       float gi_nxt[3] = {0.f, 0.f, 0.f}, eps_nxt[S];
       const bool has_next = t + 1 < p.T;
+      gi_p += G;
+      eps_p += S;
       if (unit_ok && has_next) {
 #pragma unroll
-        for (int g = 0; g < 3; ++g) gi_nxt[g] = gi_base[(t + 1) * G + g * H + i];
+        for (int g = 0; g < 3; ++g) gi_nxt[g] = gi_p[g * H];
       }
 #pragma unroll
-      for (int s = 0; s < S; ++s) eps_nxt[s] = has_next ? eps_base[(t + 1) * S + s] : 0.f;
+      for (int s = 0; s < S; ++s) eps_nxt[s] = has_next ? eps_p[s] : 0.f;
 
       float a_in[3] = {0.f, 0.f, 0.f};  // W_ih_k h_{k-1}(t) slice partials for the layer being processed
+      float2 hs[SL / 2];
 #pragma unroll
       for (int k = 0; k < NL; ++k) {
         float pr, pu, pni, pnh;
         if (k == 0) {
-          float er = gi_cur[0] + gth[0] + cb[0][0], eu = gi_cur[1] + gth[1] + cb[0][1];
-          float en = gi_cur[2] + gth[2] + cb[0][2];
+          float er = gi_cur[0] + gth[0], eu = gi_cur[1] + gth[1], en = gi_cur[2] + gth[2];
 #pragma unroll
           for (int s = 0; s < S; ++s) {
             er = fmaf(wz[0][s], z[s], er);
@@ -172,55 +206,42 @@ __global__ void __launch_bounds__(HP* KS, 1) path_fwd_fast_kernel(PathParams p) 
           pnh = fmaf(lead, cb[k][3], acc_hh[k][2]);
         }
         pr = ks_allreduce<KS>(pr);
-        pu = ks_allreduce<KS>(pu);
-        pni = ks_allreduce<KS>(pni);
         pnh = ks_allreduce<KS>(pnh);
-        const float r = sigmoid_f(pr), u = sigmoid_f(pu);
+        pni = ks_allreduce<KS>(pni);
+        pu = ks_allreduce<KS>(pu);
+        const float r = sigmoid_f(pr);
         const float n = tanh_f(fmaf(r, pnh, pni));
+        const float u = sigmoid_f(pu);
         const float hn = unit_ok ? fmaf(u, hreg[k] - n, n) : 0.f;  // (1-u) n + u h
         hreg[k] = hn;
-        if (ks == 0) hbuf[par][k][i] = hn;
-        if (p.stash && unit_ok) {
-          float* st = p.stash + (row * NL + k) * (int64_t)(kStashSlots * H);
-          // spread the five stores over the KS lanes of the unit (KS >= 4)
-          if (ks == 0) { st[kStashR * H + i] = r; st[kStashH * H + i] = hn; }
-          if (ks == 1) st[kStashU * H + i] = u;
-          if (ks == 2) st[kStashN * H + i] = n;
-          if (ks == 3) st[kStashNhh * H + i] = pnh;
+        if (ks == 0) hbuf[par][k][padded<SL>(i)] = hn;
+        {
+          float v = r;  // branch-free select of this lane's stash slot
+          v = ks == 1 ? u : v;
+          v = ks == 2 ? n : v;
+          v = ks == 3 ? pnh : v;
+          v = ks == 4 ? hn : v;
+          if (st_on) st_lane[k * kStashSlots * H] = v;
+          if (KS == 4 && st_on && ks == 0) st_lane[k * kStashSlots * H + kStashH * H] = hn;
         }
         __syncthreads();
-        float hs[SL];
-        load_slice<SL>(&hbuf[par][k][ks * SL], hs);
+        load_slice2<SL>(&hbuf[par][k][ks * (SL + 4)], hs);
         if (k + 1 < NL) {
 #pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            float a = 0.f;
-#pragma unroll
-            for (int q = 0; q < SL; ++q) a = fmaf(wih[k + 1 < NL ? k : 0][g][q], hs[q], a);
-            a_in[g] = a;
-          }
+          for (int g = 0; g < 3; ++g) a_in[g] = dot2<SL>(wih[k + 1 < NL ? k : 0][g], hs);
         }
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {
-          float a = 0.f;
-#pragma unroll
-          for (int q = 0; q < SL; ++q) a = fmaf(whh[k][g][q], hs[q], a);
-          acc_hh[k][g] = a;
-        }
+        for (int g = 0; g < 3; ++g) acc_hh[k][g] = dot2<SL>(whh[k][g], hs);
       }
-      // output projection (every warp redundantly) + reparameterised Euler-Maruyama update
-      float hv[JC], o[NOUT];
+      // output projection from the top layer's slice (already in hs) + reparameterised EM update
+      float o[NOUT];
+      {
+        float part[NP];
 #pragma unroll
-      for (int c = 0; c < JC; ++c) hv[c] = hbuf[par][NL - 1][lane + 32 * c];
+        for (int ps = 0; ps < NP; ++ps) part[ps] = ks_allreduce<KS>(dot2<SL>(wout[ps], hs));
 #pragma unroll
-      for (int m = 0; m < NOUT; ++m) {
-        float a = 0.f;
-#pragma unroll
-        for (int c = 0; c < JC; ++c) a = fmaf(wout[m][c], hv[c], a);
-        o[m] = a;
+        for (int m = 0; m < NOUT; ++m) o[m] = __shfl_sync(0xffffffffu, part[m / RPP], (m % RPP) * KS) + bout[m];
       }
-#pragma unroll
-      for (int m = 0; m < NOUT; ++m) o[m] = warp_allreduce(o[m]) + bout[m];
       float zn[S], Lm[NTRIL];
 #pragma unroll
       for (int s = 0; s < S; ++s) {
@@ -238,20 +259,25 @@ __global__ void __launch_bounds__(HP* KS, 1) path_fwd_fast_kernel(PathParams p) 
       if (lane == 0) {
         if (warp == 0) {
 #pragma unroll
-          for (int s = 0; s < S; ++s) p.paths[(b * (p.T + 1) + t + 1) * S + s] = zn[s];
+          for (int s = 0; s < S; ++s) paths_o[s] = zn[s];
         } else if (warp == 1) {
 #pragma unroll
-          for (int s = 0; s < S; ++s) p.means[row * S + s] = o[s];
+          for (int s = 0; s < S; ++s) means_o[s] = o[s];
         } else if (warp == 2) {
 #pragma unroll
           for (int s = 0; s < S; ++s)
 #pragma unroll
-            for (int j = 0; j < S; ++j) p.chol[(row * S + s) * S + j] = j <= s ? Lm[s * (s + 1) / 2 + j] : 0.f;
-        } else if (warp == 3 && p.raw) {
+            for (int j = 0; j < S; ++j) chol_o[s * S + j] = j <= s ? Lm[s * (s + 1) / 2 + j] : 0.f;
+        } else if (warp == 3 && raw_o) {
 #pragma unroll
-          for (int ti = 0; ti < NTRIL; ++ti) p.raw[row * NTRIL + ti] = o[S + ti];
+          for (int ti = 0; ti < NTRIL; ++ti) raw_o[ti] = o[S + ti];
         }
       }
+      paths_o += S;
+      means_o += S;
+      chol_o += S * S;
+      if (raw_o) raw_o += NTRIL;
+      if (st_lane) st_lane += NL * kStashSlots * H;
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         z[s] = zn[s];
@@ -269,18 +295,21 @@ __global__ void __launch_bounds__(HP* KS, 1) path_fwd_fast_kernel(PathParams p) 
 // ---------------------------------------------------------------------------------------------
 template <int HP, int KS, int NL, int S>
 __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) {
-  constexpr int SL = HP / KS, NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL, JC = HP / 32;
+  constexpr int SL = HP / KS, NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL;
+  constexpr int HB = KS * (SL + 4);
+  constexpr int RPP = 32 / KS;             // (gate, s) items per pass for the d z reduction
+  constexpr int NZ = 3 * S, NPZ = (NZ + RPP - 1) / RPP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int i = tid / KS, ks = tid % KS;
+  const int i = tid / KS, ks = tid % KS, grp = lane / KS;
   const int H = p.H, G = 3 * p.H, ld0 = p.S + p.C + p.P;
   const bool unit_ok = i < H;
-  const int64_t srow = stash_row_floats(NL, H);
+  const int srow = (int)stash_row_floats(NL, H);
 
-  __shared__ __align__(16) float dgb[2][NL][kDgSlots][HP];
+  __shared__ __align__(16) float dgb[2][NL][kDgSlots][HB];
 
   // transposed weight slices: column i, rows ks*SL .. ks*SL+SL-1 of each gate block
-  float whhT[NL][3][SL];
-  float wihT[NL > 1 ? NL - 1 : 1][3][SL];
+  float2 whhT[NL][3][SL / 2];
+  float2 wihT[NL > 1 ? NL - 1 : 1][3][SL / 2];
 #pragma unroll
   for (int k = 0; k < NL; ++k)
 #pragma unroll
@@ -289,23 +318,26 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
       for (int q = 0; q < SL; ++q) {
         const int kk = ks * SL + q;
         const bool ok = unit_ok && kk < H;
-        whhT[k][g][q] = ok ? p.w_hh[k][(int64_t)(g * H + kk) * H + i] : 0.f;
-        if (k > 0) wihT[k > 0 ? k - 1 : 0][g][q] = ok ? p.w_ih[k][(int64_t)(g * H + kk) * H + i] : 0.f;
+        const float a = ok ? p.w_hh[k][(int64_t)(g * H + kk) * H + i] : 0.f;
+        const float b = (ok && k > 0) ? p.w_ih[k][(int64_t)(g * H + kk) * H + i] : 0.f;
+        if (q & 1) whhT[k][g][q / 2].y = a; else whhT[k][g][q / 2].x = a;
+        if (k > 0) { if (q & 1) wihT[k > 0 ? k - 1 : 0][g][q / 2].y = b; else wihT[k > 0 ? k - 1 : 0][g][q / 2].x = b; }
       }
   float woutc[NOUT];
 #pragma unroll
   for (int m = 0; m < NOUT; ++m) woutc[m] = unit_ok ? p.out_w[(int64_t)m * H + i] : 0.f;
-  // state columns of W_ih_l0 for the per-warp reduction of d z: lane owns rows j = lane + 32 c
-  float wzl[3][S][JC];
+  // d z_t += W_ih_l0[:, :S]^T d_gi: group `grp` owns item (gate, s) = divmod(pass * RPP + grp, S),
+  // lane ks the K-slice of that gate's rows
+  float2 wzg[NPZ][SL / 2];
 #pragma unroll
-  for (int g = 0; g < 3; ++g)
+  for (int ps = 0; ps < NPZ; ++ps)
 #pragma unroll
-    for (int s = 0; s < S; ++s)
-#pragma unroll
-      for (int c = 0; c < JC; ++c) {
-        const int j = lane + 32 * c;
-        wzl[g][s][c] = j < H ? p.w_ih[0][(int64_t)(g * H + j) * ld0 + s] : 0.f;
-      }
+    for (int q = 0; q < SL; ++q) {
+      const int item = ps * RPP + grp, kk = ks * SL + q;
+      const int gate = item / S, s = item % S;
+      const float a = (item < NZ && kk < H) ? p.w_ih[0][(int64_t)(gate * H + kk) * ld0 + s] : 0.f;
+      if (q & 1) wzg[ps][q / 2].y = a; else wzg[ps][q / 2].x = a;
+    }
 
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     float dz[S], dhc[NL], sdg[3] = {0.f, 0.f, 0.f};
@@ -314,40 +346,49 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
 #pragma unroll
     for (int k = 0; k < NL; ++k) dhc[k] = 0.f;
 
+    // per-trajectory bases (uniform) + 32-bit per-step offsets
+    const float* gp_b = p.g_paths + b * (p.T + 1) * S;
+    const float* gm_b = p.g_means + b * p.T * S;
+    const float* gl_b = p.g_chol + b * p.T * S * S;
+    const float* ep_b = p.eps + b * p.T * S;
+    const float* raw_b = p.raw + b * p.T * NTRIL;
+    const float* st_b = p.stash + b * p.T * (int64_t)srow + (unit_ok ? i : 0);
+    float* dg_b = p.dg + b * p.T * (int64_t)(NL * kDgSlots * H) + (ks < kDgSlots ? ks : 0) * H + (unit_ok ? i : 0);
+    float* dout_b = p.dout + b * p.T * NOUT;
+
     // per-step inputs, software-prefetched one step ahead (reverse time)
     float c_gp[S], c_gm[S], c_gl[NTRIL], c_eps[S], c_rawd[S];
     float c_r[NL], c_u[NL], c_n[NL], c_nhh[NL], c_hp[NL];
-    auto load_step = [&](int64_t t, float (&gp)[S], float (&gm)[S], float (&gl)[NTRIL], float (&ep)[S],
+    auto load_step = [&](int t, float (&gp)[S], float (&gm)[S], float (&gl)[NTRIL], float (&ep)[S],
                          float (&rd)[S], float (&sr)[NL], float (&su)[NL], float (&sn)[NL],
                          float (&snh)[NL], float (&shp)[NL]) {
-      const int64_t row = b * p.T + t;
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        gp[s] = p.g_paths[(b * (p.T + 1) + t + 1) * S + s];
-        gm[s] = p.g_means[row * S + s];
-        ep[s] = p.eps[row * S + s];
-        rd[s] = p.raw[row * NTRIL + s * (s + 1) / 2 + s];
+        gp[s] = gp_b[(t + 1) * S + s];
+        gm[s] = gm_b[t * S + s];
+        ep[s] = ep_b[t * S + s];
+        rd[s] = raw_b[t * NTRIL + s * (s + 1) / 2 + s];
 #pragma unroll
-        for (int j = 0; j <= s; ++j) gl[s * (s + 1) / 2 + j] = p.g_chol[(row * S + s) * S + j];
+        for (int j = 0; j <= s; ++j) gl[s * (s + 1) / 2 + j] = gl_b[(t * S + s) * S + j];
       }
 #pragma unroll
       for (int k = 0; k < NL; ++k) {
         sr[k] = su[k] = sn[k] = snh[k] = shp[k] = 0.f;
         if (unit_ok) {
-          const float* st = p.stash + (row * NL + k) * (int64_t)(kStashSlots * H);
-          sr[k] = st[kStashR * H + i];
-          su[k] = st[kStashU * H + i];
-          sn[k] = st[kStashN * H + i];
-          snh[k] = st[kStashNhh * H + i];
-          if (t > 0) shp[k] = (st - srow)[kStashH * H + i];
+          const float* st = st_b + t * srow + k * kStashSlots * H;
+          sr[k] = st[kStashR * H];
+          su[k] = st[kStashU * H];
+          sn[k] = st[kStashN * H];
+          snh[k] = st[kStashNhh * H];
+          if (t > 0) shp[k] = (st - srow)[kStashH * H];
         }
       }
     };
-    if (p.T > 0) load_step(p.T - 1, c_gp, c_gm, c_gl, c_eps, c_rawd, c_r, c_u, c_n, c_nhh, c_hp);
+    const int T = (int)p.T;
+    if (T > 0) load_step(T - 1, c_gp, c_gm, c_gl, c_eps, c_rawd, c_r, c_u, c_n, c_nhh, c_hp);
 
-    for (int64_t t = p.T - 1; t >= 0; --t) {
-      const int par = (int)(t & 1);
-      const int64_t row = b * p.T + t;
+    for (int t = T - 1; t >= 0; --t) {
+      const int par = t & 1;
       float n_gp[S], n_gm[S], n_gl[NTRIL], n_eps[S], n_rawd[S];
       float n_r[NL], n_u[NL], n_n[NL], n_nhh[NL], n_hp[NL];
       if (t > 0) load_step(t - 1, n_gp, n_gm, n_gl, n_eps, n_rawd, n_r, n_u, n_n, n_nhh, n_hp);
@@ -363,13 +404,13 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
         for (int j = 0; j <= s; ++j) {
           const int ti = s * (s + 1) / 2 + j;
           float d = fmaf(dz[s] * c_eps[j], p.sqrt_dt, c_gl[ti]);
-          if (j == s && !(c_rawd[s] >= VISDE_DIAG_MIN || d < 0.f)) d = 0.f;  // primitives/bounds.py:20
+          if (j == s) d = (c_rawd[s] >= VISDE_DIAG_MIN || d < 0.f) ? d : 0.f;  // primitives/bounds.py:20
           dout[S + ti] = d;
         }
       }
       if (warp == 0 && lane == 0) {
 #pragma unroll
-        for (int m = 0; m < NOUT; ++m) p.dout[row * NOUT + m] = dout[m];
+        for (int m = 0; m < NOUT; ++m) dout_b[t * NOUT + m] = dout[m];
       }
       float dh = dhc[NL - 1];
 #pragma unroll
@@ -383,14 +424,16 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
         const float drp = dnp * c_nhh[k] * r * (1.f - r);
         const float dnh = dnp * r;
         const float direct = dh * u;
-        if (unit_ok) {
-          const float v = ks == 0 ? drp : ks == 1 ? dup : ks == 2 ? dnp : dnh;
-          if (ks < 4) {
-            dgb[par][k][ks][i] = v;
-            p.dg[(row * NL + k) * (int64_t)(kDgSlots * H) + ks * H + i] = v;
+        {
+          float v = drp;  // branch-free select of this lane's slot
+          v = ks == 1 ? dup : v;
+          v = ks == 2 ? dnp : v;
+          v = ks == 3 ? dnh : v;
+          v = unit_ok ? v : 0.f;
+          if (ks < kDgSlots) {
+            dgb[par][k][ks][padded<SL>(i)] = v;
+            if (unit_ok) dg_b[(t * NL + k) * (kDgSlots * H)] = v;
           }
-        } else if (ks < 4) {
-          dgb[par][k][ks][i] = 0.f;
         }
         if (k == 0) {
           sdg[0] += drp;
@@ -398,53 +441,45 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
           sdg[2] += dnp;
         }
         __syncthreads();
-        float pc = 0.f, pb = 0.f;
-        {
-          float d0[SL], d1[SL];
-          load_slice<SL>(&dgb[par][k][0][ks * SL], d0);
-          load_slice<SL>(&dgb[par][k][1][ks * SL], d1);
-#pragma unroll
-          for (int q = 0; q < SL; ++q) {
-            pc = fmaf(whhT[k][0][q], d0[q], pc);
-            pc = fmaf(whhT[k][1][q], d1[q], pc);
-            if (k > 0) {
-              pb = fmaf(wihT[k > 0 ? k - 1 : 0][0][q], d0[q], pb);
-              pb = fmaf(wihT[k > 0 ? k - 1 : 0][1][q], d1[q], pb);
-            }
-          }
-        }
-        {
-          float d3[SL];
-          load_slice<SL>(&dgb[par][k][3][ks * SL], d3);
-#pragma unroll
-          for (int q = 0; q < SL; ++q) pc = fmaf(whhT[k][2][q], d3[q], pc);
-        }
+        float2 d0[SL / 2], d1[SL / 2], d2[SL / 2], d3[SL / 2];
+        load_slice2<SL>(&dgb[par][k][0][ks * (SL + 4)], d0);
+        load_slice2<SL>(&dgb[par][k][1][ks * (SL + 4)], d1);
+        load_slice2<SL>(&dgb[par][k][2][ks * (SL + 4)], d2);
         if (k > 0) {
-          float d2[SL];
-          load_slice<SL>(&dgb[par][k][2][ks * SL], d2);
-#pragma unroll
-          for (int q = 0; q < SL; ++q) pb = fmaf(wihT[k > 0 ? k - 1 : 0][2][q], d2[q], pb);
-          pb = ks_allreduce<KS>(pb);
+          // critical path first: gradient handed to the layer below
+          const float pb = ks_allreduce<KS>(dot2<SL>(wihT[k > 0 ? k - 1 : 0][0], d0) +
+                                            dot2<SL>(wihT[k > 0 ? k - 1 : 0][1], d1) +
+                                            dot2<SL>(wihT[k > 0 ? k - 1 : 0][2], d2));
           dh = dhc[k > 0 ? k - 1 : 0] + pb;
-        }
-        pc = ks_allreduce<KS>(pc);
-        dhc[k] = direct + pc;
-        if (k == 0) {
-          // d z_t += W_ih_l0[:, :S]^T d_gi (every warp redundantly; no barrier)
-          float part[S];
+        } else {
+          // d z_t += W_ih_l0[:, :S]^T d_gi  (KS-lane groups, every warp redundantly; no barrier)
+          float part[NPZ];
 #pragma unroll
-          for (int s = 0; s < S; ++s) part[s] = 0.f;
+          for (int ps = 0; ps < NPZ; ++ps) {
+            const int item = ps * RPP + grp;
+            const int gate = item / S;
+            float2 a = make_float2(0.f, 0.f), c = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int g = 0; g < 3; ++g)
-#pragma unroll
-            for (int c = 0; c < JC; ++c) {
-              const float d = dgb[par][0][g][lane + 32 * c];
-#pragma unroll
-              for (int s = 0; s < S; ++s) part[s] = fmaf(wzl[g][s][c], d, part[s]);
+            for (int q = 0; q < SL / 2; q += 2) {
+              // pick the gate's slice without divergence
+              float2 x0 = gate == 0 ? d0[q] : gate == 1 ? d1[q] : d2[q];
+              float2 x1 = gate == 0 ? d0[q + 1] : gate == 1 ? d1[q + 1] : d2[q + 1];
+              fma2(a, wzg[ps][q], x0);
+              fma2(c, wzg[ps][q + 1], x1);
             }
+            part[ps] = ks_allreduce<KS>((a.x + a.y) + (c.x + c.y));
+          }
 #pragma unroll
-          for (int s = 0; s < S; ++s) dz[s] += warp_allreduce(part[s]);
+          for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int gate = 0; gate < 3; ++gate) {
+              const int item = gate * S + s;
+              dz[s] += __shfl_sync(0xffffffffu, part[item / RPP], (item % RPP) * KS);
+            }
         }
+        load_slice2<SL>(&dgb[par][k][3][ks * (SL + 4)], d3);
+        const float pc = ks_allreduce<KS>(dot2<SL>(whhT[k][0], d0) + dot2<SL>(whhT[k][1], d1) + dot2<SL>(whhT[k][2], d3));
+        dhc[k] = direct + pc;
       }
 #pragma unroll
       for (int s = 0; s < S; ++s) {
@@ -469,7 +504,7 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
 #pragma unroll
       for (int s = 0; s < S; ++s)
         if (s == tid) v = dz[s];
-      p.grad_x0[b * S + tid] = v + p.g_paths[b * (p.T + 1) * S + tid];
+      p.grad_x0[b * S + tid] = v + gp_b[tid];
     }
     if (unit_ok && ks < 3) {
       const float v = ks == 0 ? sdg[0] : ks == 1 ? sdg[1] : sdg[2];
@@ -517,6 +552,11 @@ int dispatch_nl(const PathParams& p, cudaStream_t st, bool bwd) {
 }
 
 int dispatch_fast(const PathParams& p, cudaStream_t st, bool bwd) {
+  // per-trajectory offsets are 32-bit inside the kernels
+  if (p.T * (int64_t)(p.NL * kStashSlots * p.H) >= (int64_t(1) << 31)) {
+    set_error("fast path: T too large for 32-bit per-trajectory offsets");
+    return VISDE_EINVAL;
+  }
   if (p.H <= 32) return dispatch_nl<32, 8>(p, st, bwd);
   if (p.H <= 64) return dispatch_nl<64, 4>(p, st, bwd);
   set_error("fast path: unsupported hidden dim %d", p.H);
@@ -525,7 +565,9 @@ int dispatch_fast(const PathParams& p, cudaStream_t st, bool bwd) {
 
 }  // namespace
 
-bool fast_supported(const PathParams& p) { return p.H <= 64 && p.NL <= 2 && p.S <= 4; }
+bool fast_supported(const PathParams& p) {
+  return p.H <= 64 && p.NL <= 2 && p.S <= 4 && p.T * (int64_t)(p.NL * kStashSlots * p.H) < (int64_t(1) << 31);
+}
 int launch_path_fwd_fast(const PathParams& p, cudaStream_t st) { return dispatch_fast(p, st, false); }
 int launch_path_bwd_fast(const PathParams& p, cudaStream_t st) { return dispatch_fast(p, st, true); }
 
