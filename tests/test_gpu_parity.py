@@ -29,14 +29,25 @@ CASES = {
     "l96s10_h64_l2": ("l96", 3, 11, dict(context_dim=32, hidden_dim=64, num_layers=2, state_dim=10)),
     "l96s5_h96_l4": ("l96", 2, 7, dict(context_dim=12, hidden_dim=96, num_layers=4, state_dim=5)),
     "ou_h130_l2": ("ou", 2, 6, dict(context_dim=7, hidden_dim=130, num_layers=2)),
+    # tensor-core GEMM eligible shapes (H = 64, C in {128, 256}); T > 128 spans several row tiles
+    "lv_h64_c128_l2": ("lv", 3, 37, dict(context_dim=128, hidden_dim=64, num_layers=2)),
+    "ou_h64_c256_l1": ("ou", 2, 150, dict(context_dim=256, hidden_dim=64, num_layers=1)),
+    "lv_h64_c256_l2": ("lv", 2, 300, dict(context_dim=256, hidden_dim=64, num_layers=2)),
+    "l96s6_h64_c128_l2": ("l96", 2, 40, dict(context_dim=128, hidden_dim=64, num_layers=2, state_dim=6)),
 }
-FAST_OK = {"ou_h32_l2", "lv_h16_l1", "ou_h64_l2", "lv_h64_l2", "lv_h48_l2", "ou_h20_l1", "l96s3_h64_l2"}
+TC_OK = {"lv_h64_c128_l2", "ou_h64_c256_l1", "lv_h64_c256_l2", "l96s6_h64_c128_l2"}
+NO_TC = 0x100  # VISDE_FLAG_NO_TENSOR_CORES
+FAST_OK = {"ou_h32_l2", "lv_h16_l1", "ou_h64_l2", "lv_h64_l2", "lv_h48_l2", "ou_h20_l1", "l96s3_h64_l2",
+           "lv_h64_c128_l2", "ou_h64_c256_l1", "lv_h64_c256_l2"}
 
 
 def _variants(name):
     from viforsdes_b200 import _lib
 
-    return [_lib.VARIANT_GENERIC, _lib.VARIANT_FAST] if name in FAST_OK else [_lib.VARIANT_GENERIC]
+    v = [_lib.VARIANT_GENERIC, _lib.VARIANT_FAST] if name in FAST_OK else [_lib.VARIANT_GENERIC]
+    if name in TC_OK:  # the same kernels with the GEMM stages forced onto the fp32 SIMT path
+        v += [x | NO_TC for x in v]
+    return v
 
 
 @pytest.fixture(autouse=True)
@@ -100,7 +111,8 @@ def test_backward_matches_oracle_autograd(name):
             assert_parity(got[nm], ref[nm], ref64[nm], name=f"{name}/v{v}/grad_{nm}")
 
 
-@pytest.mark.parametrize("name", ["ou_h64_l2", "lv_h64_l2", "lv_h16_l1", "l96s4_h24_l3", "l96s10_h64_l2"])
+@pytest.mark.parametrize("name", ["ou_h64_l2", "lv_h64_l2", "lv_h16_l1", "l96s4_h24_l3", "l96s10_h64_l2",
+                                  "lv_h64_c128_l2", "ou_h64_c256_l1", "l96s6_h64_c128_l2"])
 def test_elbo_iteration_matches_oracle(name):
     """paths, ELBO terms and every gradient of -mean(obs + sde - gen + jac): the full hot path."""
     kind, B, T, kw = CASES[name]

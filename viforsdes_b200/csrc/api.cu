@@ -69,7 +69,7 @@ StashLayout stash_layout(const visde_dims* d) {
 }
 
 struct BwdWs {
-  size_t dg, dout, sdg, partials, total, partial_floats;
+  size_t dg, dout, sdg, partials, wsplit, total, partial_floats;
 };
 BwdWs bwd_ws(const visde_dims* d) {
   BwdWs w{};
@@ -89,9 +89,15 @@ BwdWs bwd_ws(const visde_dims* d) {
   size_t pf3 = gemm_tn_partial_floats(n_out, d->H + 1, K);
   if (pf2 > pf) pf = pf2;
   if (pf3 > pf) pf = pf3;
+  if (d->H == 64 && d->NL <= 2 && (d->C == 128 || d->C == 256)) {
+    size_t pt = tc_wgrad_partial_floats(d->NL, d->C);
+    if (pt > pf) pf = pt;
+  }
   w.partial_floats = pf;
   w.partials = off;
   off += align_up(sizeof(float) * pf);
+  w.wsplit = off;
+  off += align_up(sizeof(float) * tc_weight_scratch_floats(d->H, d->C));
   w.total = off;
   return w;
 }
@@ -125,6 +131,11 @@ int check_weights(const visde_dims* d, const visde_weights* w) {
     VISDE_REQUIRE(w->w_ih[k] && w->w_hh[k] && w->b_ih[k] && w->b_hh[k], "weights of layer %d are NULL", k);
   VISDE_REQUIRE(w->out_w && w->out_b, "out_proj weights are NULL");
   return VISDE_OK;
+}
+
+bool use_tc(const visde_dims* d, const visde_ctx_view* ctx) {
+  if (d->variant & VISDE_FLAG_NO_TENSOR_CORES) return false;
+  return tc_supported(d->H, d->NL, d->C, ctx);
 }
 
 bool use_fast(const visde_dims* d, const PathParams& p) {
@@ -166,7 +177,9 @@ size_t visde_stash_bytes(const visde_dims* d) {
 
 size_t visde_workspace_bytes(const visde_dims* d, int backward) {
   if (check_dims(d) != VISDE_OK) return 0;
-  if (!backward) return align_up(sizeof(float) * (size_t)d->B * d->T * 3 * d->H) + 256;
+  if (!backward)
+    return align_up(sizeof(float) * (size_t)d->B * d->T * 3 * d->H) +
+           align_up(sizeof(float) * tc_weight_scratch_floats(d->H, d->C)) + 256;
   return bwd_ws(d).total + 256;
 }
 
@@ -207,9 +220,17 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
   if (d->T > 0) {
     // K0: context rows of W_ih_l0 as one time-parallel GEMM, b_ih_l0 folded in
     StageTimer tm(VISDE_STAGE_K0_CTX_GEMM, 1, st);
-    RowSrc A{ctx->ptr, ctx->batch_stride, ctx->time_stride, 0, d->C, ctx->dtype};
-    rc = launch_gemm_nt(A, d->B, d->T, d->C, w->w_ih[0] + d->S, d->S + d->C + d->P, 3 * d->H, w->b_ih[0], gi,
-                        3 * d->H, st);
+    if (use_tc(d, ctx)) {
+      float* wsplit = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) +
+                                               align_up(sizeof(float) * (size_t)d->B * d->T * 3 * d->H));
+      rc = tc_split_weights(w->w_ih[0], d->S + d->C + d->P, d->S, d->H, d->C, wsplit, st);
+      if (rc) return rc;
+      rc = tc_ctx_proj(ctx, d->B, d->T, d->C, d->H, wsplit, w->b_ih[0], gi, st);
+    } else {
+      RowSrc A{ctx->ptr, ctx->batch_stride, ctx->time_stride, 0, d->C, ctx->dtype};
+      rc = launch_gemm_nt(A, d->B, d->T, d->C, w->w_ih[0] + d->S, d->S + d->C + d->P, 3 * d->H, w->b_ih[0], gi,
+                          3 * d->H, st);
+    }
     if (rc) return rc;
   }
   StageTimer tm(VISDE_STAGE_K1_PATH_FWD, 1, st);
@@ -287,45 +308,71 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
   };
   const RowSrc ones{nullptr, 0, 0, 0, 1, VISDE_F32};
 
+  const bool tc = use_tc(d, ctx) && (grad_ctx->batch_stride % 4 == 0) && (grad_ctx->time_stride % 4 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(grad_ctx->ptr) & 15) == 0);
+  float* wsplit = reinterpret_cast<float*>(wsb + ws.wsplit);
   // K3: grad_context = d_gi_l0 . W_ih_l0[:, S:S+C]
   {
-  StageTimer tm3(VISDE_STAGE_K3_GRAD_CTX, (C > 0) + (P > 0), st);
-  if (C > 0) {
-    rc = launch_gemm_nn(dg_src(0), d->B, d->T, G, w->w_ih[0] + S, ld0, C, grad_ctx->ptr, grad_ctx->batch_stride,
-                        grad_ctx->time_stride, grad_ctx->dtype, st);
-    if (rc) return rc;
-  }
-  // grad_theta (through the GRU input) = (sum_t d_gi_l0) . W_ih_l0[:, S+C:]
-  if (P > 0) {
-    RowSrc A{p.sdg, G, 0, 0, G, VISDE_F32};
-    rc = launch_gemm_nn(A, d->B, 1, G, w->w_ih[0] + S + C, ld0, P, grad_theta, P, 0, VISDE_F32, st);
-    if (rc) return rc;
+    StageTimer tm3(VISDE_STAGE_K3_GRAD_CTX, (C > 0) + (P > 0), st);
+    if (tc) {
+      rc = tc_split_weights(w->w_ih[0], ld0, S, H, C, wsplit, st);
+      if (rc) return rc;
+      rc = tc_grad_ctx(p.dg, dg_t, d->B, d->T, C, H, wsplit, grad_ctx, st);
+      if (rc) return rc;
+    } else if (C > 0) {
+      rc = launch_gemm_nn(dg_src(0), d->B, d->T, G, w->w_ih[0] + S, ld0, C, grad_ctx->ptr, grad_ctx->batch_stride,
+                          grad_ctx->time_stride, grad_ctx->dtype, st);
+      if (rc) return rc;
+    }
+    // grad_theta (through the GRU input) = (sum_t d_gi_l0) . W_ih_l0[:, S+C:]
+    if (P > 0) {
+      RowSrc A{p.sdg, G, 0, 0, G, VISDE_F32};
+      rc = launch_gemm_nn(A, d->B, 1, G, w->w_ih[0] + S + C, ld0, P, grad_theta, P, 0, VISDE_F32, st);
+      if (rc) return rc;
+    }
   }
   // K4: weight gradients (bias gradients ride along as a column of ones)
+  StageTimer tm4(VISDE_STAGE_K4_WGRAD, tc ? 2 + 2 * (2 * NL + 1) : 2 * (2 * NL + 1), st);
+  if (tc) {
+    // tensor-core part: dW_ih0[:, S:S+C], dW_hh_k, dW_ih_1 (tc_gemm.cu); the thin remainder below
+    rc = tc_wgrads(ctx, p.dg, p.stash, d->B, d->T, S, C, P, H, NL, gw, partials, ws.partial_floats, st);
+    if (rc) return rc;
   }
-  StageTimer tm4(VISDE_STAGE_K4_WGRAD, 2 * (2 * NL + 1), st);
   {
     RowSrc bs[4];
     int n = 0;
     bs[n++] = RowSrc{paths, (int64_t)(d->T + 1) * S, S, 0, S, VISDE_F32};
-    if (C > 0) bs[n++] = RowSrc{ctx->ptr, ctx->batch_stride, ctx->time_stride, 0, C, ctx->dtype};
+    if (C > 0 && !tc) bs[n++] = RowSrc{ctx->ptr, ctx->batch_stride, ctx->time_stride, 0, C, ctx->dtype};
     if (P > 0) bs[n++] = RowSrc{theta, P, 0, 0, P, VISDE_F32};
     bs[n++] = ones;
-    TnOut outs[2] = {{gw->w_ih[0], ld0, 0, ld0}, {gw->b_ih[0], 1, ld0, 1}};
-    rc = launch_gemm_tn(dg_src(0), G, G, 0, bs, n, d->B, d->T, outs, 2, partials, ws.partial_floats, st);
+    if (tc) {
+      TnOut outs[3] = {{gw->w_ih[0], ld0, 0, S}, {P > 0 ? gw->w_ih[0] + S + C : nullptr, ld0, S, P}, {gw->b_ih[0], 1, S + P, 1}};
+      rc = launch_gemm_tn(dg_src(0), G, G, 0, bs, n, d->B, d->T, outs, 3, partials, ws.partial_floats, st);
+    } else {
+      TnOut outs[2] = {{gw->w_ih[0], ld0, 0, ld0}, {gw->b_ih[0], 1, ld0, 1}};
+      rc = launch_gemm_tn(dg_src(0), G, G, 0, bs, n, d->B, d->T, outs, 2, partials, ws.partial_floats, st);
+    }
     if (rc) return rc;
   }
   for (int k = 0; k < NL; ++k) {
     {
       RowSrc bs[2] = {h_src(k, -1), ones};
       TnOut outs[2] = {{gw->w_hh[k], H, 0, H}, {gw->b_hh[k], 1, H, 1}};
-      rc = launch_gemm_tn(dg_src(k), G, 2 * H, H, bs, 2, d->B, d->T, outs, 2, partials, ws.partial_floats, st);
+      TnOut bias_only{gw->b_hh[k], 1, 0, 1};
+      if (tc)
+        rc = launch_gemm_tn(dg_src(k), G, 2 * H, H, &bs[1], 1, d->B, d->T, &bias_only, 1, partials, ws.partial_floats, st);
+      else
+        rc = launch_gemm_tn(dg_src(k), G, 2 * H, H, bs, 2, d->B, d->T, outs, 2, partials, ws.partial_floats, st);
       if (rc) return rc;
     }
     if (k > 0) {
       RowSrc bs[2] = {h_src(k - 1, 0), ones};
       TnOut outs[2] = {{gw->w_ih[k], H, 0, H}, {gw->b_ih[k], 1, H, 1}};
-      rc = launch_gemm_tn(dg_src(k), G, G, 0, bs, 2, d->B, d->T, outs, 2, partials, ws.partial_floats, st);
+      TnOut bias_only{gw->b_ih[k], 1, 0, 1};
+      if (tc)
+        rc = launch_gemm_tn(dg_src(k), G, G, 0, &bs[1], 1, d->B, d->T, &bias_only, 1, partials, ws.partial_floats, st);
+      else
+        rc = launch_gemm_tn(dg_src(k), G, G, 0, bs, 2, d->B, d->T, outs, 2, partials, ws.partial_floats, st);
       if (rc) return rc;
     }
   }

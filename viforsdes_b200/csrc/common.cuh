@@ -142,6 +142,18 @@ int launch_gemm_tn(const RowSrc& A, int M, int a_split, int a_skip, const RowSrc
                    size_t partial_floats, cudaStream_t st);
 size_t gemm_tn_partial_floats(int M, int N, int64_t K);
 
+// --- tensor-core (tcgen05, 3xTF32) versions of K0 / K3 / K4 (tc_gemm.cu) ------------------------
+bool tc_supported(int H, int NL, int C, const visde_ctx_view* ctx);
+size_t tc_weight_scratch_floats(int H, int C);
+size_t tc_wgrad_partial_floats(int NL, int C);
+int tc_split_weights(const float* w_ih0, int ld0, int S, int H, int C, float* scratch, cudaStream_t st);
+int tc_ctx_proj(const visde_ctx_view* ctx, int64_t B, int64_t T, int C, int H, const float* wsplit, const float* bias,
+                float* gi_ctx, cudaStream_t st);
+int tc_grad_ctx(const float* dg, int64_t dg_row, int64_t B, int64_t T, int C, int H, const float* wsplit,
+                const visde_ctx_grad_view* out, cudaStream_t st);
+int tc_wgrads(const visde_ctx_view* ctx, const float* dg, const float* stash, int64_t B, int64_t T, int S, int C, int P,
+              int H, int NL, const visde_weight_grads* gw, float* partials, size_t partial_floats, cudaStream_t st);
+
 // --- ELBO ---------------------------------------------------------------------------------
 struct ElboParams {
   int64_t B, T;

@@ -1,0 +1,721 @@
+// Tensor-core versions of the time-parallel GEMMs (K0, K3, K4) for sm_100a:
+// tcgen05.mma kind::tf32 with FP32 accumulators in TMEM, operands staged by TMA
+// (cp.async.bulk.tensor, 128-byte swizzle) straight from the caller's strided [B,T,*] tensors
+// through 3-D tensor maps (out-of-range rows -- the t-1 shift, ragged T -- are zero-filled by the
+// TMA unit, so there is no padding or copy pass), and a 3xTF32 split (hi*hi + hi*lo + lo*hi) done
+// in shared memory by a warpgroup between the TMA and MMA stages so that results keep FP32-grade
+// accuracy (|err| ~ 2^-21 relative per product; BASELINE.json asks for rtol 1e-4 in FP32).
+//
+//   tc_rows_kernel<N, B_MN>  one 128-row (b, t-chunk) tile per CTA, K = C or 3H:
+//       K0: gi_ctx  = ctx     . Wc^T + b_ih_l0      (A K-major, B K-major,  N = 3H = 192)
+//       K3: grad_ctx = d_gi_l0 . Wc                 (A K-major, B MN-major, N = C chunk of 256)
+//   tc_wgrad_kernel          split-K over (b, t) with both operands MN-major (rows are k):
+//       D[128, 192] += X[k, 128 cols]^T . dG[k, 192 cols]   for 5 (X, dG) pairs: ctx halves x d_gi_l0,
+//       [h_l0|h_l1](t-1) x d_gh_l0, [h_l0|h_l1](t) x d_gi_l1, [h_l0|h_l1](t-1) x d_gh_l1;
+//       per-CTA partials are summed in fixed order by tc_wgrad_reduce_kernel (deterministic).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..5 = hi/lo split, then epilogue (tcgen05.ld -> global).  Two smem stages.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace visde {
+namespace {
+
+constexpr int kTcThreads = 192;
+constexpr int kStages = 2;
+constexpr uint32_t kTf32Mask = 0xffffe000u;  // keep sign, exponent and the 10 tf32 mantissa bits
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane = row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory matrix descriptor, 128-byte swizzle (cute/arch/mma_sm100_desc.hpp bit layout):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+// K-major tile [rows][32 tf32] (128-byte rows, 8-row groups 1024 B apart), SWIZZLE_128B (layout 2);
+// K slice j of 8 -> +32 B
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int j) { return umma_desc(tile + j * 32, 16, 1024, 2); }
+// MN-major tf32 tile: the only legal layout is SWIZZLE_128B_BASE32B (layout 1; TMA's
+// SWIZZLE_128B_ATOM_32B): slabs of [32 k-rows][32 tf32 along MN] (4 KB apart = LBO), swizzle atoms of
+// 4 k-rows (512 B apart = SBO); K slice j of 8 rows -> +1024 B
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int j) { return umma_desc(tile + j * 1024, 4096, 512, 1); }
+
+// instruction descriptor: D fp32, A/B tf32, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// in place hi = trunc_tf32(x); lo = trunc_tf32(x - hi), for `nvec` float4 handled by 128 threads
+__device__ __forceinline__ void split_tile(float4* hi, float4* lo, int nvec, int tid128) {
+  for (int v = tid128; v < nvec; v += 128) {
+    float4 x = hi[v];
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(x.x) & kTf32Mask);
+    h.y = __uint_as_float(__float_as_uint(x.y) & kTf32Mask);
+    h.z = __uint_as_float(__float_as_uint(x.z) & kTf32Mask);
+    h.w = __uint_as_float(__float_as_uint(x.w) & kTf32Mask);
+    l.x = __uint_as_float(__float_as_uint(x.x - h.x) & kTf32Mask);
+    l.y = __uint_as_float(__float_as_uint(x.y - h.y) & kTf32Mask);
+    l.z = __uint_as_float(__float_as_uint(x.z - h.z) & kTf32Mask);
+    l.w = __uint_as_float(__float_as_uint(x.w - h.w) & kTf32Mask);
+    hi[v] = h;
+    lo[v] = l;
+  }
+}
+
+struct TcBarriers {
+  uint64_t full[kStages];   // TMA bytes landed
+  uint64_t split[kStages];  // hi/lo tiles written (128 arrivals)
+  uint64_t empty[kStages];  // MMAs that read the stage have completed
+  uint64_t accum;           // all MMAs of the tile done
+  uint32_t tmem_base;
+};
+
+// ------------------------------------------------------------------------------------------
+// K0 / K3: rows kernel
+// ------------------------------------------------------------------------------------------
+struct RowsArgs {
+  int64_t T;
+  int tiles_per_b;  // ceil(T / 128)
+  int num_kblocks;  // K / 32
+  int n0;           // first output column handled (K3 with C > 256 launches several column chunks)
+  const float* bias;
+  void* out;
+  int64_t out_bstride, out_tstride;
+  int out_dtype;
+  int out_cols;     // valid output columns in this chunk
+};
+
+template <int N, bool B_MN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+               const __grid_constant__ CUtensorMap tmBlo, RowsArgs a) {
+  constexpr int A_BYTES = 128 * 128, B_BYTES = N * 128;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr uint32_t TMEM_COLS = N <= 128 ? 128 : 256;
+  constexpr uint32_t IDESC = make_idesc(N, false, B_MN);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + kStages * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int b = tile / a.tiles_per_b, t0 = (tile % a.tiles_per_b) * 128;
+  const int nk = a.num_kblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->split[s], 128);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % kStages;
+        if (kb >= kStages) mbar_wait(&bars->empty[s], ((kb / kStages) - 1) & 1);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        mbar_expect_tx(&bars->full[s], A_BYTES + 2 * B_BYTES);
+        tma_load_3d(st, &tmA, &bars->full[s], kb * 32, t0, b);
+        if (B_MN) {
+#pragma unroll
+          for (int sl = 0; sl < N / 32; ++sl) {
+            tma_load_2d(st + 2 * A_BYTES + sl * 4096, &tmBhi, &bars->full[s], a.n0 + sl * 32, kb * 32);
+            tma_load_2d(st + 2 * A_BYTES + B_BYTES + sl * 4096, &tmBlo, &bars->full[s], a.n0 + sl * 32, kb * 32);
+          }
+        } else {
+          tma_load_2d(st + 2 * A_BYTES, &tmBhi, &bars->full[s], kb * 32, a.n0);
+          tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmBlo, &bars->full[s], kb * 32, a.n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&bars->full[s], ph);
+        mbar_wait(&bars->split[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t dah = desc_kmajor(a_hi, j), dal = desc_kmajor(a_lo, j);
+          const uint64_t dbh = B_MN ? desc_mnmajor(b_hi, j) : desc_kmajor(b_hi, j);
+          const uint64_t dbl = B_MN ? desc_mnmajor(b_lo, j) : desc_kmajor(b_lo, j);
+          umma_tf32(tmem_d, dal, dbh, IDESC, (kb | j) != 0);  // small terms first
+          umma_tf32(tmem_d, dah, dbl, IDESC, 1);
+          umma_tf32(tmem_d, dah, dbh, IDESC, 1);
+        }
+        umma_commit(&bars->empty[s]);
+      }
+      umma_commit(&bars->accum);
+    }
+  } else {
+    const int tid128 = threadIdx.x - 64;
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % kStages;
+      mbar_wait(&bars->full[s], (kb / kStages) & 1);
+      uint8_t* st = smem + s * STAGE_BYTES;
+      split_tile(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + A_BYTES), A_BYTES / 16, tid128);
+      fence_proxy_async();
+      mbar_arrive(&bars->split[s]);
+    }
+    // epilogue: TMEM lane quadrant of this warp = warp % 4
+    mbar_wait(&bars->accum, 0);
+    tc_fence_after();
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int t = t0 + row;
+    const bool row_ok = t < a.T;
+    const int64_t obase = (int64_t)b * a.out_bstride + (int64_t)t * a.out_tstride + a.n0;
+#pragma unroll 1
+    for (int c = 0; c < N / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + c * 32, v);
+      if (row_ok) {
+        if (a.out_dtype == VISDE_BF16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + obase + c * 32;
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (c * 32 + q < a.out_cols) o[q] = __float2bfloat16(v[q] + (a.bias ? a.bias[a.n0 + c * 32 + q] : 0.f));
+        } else {
+          float* o = reinterpret_cast<float*>(a.out) + obase + c * 32;
+          if (c * 32 + 32 <= a.out_cols && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+              float4 w;
+              w.x = v[q] + (a.bias ? a.bias[a.n0 + c * 32 + q] : 0.f);
+              w.y = v[q + 1] + (a.bias ? a.bias[a.n0 + c * 32 + q + 1] : 0.f);
+              w.z = v[q + 2] + (a.bias ? a.bias[a.n0 + c * 32 + q + 2] : 0.f);
+              w.w = v[q + 3] + (a.bias ? a.bias[a.n0 + c * 32 + q + 3] : 0.f);
+              *reinterpret_cast<float4*>(o + q) = w;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (c * 32 + q < a.out_cols) o[q] = v[q] + (a.bias ? a.bias[a.n0 + c * 32 + q] : 0.f);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: split-K weight-gradient kernel (both operands MN-major)
+// ------------------------------------------------------------------------------------------
+struct WgProblem {
+  int a_map, b_map;  // which tensor map (0 = ctx, 1 = dg, 2 = stash)
+  int a_cols[4];     // column coordinate of each 32-wide A slab (M = 128)
+  int b_cols[6];     // column coordinate of each 32-wide B slab (N = 192)
+  int a_tshift, b_tshift;
+};
+struct WgArgs {
+  WgProblem prob[5];
+  int nprob, nsplit;
+  int64_t total_kblocks;  // B * ceil(T / 32)
+  int kb_per_b;           // ceil(T / 32)
+  float* partials;        // [nprob][nsplit][128][192]
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                const __grid_constant__ CUtensorMap tm2, WgArgs a) {
+  constexpr int N = 192;
+  constexpr int A_BYTES = 128 * 128, B_BYTES = N * 128;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr uint32_t TMEM_COLS = 256;
+  constexpr uint32_t IDESC = make_idesc(N, true, true);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + kStages * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pi = blockIdx.y, split = blockIdx.x;
+  const WgProblem& pr = a.prob[pi];
+  const int64_t per = (a.total_kblocks + a.nsplit - 1) / a.nsplit;
+  const int64_t kb0 = split * per;
+  const int64_t kb1 = kb0 + per < a.total_kblocks ? kb0 + per : a.total_kblocks;
+  const int nk = kb1 > kb0 ? (int)(kb1 - kb0) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->split[s], 128);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* mA = pr.a_map == 0 ? &tm0 : pr.a_map == 1 ? &tm1 : &tm2;
+      const CUtensorMap* mB = pr.b_map == 0 ? &tm0 : pr.b_map == 1 ? &tm1 : &tm2;
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % kStages;
+        if (kb >= kStages) mbar_wait(&bars->empty[s], ((kb / kStages) - 1) & 1);
+        const int64_t g = kb0 + kb;
+        const int b = (int)(g / a.kb_per_b), t32 = (int)(g % a.kb_per_b) * 32;
+        uint8_t* st = smem + s * STAGE_BYTES;
+        mbar_expect_tx(&bars->full[s], A_BYTES + B_BYTES);
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl)
+          tma_load_3d(st + sl * 4096, mA, &bars->full[s], pr.a_cols[sl], t32 + pr.a_tshift, b);
+#pragma unroll
+        for (int sl = 0; sl < 6; ++sl)
+          tma_load_3d(st + 2 * A_BYTES + sl * 4096, mB, &bars->full[s], pr.b_cols[sl], t32 + pr.b_tshift, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&bars->split[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t dah = desc_mnmajor(a_hi, j), dal = desc_mnmajor(a_lo, j);
+          const uint64_t dbh = desc_mnmajor(b_hi, j), dbl = desc_mnmajor(b_lo, j);
+          umma_tf32(tmem_d, dal, dbh, IDESC, (kb | j) != 0);
+          umma_tf32(tmem_d, dah, dbl, IDESC, 1);
+          umma_tf32(tmem_d, dah, dbh, IDESC, 1);
+        }
+        umma_commit(&bars->empty[s]);
+      }
+      if (nk > 0) umma_commit(&bars->accum); else mbar_arrive(&bars->accum);
+    }
+  } else {
+    const int tid128 = threadIdx.x - 64;
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % kStages;
+      mbar_wait(&bars->full[s], (kb / kStages) & 1);
+      uint8_t* st = smem + s * STAGE_BYTES;
+      split_tile(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + A_BYTES), A_BYTES / 16, tid128);
+      split_tile(reinterpret_cast<float4*>(st + 2 * A_BYTES), reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES),
+                 B_BYTES / 16, tid128);
+      fence_proxy_async();
+      mbar_arrive(&bars->split[s]);
+    }
+    mbar_wait(&bars->accum, 0);
+    tc_fence_after();
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    float* out = a.partials + (((int64_t)pi * a.nsplit + split) * 128 + row) * N;
+#pragma unroll 1
+    for (int c = 0; c < N / 32; ++c) {
+      float v[32];
+      if (nk > 0) {
+        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + c * 32, v);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 32; q += 4)
+        *reinterpret_cast<float4*>(out + c * 32 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+// fixed-order sum over splits + scatter (transposed) into the gradient tensors
+struct WgScatter {
+  float* dst;      // dst[n * ld + col0 + (row - row0)] = sum_split partial[row][n]
+  int ld, col0, row0, nrows;
+};
+struct WgReduceArgs {
+  const float* partials;
+  int nsplit;
+  WgScatter sc[5];
+  int nprob;
+};
+__global__ void tc_wgrad_reduce_kernel(WgReduceArgs r) {
+  const int pi = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over 128 * 192, n fastest
+  if (idx >= 128 * 192) return;
+  const int row = idx / 192, n = idx % 192;
+  const WgScatter& s = r.sc[pi];
+  if (row < s.row0 || row >= s.row0 + s.nrows) return;
+  const float* p = r.partials + (int64_t)pi * r.nsplit * 128 * 192 + idx;
+  float acc = 0.f;
+  for (int z = 0; z < r.nsplit; ++z) acc += p[(int64_t)z * 128 * 192];
+  s.dst[(int64_t)n * s.ld + s.col0 + (row - s.row0)] = acc;
+}
+
+// hi/lo split of the context columns of W_ih_l0, packed [3H, C] (K0: K-major B; K3: MN-major B)
+__global__ void split_weights_kernel(const float* __restrict__ w, int ld, int col0, int rows, int cols, float* hi,
+                                     float* lo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int r = idx / cols, c = idx % cols;
+  const float x = w[(int64_t)r * ld + col0 + c];
+  const float h = __uint_as_float(__float_as_uint(x) & kTf32Mask);
+  hi[idx] = h;
+  lo[idx] = __uint_as_float(__float_as_uint(x - h) & kTf32Mask);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp32 tensor [d2][d1][d0] (d0 contiguous), strides in elements; box [b1 rows of dim1][b0 cols of dim0]
+int make_map(CUtensorMap* m, const void* base, int rank, const int64_t* dims, const int64_t* strides_elems,
+             const int* box, bool mn_major = false) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled unavailable");
+    return VISDE_ECUDA;
+  }
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = (cuuint64_t)strides_elems[i] * sizeof(float);
+  CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d)", (int)rc);
+    return VISDE_ECUDA;
+  }
+  return VISDE_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int N, bool B_MN>
+int launch_rows(const CUtensorMap& mA, const CUtensorMap& mBh, const CUtensorMap& mBl, const RowsArgs& a, int64_t B,
+                cudaStream_t st) {
+  constexpr int STAGE_BYTES = 2 * 128 * 128 + 2 * N * 128;
+  const size_t smem = kStages * STAGE_BYTES + sizeof(TcBarriers) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VISDE_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_kernel<N, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  tc_rows_kernel<N, B_MN><<<(unsigned)(B * a.tiles_per_b), kTcThreads, smem, st>>>(mA, mBh, mBl, a);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  return VISDE_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// public (internal) entry points
+// ------------------------------------------------------------------------------------------
+bool tc_supported(int H, int NL, int C, const visde_ctx_view* ctx) {
+  if (H != 64 || NL > 2 || (C != 128 && C != 256)) return false;
+  if (!ctx || ctx->dtype != VISDE_F32 || !aligned16(ctx->ptr)) return false;
+  if (ctx->batch_stride % 4 != 0 || ctx->time_stride % 4 != 0) return false;
+  return get_encode() != nullptr;
+}
+
+size_t tc_weight_scratch_floats(int H, int C) { return (size_t)2 * 3 * H * C; }
+size_t tc_wgrad_partial_floats(int NL, int C) {
+  const int nprob = C / 128 + (NL == 1 ? 1 : 3);
+  const int nsplit = 148 / nprob;
+  return (size_t)nprob * nsplit * 128 * 192;
+}
+
+// packed hi / lo copies of W_ih_l0[:, S:S+C] into scratch (hi at scratch, lo at scratch + 3H*C)
+int tc_split_weights(const float* w_ih0, int ld0, int S, int H, int C, float* scratch, cudaStream_t st) {
+  const int n = 3 * H * C;
+  split_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(w_ih0, ld0, S, 3 * H, C, scratch, scratch + n);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  return VISDE_OK;
+}
+
+// K0: gi_ctx[B,T,192] = ctx . Wc^T + b_ih0
+int tc_ctx_proj(const visde_ctx_view* ctx, int64_t B, int64_t T, int C, int H, const float* wsplit, const float* bias,
+                float* gi_ctx, cudaStream_t st) {
+  CUtensorMap mA, mBh, mBl;
+  const int64_t dA[3] = {C, T, B}, sA[2] = {ctx->time_stride, ctx->batch_stride};
+  const int boxA[3] = {32, 128, 1};
+  int rc = make_map(&mA, ctx->ptr, 3, dA, sA, boxA);
+  if (rc) return rc;
+  const int64_t dB[2] = {C, 3 * H}, sB[1] = {C};
+  const int boxB[2] = {32, 3 * H};
+  if ((rc = make_map(&mBh, wsplit, 2, dB, sB, boxB))) return rc;
+  if ((rc = make_map(&mBl, wsplit + (size_t)3 * H * C, 2, dB, sB, boxB))) return rc;
+  RowsArgs a{};
+  a.T = T;
+  a.tiles_per_b = (int)((T + 127) / 128);
+  a.num_kblocks = C / 32;
+  a.n0 = 0;
+  a.bias = bias;
+  a.out = gi_ctx;
+  a.out_bstride = T * (int64_t)(3 * H);
+  a.out_tstride = 3 * H;
+  a.out_dtype = VISDE_F32;
+  a.out_cols = 3 * H;
+  return launch_rows<192, false>(mA, mBh, mBl, a, B, st);
+}
+
+// K3: grad_ctx[b,t,:] = d_gi_l0[(b,t), :192] . Wc   (dg rows have `dg_row` floats)
+int tc_grad_ctx(const float* dg, int64_t dg_row, int64_t B, int64_t T, int C, int H, const float* wsplit,
+                const visde_ctx_grad_view* out, cudaStream_t st) {
+  CUtensorMap mA, mBh, mBl;
+  const int64_t dA[3] = {3 * H, T, B}, sA[2] = {dg_row, T * dg_row};
+  const int boxA[3] = {32, 128, 1};
+  int rc = make_map(&mA, dg, 3, dA, sA, boxA);
+  if (rc) return rc;
+  const int64_t dB[2] = {C, 3 * H}, sB[1] = {C};
+  const int boxB[2] = {32, 32};
+  if ((rc = make_map(&mBh, wsplit, 2, dB, sB, boxB, true))) return rc;
+  if ((rc = make_map(&mBl, wsplit + (size_t)3 * H * C, 2, dB, sB, boxB, true))) return rc;
+  for (int n0 = 0; n0 < C; n0 += 256) {
+    RowsArgs a{};
+    a.T = T;
+    a.tiles_per_b = (int)((T + 127) / 128);
+    a.num_kblocks = 3 * H / 32;
+    a.n0 = n0;
+    a.bias = nullptr;
+    a.out = out->ptr;
+    a.out_bstride = out->batch_stride;
+    a.out_tstride = out->time_stride;
+    a.out_dtype = out->dtype;
+    a.out_cols = C - n0 < 256 ? C - n0 : 256;
+    if (a.out_cols == 256)
+      rc = launch_rows<256, true>(mA, mBh, mBl, a, B, st);
+    else
+      rc = launch_rows<128, true>(mA, mBh, mBl, a, B, st);
+    if (rc) return rc;
+  }
+  return VISDE_OK;
+}
+
+// K4 (big part): dW_ih0[:, S:S+C], dW_hh0, dW_ih1, dW_hh1 from ctx, dg and the h slots of the stash
+int tc_wgrads(const visde_ctx_view* ctx, const float* dg, const float* stash, int64_t B, int64_t T, int S, int C, int P,
+              int H, int NL, const visde_weight_grads* gw, float* partials, size_t partial_floats, cudaStream_t st) {
+  const int64_t dg_row = (int64_t)NL * kDgSlots * H, st_row = stash_row_floats(NL, H);
+  CUtensorMap m0, m1, m2;
+  const int box[3] = {32, 32, 1};
+  {
+    const int64_t d[3] = {C, T, B}, s[2] = {ctx->time_stride, ctx->batch_stride};
+    int rc = make_map(&m0, ctx->ptr, 3, d, s, box, true);
+    if (rc) return rc;
+  }
+  {
+    const int64_t d[3] = {dg_row, T, B}, s[2] = {dg_row, T * dg_row};
+    int rc = make_map(&m1, dg, 3, d, s, box, true);
+    if (rc) return rc;
+  }
+  {
+    const int64_t d[3] = {st_row, T, B}, s[2] = {st_row, T * st_row};
+    int rc = make_map(&m2, stash, 3, d, s, box, true);
+    if (rc) return rc;
+  }
+  WgArgs a{};
+  WgReduceArgs r{};
+  int np = 0;
+  const int ld0 = S + C + P;
+  auto set_b = [&](WgProblem& p, int layer, bool gh) {
+    const int base = layer * kDgSlots * H;
+    for (int sl = 0; sl < 6; ++sl) {
+      int col = sl * 32;
+      if (gh && col >= 2 * H) col += H;  // (r, u, n_hh) slots
+      p.b_cols[sl] = base + col;
+    }
+    p.b_map = 1;
+    p.b_tshift = 0;
+  };
+  auto hcat = [&](WgProblem& p, int tshift) {
+    const int h0 = kStashH * H, h1 = (NL > 1 ? kStashSlots + kStashH : kStashH) * H;
+    p.a_map = 2;
+    p.a_cols[0] = h0;
+    p.a_cols[1] = h0 + 32;
+    p.a_cols[2] = h1;
+    p.a_cols[3] = h1 + 32;
+    p.a_tshift = tshift;
+  };
+  for (int c0 = 0; c0 < C; c0 += 128) {  // dW_ih0[:, S + c0 : S + c0 + 128]
+    WgProblem& p = a.prob[np];
+    p.a_map = 0;
+    for (int sl = 0; sl < 4; ++sl) p.a_cols[sl] = c0 + sl * 32;
+    p.a_tshift = 0;
+    set_b(p, 0, false);
+    r.sc[np] = WgScatter{gw->w_ih[0], ld0, S + c0, 0, 128};
+    ++np;
+  }
+  {  // dW_hh0 = d_gh0^T h0(t-1)
+    WgProblem& p = a.prob[np];
+    hcat(p, -1);
+    set_b(p, 0, true);
+    r.sc[np] = WgScatter{gw->w_hh[0], H, 0, 0, H};
+    ++np;
+  }
+  if (NL > 1) {
+    {  // dW_ih1 = d_gi1^T h0(t)
+      WgProblem& p = a.prob[np];
+      hcat(p, 0);
+      set_b(p, 1, false);
+      r.sc[np] = WgScatter{gw->w_ih[1], H, 0, 0, H};
+      ++np;
+    }
+    {  // dW_hh1 = d_gh1^T h1(t-1)
+      WgProblem& p = a.prob[np];
+      hcat(p, -1);
+      set_b(p, 1, true);
+      r.sc[np] = WgScatter{gw->w_hh[1], H, 0, H, H};
+      ++np;
+    }
+  }
+  a.nprob = np;
+  a.nsplit = 148 / np;
+  a.kb_per_b = (int)((T + 31) / 32);
+  a.total_kblocks = B * a.kb_per_b;
+  if (a.total_kblocks < a.nsplit) a.nsplit = (int)a.total_kblocks;
+  a.partials = partials;
+  if ((size_t)np * a.nsplit * 128 * 192 > partial_floats) {
+    set_error("tc_wgrads: workspace too small");
+    return VISDE_EWORKSPACE;
+  }
+  constexpr int STAGE_BYTES = 2 * 128 * 128 + 2 * 192 * 128;
+  const size_t smem = kStages * STAGE_BYTES + sizeof(TcBarriers) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VISDE_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  tc_wgrad_kernel<<<dim3(a.nsplit, np), kTcThreads, smem, st>>>(m0, m1, m2, a);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  r.partials = partials;
+  r.nsplit = a.nsplit;
+  r.nprob = np;
+  tc_wgrad_reduce_kernel<<<dim3((128 * 192 + 255) / 256, np), 256, 0, st>>>(r);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  return VISDE_OK;
+}
+
+}  // namespace visde
