@@ -69,7 +69,7 @@ StashLayout stash_layout(const visde_dims* d) {
 }
 
 struct BwdWs {
-  size_t dg, dout, sdg, partials, wsplit, total, partial_floats;
+  size_t dg, dout, sdg, partials, wsplit, cta_part, total, partial_floats;
 };
 BwdWs bwd_ws(const visde_dims* d) {
   BwdWs w{};
@@ -98,6 +98,8 @@ BwdWs bwd_ws(const visde_dims* d) {
   off += align_up(sizeof(float) * pf);
   w.wsplit = off;
   off += align_up(sizeof(float) * tc_weight_scratch_floats(d->H, d->C));
+  w.cta_part = off;
+  off += align_up(sizeof(float) * fast_partials_floats(d->NL, d->H, d->S));
   w.total = off;
   return w;
 }
@@ -278,12 +280,15 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
   p.dg = reinterpret_cast<float*>(wsb + ws.dg);
   p.dout = reinterpret_cast<float*>(wsb + ws.dout);
   p.sdg = reinterpret_cast<float*>(wsb + ws.sdg);
+  p.paths = const_cast<float*>(paths);
+  const bool fastk = use_fast(d, p);
+  p.cta_part = fastk ? reinterpret_cast<float*>(wsb + ws.cta_part) : nullptr;
   float* partials = reinterpret_cast<float*>(wsb + ws.partials);
 
   // K2: reverse-time recurrence
   {
     StageTimer tm(VISDE_STAGE_K2_PATH_BWD, 1, st);
-    rc = use_fast(d, p) ? launch_path_bwd_fast(p, st) : launch_path_bwd_generic(p, st);
+    rc = fastk ? launch_path_bwd_fast(p, st) : launch_path_bwd_generic(p, st);
     if (rc) return rc;
   }
   if (d->T == 0) {
@@ -331,8 +336,40 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
       if (rc) return rc;
     }
   }
-  // K4: weight gradients (bias gradients ride along as a column of ones)
-  StageTimer tm4(VISDE_STAGE_K4_WGRAD, tc ? 2 + 2 * (2 * NL + 1) : 2 * (2 * NL + 1), st);
+  // K4: weight gradients
+  StageTimer tm4(VISDE_STAGE_K4_WGRAD, fastk ? (tc ? 5 : 3 + 2 * (2 * NL)) : (tc ? 2 + 2 * (2 * NL + 1) : 2 * (2 * NL + 1)), st);
+  if (fastk) {
+    // fast family: biases, dW_ih_l0[:, :S], dW_out, db_out were accumulated inside K2 (per-CTA partials)
+    rc = launch_fast_partials_reduce(p, gw, st);
+    if (rc) return rc;
+    if (P > 0) {  // theta columns of dW_ih_l0 = (sum_t d_gi_l0)^T theta: only B rows
+      RowSrc A{p.sdg, G, 0, 0, G, VISDE_F32};
+      RowSrc bs[1] = {RowSrc{theta, P, 0, 0, P, VISDE_F32}};
+      TnOut o{gw->w_ih[0] + S + C, ld0, 0, P};
+      rc = launch_gemm_tn(A, G, G, 0, bs, 1, d->B, 1, &o, 1, partials, ws.partial_floats, st);
+      if (rc) return rc;
+    }
+    if (tc) return tc_wgrads(ctx, p.dg, p.stash, d->B, d->T, S, C, P, H, NL, gw, partials, ws.partial_floats, st);
+    if (C > 0) {
+      RowSrc bs[1] = {RowSrc{ctx->ptr, ctx->batch_stride, ctx->time_stride, 0, C, ctx->dtype}};
+      TnOut o{gw->w_ih[0] + S, ld0, 0, C};
+      rc = launch_gemm_tn(dg_src(0), G, G, 0, bs, 1, d->B, d->T, &o, 1, partials, ws.partial_floats, st);
+      if (rc) return rc;
+    }
+    for (int k = 0; k < NL; ++k) {
+      RowSrc bh[1] = {h_src(k, -1)};
+      TnOut oh{gw->w_hh[k], H, 0, H};
+      rc = launch_gemm_tn(dg_src(k), G, 2 * H, H, bh, 1, d->B, d->T, &oh, 1, partials, ws.partial_floats, st);
+      if (rc) return rc;
+      if (k > 0) {
+        RowSrc bi[1] = {h_src(k - 1, 0)};
+        TnOut oi{gw->w_ih[k], H, 0, H};
+        rc = launch_gemm_tn(dg_src(k), G, G, 0, bi, 1, d->B, d->T, &oi, 1, partials, ws.partial_floats, st);
+        if (rc) return rc;
+      }
+    }
+    return VISDE_OK;
+  }
   if (tc) {
     // tensor-core part: dW_ih0[:, S:S+C], dW_hh_k, dW_ih_1 (tc_gemm.cu); the thin remainder below
     rc = tc_wgrads(ctx, p.dg, p.stash, d->B, d->T, S, C, P, H, NL, gw, partials, ws.partial_floats, st);

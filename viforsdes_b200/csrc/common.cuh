@@ -66,6 +66,7 @@ struct PathParams {
   float* dg;       // [B*T,NL,4,H]
   float* dout;     // [B*T,n_out]
   float* sdg;      // [B,3H]  sum_t d_gi of layer 0
+  float* cta_part; // fast family: per-CTA partial sums of the thin weight-gradient pieces (or nullptr)
 };
 
 __host__ __device__ inline int64_t stash_row_floats(int NL, int H) { return (int64_t)NL * kStashSlots * H; }
@@ -109,6 +110,9 @@ int launch_path_bwd_generic(const PathParams& p, cudaStream_t st);
 bool fast_supported(const PathParams& p);
 int launch_path_fwd_fast(const PathParams& p, cudaStream_t st);
 int launch_path_bwd_fast(const PathParams& p, cudaStream_t st);
+size_t fast_partials_floats(int NL, int H, int S);
+// biases, dW_ih_l0[:, :S], dW_out, db_out from the per-CTA partials written by path_bwd_fast
+int launch_fast_partials_reduce(const PathParams& p, const visde_weight_grads* gw, cudaStream_t st);
 
 // --- SIMT fp32 GEMMs with (b,t) row gathering -------------------------------------------
 // A "row source": row k = (b, t) with b = k / T, t = k % T lives at

@@ -57,6 +57,11 @@ __device__ __forceinline__ float dot2(const float2 (&w)[SL / 2], const float2 (&
   return (a.x + a.y) + (b.x + b.y);
 }
 
+// floats of one CTA's partial-sum record: biases [NL][4][H], dW_ih_l0[:, :S] [3S][H], dW_out [n_out][H], db_out
+__host__ __device__ constexpr int fast_part_floats(int NL, int H, int S) {
+  return NL * kDgSlots * H + 3 * S * H + (S + S * (S + 1) / 2) * H + (S + S * (S + 1) / 2);
+}
+
 // bank-padded slice layout of an H-vector in shared memory: slice ks starts at ks * (SL + 4)
 template <int SL>
 __device__ __forceinline__ int padded(int j) {
@@ -339,8 +344,19 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
       if (q & 1) wzg[ps][q / 2].y = a; else wzg[ps][q / 2].x = a;
     }
 
+  // small weight-gradient pieces accumulated in registers over every step of every trajectory this
+  // CTA owns; each of the KS lanes of a unit keeps a different share (no redundant accumulators)
+  constexpr int NQZ = (3 * S + KS - 1) / KS, NQO = (NOUT + KS - 1) / KS;
+  float sb[NL], wzacc[NQZ], woacc[NQO], dsum[NQO];
+#pragma unroll
+  for (int k = 0; k < NL; ++k) sb[k] = 0.f;
+#pragma unroll
+  for (int q = 0; q < NQZ; ++q) wzacc[q] = 0.f;
+#pragma unroll
+  for (int q = 0; q < NQO; ++q) woacc[q] = dsum[q] = 0.f;
+
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
-    float dz[S], dhc[NL], sdg[3] = {0.f, 0.f, 0.f};
+    float dz[S], dhc[NL], sdg_lane = 0.f;
 #pragma unroll
     for (int s = 0; s < S; ++s) dz[s] = 0.f;
 #pragma unroll
@@ -352,18 +368,20 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
     const float* gl_b = p.g_chol + b * p.T * S * S;
     const float* ep_b = p.eps + b * p.T * S;
     const float* raw_b = p.raw + b * p.T * NTRIL;
+    const float* z_b = p.paths + b * (p.T + 1) * S;
     const float* st_b = p.stash + b * p.T * (int64_t)srow + (unit_ok ? i : 0);
     float* dg_b = p.dg + b * p.T * (int64_t)(NL * kDgSlots * H) + (ks < kDgSlots ? ks : 0) * H + (unit_ok ? i : 0);
     float* dout_b = p.dout + b * p.T * NOUT;
 
     // per-step inputs, software-prefetched one step ahead (reverse time)
-    float c_gp[S], c_gm[S], c_gl[NTRIL], c_eps[S], c_rawd[S];
+    float c_gp[S], c_gm[S], c_gl[NTRIL], c_eps[S], c_rawd[S], c_z[S];
     float c_r[NL], c_u[NL], c_n[NL], c_nhh[NL], c_hp[NL];
     auto load_step = [&](int t, float (&gp)[S], float (&gm)[S], float (&gl)[NTRIL], float (&ep)[S],
-                         float (&rd)[S], float (&sr)[NL], float (&su)[NL], float (&sn)[NL],
+                         float (&rd)[S], float (&zz)[S], float (&sr)[NL], float (&su)[NL], float (&sn)[NL],
                          float (&snh)[NL], float (&shp)[NL]) {
 #pragma unroll
       for (int s = 0; s < S; ++s) {
+        zz[s] = z_b[t * S + s];
         gp[s] = gp_b[(t + 1) * S + s];
         gm[s] = gm_b[t * S + s];
         ep[s] = ep_b[t * S + s];
@@ -385,13 +403,15 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
       }
     };
     const int T = (int)p.T;
-    if (T > 0) load_step(T - 1, c_gp, c_gm, c_gl, c_eps, c_rawd, c_r, c_u, c_n, c_nhh, c_hp);
+    if (T > 0) load_step(T - 1, c_gp, c_gm, c_gl, c_eps, c_rawd, c_z, c_r, c_u, c_n, c_nhh, c_hp);
+    // h_top(t) of this thread's unit: h(T-1) now, afterwards the h(t-1) loaded for the previous step
+    float htop = (unit_ok && T > 0) ? (st_b + (T - 1) * srow + (NL - 1) * kStashSlots * H)[kStashH * H] : 0.f;
 
     for (int t = T - 1; t >= 0; --t) {
       const int par = t & 1;
-      float n_gp[S], n_gm[S], n_gl[NTRIL], n_eps[S], n_rawd[S];
+      float n_gp[S], n_gm[S], n_gl[NTRIL], n_eps[S], n_rawd[S], n_z[S];
       float n_r[NL], n_u[NL], n_n[NL], n_nhh[NL], n_hp[NL];
-      if (t > 0) load_step(t - 1, n_gp, n_gm, n_gl, n_eps, n_rawd, n_r, n_u, n_n, n_nhh, n_hp);
+      if (t > 0) load_step(t - 1, n_gp, n_gm, n_gl, n_eps, n_rawd, n_z, n_r, n_u, n_n, n_nhh, n_hp);
 
       // cotangent of the output projection
       float dout[NOUT];
@@ -415,6 +435,16 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
       float dh = dhc[NL - 1];
 #pragma unroll
       for (int m = 0; m < NOUT; ++m) dh = fmaf(woutc[m], dout[m], dh);
+      // lane ks of unit i owns rows m = q*KS + ks of dW_out[:, i] and of db_out
+#pragma unroll
+      for (int q = 0; q < NQO; ++q) {
+        float dsel = 0.f;
+#pragma unroll
+        for (int m = q * KS; m < NOUT && m < (q + 1) * KS; ++m) dsel = (m - q * KS == ks) ? dout[m] : dsel;
+        woacc[q] = fmaf(dsel, htop, woacc[q]);
+        dsum[q] += dsel;
+      }
+      htop = c_hp[NL - 1];
 
 #pragma unroll
       for (int k = NL - 1; k >= 0; --k) {
@@ -435,10 +465,26 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
             if (unit_ok) dg_b[(t * NL + k) * (kDgSlots * H)] = v;
           }
         }
-        if (k == 0) {
-          sdg[0] += drp;
-          sdg[1] += dup;
-          sdg[2] += dnp;
+        {
+          float v = drp;
+          v = ks == 1 ? dup : v;
+          v = ks == 2 ? dnp : v;
+          v = ks == 3 ? dnh : v;
+          v = unit_ok ? v : 0.f;
+          sb[k] += v;  // bias gradients: slot ks of layer k
+          if (k == 0) {
+            sdg_lane += v;  // per-trajectory sum_t d_gi (lanes 0..2) for grad_theta
+            // dW_ih_l0[:, :S]: lane ks owns items (gate, s) = divmod(q*KS + ks, S)
+#pragma unroll
+            for (int q = 0; q < NQZ; ++q) {
+              const int item = q * KS + ks, gate = item / S, sidx = item % S;
+              float gsel = gate == 0 ? drp : gate == 1 ? dup : dnp;
+              float zsel = 0.f;
+#pragma unroll
+              for (int s2 = 0; s2 < S; ++s2) zsel = sidx == s2 ? c_z[s2] : zsel;
+              wzacc[q] = fmaf(item < 3 * S ? gsel : 0.f, zsel, wzacc[q]);
+            }
+          }
         }
         __syncthreads();
         float2 d0[SL / 2], d1[SL / 2], d2[SL / 2], d3[SL / 2];
@@ -487,6 +533,7 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
         c_gm[s] = n_gm[s];
         c_eps[s] = n_eps[s];
         c_rawd[s] = n_rawd[s];
+        c_z[s] = n_z[s];
       }
 #pragma unroll
       for (int ti = 0; ti < NTRIL; ++ti) c_gl[ti] = n_gl[ti];
@@ -506,12 +553,73 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
         if (s == tid) v = dz[s];
       p.grad_x0[b * S + tid] = v + gp_b[tid];
     }
-    if (unit_ok && ks < 3) {
-      const float v = ks == 0 ? sdg[0] : ks == 1 ? sdg[1] : sdg[2];
-      p.sdg[b * G + ks * H + i] = v;
-    }
+    if (unit_ok && ks < 3) p.sdg[b * G + ks * H + i] = sdg_lane;
     __syncthreads();
   }
+  // per-CTA partial sums -> workspace; summed over CTAs in fixed order by fast_partials_reduce_kernel
+  if (p.cta_part && unit_ok) {
+    float* part = p.cta_part + (int64_t)blockIdx.x * fast_part_floats(NL, H, S);
+    if (ks < kDgSlots) {
+#pragma unroll
+      for (int k = 0; k < NL; ++k) part[(k * kDgSlots + ks) * H + i] = sb[k];
+    }
+    float* pz = part + NL * kDgSlots * H;
+#pragma unroll
+    for (int q = 0; q < NQZ; ++q)
+      if (q * KS + ks < 3 * S) pz[(q * KS + ks) * H + i] = wzacc[q];
+    float* po = pz + 3 * S * H;
+#pragma unroll
+    for (int q = 0; q < NQO; ++q)
+      if (q * KS + ks < NOUT) {
+        po[(q * KS + ks) * H + i] = woacc[q];
+        if (i == 0) po[NOUT * H + q * KS + ks] = dsum[q];
+      }
+  }
+}
+
+// sums the per-CTA partials and scatters them into the gradient tensors
+struct FastReduceArgs {
+  const float* part;
+  int ncta, NL, H, S, n_out, ld0;
+  float* b_ih[VISDE_MAX_LAYERS];
+  float* b_hh[VISDE_MAX_LAYERS];
+  float* w_ih0;
+  float* out_w;
+  float* out_b;
+};
+__global__ void fast_partials_reduce_kernel(FastReduceArgs a) {
+  const int total = fast_part_floats(a.NL, a.H, a.S);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  float acc = 0.f;
+  for (int c = 0; c < a.ncta; ++c) acc += a.part[(int64_t)c * total + idx];
+  const int H = a.H;
+  int off = idx;
+  if (off < a.NL * kDgSlots * H) {
+    const int k = off / (kDgSlots * H), slot = (off / H) % kDgSlots, i = off % H;
+    if (slot < 2) {
+      a.b_ih[k][slot * H + i] = acc;
+      a.b_hh[k][slot * H + i] = acc;
+    } else if (slot == 2) {
+      a.b_ih[k][2 * H + i] = acc;
+    } else {
+      a.b_hh[k][2 * H + i] = acc;
+    }
+    return;
+  }
+  off -= a.NL * kDgSlots * H;
+  if (off < 3 * a.S * H) {
+    const int item = off / H, i = off % H, gate = item / a.S, s = item % a.S;
+    a.w_ih0[(int64_t)(gate * H + i) * a.ld0 + s] = acc;
+    return;
+  }
+  off -= 3 * a.S * H;
+  if (off < a.n_out * H) {
+    a.out_w[off] = acc;  // [m][i]
+    return;
+  }
+  off -= a.n_out * H;
+  a.out_b[off] = acc;
 }
 
 int fast_grid(int64_t B) {
@@ -570,5 +678,29 @@ bool fast_supported(const PathParams& p) {
 }
 int launch_path_fwd_fast(const PathParams& p, cudaStream_t st) { return dispatch_fast(p, st, false); }
 int launch_path_bwd_fast(const PathParams& p, cudaStream_t st) { return dispatch_fast(p, st, true); }
+
+size_t fast_partials_floats(int NL, int H, int S) { return (size_t)256 * fast_part_floats(NL, H, S); }
+
+int launch_fast_partials_reduce(const PathParams& p, const visde_weight_grads* gw, cudaStream_t st) {
+  FastReduceArgs a{};
+  a.part = p.cta_part;
+  a.ncta = fast_grid(p.B);
+  a.NL = p.NL;
+  a.H = p.H;
+  a.S = p.S;
+  a.n_out = p.n_out;
+  a.ld0 = p.S + p.C + p.P;
+  for (int k = 0; k < p.NL; ++k) {
+    a.b_ih[k] = gw->b_ih[k];
+    a.b_hh[k] = gw->b_hh[k];
+  }
+  a.w_ih0 = gw->w_ih[0];
+  a.out_w = gw->out_w;
+  a.out_b = gw->out_b;
+  const int total = fast_part_floats(p.NL, p.H, p.S);
+  fast_partials_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(a);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  return VISDE_OK;
+}
 
 }  // namespace visde
