@@ -197,7 +197,7 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
   VISDE_REQUIRE(x0 && paths, "x0 / paths is NULL");
   VISDE_REQUIRE(d->T == 0 || (ctx && ctx->ptr && eps && means && chol), "NULL tensor argument");
   VISDE_REQUIRE(d->P == 0 || theta, "theta is NULL");
-  VISDE_REQUIRE((d->variant & 0xff) != VISDE_VARIANT_FAST || (d->H <= 64 && d->NL <= 2 && d->S <= 4),
+  VISDE_REQUIRE((d->variant & 0xff) != VISDE_VARIANT_FAST || (d->H <= 64 && d->H % 4 == 0 && d->NL <= 2 && d->S <= 4),
                 "fast variant requested for an unsupported shape (H=%d NL=%d S=%d)", d->H, d->NL, d->S);
   if (workspace_bytes < visde_workspace_bytes(d, 0) - 256 || (!workspace && d->T > 0)) {
     set_error("path_fwd: workspace too small (%zu < %zu)", workspace_bytes, visde_workspace_bytes(d, 0));

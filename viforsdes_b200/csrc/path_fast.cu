@@ -23,6 +23,7 @@
 //     (K4) instead of accumulating weight gradients with atomics.
 // The stall profile that shaped this layout is in profiles/r1_path_kernels.md.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace visde {
 namespace {
@@ -355,83 +356,129 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
 #pragma unroll
   for (int q = 0; q < NQO; ++q) woacc[q] = dsum[q] = 0.f;
 
+  // ---- staged per-step inputs -------------------------------------------------------------
+  // (A) stash rows [NL][5][H] (2.5 KB at H=64): one cp.async.bulk per step into a 4-slot ring, three
+  //     steps ahead, completion on an mbarrier per slot (issued by thread 0);
+  // (B) the per-step uniform scalars (gP, gM, eps, z, raw diag, gL: SMALL floats): thread j < SMALL
+  //     loads element j two steps ahead into a register and parks it in a 3-slot shared ring one step
+  //     later, so no warp ever waits on HBM inside the serial loop.
+  constexpr int NSR = 4;
+  constexpr int SMALL = 5 * S + S * S, SMALLP = (SMALL + 3) / 4 * 4;
+  constexpr int O_GP = 0, O_GM = S, O_EPS = 2 * S, O_Z = 3 * S, O_RAW = 4 * S, O_GL = 5 * S;
+  __shared__ __align__(16) float sring[NSR][NL * kStashSlots * HP];
+  __shared__ __align__(16) float small[3][SMALLP];
+  __shared__ __align__(8) uint64_t sbar[NSR];
+  const uint32_t row_bytes = (uint32_t)srow * 4u;
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < NSR; ++q) mbar_init(&sbar[q], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  uint32_t rows_issued = 0;  // total stash rows issued so far by this CTA (slot / phase bookkeeping)
+
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     float dz[S], dhc[NL], sdg_lane = 0.f;
 #pragma unroll
     for (int s = 0; s < S; ++s) dz[s] = 0.f;
 #pragma unroll
     for (int k = 0; k < NL; ++k) dhc[k] = 0.f;
-
-    // per-trajectory bases (uniform) + 32-bit per-step offsets
-    const float* gp_b = p.g_paths + b * (p.T + 1) * S;
-    const float* gm_b = p.g_means + b * p.T * S;
-    const float* gl_b = p.g_chol + b * p.T * S * S;
-    const float* ep_b = p.eps + b * p.T * S;
-    const float* raw_b = p.raw + b * p.T * NTRIL;
-    const float* z_b = p.paths + b * (p.T + 1) * S;
-    const float* st_b = p.stash + b * p.T * (int64_t)srow + (unit_ok ? i : 0);
-    float* dg_b = p.dg + b * p.T * (int64_t)(NL * kDgSlots * H) + (ks < kDgSlots ? ks : 0) * H + (unit_ok ? i : 0);
-    float* dout_b = p.dout + b * p.T * NOUT;
-
-    // per-step inputs, software-prefetched one step ahead (reverse time)
-    float c_gp[S], c_gm[S], c_gl[NTRIL], c_eps[S], c_rawd[S], c_z[S];
-    float c_r[NL], c_u[NL], c_n[NL], c_nhh[NL], c_hp[NL];
-    auto load_step = [&](int t, float (&gp)[S], float (&gm)[S], float (&gl)[NTRIL], float (&ep)[S],
-                         float (&rd)[S], float (&zz)[S], float (&sr)[NL], float (&su)[NL], float (&sn)[NL],
-                         float (&snh)[NL], float (&shp)[NL]) {
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        zz[s] = z_b[t * S + s];
-        gp[s] = gp_b[(t + 1) * S + s];
-        gm[s] = gm_b[t * S + s];
-        ep[s] = ep_b[t * S + s];
-        rd[s] = raw_b[t * NTRIL + s * (s + 1) / 2 + s];
-#pragma unroll
-        for (int j = 0; j <= s; ++j) gl[s * (s + 1) / 2 + j] = gl_b[(t * S + s) * S + j];
-      }
-#pragma unroll
-      for (int k = 0; k < NL; ++k) {
-        sr[k] = su[k] = sn[k] = snh[k] = shp[k] = 0.f;
-        if (unit_ok) {
-          const float* st = st_b + t * srow + k * kStashSlots * H;
-          sr[k] = st[kStashR * H];
-          su[k] = st[kStashU * H];
-          sn[k] = st[kStashN * H];
-          snh[k] = st[kStashNhh * H];
-          if (t > 0) shp[k] = (st - srow)[kStashH * H];
-        }
-      }
-    };
     const int T = (int)p.T;
-    if (T > 0) load_step(T - 1, c_gp, c_gm, c_gl, c_eps, c_rawd, c_z, c_r, c_u, c_n, c_nhh, c_hp);
-    // h_top(t) of this thread's unit: h(T-1) now, afterwards the h(t-1) loaded for the previous step
-    float htop = (unit_ok && T > 0) ? (st_b + (T - 1) * srow + (NL - 1) * kStashSlots * H)[kStashH * H] : 0.f;
+
+    // per-trajectory bases
+    const float* st_b = p.stash + b * p.T * (int64_t)srow;
+    float* dg_p = p.dg + (b * p.T + (T - 1)) * (int64_t)(NL * kDgSlots * H) + (ks < kDgSlots ? ks : 0) * H + (unit_ok ? i : 0);
+    float* dout_p = p.dout + (b * p.T + (T - 1)) * NOUT;
+    // loader thread j: pointer to element j of row r and its per-row stride
+    const float* src = nullptr;
+    int dec = 0;
+    if (tid < SMALL) {
+      const int j = tid;
+      if (j < O_GM) { src = p.g_paths + b * (p.T + 1) * S + S + j; dec = S; }
+      else if (j < O_EPS) { src = p.g_means + b * p.T * S + (j - O_GM); dec = S; }
+      else if (j < O_Z) { src = p.eps + b * p.T * S + (j - O_EPS); dec = S; }
+      else if (j < O_RAW) { src = p.paths + b * (p.T + 1) * S + (j - O_Z); dec = S; }
+      else if (j < O_GL) { const int d = j - O_RAW; src = p.raw + b * p.T * NTRIL + d * (d + 1) / 2 + d; dec = NTRIL; }
+      else { src = p.g_chol + b * p.T * S * S + (j - O_GL); dec = S * S; }
+    }
+    // prologue: rows T-1, T-2 of the small ring directly, row T-3 pending; stash rows T-1..T-3 in flight
+    float pend = 0.f;
+    if (tid < SMALL) {
+      if (T >= 1) small[(T - 1) % 3][tid] = src[(int64_t)(T - 1) * dec];
+      if (T >= 2) small[(T - 2) % 3][tid] = src[(int64_t)(T - 2) * dec];
+      if (T >= 3) pend = src[(int64_t)(T - 3) * dec];
+      src += (int64_t)(T - 4) * dec;  // next row to fetch (may point before the array; guarded by t)
+    }
+    const uint32_t row0 = rows_issued;  // row r of this trajectory is issue number row0 + (T-1-r)
+    if (tid == 0) {
+      for (int r = T - 1; r >= 0 && r >= T - 3; --r) {
+        const uint32_t n = row0 + (uint32_t)(T - 1 - r);
+        mbar_expect_tx(&sbar[n % NSR], row_bytes);
+        bulk_load_1d(&sring[n % NSR][0], st_b + (int64_t)r * srow, row_bytes, &sbar[n % NSR]);
+      }
+    }
+    rows_issued += (uint32_t)T;
+    __syncthreads();
+    if (T > 0) mbar_wait(&sbar[row0 % NSR], (row0 / NSR) & 1);  // row T-1
+    float htop = (unit_ok && T > 0) ? sring[row0 % NSR][((NL - 1) * kStashSlots + kStashH) * H + i] : 0.f;
 
     for (int t = T - 1; t >= 0; --t) {
       const int par = t & 1;
-      float n_gp[S], n_gm[S], n_gl[NTRIL], n_eps[S], n_rawd[S], n_z[S];
-      float n_r[NL], n_u[NL], n_n[NL], n_nhh[NL], n_hp[NL];
-      if (t > 0) load_step(t - 1, n_gp, n_gm, n_gl, n_eps, n_rawd, n_z, n_r, n_u, n_n, n_nhh, n_hp);
+      const uint32_t n_cur = row0 + (uint32_t)(T - 1 - t);
+      const float* row_cur = &sring[n_cur % NSR][0];
+      const float* row_prev = &sring[(n_cur + 1) % NSR][0];
+      // keep the pipelines full: stash row t-3, small row t-3 (parked next step), park row t-2
+      if (tid == 0 && t >= 3) {
+        const uint32_t n = n_cur + 3;
+        mbar_expect_tx(&sbar[n % NSR], row_bytes);
+        bulk_load_1d(&sring[n % NSR][0], st_b + (int64_t)(t - 3) * srow, row_bytes, &sbar[n % NSR]);
+      }
+      if (tid < SMALL) {
+        if (t >= 2) small[(t - 2) % 3][tid] = pend;
+        if (t >= 3) pend = *src;
+        src -= dec;
+      }
+      if (t >= 1) mbar_wait(&sbar[(n_cur + 1) % NSR], ((n_cur + 1) / NSR) & 1);  // row t-1 (h_prev)
+
+      // this step's uniform scalars from the shared ring
+      float sm[SMALLP];
+#pragma unroll
+      for (int q = 0; q < SMALLP / 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(&small[t % 3][4 * q]);
+        sm[4 * q] = v.x; sm[4 * q + 1] = v.y; sm[4 * q + 2] = v.z; sm[4 * q + 3] = v.w;
+      }
+      // this unit's stashed gates (row t) and previous hidden state (row t-1)
+      float c_r[NL], c_u[NL], c_n[NL], c_nhh[NL], c_hp[NL];
+#pragma unroll
+      for (int k = 0; k < NL; ++k) {
+        const int o = k * kStashSlots * H + (unit_ok ? i : 0);
+        c_r[k] = row_cur[o + kStashR * H];
+        c_u[k] = row_cur[o + kStashU * H];
+        c_n[k] = row_cur[o + kStashN * H];
+        c_nhh[k] = row_cur[o + kStashNhh * H];
+        c_hp[k] = t > 0 ? row_prev[o + kStashH * H] : 0.f;
+      }
 
       // cotangent of the output projection
       float dout[NOUT];
 #pragma unroll
-      for (int s = 0; s < S; ++s) dz[s] += c_gp[s];
+      for (int s = 0; s < S; ++s) dz[s] += sm[O_GP + s];
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        dout[s] = fmaf(dz[s], p.dt, c_gm[s]);
+        dout[s] = fmaf(dz[s], p.dt, sm[O_GM + s]);
 #pragma unroll
         for (int j = 0; j <= s; ++j) {
           const int ti = s * (s + 1) / 2 + j;
-          float d = fmaf(dz[s] * c_eps[j], p.sqrt_dt, c_gl[ti]);
-          if (j == s) d = (c_rawd[s] >= VISDE_DIAG_MIN || d < 0.f) ? d : 0.f;  // primitives/bounds.py:20
+          float d = fmaf(dz[s] * sm[O_EPS + j], p.sqrt_dt, sm[O_GL + s * S + j]);
+          if (j == s) d = (sm[O_RAW + s] >= VISDE_DIAG_MIN || d < 0.f) ? d : 0.f;  // primitives/bounds.py:20
           dout[S + ti] = d;
         }
       }
       if (warp == 0 && lane == 0) {
 #pragma unroll
-        for (int m = 0; m < NOUT; ++m) dout_b[t * NOUT + m] = dout[m];
+        for (int m = 0; m < NOUT; ++m) dout_p[m] = dout[m];
       }
+      dout_p -= NOUT;
       float dh = dhc[NL - 1];
 #pragma unroll
       for (int m = 0; m < NOUT; ++m) dh = fmaf(woutc[m], dout[m], dh);
@@ -462,15 +509,8 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
           v = unit_ok ? v : 0.f;
           if (ks < kDgSlots) {
             dgb[par][k][ks][padded<SL>(i)] = v;
-            if (unit_ok) dg_b[(t * NL + k) * (kDgSlots * H)] = v;
+            if (unit_ok) dg_p[k * kDgSlots * H] = v;
           }
-        }
-        {
-          float v = drp;
-          v = ks == 1 ? dup : v;
-          v = ks == 2 ? dnp : v;
-          v = ks == 3 ? dnh : v;
-          v = unit_ok ? v : 0.f;
           sb[k] += v;  // bias gradients: slot ks of layer k
           if (k == 0) {
             sdg_lane += v;  // per-trajectory sum_t d_gi (lanes 0..2) for grad_theta
@@ -481,7 +521,7 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
               float gsel = gate == 0 ? drp : gate == 1 ? dup : dnp;
               float zsel = 0.f;
 #pragma unroll
-              for (int s2 = 0; s2 < S; ++s2) zsel = sidx == s2 ? c_z[s2] : zsel;
+              for (int s2 = 0; s2 < S; ++s2) zsel = sidx == s2 ? sm[O_Z + s2] : zsel;
               wzacc[q] = fmaf(item < 3 * S ? gsel : 0.f, zsel, wzacc[q]);
             }
           }
@@ -527,31 +567,14 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
         const float pc = ks_allreduce<KS>(dot2<SL>(whhT[k][0], d0) + dot2<SL>(whhT[k][1], d1) + dot2<SL>(whhT[k][2], d3));
         dhc[k] = direct + pc;
       }
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        c_gp[s] = n_gp[s];
-        c_gm[s] = n_gm[s];
-        c_eps[s] = n_eps[s];
-        c_rawd[s] = n_rawd[s];
-        c_z[s] = n_z[s];
-      }
-#pragma unroll
-      for (int ti = 0; ti < NTRIL; ++ti) c_gl[ti] = n_gl[ti];
-#pragma unroll
-      for (int k = 0; k < NL; ++k) {
-        c_r[k] = n_r[k];
-        c_u[k] = n_u[k];
-        c_n[k] = n_n[k];
-        c_nhh[k] = n_nhh[k];
-        c_hp[k] = n_hp[k];
-      }
+      dg_p -= NL * kDgSlots * H;
     }
     if (tid < S) {
       float v = 0.f;
 #pragma unroll
       for (int s = 0; s < S; ++s)
         if (s == tid) v = dz[s];
-      p.grad_x0[b * S + tid] = v + gp_b[tid];
+      p.grad_x0[b * S + tid] = v + p.g_paths[b * (p.T + 1) * S + tid];
     }
     if (unit_ok && ks < 3) p.sdg[b * G + ks * H + i] = sdg_lane;
     __syncthreads();
@@ -674,7 +697,9 @@ int dispatch_fast(const PathParams& p, cudaStream_t st, bool bwd) {
 }  // namespace
 
 bool fast_supported(const PathParams& p) {
-  return p.H <= 64 && p.NL <= 2 && p.S <= 4 && p.T * (int64_t)(p.NL * kStashSlots * p.H) < (int64_t(1) << 31);
+  // H % 4: the backward stages stash rows with 16-byte-granular bulk copies
+  return p.H <= 64 && p.H % 4 == 0 && p.NL <= 2 && p.S <= 4 &&
+         p.T * (int64_t)(p.NL * kStashSlots * p.H) < (int64_t(1) << 31);
 }
 int launch_path_fwd_fast(const PathParams& p, cudaStream_t st) { return dispatch_fast(p, st, false); }
 int launch_path_bwd_fast(const PathParams& p, cudaStream_t st) { return dispatch_fast(p, st, true); }
