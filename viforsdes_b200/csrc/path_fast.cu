@@ -364,6 +364,8 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
   //     later, so no warp ever waits on HBM inside the serial loop.
   constexpr int NSR = 4;
   constexpr int SMALL = 5 * S + S * S, SMALLP = (SMALL + 3) / 4 * 4;
+  constexpr int NTHR = HP * KS;
+  constexpr int kTmaThread = NTHR - 32, kLoaderBase = NTHR - 64 - (SMALL > 32 ? 32 : 0), kDoutThread = NTHR / 2;
   constexpr int O_GP = 0, O_GM = S, O_EPS = 2 * S, O_Z = 3 * S, O_RAW = 4 * S, O_GL = 5 * S;
   __shared__ __align__(16) float sring[NSR][NL * kStashSlots * HP];
   __shared__ __align__(16) float small[3][SMALLP];
@@ -392,8 +394,9 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
     // loader thread j: pointer to element j of row r and its per-row stride
     const float* src = nullptr;
     int dec = 0;
-    if (tid < SMALL) {
-      const int j = tid;
+    const int lt = tid - kLoaderBase;  // loader lanes live in the last warps, away from warp 0's stores
+    if (lt >= 0 && lt < SMALL) {
+      const int j = lt;
       if (j < O_GM) { src = p.g_paths + b * (p.T + 1) * S + S + j; dec = S; }
       else if (j < O_EPS) { src = p.g_means + b * p.T * S + (j - O_GM); dec = S; }
       else if (j < O_Z) { src = p.eps + b * p.T * S + (j - O_EPS); dec = S; }
@@ -403,14 +406,14 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
     }
     // prologue: rows T-1, T-2 of the small ring directly, row T-3 pending; stash rows T-1..T-3 in flight
     float pend = 0.f;
-    if (tid < SMALL) {
-      if (T >= 1) small[(T - 1) % 3][tid] = src[(int64_t)(T - 1) * dec];
-      if (T >= 2) small[(T - 2) % 3][tid] = src[(int64_t)(T - 2) * dec];
+    if (lt >= 0 && lt < SMALL) {
+      if (T >= 1) small[(T - 1) % 3][lt] = src[(int64_t)(T - 1) * dec];
+      if (T >= 2) small[(T - 2) % 3][lt] = src[(int64_t)(T - 2) * dec];
       if (T >= 3) pend = src[(int64_t)(T - 3) * dec];
       src += (int64_t)(T - 4) * dec;  // next row to fetch (may point before the array; guarded by t)
     }
     const uint32_t row0 = rows_issued;  // row r of this trajectory is issue number row0 + (T-1-r)
-    if (tid == 0) {
+    if (tid == kTmaThread) {
       for (int r = T - 1; r >= 0 && r >= T - 3; --r) {
         const uint32_t n = row0 + (uint32_t)(T - 1 - r);
         mbar_expect_tx(&sbar[n % NSR], row_bytes);
@@ -428,13 +431,13 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
       const float* row_cur = &sring[n_cur % NSR][0];
       const float* row_prev = &sring[(n_cur + 1) % NSR][0];
       // keep the pipelines full: stash row t-3, small row t-3 (parked next step), park row t-2
-      if (tid == 0 && t >= 3) {
+      if (tid == kTmaThread && t >= 3) {
         const uint32_t n = n_cur + 3;
         mbar_expect_tx(&sbar[n % NSR], row_bytes);
         bulk_load_1d(&sring[n % NSR][0], st_b + (int64_t)(t - 3) * srow, row_bytes, &sbar[n % NSR]);
       }
-      if (tid < SMALL) {
-        if (t >= 2) small[(t - 2) % 3][tid] = pend;
+      if (lt >= 0 && lt < SMALL) {
+        if (t >= 2) small[(t - 2) % 3][lt] = pend;
         if (t >= 3) pend = *src;
         src -= dec;
       }
@@ -474,7 +477,7 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
           dout[S + ti] = d;
         }
       }
-      if (warp == 0 && lane == 0) {
+      if (tid == kDoutThread) {
 #pragma unroll
         for (int m = 0; m < NOUT; ++m) dout_p[m] = dout[m];
       }
