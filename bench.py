@@ -126,6 +126,11 @@ def cpu_baseline(workload: str, n_steps_sample: int | None, iters: int, warm: in
 
     kind, B, T, dt = WORKLOADS[workload]
     Ts = T if n_steps_sample is None else min(T, n_steps_sample)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core this process may run on
+    try:
+        torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     O.run_fwd_bwd(O.make_problem(kind, min(B, 16), 20, dt=dt))  # thread pools, allocator
     p = O.make_problem(kind, B, Ts, dt=dt)
     for _ in range(warm):
@@ -188,6 +193,7 @@ def main() -> None:
     from viforsdes_b200.session import HostSession
     from viforsdes_b200.synthetic import WORKLOADS, make_inputs
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("VISDE_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     rank, local_rank, world = init_process_group()
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local_rank)
@@ -209,7 +215,7 @@ def main() -> None:
         it.step()
         if world > 1:  # the path's one exchange step
             it.bucket.allreduce_mean_()
-            torch.sum(it.terms[:, 0] + it.terms[:, 1] - it.terms[:, 2] + it.terms[:, 3], out=elbo_scalar[0])
+            elbo_scalar.copy_((it.terms[:, 0] + it.terms[:, 1] - it.terms[:, 2] + it.terms[:, 3]).mean().reshape(1))
             allreduce_mean_(elbo_scalar)
 
     K, W = args.steps, args.warmup
