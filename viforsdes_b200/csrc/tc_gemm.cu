@@ -124,6 +124,7 @@ struct TcBarriers {
 struct RowsArgs {
   int64_t T;
   int tiles_per_b;  // ceil(T / 128)
+  int num_tiles;    // B * tiles_per_b
   int num_kblocks;  // K / 32
   int n0;           // first output column handled (K3 with C > 256 launches several column chunks)
   const float* bias;
@@ -133,29 +134,52 @@ struct RowsArgs {
   int out_cols;     // valid output columns in this chunk
 };
 
-template <int N, bool B_MN>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// Persistent, warp-specialised (352 threads):
+//   warp 0      A producer  : raw fp32 A tiles, NA-deep ring (the HBM stream: 16 KB per k-block)
+//   warp 10     B producer  : weight hi/lo tiles (L2-resident), 2-deep ring
+//   warps 2..5  split       : A raw -> hi (in place) + lo (2-deep ring shared with the B slot)
+//   warp 1      MMA issuer  : 3xTF32 into one of two TMEM accumulators (tile i+1 overlaps the epilogue of i)
+//   warps 6..9  epilogue    : tcgen05.ld -> (+bias) -> global
+constexpr int kRowsThreads = 352;
+
+template <int N, int NA>
+struct RowsSmem {
+  static constexpr int A_BYTES = 128 * 128, B_BYTES = N * 128;
+  static constexpr int OFF_ALO = NA * A_BYTES, OFF_B = OFF_ALO + 2 * A_BYTES, OFF_BAR = OFF_B + 2 * 2 * B_BYTES;
+  struct Bars {
+    uint64_t fullA[NA], emptyA[NA], fullB[2], emptyB[2], split[2], tmemFull[2], tmemEmpty[2];
+    uint32_t tmem_base;
+  };
+  static constexpr size_t bytes = OFF_BAR + sizeof(Bars) + 1024;
+};
+
+template <int N, bool B_MN, int NA>
+__global__ void __launch_bounds__(kRowsThreads, 1)
 tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, RowsArgs a) {
-  constexpr int A_BYTES = 128 * 128, B_BYTES = N * 128;
-  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  constexpr uint32_t TMEM_COLS = N <= 128 ? 128 : 256;
+  using L = RowsSmem<N, NA>;
+  constexpr int A_BYTES = L::A_BYTES, B_BYTES = L::B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * N <= 256 ? 256 : 512;
   constexpr uint32_t IDESC = make_idesc(N, false, B_MN);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + kStages * STAGE_BYTES);
+  typename L::Bars* bars = reinterpret_cast<typename L::Bars*>(smem + L::OFF_BAR);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int b = tile / a.tiles_per_b, t0 = (tile % a.tiles_per_b) * 128;
   const int nk = a.num_kblocks;
+  const int ntiles = a.num_tiles;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->split[s], 128);
-      mbar_init(&bars->empty[s], 1);
+    for (int s = 0; s < NA; ++s) {
+      mbar_init(&bars->fullA[s], 1);
+      mbar_init(&bars->emptyA[s], 1);
     }
-    mbar_init(&bars->accum, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->fullB[s], 1);
+      mbar_init(&bars->emptyB[s], 1);
+      mbar_init(&bars->split[s], 128);
+      mbar_init(&bars->tmemFull[s], 1);
+      mbar_init(&bars->tmemEmpty[s], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, TMEM_COLS);
@@ -166,94 +190,127 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % kStages;
-        if (kb >= kStages) mbar_wait(&bars->empty[s], ((kb / kStages) - 1) & 1);
-        uint8_t* st = smem + s * STAGE_BYTES;
-        mbar_expect_tx(&bars->full[s], A_BYTES + 2 * B_BYTES);
-        tma_load_3d(st, &tmA, &bars->full[s], kb * 32, t0, b);
-        if (B_MN) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / a.tiles_per_b, t0 = (tile % a.tiles_per_b) * 128;
+        for (int kb = 0; kb < nk; ++kb, ++g) {
+          const uint32_t sa = g % NA;
+          if (g >= NA) mbar_wait(&bars->emptyA[sa], ((g / NA) - 1) & 1);
+          mbar_expect_tx(&bars->fullA[sa], A_BYTES);
+          tma_load_3d(smem + sa * A_BYTES, &tmA, &bars->fullA[sa], kb * 32, t0, b);
+        }
+      }
+    }
+  } else if (warp == 10) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int kb = 0; kb < nk; ++kb, ++g) {
+          const uint32_t sb = g & 1;
+          if (g >= 2) mbar_wait(&bars->emptyB[sb], ((g >> 1) - 1) & 1);
+          uint8_t* bh = smem + L::OFF_B + sb * 2 * B_BYTES;
+          mbar_expect_tx(&bars->fullB[sb], 2 * B_BYTES);
+          if (B_MN) {
 #pragma unroll
-          for (int sl = 0; sl < N / 32; ++sl) {
-            tma_load_2d(st + 2 * A_BYTES + sl * 4096, &tmBhi, &bars->full[s], a.n0 + sl * 32, kb * 32);
-            tma_load_2d(st + 2 * A_BYTES + B_BYTES + sl * 4096, &tmBlo, &bars->full[s], a.n0 + sl * 32, kb * 32);
+            for (int sl = 0; sl < N / 32; ++sl) {
+              tma_load_2d(bh + sl * 4096, &tmBhi, &bars->fullB[sb], a.n0 + sl * 32, kb * 32);
+              tma_load_2d(bh + B_BYTES + sl * 4096, &tmBlo, &bars->fullB[sb], a.n0 + sl * 32, kb * 32);
+            }
+          } else {
+            tma_load_2d(bh, &tmBhi, &bars->fullB[sb], kb * 32, a.n0);
+            tma_load_2d(bh + B_BYTES, &tmBlo, &bars->fullB[sb], kb * 32, a.n0);
           }
-        } else {
-          tma_load_2d(st + 2 * A_BYTES, &tmBhi, &bars->full[s], kb * 32, a.n0);
-          tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmBlo, &bars->full[s], kb * 32, a.n0);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&bars->full[s], ph);
-        mbar_wait(&bars->split[s], ph);
+      uint32_t g = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+        const uint32_t acc = lt & 1;
+        if (lt >= 2) mbar_wait(&bars->tmemEmpty[acc], ((lt >> 1) - 1) & 1);
         tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+        const uint32_t dcol = tmem_d + acc * N;
+        for (int kb = 0; kb < nk; ++kb, ++g) {
+          const uint32_t sa = g % NA, sb = g & 1, ph = (g >> 1) & 1;
+          mbar_wait(&bars->fullB[sb], ph);
+          mbar_wait(&bars->split[sb], ph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + sa * A_BYTES), a_lo = smem_u32(smem + L::OFF_ALO + sb * A_BYTES);
+          const uint32_t b_hi = smem_u32(smem + L::OFF_B + sb * 2 * B_BYTES), b_lo = b_hi + B_BYTES;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint64_t dah = desc_kmajor(a_hi, j), dal = desc_kmajor(a_lo, j);
-          const uint64_t dbh = B_MN ? desc_mnmajor(b_hi, j) : desc_kmajor(b_hi, j);
-          const uint64_t dbl = B_MN ? desc_mnmajor(b_lo, j) : desc_kmajor(b_lo, j);
-          umma_tf32(tmem_d, dal, dbh, IDESC, (kb | j) != 0);  // small terms first
-          umma_tf32(tmem_d, dah, dbl, IDESC, 1);
-          umma_tf32(tmem_d, dah, dbh, IDESC, 1);
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t dah = desc_kmajor(a_hi, j), dal = desc_kmajor(a_lo, j);
+            const uint64_t dbh = B_MN ? desc_mnmajor(b_hi, j) : desc_kmajor(b_hi, j);
+            const uint64_t dbl = B_MN ? desc_mnmajor(b_lo, j) : desc_kmajor(b_lo, j);
+            umma_tf32(dcol, dal, dbh, IDESC, (kb | j) != 0);  // small terms first
+            umma_tf32(dcol, dah, dbl, IDESC, 1);
+            umma_tf32(dcol, dah, dbh, IDESC, 1);
+          }
+          umma_commit(&bars->emptyA[sa]);
+          umma_commit(&bars->emptyB[sb]);
         }
-        umma_commit(&bars->empty[s]);
+        umma_commit(&bars->tmemFull[acc]);
       }
-      umma_commit(&bars->accum);
     }
-  } else {
+  } else if (warp >= 2 && warp <= 5) {
     const int tid128 = threadIdx.x - 64;
-    for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % kStages;
-      mbar_wait(&bars->full[s], (kb / kStages) & 1);
-      uint8_t* st = smem + s * STAGE_BYTES;
-      split_tile(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + A_BYTES), A_BYTES / 16, tid128);
-      fence_proxy_async();
-      mbar_arrive(&bars->split[s]);
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int kb = 0; kb < nk; ++kb, ++g) {
+        const uint32_t sa = g % NA, sb = g & 1;
+        mbar_wait(&bars->fullA[sa], (g / NA) & 1);
+        if (g >= 2) mbar_wait(&bars->emptyB[sb], ((g >> 1) - 1) & 1);  // lo slot released by the MMAs of g-2
+        split_tile(reinterpret_cast<float4*>(smem + sa * A_BYTES),
+                   reinterpret_cast<float4*>(smem + L::OFF_ALO + sb * A_BYTES), A_BYTES / 16, tid128);
+        fence_proxy_async();
+        mbar_arrive(&bars->split[sb]);
+      }
     }
-    // epilogue: TMEM lane quadrant of this warp = warp % 4
-    mbar_wait(&bars->accum, 0);
-    tc_fence_after();
-    const int quad = warp & 3;
+  } else if (warp >= 6 && warp <= 9) {
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
-    const int t = t0 + row;
-    const bool row_ok = t < a.T;
-    const int64_t obase = (int64_t)b * a.out_bstride + (int64_t)t * a.out_tstride + a.n0;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+      const int b = tile / a.tiles_per_b, t0 = (tile % a.tiles_per_b) * 128;
+      const uint32_t acc = lt & 1;
+      mbar_wait(&bars->tmemFull[acc], (lt >> 1) & 1);
+      tc_fence_after();
+      const int t = t0 + row;
+      const bool row_ok = t < a.T;
+      const int64_t obase = (int64_t)b * a.out_bstride + (int64_t)t * a.out_tstride + a.n0;
 #pragma unroll 1
-    for (int c = 0; c < N / 32; ++c) {
-      float v[32];
-      tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + c * 32, v);
-      if (row_ok) {
-        if (a.out_dtype == VISDE_BF16) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + obase + c * 32;
-#pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if (c * 32 + q < a.out_cols) o[q] = __float2bfloat16(v[q] + (a.bias ? a.bias[a.n0 + c * 32 + q] : 0.f));
-        } else {
-          float* o = reinterpret_cast<float*>(a.out) + obase + c * 32;
-          if (c * 32 + 32 <= a.out_cols && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-#pragma unroll
-            for (int q = 0; q < 32; q += 4) {
-              float4 w;
-              w.x = v[q] + (a.bias ? a.bias[a.n0 + c * 32 + q] : 0.f);
-              w.y = v[q + 1] + (a.bias ? a.bias[a.n0 + c * 32 + q + 1] : 0.f);
-              w.z = v[q + 2] + (a.bias ? a.bias[a.n0 + c * 32 + q + 2] : 0.f);
-              w.w = v[q + 3] + (a.bias ? a.bias[a.n0 + c * 32 + q + 3] : 0.f);
-              *reinterpret_cast<float4*>(o + q) = w;
-            }
-          } else {
+      for (int c = 0; c < N / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + acc * N + c * 32, v);
+        if (row_ok) {
+          if (a.out_dtype == VISDE_BF16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + obase + c * 32;
 #pragma unroll
             for (int q = 0; q < 32; ++q)
-              if (c * 32 + q < a.out_cols) o[q] = v[q] + (a.bias ? a.bias[a.n0 + c * 32 + q] : 0.f);
+              if (c * 32 + q < a.out_cols) o[q] = __float2bfloat16(v[q] + (a.bias ? a.bias[a.n0 + c * 32 + q] : 0.f));
+          } else {
+            float* o = reinterpret_cast<float*>(a.out) + obase + c * 32;
+            if (c * 32 + 32 <= a.out_cols && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+              for (int q = 0; q < 32; q += 4) {
+                float4 w;
+                w.x = v[q] + (a.bias ? a.bias[a.n0 + c * 32 + q] : 0.f);
+                w.y = v[q + 1] + (a.bias ? a.bias[a.n0 + c * 32 + q + 1] : 0.f);
+                w.z = v[q + 2] + (a.bias ? a.bias[a.n0 + c * 32 + q + 2] : 0.f);
+                w.w = v[q + 3] + (a.bias ? a.bias[a.n0 + c * 32 + q + 3] : 0.f);
+                *reinterpret_cast<float4*>(o + q) = w;
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; ++q)
+                if (c * 32 + q < a.out_cols) o[q] = v[q] + (a.bias ? a.bias[a.n0 + c * 32 + q] : 0.f);
+            }
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&bars->tmemEmpty[acc]);
     }
   }
   tc_fence_before();
@@ -472,17 +529,21 @@ int make_map(CUtensorMap* m, const void* base, int rank, const int64_t* dims, co
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int N, bool B_MN>
-int launch_rows(const CUtensorMap& mA, const CUtensorMap& mBh, const CUtensorMap& mBl, const RowsArgs& a, int64_t B,
+template <int N, bool B_MN, int NA>
+int launch_rows(const CUtensorMap& mA, const CUtensorMap& mBh, const CUtensorMap& mBl, RowsArgs a, int64_t B,
                 cudaStream_t st) {
-  constexpr int STAGE_BYTES = 2 * 128 * 128 + 2 * N * 128;
-  const size_t smem = kStages * STAGE_BYTES + sizeof(TcBarriers) + 1024;
+  const size_t smem = RowsSmem<N, NA>::bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    VISDE_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_kernel<N, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VISDE_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_kernel<N, B_MN, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  tc_rows_kernel<N, B_MN><<<(unsigned)(B * a.tiles_per_b), kTcThreads, smem, st>>>(mA, mBh, mBl, a);
+  a.num_tiles = (int)(B * a.tiles_per_b);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+  tc_rows_kernel<N, B_MN, NA><<<grid, kRowsThreads, smem, st>>>(mA, mBh, mBl, a);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
@@ -537,7 +598,7 @@ int tc_ctx_proj(const visde_ctx_view* ctx, int64_t B, int64_t T, int C, int H, c
   a.out_tstride = 3 * H;
   a.out_dtype = VISDE_F32;
   a.out_cols = 3 * H;
-  return launch_rows<192, false>(mA, mBh, mBl, a, B, st);
+  return launch_rows<192, false, 4>(mA, mBh, mBl, a, B, st);
 }
 
 // K3: grad_ctx[b,t,:] = d_gi_l0[(b,t), :192] . Wc   (dg rows have `dg_row` floats)
@@ -565,9 +626,9 @@ int tc_grad_ctx(const float* dg, int64_t dg_row, int64_t B, int64_t T, int C, in
     a.out_dtype = out->dtype;
     a.out_cols = C - n0 < 256 ? C - n0 : 256;
     if (a.out_cols == 256)
-      rc = launch_rows<256, true>(mA, mBh, mBl, a, B, st);
+      rc = launch_rows<256, true, 3>(mA, mBh, mBl, a, B, st);
     else
-      rc = launch_rows<128, true>(mA, mBh, mBl, a, B, st);
+      rc = launch_rows<128, true, 4>(mA, mBh, mBl, a, B, st);
     if (rc) return rc;
   }
   return VISDE_OK;
