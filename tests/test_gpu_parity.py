@@ -37,14 +37,17 @@ CASES = {
 }
 TC_OK = {"lv_h64_c128_l2", "ou_h64_c256_l1", "lv_h64_c256_l2", "l96s6_h64_c128_l2"}
 NO_TC = 0x100  # VISDE_FLAG_NO_TENSOR_CORES
-FAST_OK = {"ou_h32_l2", "lv_h16_l1", "ou_h64_l2", "lv_h64_l2", "lv_h48_l2", "ou_h20_l1", "l96s3_h64_l2",
+# batch sizes that do not divide the tile of the batch-tiled family
+CASES["lv_h64_b37_ragged_tile"] = ("lv", 37, 9, dict(context_dim=16, hidden_dim=64, num_layers=2))
+CASES["ou_h32_b13_ragged_tile"] = ("ou", 13, 7, dict(context_dim=8, hidden_dim=32, num_layers=1))
+FAST_OK = {"lv_h64_b37_ragged_tile", "ou_h32_b13_ragged_tile", "ou_h32_l2", "lv_h16_l1", "ou_h64_l2", "lv_h64_l2", "lv_h48_l2", "ou_h20_l1", "l96s3_h64_l2",
            "lv_h64_c128_l2", "ou_h64_c256_l1", "lv_h64_c256_l2"}
 
 
 def _variants(name):
     from viforsdes_b200 import _lib
 
-    v = [_lib.VARIANT_GENERIC, _lib.VARIANT_FAST] if name in FAST_OK else [_lib.VARIANT_GENERIC]
+    v = [_lib.VARIANT_GENERIC, _lib.VARIANT_FAST, _lib.VARIANT_TILED] if name in FAST_OK else [_lib.VARIANT_GENERIC]
     if name in TC_OK:  # the same kernels with the GEMM stages forced onto the fp32 SIMT path
         v += [x | NO_TC for x in v]
     return v

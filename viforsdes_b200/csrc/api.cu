@@ -197,7 +197,8 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
   VISDE_REQUIRE(x0 && paths, "x0 / paths is NULL");
   VISDE_REQUIRE(d->T == 0 || (ctx && ctx->ptr && eps && means && chol), "NULL tensor argument");
   VISDE_REQUIRE(d->P == 0 || theta, "theta is NULL");
-  VISDE_REQUIRE((d->variant & 0xff) != VISDE_VARIANT_FAST || (d->H <= 64 && d->H % 4 == 0 && d->NL <= 2 && d->S <= 4),
+  VISDE_REQUIRE(((d->variant & 0xff) != VISDE_VARIANT_FAST && (d->variant & 0xff) != VISDE_VARIANT_TILED) ||
+                    (d->H <= 64 && d->H % 4 == 0 && d->NL <= 2 && d->S <= 4),
                 "fast variant requested for an unsupported shape (H=%d NL=%d S=%d)", d->H, d->NL, d->S);
   if (workspace_bytes < visde_workspace_bytes(d, 0) - 256 || (!workspace && d->T > 0)) {
     set_error("path_fwd: workspace too small (%zu < %zu)", workspace_bytes, visde_workspace_bytes(d, 0));
@@ -236,7 +237,12 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
     if (rc) return rc;
   }
   StageTimer tm(VISDE_STAGE_K1_PATH_FWD, 1, st);
-  return use_fast(d, p) ? launch_path_fwd_fast(p, st) : launch_path_fwd_generic(p, st);
+  if (use_fast(d, p)) {
+    const int fam = d->variant & 0xff;
+    const int nb = fam == VISDE_VARIANT_FAST ? 0 : tiled_batch_tile(d->B, fam == VISDE_VARIANT_TILED);
+    return nb > 0 ? launch_path_fwd_tiled(p, nb, st) : launch_path_fwd_fast(p, st);
+  }
+  return launch_path_fwd_generic(p, st);
 }
 
 int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const float* g_means,

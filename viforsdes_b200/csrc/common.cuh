@@ -110,6 +110,9 @@ int launch_path_bwd_generic(const PathParams& p, cudaStream_t st);
 bool fast_supported(const PathParams& p);
 int launch_path_fwd_fast(const PathParams& p, cudaStream_t st);
 int launch_path_bwd_fast(const PathParams& p, cudaStream_t st);
+// batch-tiled family for B > #SM (path_tiled.cu): NB trajectories per CTA, weights in shared memory
+int tiled_batch_tile(int64_t B, bool force);
+int launch_path_fwd_tiled(const PathParams& p, int NB, cudaStream_t st);
 size_t fast_partials_floats(int NL, int H, int S);
 // biases, dW_ih_l0[:, :S], dW_out, db_out from the per-CTA partials written by path_bwd_fast
 int launch_fast_partials_reduce(const PathParams& p, const visde_weight_grads* gw, cudaStream_t st);
