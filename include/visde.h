@@ -201,6 +201,20 @@ int visde_session_step(visde_session* s, float dt, const float* x0, const float*
                        const visde_obs* obs_host, float* terms, float* grad_x0, float* grad_theta,
                        const visde_weight_grads* gw_host, float* grad_context);
 
+/* Pipelined form of visde_session_step (same arguments): enqueue the H2D copies on the session's
+ * copy stream and the kernels + D2H on its compute stream, and return without waiting.  The session
+ * holds two device input sets, so up to TWO iterations may be in flight: the copies of iteration
+ * i+1 overlap the kernels of iteration i (VISDE_EINVAL when a third is submitted).  Host input
+ * buffers must stay valid, and the host output buffers of in-flight iterations distinct, until the
+ * matching visde_session_wait, which blocks until the OLDEST in-flight iteration's outputs are in
+ * host memory.  Pinned host memory is required for the overlap (pageable memory degrades to
+ * synchronous copies).  visde_session_step == submit + wait. */
+int visde_session_submit(visde_session* s, float dt, const float* x0, const float* context,
+                         const float* theta, const float* eps, const visde_weights* w_host,
+                         const visde_obs* obs_host, float* terms, float* grad_x0, float* grad_theta,
+                         const visde_weight_grads* gw_host, float* grad_context);
+int visde_session_wait(visde_session* s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -262,6 +262,39 @@ def test_session_host_step_matches_oracle():
     sess.close()
 
 
+def test_session_pipelined_submit_wait_matches_sync():
+    """visde_session_submit / _wait (two iterations in flight, H2D of i+1 overlapping the kernels of i)
+    returns bit-identical outputs to the synchronous visde_session_step, in submission order, and
+    refuses a third in-flight iteration."""
+    from viforsdes_b200.session import HostSession
+
+    p = O.make_problem("lv", 6, 30, context_dim=32, hidden_dim=64, num_layers=2)
+    sess = HostSession.from_problem(p, want_grad_context=True)
+    ref = sess.step()
+    ref = {"terms": ref["terms"].clone(), "grads": {k: v.clone() for k, v in ref["grads"].items()}}
+    sess.submit()
+    sess.submit()
+    with pytest.raises(ValueError):
+        sess.submit()
+    for _ in range(2):
+        res = sess.wait()
+        assert torch.equal(res["terms"], ref["terms"])
+        for k, v in ref["grads"].items():
+            assert torch.equal(res["grads"][k], v), k
+    with pytest.raises(ValueError):
+        sess.wait()
+    # changed inputs between iterations are picked up by the second input set
+    sess.submit()
+    sess.wait()
+    sess.eps.mul_(0.5)
+    sess.submit()
+    res2 = sess.wait()
+    assert not torch.equal(res2["terms"], ref["terms"])
+    sess.eps.mul_(2.0)
+    assert torch.equal(sess.step()["terms"], ref["terms"])
+    sess.close()
+
+
 def test_full_size_properties():
     """BASELINE config 2 size (LV, B=128, T=800, C=256, H=64x2): size-independent properties --
     run-to-run determinism (no atomics), agreement of the two kernel families, linearity of the

@@ -63,6 +63,9 @@ PROTOTYPES = {
     "visde_session_launches": (C.c_int, [_fp]),
     "visde_session_step": (C.c_int, [_fp, C.c_float, _fp, _fp, _fp, _fp, C.POINTER(Weights), C.POINTER(Obs), _fp, _fp,
                                      _fp, C.POINTER(Weights), _fp]),
+    "visde_session_submit": (C.c_int, [_fp, C.c_float, _fp, _fp, _fp, _fp, C.POINTER(Weights), C.POINTER(Obs), _fp, _fp,
+                                       _fp, C.POINTER(Weights), _fp]),
+    "visde_session_wait": (C.c_int, [_fp]),
 }
 
 _lib: C.CDLL | None = None

@@ -551,22 +551,34 @@ int visde_profile_end(double* ms_per_stage, int* launches_per_stage) {
 // ------------------------------------------------------------------------------------------
 // host-buffer session
 // ------------------------------------------------------------------------------------------
+// Two input sets so that the H2D copies of iteration i+1 (copy stream) overlap the kernels of
+// iteration i (compute stream): visde_session_submit / visde_session_wait.  Everything downstream
+// of the inputs (paths, stash, workspaces, gradients) exists once: the compute stream serialises it.
+struct visde_session_inputs {
+  float *x0, *ctx, *theta, *eps;
+  visde_weights w;
+  int32_t* obs_idx;
+  float *obs_values, *obs_matrix;
+  cudaEvent_t loaded;    // copy stream: this set's H2D copies are complete
+  cudaEvent_t consumed;  // compute stream: the kernels that read this set are complete
+  cudaEvent_t done;      // compute stream: kernels + D2H of the iteration that used this set
+};
+
 struct visde_session {
   visde_dims d;
   int sde_kind;
   uint32_t pos_mask;
   int n_obs, obs_dim;
-  cudaStream_t st;
+  cudaStream_t st, copy_st;
   std::vector<void*> allocs;
+  visde_session_inputs in[2];
+  uint64_t n_submitted, n_waited;
   // device buffers
-  float *x0, *ctx, *theta, *eps, *paths, *means, *chol, *terms, *g_terms;
+  float *paths, *means, *chol, *terms, *g_terms;
   float *g_z, *g_means, *g_chol, *g_theta_elbo, *grad_x0, *grad_theta, *grad_ctx;
   void *stash, *ws_f, *ws_b;
   size_t ws_f_bytes, ws_b_bytes;
-  visde_weights w;
   visde_weight_grads gw;
-  int32_t* obs_idx;
-  float *obs_values, *obs_matrix;
   size_t h2d, d2h;
   int launches;
 };
@@ -583,6 +595,49 @@ int dev_alloc(visde_session* s, Tp** p, size_t bytes) {
   return VISDE_OK;
 }
 size_t w_ih_floats(const visde_dims& d, int k) { return (size_t)3 * d.H * (k ? d.H : d.S + d.C + d.P); }
+
+int session_alloc(visde_session* s) {
+  const visde_dims* d = &s->d;
+  const size_t B = d->B, T = d->T, S = d->S, C = d->C, P = d->P, H = d->H, G = 3 * H;
+  const size_t n_out = S + S * (S + 1) / 2;
+  int rc;
+#define A_(ptr, n) if ((rc = dev_alloc(s, &(ptr), sizeof(float) * (n)))) return rc;
+  for (int q = 0; q < 2; ++q) {
+    visde_session_inputs& in = s->in[q];
+    A_(in.x0, B * S) A_(in.ctx, B * (T + 1) * C) A_(in.theta, B * P) A_(in.eps, B * T * S)
+    A_(in.obs_values, (size_t)s->n_obs * s->obs_dim) A_(in.obs_matrix, (size_t)s->obs_dim * S)
+    if ((rc = dev_alloc(s, &in.obs_idx, sizeof(int32_t) * s->n_obs))) return rc;
+    for (int k = 0; k < d->NL; ++k) {
+      float *a, *b2, *c2, *e2;
+      A_(a, w_ih_floats(*d, k)) A_(b2, G * H) A_(c2, G) A_(e2, G)
+      in.w.w_ih[k] = a; in.w.w_hh[k] = b2; in.w.b_ih[k] = c2; in.w.b_hh[k] = e2;
+    }
+    float *a, *b2;
+    A_(a, n_out * H) A_(b2, n_out)
+    in.w.out_w = a; in.w.out_b = b2;
+    VISDE_CUDA_CHECK(cudaEventCreateWithFlags(&in.loaded, cudaEventDisableTiming));
+    VISDE_CUDA_CHECK(cudaEventCreateWithFlags(&in.consumed, cudaEventDisableTiming));
+    VISDE_CUDA_CHECK(cudaEventCreateWithFlags(&in.done, cudaEventDisableTiming));
+  }
+  A_(s->paths, B * (T + 1) * S) A_(s->means, B * T * S) A_(s->chol, B * T * S * S) A_(s->terms, B * 4) A_(s->g_terms, B * 4)
+  A_(s->g_z, B * (T + 1) * S) A_(s->g_means, B * T * S) A_(s->g_chol, B * T * S * S) A_(s->g_theta_elbo, B * P)
+  A_(s->grad_x0, B * S) A_(s->grad_theta, B * P) A_(s->grad_ctx, B * (T + 1) * C)
+  if ((rc = dev_alloc(s, &s->stash, visde_stash_bytes(d)))) return rc;
+  s->ws_f_bytes = visde_workspace_bytes(d, 0);
+  s->ws_b_bytes = visde_workspace_bytes(d, 1);
+  if ((rc = dev_alloc(s, &s->ws_f, s->ws_f_bytes))) return rc;
+  if ((rc = dev_alloc(s, &s->ws_b, s->ws_b_bytes))) return rc;
+  for (int k = 0; k < d->NL; ++k) {
+    float *ga, *gb, *gc, *ge;
+    A_(ga, w_ih_floats(*d, k)) A_(gb, G * H) A_(gc, G) A_(ge, G)
+    s->gw.w_ih[k] = ga; s->gw.w_hh[k] = gb; s->gw.b_ih[k] = gc; s->gw.b_hh[k] = ge;
+  }
+  float *ga, *gb;
+  A_(ga, n_out * H) A_(gb, n_out)
+  s->gw.out_w = ga; s->gw.out_b = gb;
+#undef A_
+  return VISDE_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -595,6 +650,7 @@ int visde_session_create(const visde_dims* d, int sde_kind, uint32_t positive_ma
   VISDE_REQUIRE(sde_kind == VISDE_SDE_OU || sde_kind == VISDE_SDE_LV,
                 "the host session supports the built-in OU / LV functors only");
   VISDE_REQUIRE(d->B > 0 && d->T > 0, "session needs B > 0 and T > 0");
+  VISDE_REQUIRE(n_obs >= 0 && obs_dim >= 0, "bad observation sizes");
   visde_session* s = new visde_session();
   s->d = *d;
   s->sde_kind = sde_kind;
@@ -603,48 +659,18 @@ int visde_session_create(const visde_dims* d, int sde_kind, uint32_t positive_ma
   s->obs_dim = obs_dim;
   const size_t B = d->B, T = d->T, S = d->S, C = d->C, P = d->P, H = d->H, G = 3 * H;
   const size_t n_out = S + S * (S + 1) / 2;
-#define A_(ptr, n) if ((rc = dev_alloc(s, &s->ptr, sizeof(float) * (n)))) { visde_session_destroy(s); return rc; }
-  if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&s->copy_st, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("cudaStreamCreate failed");
-    delete s;
+    visde_session_destroy(s);
     return VISDE_ECUDA;
   }
-  A_(x0, B * S) A_(ctx, B * (T + 1) * C) A_(theta, B * P) A_(eps, B * T * S)
-  A_(paths, B * (T + 1) * S) A_(means, B * T * S) A_(chol, B * T * S * S) A_(terms, B * 4) A_(g_terms, B * 4)
-  A_(g_z, B * (T + 1) * S) A_(g_means, B * T * S) A_(g_chol, B * T * S * S) A_(g_theta_elbo, B * P)
-  A_(grad_x0, B * S) A_(grad_theta, B * P) A_(grad_ctx, B * (T + 1) * C)
-  A_(obs_values, (size_t)n_obs * obs_dim) A_(obs_matrix, (size_t)obs_dim * S)
-  if ((rc = dev_alloc(s, &s->obs_idx, sizeof(int32_t) * n_obs))) { visde_session_destroy(s); return rc; }
-  if ((rc = dev_alloc(s, &s->stash, visde_stash_bytes(d)))) { visde_session_destroy(s); return rc; }
-  s->ws_f_bytes = visde_workspace_bytes(d, 0);
-  s->ws_b_bytes = visde_workspace_bytes(d, 1);
-  if ((rc = dev_alloc(s, &s->ws_f, s->ws_f_bytes))) { visde_session_destroy(s); return rc; }
-  if ((rc = dev_alloc(s, &s->ws_b, s->ws_b_bytes))) { visde_session_destroy(s); return rc; }
-  size_t wfloats = 0;
-  for (int k = 0; k < d->NL; ++k) {
-    float *a, *b2, *c2, *e2, *ga, *gb, *gc, *ge;
-    if ((rc = dev_alloc(s, &a, sizeof(float) * w_ih_floats(*d, k))) || (rc = dev_alloc(s, &b2, sizeof(float) * G * H)) ||
-        (rc = dev_alloc(s, &c2, sizeof(float) * G)) || (rc = dev_alloc(s, &e2, sizeof(float) * G)) ||
-        (rc = dev_alloc(s, &ga, sizeof(float) * w_ih_floats(*d, k))) || (rc = dev_alloc(s, &gb, sizeof(float) * G * H)) ||
-        (rc = dev_alloc(s, &gc, sizeof(float) * G)) || (rc = dev_alloc(s, &ge, sizeof(float) * G))) {
-      visde_session_destroy(s);
-      return rc;
-    }
-    s->w.w_ih[k] = a; s->w.w_hh[k] = b2; s->w.b_ih[k] = c2; s->w.b_hh[k] = e2;
-    s->gw.w_ih[k] = ga; s->gw.w_hh[k] = gb; s->gw.b_ih[k] = gc; s->gw.b_hh[k] = ge;
-    wfloats += w_ih_floats(*d, k) + G * H + 2 * G;
+  if ((rc = session_alloc(s))) {
+    visde_session_destroy(s);
+    return rc;
   }
-  {
-    float *a, *b2, *ga, *gb;
-    if ((rc = dev_alloc(s, &a, sizeof(float) * n_out * H)) || (rc = dev_alloc(s, &b2, sizeof(float) * n_out)) ||
-        (rc = dev_alloc(s, &ga, sizeof(float) * n_out * H)) || (rc = dev_alloc(s, &gb, sizeof(float) * n_out))) {
-      visde_session_destroy(s);
-      return rc;
-    }
-    s->w.out_w = a; s->w.out_b = b2; s->gw.out_w = ga; s->gw.out_b = gb;
-    wfloats += n_out * H + n_out;
-  }
-#undef A_
+  size_t wfloats = n_out * H + n_out;
+  for (int k = 0; k < d->NL; ++k) wfloats += w_ih_floats(*d, k) + G * H + 2 * G;
   // grad_ctx row T is never written by the kernels: zero it once
   cudaMemsetAsync(s->grad_ctx, 0, sizeof(float) * B * (T + 1) * C, s->st);
   cudaStreamSynchronize(s->st);
@@ -659,8 +685,16 @@ int visde_session_create(const visde_dims* d, int sde_kind, uint32_t positive_ma
 
 void visde_session_destroy(visde_session* s) {
   if (!s) return;
+  if (s->st) cudaStreamSynchronize(s->st);
+  if (s->copy_st) cudaStreamSynchronize(s->copy_st);
   for (void* p : s->allocs) cudaFree(p);
+  for (int q = 0; q < 2; ++q) {
+    if (s->in[q].loaded) cudaEventDestroy(s->in[q].loaded);
+    if (s->in[q].consumed) cudaEventDestroy(s->in[q].consumed);
+    if (s->in[q].done) cudaEventDestroy(s->in[q].done);
+  }
   if (s->st) cudaStreamDestroy(s->st);
+  if (s->copy_st) cudaStreamDestroy(s->copy_st);
   delete s;
 }
 
@@ -668,59 +702,66 @@ size_t visde_session_h2d_bytes(const visde_session* s) { return s ? s->h2d : 0; 
 size_t visde_session_d2h_bytes(const visde_session* s) { return s ? s->d2h : 0; }
 int visde_session_launches(const visde_session* s) { return s ? s->launches : 0; }
 
-int visde_session_step(visde_session* s, float dt, const float* x0, const float* context,
-                       const float* theta, const float* eps, const visde_weights* w_host,
-                       const visde_obs* obs_host, float* terms, float* grad_x0, float* grad_theta,
-                       const visde_weight_grads* gw_host, float* grad_context) {
+int visde_session_submit(visde_session* s, float dt, const float* x0, const float* context,
+                         const float* theta, const float* eps, const visde_weights* w_host,
+                         const visde_obs* obs_host, float* terms, float* grad_x0, float* grad_theta,
+                         const visde_weight_grads* gw_host, float* grad_context) {
   VISDE_REQUIRE(s && x0 && context && theta && eps && w_host && obs_host && terms && grad_x0 && grad_theta && gw_host,
-                "session_step: NULL argument");
-  VISDE_REQUIRE(obs_host->n_obs == s->n_obs && obs_host->obs_dim == s->obs_dim, "session_step: observation shape changed");
+                "session_submit: NULL argument");
+  VISDE_REQUIRE(obs_host->n_obs == s->n_obs && obs_host->obs_dim == s->obs_dim, "session_submit: observation shape changed");
+  VISDE_REQUIRE(s->n_submitted - s->n_waited < 2, "session_submit: two iterations already in flight; call visde_session_wait");
   const visde_dims& d = s->d;
   const size_t B = d.B, T = d.T, S = d.S, C = d.C, P = d.P, H = d.H, G = 3 * H;
   const size_t n_out = S + S * (S + 1) / 2;
-  cudaStream_t st = s->st;
-#define H2D(dst, src, n) VISDE_CUDA_CHECK(cudaMemcpyAsync((void*)(dst), (src), sizeof(float) * (n), cudaMemcpyHostToDevice, st))
+  visde_session_inputs& in = s->in[s->n_submitted & 1];
+  cudaStream_t st = s->st, cs = s->copy_st;
+  // this set was last read by iteration n_submitted - 2
+  VISDE_CUDA_CHECK(cudaStreamWaitEvent(cs, in.consumed, 0));
+#define H2D(dst, src, n) VISDE_CUDA_CHECK(cudaMemcpyAsync((void*)(dst), (src), sizeof(float) * (n), cudaMemcpyHostToDevice, cs))
 #define D2H(dst, src, n) VISDE_CUDA_CHECK(cudaMemcpyAsync((dst), (src), sizeof(float) * (n), cudaMemcpyDeviceToHost, st))
-  H2D(s->x0, x0, B * S);
-  H2D(s->ctx, context, B * (T + 1) * C);
-  H2D(s->theta, theta, B * P);
-  H2D(s->eps, eps, B * T * S);
+  H2D(in.x0, x0, B * S);
+  H2D(in.ctx, context, B * (T + 1) * C);
+  H2D(in.theta, theta, B * P);
+  H2D(in.eps, eps, B * T * S);
   for (int k = 0; k < d.NL; ++k) {
-    H2D(s->w.w_ih[k], w_host->w_ih[k], w_ih_floats(d, k));
-    H2D(s->w.w_hh[k], w_host->w_hh[k], G * H);
-    H2D(s->w.b_ih[k], w_host->b_ih[k], G);
-    H2D(s->w.b_hh[k], w_host->b_hh[k], G);
+    H2D(in.w.w_ih[k], w_host->w_ih[k], w_ih_floats(d, k));
+    H2D(in.w.w_hh[k], w_host->w_hh[k], G * H);
+    H2D(in.w.b_ih[k], w_host->b_ih[k], G);
+    H2D(in.w.b_hh[k], w_host->b_hh[k], G);
   }
-  H2D(s->w.out_w, w_host->out_w, n_out * H);
-  H2D(s->w.out_b, w_host->out_b, n_out);
+  H2D(in.w.out_w, w_host->out_w, n_out * H);
+  H2D(in.w.out_b, w_host->out_b, n_out);
   visde_obs od = *obs_host;
   if (s->n_obs) {
-    H2D(s->obs_values, obs_host->values, (size_t)s->n_obs * s->obs_dim);
-    VISDE_CUDA_CHECK(cudaMemcpyAsync(s->obs_idx, obs_host->idx, sizeof(int32_t) * s->n_obs, cudaMemcpyHostToDevice, st));
-    if (obs_host->obs_matrix) H2D(s->obs_matrix, obs_host->obs_matrix, (size_t)s->obs_dim * S);
+    H2D(in.obs_values, obs_host->values, (size_t)s->n_obs * s->obs_dim);
+    VISDE_CUDA_CHECK(cudaMemcpyAsync(in.obs_idx, obs_host->idx, sizeof(int32_t) * s->n_obs, cudaMemcpyHostToDevice, cs));
+    if (obs_host->obs_matrix) H2D(in.obs_matrix, obs_host->obs_matrix, (size_t)s->obs_dim * S);
   }
-  od.idx = s->obs_idx;
-  od.values = s->obs_values;
-  od.obs_matrix = obs_host->obs_matrix ? s->obs_matrix : nullptr;
+  od.idx = in.obs_idx;
+  od.values = in.obs_values;
+  od.obs_matrix = obs_host->obs_matrix ? in.obs_matrix : nullptr;
+  VISDE_CUDA_CHECK(cudaEventRecord(in.loaded, cs));
+  VISDE_CUDA_CHECK(cudaStreamWaitEvent(st, in.loaded, 0));
 
-  visde_ctx_view cv{s->ctx, (int64_t)((T + 1) * C), (int64_t)C, VISDE_F32};
+  visde_ctx_view cv{in.ctx, (int64_t)((T + 1) * C), (int64_t)C, VISDE_F32};
   visde_ctx_grad_view gv{s->grad_ctx, (int64_t)((T + 1) * C), (int64_t)C, VISDE_F32};
-  int rc = visde_path_fwd(&d, dt, s->x0, &cv, s->theta, s->eps, &s->w, s->paths, s->means, s->chol, s->stash, s->ws_f,
+  int rc = visde_path_fwd(&d, dt, in.x0, &cv, in.theta, in.eps, &in.w, s->paths, s->means, s->chol, s->stash, s->ws_f,
                           s->ws_f_bytes, st);
   if (rc) return rc;
-  rc = visde_elbo_fwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, s->theta, nullptr, nullptr, &od,
+  rc = visde_elbo_fwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, in.theta, nullptr, nullptr, &od,
                       s->terms, st);
   if (rc) return rc;
   fill_loss_cotangent_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(s->g_terms, (int64_t)B);
   VISDE_CUDA_CHECK(cudaGetLastError());
-  rc = visde_elbo_bwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, s->theta, nullptr, nullptr, &od,
+  rc = visde_elbo_bwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, in.theta, nullptr, nullptr, &od,
                       s->g_terms, s->g_z, s->g_means, s->g_chol, s->g_theta_elbo, nullptr, nullptr, st);
   if (rc) return rc;
-  rc = visde_path_bwd(&d, dt, s->g_z, s->g_means, s->g_chol, &cv, s->theta, s->eps, &s->w, s->paths, s->stash,
+  rc = visde_path_bwd(&d, dt, s->g_z, s->g_means, s->g_chol, &cv, in.theta, in.eps, &in.w, s->paths, s->stash,
                       s->grad_x0, &gv, s->grad_theta, &s->gw, s->ws_b, s->ws_b_bytes, st);
   if (rc) return rc;
   add_inplace_kernel<<<(unsigned)((B * P + 255) / 256), 256, 0, st>>>(s->grad_theta, s->g_theta_elbo, (int64_t)(B * P));
   VISDE_CUDA_CHECK(cudaGetLastError());
+  VISDE_CUDA_CHECK(cudaEventRecord(in.consumed, st));
 
   D2H(terms, s->terms, B * 4);
   D2H(grad_x0, s->grad_x0, B * S);
@@ -736,8 +777,29 @@ int visde_session_step(visde_session* s, float dt, const float* x0, const float*
   if (grad_context) D2H(grad_context, s->grad_ctx, B * (T + 1) * C);
 #undef H2D
 #undef D2H
-  VISDE_CUDA_CHECK(cudaStreamSynchronize(st));
+  VISDE_CUDA_CHECK(cudaEventRecord(in.done, st));
+  ++s->n_submitted;
   return VISDE_OK;
+}
+
+int visde_session_wait(visde_session* s) {
+  VISDE_REQUIRE(s != nullptr, "session_wait: NULL session");
+  VISDE_REQUIRE(s->n_waited < s->n_submitted, "session_wait: nothing in flight");
+  VISDE_CUDA_CHECK(cudaEventSynchronize(s->in[s->n_waited & 1].done));
+  ++s->n_waited;
+  return VISDE_OK;
+}
+
+int visde_session_step(visde_session* s, float dt, const float* x0, const float* context,
+                       const float* theta, const float* eps, const visde_weights* w_host,
+                       const visde_obs* obs_host, float* terms, float* grad_x0, float* grad_theta,
+                       const visde_weight_grads* gw_host, float* grad_context) {
+  VISDE_REQUIRE(s != nullptr, "session_step: NULL session");
+  VISDE_REQUIRE(s->n_submitted == s->n_waited, "session_step: iterations still in flight; call visde_session_wait first");
+  int rc = visde_session_submit(s, dt, x0, context, theta, eps, w_host, obs_host, terms, grad_x0, grad_theta, gw_host,
+                                grad_context);
+  if (rc) return rc;
+  return visde_session_wait(s);
 }
 
 }  // extern "C"

@@ -31,12 +31,9 @@ class HostSession:
         self.x0, self.ctx, self.theta, self.eps = _pin(x0), _pin(context_full), _pin(theta), _pin(eps)
         self.w = [[_pin(t) for t in ws] for ws in (w_ih, w_hh, b_ih, b_hh)]
         self.out_w, self.out_b = _pin(out_w), _pin(out_b)
-        self.gw = [[torch.empty_like(t).pin_memory() for t in ws] for ws in self.w]
-        self.g_out_w, self.g_out_b = torch.empty_like(self.out_w).pin_memory(), torch.empty_like(self.out_b).pin_memory()
-        self.terms = torch.empty(B, 4).pin_memory()
-        self.grad_x0 = torch.empty(B, S).pin_memory()
-        self.grad_theta = torch.empty(B, P).pin_memory()
-        self.grad_ctx = torch.empty(B, T + 1, Cd).pin_memory() if want_grad_context else None
+        # two host output sets: iteration i+1 may be submitted before the outputs of i are consumed
+        self._out = [self._make_outputs(B, S, P, T, Cd, want_grad_context) for _ in range(2)]
+        self._submitted = self._waited = 0
         self.obs_idx = obs_idx.detach().to(torch.int32).contiguous().cpu()
         self.obs_values = obs_values.detach().to(torch.float32).contiguous().cpu()
         self.obs = _lib.Obs(self.obs_idx.shape[0], self.obs_values.shape[1], self.obs_idx.data_ptr(),
@@ -83,27 +80,60 @@ class HostSession:
 
     @property
     def d2h_bytes(self) -> int:
-        extra = self.grad_ctx.numel() * 4 if self.grad_ctx is not None else 0
+        g = self._out[0]["grad_ctx"]
+        extra = g.numel() * 4 if g is not None else 0
         return int(self.lib.visde_session_d2h_bytes(self.handle)) + extra
 
     @property
     def launches(self) -> int:
         return int(self.lib.visde_session_launches(self.handle))
 
-    def step(self) -> Dict[str, object]:
+    def _make_outputs(self, B: int, S: int, P: int, T: int, Cd: int, want_grad_context: bool) -> Dict[str, object]:
+        pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+        return {
+            "gw": [[pin(torch.empty_like(t)) for t in ws] for ws in self.w],
+            "g_out_w": pin(torch.empty_like(self.out_w)), "g_out_b": pin(torch.empty_like(self.out_b)),
+            "terms": pin(torch.empty(B, 4)), "grad_x0": pin(torch.empty(B, S)), "grad_theta": pin(torch.empty(B, P)),
+            "grad_ctx": pin(torch.empty(B, T + 1, Cd)) if want_grad_context else None,
+        }
+
+    def _call(self, fn, o) -> None:
         w = self._wstruct(self.w, self.out_w, self.out_b)
-        gw = self._wstruct(self.gw, self.g_out_w, self.g_out_b)
-        _lib.check(self.lib.visde_session_step(
+        gw = self._wstruct(o["gw"], o["g_out_w"], o["g_out_b"])
+        _lib.check(fn(
             self.handle, self.dt, self.x0.data_ptr(), self.ctx.data_ptr(), self.theta.data_ptr(), self.eps.data_ptr(),
-            C.byref(w), C.byref(self.obs), self.terms.data_ptr(), self.grad_x0.data_ptr(), self.grad_theta.data_ptr(),
-            C.byref(gw), None if self.grad_ctx is None else self.grad_ctx.data_ptr()))
-        grads = {"x0": self.grad_x0, "theta": self.grad_theta, "out_w": self.g_out_w, "out_b": self.g_out_b}
+            C.byref(w), C.byref(self.obs), o["terms"].data_ptr(), o["grad_x0"].data_ptr(), o["grad_theta"].data_ptr(),
+            C.byref(gw), None if o["grad_ctx"] is None else o["grad_ctx"].data_ptr()))
+
+    def _results(self, o) -> Dict[str, object]:
+        grads = {"x0": o["grad_x0"], "theta": o["grad_theta"], "out_w": o["g_out_w"], "out_b": o["g_out_b"]}
         for k in range(self.dims.NL):
-            grads[f"w_ih_l{k}"], grads[f"w_hh_l{k}"] = self.gw[0][k], self.gw[1][k]
-            grads[f"b_ih_l{k}"], grads[f"b_hh_l{k}"] = self.gw[2][k], self.gw[3][k]
-        if self.grad_ctx is not None:
-            grads["context"] = self.grad_ctx[:, : self.dims.T]
-        return {"terms": self.terms, "grads": grads}
+            grads[f"w_ih_l{k}"], grads[f"w_hh_l{k}"] = o["gw"][0][k], o["gw"][1][k]
+            grads[f"b_ih_l{k}"], grads[f"b_hh_l{k}"] = o["gw"][2][k], o["gw"][3][k]
+        if o["grad_ctx"] is not None:
+            grads["context"] = o["grad_ctx"][:, : self.dims.T]
+        return {"terms": o["terms"], "grads": grads}
+
+    def step(self) -> Dict[str, object]:
+        """One synchronous iteration (visde_session_step): H2D, kernels, D2H, wait."""
+        o = self._out[self._submitted & 1]
+        self._call(self.lib.visde_session_step, o)
+        self._submitted += 1
+        self._waited += 1
+        return self._results(o)
+
+    def submit(self) -> None:
+        """Enqueue one iteration without waiting (visde_session_submit); at most two in flight.  The host
+        inputs are read when the copies run: change them only after the matching wait()."""
+        self._call(self.lib.visde_session_submit, self._out[self._submitted & 1])
+        self._submitted += 1
+
+    def wait(self) -> Dict[str, object]:
+        """Block until the oldest in-flight iteration's outputs are in host memory and return them."""
+        _lib.check(self.lib.visde_session_wait(self.handle))
+        o = self._out[self._waited & 1]
+        self._waited += 1
+        return self._results(o)
 
     def close(self) -> None:
         if self.handle:
