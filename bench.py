@@ -176,6 +176,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "generic", "fast", "tiled", "tc"],
+                    help="recurrence kernel family (ad-hoc comparisons; production is auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -205,7 +207,9 @@ def main() -> None:
     if world > 1:  # replicated parameters: all ranks use rank 0's weights
         ref = make_inputs(kind, 1, 1, dt=dt, seed=0)
         inp.w_ih, inp.w_hh, inp.b_ih, inp.b_hh, inp.out_w, inp.out_b = ref.w_ih, ref.w_hh, ref.b_ih, ref.b_hh, ref.out_w, ref.out_b
-    it = PathIteration(inp, dev)
+    variant = {"auto": _lib.VARIANT_AUTO, "generic": _lib.VARIANT_GENERIC, "fast": _lib.VARIANT_FAST,
+               "tiled": _lib.VARIANT_TILED, "tc": _lib.VARIANT_TC}[args.variant]
+    it = PathIteration(inp, dev, variant=variant)
     S, Cd, H, NL = it.S, it.C, it.H, it.NL
     units = B * T
     flush = torch.empty(512 << 20, device=dev, dtype=torch.uint8)
@@ -329,7 +333,7 @@ def main() -> None:
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": args.workload, "sde": kind, "batch_per_gpu": B, "n_steps": T, "dt": dt, "state_dim": S,
-                   "context_dim": Cd, "hidden_dim": H, "num_layers": NL, "parallelism": f"dp{world}",
+                   "context_dim": Cd, "hidden_dim": H, "num_layers": NL, "parallelism": f"dp{world}", "variant": args.variant,
                    "l2": "512 MB flush write between timed steps; per-step working set ~0.9 GB > 126 MB L2"},
         "e2e": e2e, "gpu_launches": int(sum(cnt)),
         "roofline": roofline, "step_roofline": step_roofline, "stages": stages, "cpu_baseline": cb,

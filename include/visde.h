@@ -54,7 +54,13 @@ enum {
 
 enum { VISDE_F32 = 0, VISDE_BF16 = 1 };                 /* dtype of context / grad_context */
 enum { VISDE_SDE_GENERIC = 0, VISDE_SDE_OU = 1, VISDE_SDE_LV = 2 };
-enum { VISDE_VARIANT_AUTO = 0, VISDE_VARIANT_GENERIC = 1, VISDE_VARIANT_FAST = 2, VISDE_VARIANT_TILED = 3 };
+/* kernel family of the recurrence: GENERIC any shape; FAST one trajectory per CTA, weights in registers;
+ * TILED 4-8 trajectories per CTA, weights in shared memory (fp32 SIMT); TC 128 trajectories per CTA with the
+ * gate GEMMs on tcgen05 tensor cores (fp16 hi/lo 3-pass split, FP32 accumulate).  AUTO picks by batch size. */
+enum {
+  VISDE_VARIANT_AUTO = 0, VISDE_VARIANT_GENERIC = 1, VISDE_VARIANT_FAST = 2, VISDE_VARIANT_TILED = 3,
+  VISDE_VARIANT_TC = 4
+};
 /* OR-ed into visde_dims.variant: run the time-parallel GEMMs (K0/K3/K4) on the fp32 SIMT kernels
  * instead of tcgen05 3xTF32 (testing aid: the two implementations cross-check each other) */
 #define VISDE_FLAG_NO_TENSOR_CORES 0x100

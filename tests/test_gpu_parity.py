@@ -35,13 +35,20 @@ CASES = {
     "lv_h64_c256_l2": ("lv", 2, 300, dict(context_dim=256, hidden_dim=64, num_layers=2)),
     "l96s6_h64_c128_l2": ("l96", 2, 40, dict(context_dim=128, hidden_dim=64, num_layers=2, state_dim=6)),
 }
-TC_OK = {"lv_h64_c128_l2", "ou_h64_c256_l1", "lv_h64_c256_l2", "l96s6_h64_c128_l2"}
+# tensor-core recurrence eligible (H = 64, NL <= 2, S <= 4, tcgen05 K0); two 128-trajectory tiles, the second ragged
+CASES["lv_h64_c128_b150_two_tiles"] = ("lv", 150, 12, dict(context_dim=128, hidden_dim=64, num_layers=2))
+CASES["ou_h64_c128_l1_b130"] = ("ou", 130, 9, dict(context_dim=128, hidden_dim=64, num_layers=1))
+CASES["l96s4_h64_c128_l2"] = ("l96", 5, 21, dict(context_dim=128, hidden_dim=64, num_layers=2, state_dim=4))
+TC_OK = {"lv_h64_c128_l2", "ou_h64_c256_l1", "lv_h64_c256_l2", "l96s6_h64_c128_l2", "lv_h64_c128_b150_two_tiles",
+         "ou_h64_c128_l1_b130", "l96s4_h64_c128_l2"}
+TC_REC_OK = TC_OK - {"l96s6_h64_c128_l2"}
 NO_TC = 0x100  # VISDE_FLAG_NO_TENSOR_CORES
 # batch sizes that do not divide the tile of the batch-tiled family
 CASES["lv_h64_b37_ragged_tile"] = ("lv", 37, 9, dict(context_dim=16, hidden_dim=64, num_layers=2))
 CASES["ou_h32_b13_ragged_tile"] = ("ou", 13, 7, dict(context_dim=8, hidden_dim=32, num_layers=1))
 FAST_OK = {"lv_h64_b37_ragged_tile", "ou_h32_b13_ragged_tile", "ou_h32_l2", "lv_h16_l1", "ou_h64_l2", "lv_h64_l2", "lv_h48_l2", "ou_h20_l1", "l96s3_h64_l2",
-           "lv_h64_c128_l2", "ou_h64_c256_l1", "lv_h64_c256_l2"}
+           "lv_h64_c128_l2", "ou_h64_c256_l1", "lv_h64_c256_l2", "lv_h64_c128_b150_two_tiles", "ou_h64_c128_l1_b130",
+           "l96s4_h64_c128_l2"}
 
 
 def _variants(name):
@@ -50,6 +57,8 @@ def _variants(name):
     v = [_lib.VARIANT_GENERIC, _lib.VARIANT_FAST, _lib.VARIANT_TILED] if name in FAST_OK else [_lib.VARIANT_GENERIC]
     if name in TC_OK:  # the same kernels with the GEMM stages forced onto the fp32 SIMT path
         v += [x | NO_TC for x in v]
+    if name in TC_REC_OK:  # gate GEMMs of the recurrence on tcgen05 (fp16 hi/lo 3-pass split)
+        v.append(_lib.VARIANT_TC)
     return v
 
 

@@ -13,7 +13,7 @@ MAX_LAYERS = 4
 
 F32, BF16 = 0, 1
 SDE_GENERIC, SDE_OU, SDE_LV = 0, 1, 2
-VARIANT_AUTO, VARIANT_GENERIC, VARIANT_FAST, VARIANT_TILED = 0, 1, 2, 3
+VARIANT_AUTO, VARIANT_GENERIC, VARIANT_FAST, VARIANT_TILED, VARIANT_TC = 0, 1, 2, 3, 4
 OK, EINVAL, ECUDA, EWORKSPACE = 0, -1, -2, -3
 STAGES = ("K0_ctx_gemm", "K1_path_fwd", "K5_elbo_fwd", "K6_elbo_bwd", "K2_path_bwd", "K3_grad_ctx", "K4_wgrad")
 

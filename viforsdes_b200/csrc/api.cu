@@ -140,6 +140,19 @@ bool use_tc(const visde_dims* d, const visde_ctx_view* ctx) {
   return tc_supported(d->H, d->NL, d->C, ctx);
 }
 
+// tensor-core recurrence: explicit request, or AUTO once the batch is large enough that 128-trajectory tiles
+// beat the fp32 SIMT families (needs the tcgen05 K0, which folds the per-trajectory constants into gi_ctx)
+constexpr int64_t kTcRecMinBatch = 1024;
+bool use_tc_rec(const visde_dims* d, const PathParams& p, const visde_ctx_view* ctx) {
+  const int fam = d->variant & 0xff;
+  if (fam != VISDE_VARIANT_TC && !(fam == VISDE_VARIANT_AUTO && d->B >= kTcRecMinBatch)) return false;
+  return tc_rec_supported(p) && use_tc(d, ctx);
+}
+
+size_t fwd_gi_bytes(const visde_dims* d) { return align_up(sizeof(float) * (size_t)d->B * d->T * 3 * d->H); }
+size_t fwd_wsplit_bytes(const visde_dims* d) { return align_up(sizeof(float) * tc_weight_scratch_floats(d->H, d->C)); }
+size_t fwd_gth_bytes(const visde_dims* d) { return align_up(sizeof(float) * (size_t)d->B * 3 * d->H); }
+
 bool use_fast(const visde_dims* d, const PathParams& p) {
   if ((d->variant & 0xff) == VISDE_VARIANT_GENERIC) return false;
   return fast_supported(p);
@@ -179,9 +192,7 @@ size_t visde_stash_bytes(const visde_dims* d) {
 
 size_t visde_workspace_bytes(const visde_dims* d, int backward) {
   if (check_dims(d) != VISDE_OK) return 0;
-  if (!backward)
-    return align_up(sizeof(float) * (size_t)d->B * d->T * 3 * d->H) +
-           align_up(sizeof(float) * tc_weight_scratch_floats(d->H, d->C)) + 256;
+  if (!backward) return fwd_gi_bytes(d) + fwd_wsplit_bytes(d) + fwd_gth_bytes(d) + 256;
   return bwd_ws(d).total + 256;
 }
 
@@ -200,6 +211,9 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
   VISDE_REQUIRE(((d->variant & 0xff) != VISDE_VARIANT_FAST && (d->variant & 0xff) != VISDE_VARIANT_TILED) ||
                     (d->H <= 64 && d->H % 4 == 0 && d->NL <= 2 && d->S <= 4),
                 "fast variant requested for an unsupported shape (H=%d NL=%d S=%d)", d->H, d->NL, d->S);
+  VISDE_REQUIRE((d->variant & 0xff) != VISDE_VARIANT_TC || (d->H == 64 && d->NL <= 2 && d->S <= 4 && use_tc(d, ctx)),
+                "tensor-core recurrence requested for an unsupported shape (needs H=64, NL<=2, S<=4, fp32 16-byte "
+                "aligned context with C in {128, 256}; got H=%d NL=%d S=%d C=%d)", d->H, d->NL, d->S, d->C);
   if (workspace_bytes < visde_workspace_bytes(d, 0) - 256 || (!workspace && d->T > 0)) {
     set_error("path_fwd: workspace too small (%zu < %zu)", workspace_bytes, visde_workspace_bytes(d, 0));
     return VISDE_EWORKSPACE;
@@ -220,15 +234,24 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
     p.stash = reinterpret_cast<float*>(stash);
     p.raw = reinterpret_cast<float*>(reinterpret_cast<char*>(stash) + align_up(sizeof(float) * s.h_floats));
   }
+  const bool tcrec = d->T > 0 && use_tc_rec(d, p, ctx);
   if (d->T > 0) {
     // K0: context rows of W_ih_l0 as one time-parallel GEMM, b_ih_l0 folded in
-    StageTimer tm(VISDE_STAGE_K0_CTX_GEMM, 1, st);
+    StageTimer tm(VISDE_STAGE_K0_CTX_GEMM, tcrec ? 3 : 1, st);
     if (use_tc(d, ctx)) {
-      float* wsplit = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) +
-                                               align_up(sizeof(float) * (size_t)d->B * d->T * 3 * d->H));
+      float* wsplit = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + fwd_gi_bytes(d));
       rc = tc_split_weights(w->w_ih[0], d->S + d->C + d->P, d->S, d->H, d->C, wsplit, st);
       if (rc) return rc;
-      rc = tc_ctx_proj(ctx, d->B, d->T, d->C, d->H, wsplit, w->b_ih[0], gi, st);
+      if (tcrec) {
+        // the tensor-core recurrence takes every per-trajectory constant of the layer-0 gates (theta columns,
+        // b_ih_l0, b_hh_l0[r, u]) from gi_ctx: K0 adds them as a row bias
+        float* gth = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + fwd_gi_bytes(d) + fwd_wsplit_bytes(d));
+        rc = launch_gth(p, gth, st);
+        if (rc) return rc;
+        rc = tc_ctx_proj(ctx, d->B, d->T, d->C, d->H, wsplit, nullptr, gth, gi, st);
+      } else {
+        rc = tc_ctx_proj(ctx, d->B, d->T, d->C, d->H, wsplit, w->b_ih[0], nullptr, gi, st);
+      }
     } else {
       RowSrc A{ctx->ptr, ctx->batch_stride, ctx->time_stride, 0, d->C, ctx->dtype};
       rc = launch_gemm_nt(A, d->B, d->T, d->C, w->w_ih[0] + d->S, d->S + d->C + d->P, 3 * d->H, w->b_ih[0], gi,
@@ -237,9 +260,10 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
     if (rc) return rc;
   }
   StageTimer tm(VISDE_STAGE_K1_PATH_FWD, 1, st);
+  if (tcrec) return launch_path_fwd_tc(p, st);
   if (use_fast(d, p)) {
     const int fam = d->variant & 0xff;
-    const int nb = fam == VISDE_VARIANT_FAST ? 0 : tiled_batch_tile(d->B, fam == VISDE_VARIANT_TILED);
+    const int nb = (fam == VISDE_VARIANT_FAST || fam == VISDE_VARIANT_TC) ? 0 : tiled_batch_tile(d->B, fam == VISDE_VARIANT_TILED);
     return nb > 0 ? launch_path_fwd_tiled(p, nb, st) : launch_path_fwd_fast(p, st);
   }
   return launch_path_fwd_generic(p, st);

@@ -1,0 +1,577 @@
+// Tensor-core recurrence kernels for large batches (B >> #SM, H = 64): K1c path_fwd_tc.
+//
+// At large batch the gate products of the recurrence are dense GEMMs: a CTA owns a tile of 128
+// trajectories (the MMA M dimension, one TMEM lane per trajectory) and every step runs
+//     D0[128,192]  = h0(t-1) . W_hh_l0^T                      (issued one step ahead)
+//     D1[128,256]  = h1(t-1) . W_hh_l1^T  (+)=  h0(t) . W_ih_l1^T     (r, u share columns; n_i / n_h apart)
+//     Dout[128,16] = h_top(t) . W_out^T
+// as tcgen05.mma kind::f16 with FP32 accumulators in TMEM.  FP32-grade accuracy comes from a 3-pass
+// split of both operands into fp16 hi + lo halves (hi*hi + hi*lo + lo*hi, 22 mantissa bits) after an
+// exact power-of-two scaling that keeps both halves in fp16's normal range: weights by 2^a
+// (max |w| 2^a in [2^13, 2^14)), hidden states (|h| < 1) by 2^14; the accumulator is scaled back by
+// 2^-(a+14) in the epilogue.  fp16 rather than tf32 because the three recurrent matrices then fit in
+// shared memory as resident hi/lo tiles (144 KB instead of 288 KB) and the MMA rate doubles.
+//
+// Warp roles (288 threads): warps 0..7 are the gate epilogue -- warp w reads TMEM lane quadrant w % 4
+// (32 trajectories) and hidden units [32 * (w / 4), +32): tcgen05.ld -> gates (raw MUFU) -> h(t) kept
+// in registers for the next step's update, written as fp16 hi/lo into the K-major SWIZZLE_128B A
+// tiles, and stashed for the backward; warp 8 allocates TMEM and one of its lanes issues every MMA.
+// mbarriers: d0 / d1 / out (tcgen05.commit: accumulators ready), a0 / a1 (256 arrivals: A tile
+// written and accumulator drained), init (tile start).  The state-column and theta terms of layer 0
+// and the biases do not go through the tensor cores: theta and bias terms are folded into gi_ctx by
+// K0 (per-trajectory row bias), the S state columns are S FMAs per gate in the epilogue.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tc.cuh"
+
+namespace visde {
+namespace {
+
+constexpr int kTileRows = 128;
+constexpr int kWTileBytes = 192 * 128;  // one weight tile: 192 gate rows x 64 fp16
+constexpr int kATileBytes = 128 * 128;  // one operand tile: 128 trajectories x 64 fp16
+constexpr int kOutTileBytes = 16 * 128;
+constexpr int kEpiThreads = 256, kTcRecThreads = 288;
+constexpr int kUPT = 32;    // hidden units per epilogue thread
+constexpr int kHExp = 14;   // hidden states are scaled by 2^14 before the fp16 split
+
+// instruction descriptor: D fp32, A/B fp16 K-major, M = 128
+__host__ __device__ constexpr uint32_t idesc_f16(int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// byte offset of 16-byte chunk c (8 fp16) of row r in a K-major SWIZZLE_128B tile with 128-byte rows
+__device__ __forceinline__ uint32_t sw128(int r, int c) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+// fp16 hi / lo halves of 8 (already scaled) floats, packed in K order
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const __half2 hh = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+    const float2 back = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x[2 * q] - back.x, x[2 * q + 1] - back.y);
+    h[q] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[q] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// power-of-two exponent a with amax * 2^a in [2^13, 2^14)
+__device__ __forceinline__ int scale_exp(uint32_t amax_bits) {
+  if (amax_bits == 0) return 0;
+  const int e = (int)(amax_bits >> 23) - 127;
+  const int a = 13 - e;
+  return a > 100 ? 100 : a;
+}
+__device__ __forceinline__ float exp2i(int a) { return __uint_as_float((uint32_t)(a + 127) << 23); }
+
+template <int NL, int S>
+struct TcFwdSmem {
+  static constexpr int NMAT = 2 * NL - 1;
+  static constexpr int CS = (3 * S + 1 <= 4) ? 4 : (3 * S + 1 <= 8 ? 8 : 16);  // floats per unit in c0
+  static constexpr int OFF_W = 0;                                  // [NMAT][hi, lo][192][128 B]
+  static constexpr int OFF_WOUT = OFF_W + NMAT * 2 * kWTileBytes;  // [hi, lo][16][128 B]
+  static constexpr int OFF_A = OFF_WOUT + 2 * kOutTileBytes;       // [NL][hi, lo][128][128 B]
+  static constexpr int OFF_C0 = OFF_A + NL * 2 * kATileBytes;      // float [64][CS]: W_z rows, b_hn of layer 0
+  static constexpr int OFF_C1 = OFF_C0 + 64 * CS * 4;              // float [64][4]: layer-1 bias terms
+  static constexpr int OFF_OUTB = OFF_C1 + 64 * 4 * 4;             // float [16]
+  static constexpr int OFF_BAR = OFF_OUTB + 64;
+  struct Bars {
+    uint64_t init, d0, a0, d1, a1, out;
+    uint32_t tmem_base;
+    uint32_t amax[2];
+  };
+  static constexpr size_t bytes = OFF_BAR + sizeof(Bars) + 1024;
+};
+
+// 12 MMAs: D[128, N] (+)= A[128, 64] . B[N, 64]^T with the 3-pass hi/lo split (small terms first)
+__device__ __forceinline__ void issue_gemm(uint32_t dcol, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                           uint32_t idesc, bool accumulate) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint64_t dah = umma_desc(a_hi + j * 32, 16, 1024, 2), dal = umma_desc(a_lo + j * 32, 16, 1024, 2);
+    const uint64_t dbh = umma_desc(b_hi + j * 32, 16, 1024, 2), dbl = umma_desc(b_lo + j * 32, 16, 1024, 2);
+    umma_f16(dcol, dal, dbh, idesc, (accumulate || j > 0) ? 1u : 0u);
+    umma_f16(dcol, dah, dbl, idesc, 1u);
+    umma_f16(dcol, dah, dbh, idesc, 1u);
+  }
+}
+
+template <int NL, int S>
+__global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParams p) {
+  using L = TcFwdSmem<NL, S>;
+  constexpr int NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL, CS = L::CS, NMAT = L::NMAT;
+  static_assert(NOUT <= 16, "output projection tile holds 16 rows");
+  constexpr uint32_t TMEM_COLS = NL == 2 ? 512 : 256;
+  constexpr uint32_t D0_COL = 0, D1_COL = 192, DOUT_COL = NL == 2 ? 448 : 192;
+  extern __shared__ __align__(1024) uint8_t smem_raw_tc[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023));
+  typename L::Bars* bars = reinterpret_cast<typename L::Bars*>(smem + L::OFF_BAR);
+  float* c0 = reinterpret_cast<float*>(smem + L::OFF_C0);
+  float* c1 = reinterpret_cast<float*>(smem + L::OFF_C1);
+  float* outb = reinterpret_cast<float*>(smem + L::OFF_OUTB);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ld0 = S + p.C + p.P;
+  const int64_t T = p.T;
+
+  // ---- scaling exponents: one for the recurrent matrices (their products share accumulators), one for W_out
+  if (tid == 0) bars->amax[0] = bars->amax[1] = 0u;
+  __syncthreads();
+  {
+    float mx = 0.f, mo = 0.f;
+    for (int m = 0; m < NMAT; ++m) {
+      const float* src = m == 0 ? p.w_hh[0] : (m == 1 ? p.w_ih[1] : p.w_hh[1]);
+      for (int idx = tid; idx < 192 * 64; idx += kTcRecThreads) mx = fmaxf(mx, fabsf(src[idx]));
+    }
+    for (int idx = tid; idx < NOUT * 64; idx += kTcRecThreads) mo = fmaxf(mo, fabsf(p.out_w[idx]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mo = fmaxf(mo, __shfl_xor_sync(0xffffffffu, mo, o));
+    }
+    if (lane == 0) {
+      atomicMax(&bars->amax[0], __float_as_uint(mx));
+      atomicMax(&bars->amax[1], __float_as_uint(mo));
+    }
+  }
+  __syncthreads();
+  const int ew = scale_exp(bars->amax[0]), eo = scale_exp(bars->amax[1]);
+  const float w_scale = exp2i(ew), o_scale = exp2i(eo);
+  const float sc = exp2i(-(ew + kHExp)), sco = exp2i(-(eo + kHExp));
+
+  // ---- resident weight tiles (fp16 hi / lo, K-major, 128-byte swizzle)
+  for (int m = 0; m < NMAT; ++m) {
+    const float* src = m == 0 ? p.w_hh[0] : (m == 1 ? p.w_ih[1] : p.w_hh[1]);
+    uint8_t* thi = smem + L::OFF_W + (m * 2) * kWTileBytes;
+    uint8_t* tlo = thi + kWTileBytes;
+    for (int idx = tid; idx < 192 * 8; idx += kTcRecThreads) {
+      const int n = idx >> 3, c = idx & 7;
+      float x[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) x[q] = src[n * 64 + c * 8 + q] * w_scale;
+      uint4 hi, lo;
+      split8(x, hi, lo);
+      *reinterpret_cast<uint4*>(thi + sw128(n, c)) = hi;
+      *reinterpret_cast<uint4*>(tlo + sw128(n, c)) = lo;
+    }
+  }
+  for (int idx = tid; idx < 16 * 8; idx += kTcRecThreads) {
+    const int n = idx >> 3, c = idx & 7;
+    float x[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) x[q] = n < NOUT ? p.out_w[n * 64 + c * 8 + q] * o_scale : 0.f;
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    *reinterpret_cast<uint4*>(smem + L::OFF_WOUT + sw128(n, c)) = hi;
+    *reinterpret_cast<uint4*>(smem + L::OFF_WOUT + kOutTileBytes + sw128(n, c)) = lo;
+  }
+  for (int idx = tid; idx < 64 * CS; idx += kTcRecThreads) {
+    const int j = idx / CS, q = idx % CS;
+    float v = 0.f;
+    if (q < 3 * S) v = p.w_ih[0][(int64_t)((q / S) * 64 + j) * ld0 + (q % S)];
+    else if (q == 3 * S) v = p.b_hh[0][128 + j];
+    c0[idx] = v;
+  }
+  if (NL == 2) {
+    for (int j = tid; j < 64; j += kTcRecThreads) {
+      c1[j * 4 + 0] = p.b_ih[1][j] + p.b_hh[1][j];
+      c1[j * 4 + 1] = p.b_ih[1][64 + j] + p.b_hh[1][64 + j];
+      c1[j * 4 + 2] = p.b_ih[1][128 + j];
+      c1[j * 4 + 3] = p.b_hh[1][128 + j];
+    }
+  }
+  if (tid < 16) outb[tid] = tid < NOUT ? p.out_b[tid] : 0.f;
+
+  if (tid == 0) {
+    mbar_init(&bars->init, kEpiThreads);
+    mbar_init(&bars->d0, 1);
+    mbar_init(&bars->a0, kEpiThreads);
+    mbar_init(&bars->d1, 1);
+    mbar_init(&bars->a1, kEpiThreads);
+    mbar_init(&bars->out, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  fence_proxy_async();  // the weight tiles were written through the generic proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const int64_t ntiles = (p.B + kTileRows - 1) / kTileRows;
+
+  if (warp == 8) {
+    // ======================= MMA issuer ==========================================================
+    if (lane == 0) {
+      const uint32_t w0 = smem_u32(smem + L::OFF_W);
+      auto whi = [&](int m) { return w0 + (uint32_t)(m * 2) * kWTileBytes; };
+      auto wlo = [&](int m) { return w0 + (uint32_t)(m * 2 + 1) * kWTileBytes; };
+      const uint32_t a0h = smem_u32(smem + L::OFF_A), a0l = a0h + kATileBytes;
+      const uint32_t a1h = a0h + 2 * kATileBytes, a1l = a1h + kATileBytes;
+      const uint32_t woh = smem_u32(smem + L::OFF_WOUT), wol = woh + kOutTileBytes;
+      constexpr uint32_t ID192 = idesc_f16(192), ID128 = idesc_f16(128), ID64 = idesc_f16(64), ID16 = idesc_f16(16);
+      constexpr uint32_t NROWS = 128 * 128;  // byte offset of gate rows 128.. (the n block) in a weight tile
+      uint32_t ph_init = 0, ph_a0 = 0, ph_a1 = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(&bars->init, ph_init);
+        ph_init ^= 1;
+        tc_fence_after();
+        // h(-1) = 0: the A tiles are zero, so these just clear the accumulators
+        issue_gemm(tmem + D0_COL, a0h, a0l, whi(0), wlo(0), ID192, false);
+        umma_commit(&bars->d0);
+        if (NL == 2) {
+          issue_gemm(tmem + D1_COL, a1h, a1l, whi(2), wlo(2), ID128, false);
+          issue_gemm(tmem + D1_COL + 192, a1h, a1l, whi(2) + NROWS, wlo(2) + NROWS, ID64, false);
+        }
+        for (int64_t t = 0; t < T; ++t) {
+          mbar_wait(&bars->a0, ph_a0);
+          ph_a0 ^= 1;
+          tc_fence_after();
+          if (NL == 2) {
+            // layer 1 input part: r, u accumulate onto the recurrent part, n_i has its own columns
+            issue_gemm(tmem + D1_COL, a0h, a0l, whi(1), wlo(1), ID128, true);
+            issue_gemm(tmem + D1_COL + 128, a0h, a0l, whi(1) + NROWS, wlo(1) + NROWS, ID64, false);
+            umma_commit(&bars->d1);
+          } else {
+            issue_gemm(tmem + DOUT_COL, a0h, a0l, woh, wol, ID16, false);
+            umma_commit(&bars->out);
+          }
+          if (t + 1 < T) {
+            issue_gemm(tmem + D0_COL, a0h, a0l, whi(0), wlo(0), ID192, false);  // W_hh_l0 h0(t) for step t+1
+            umma_commit(&bars->d0);
+          }
+          if (NL == 2) {
+            mbar_wait(&bars->a1, ph_a1);
+            ph_a1 ^= 1;
+            tc_fence_after();
+            issue_gemm(tmem + DOUT_COL, a1h, a1l, woh, wol, ID16, false);
+            umma_commit(&bars->out);
+            if (t + 1 < T) {
+              issue_gemm(tmem + D1_COL, a1h, a1l, whi(2), wlo(2), ID128, false);
+              issue_gemm(tmem + D1_COL + 192, a1h, a1l, whi(2) + NROWS, wlo(2) + NROWS, ID64, false);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= gate epilogue =======================================================
+    const int quad = warp & 3, cg = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
+    const int u0 = cg * kUPT;
+    uint8_t* a_tiles = smem + L::OFF_A;
+    const float hs = exp2i(kHExp);
+    uint32_t ph_d0 = 0, ph_d1 = 0, ph_out = 0;
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t b_raw = tile * kTileRows + row;
+      const bool ok = b_raw < p.B;
+      const int64_t b = ok ? b_raw : p.B - 1;
+      const bool writer = ok && cg == 0;
+      // h(-1) = 0
+#pragma unroll
+      for (int k = 0; k < NL; ++k)
+#pragma unroll
+        for (int c = 0; c < kUPT / 8; ++c) {
+          const uint32_t off = sw128(row, (u0 >> 3) + c);
+          *reinterpret_cast<uint4*>(a_tiles + (2 * k) * kATileBytes + off) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(a_tiles + (2 * k + 1) * kATileBytes + off) = make_uint4(0, 0, 0, 0);
+        }
+      fence_proxy_async();
+      mbar_arrive(&bars->init);
+
+      float z[S], eps_cur[S], hprev[NL][kUPT];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        z[s] = p.x0[b * S + s];
+        eps_cur[s] = p.eps[b * T * S + s];
+        if (writer) p.paths[b * (T + 1) * S + s] = z[s];
+      }
+#pragma unroll
+      for (int k = 0; k < NL; ++k)
+#pragma unroll
+        for (int j = 0; j < kUPT; ++j) hprev[k][j] = 0.f;
+      const float* gi_p = p.gi_ctx + b * T * 192 + u0;  // this thread's 32 units of gate r; u at +64, n at +128
+      float* st_p = p.stash ? p.stash + b * T * (int64_t)(NL * kStashSlots * 64) + u0 : nullptr;
+      const float* eps_p = p.eps + b * T * S;
+      float* paths_o = p.paths + (b * (T + 1) + 1) * S;
+      float* means_o = p.means + b * T * S;
+      float* chol_o = p.chol + b * T * S * S;
+      float* raw_o = p.raw ? p.raw + b * T * NTRIL : nullptr;
+
+      float4 gnx[3][2];  // next 8-unit chunk of gi_ctx (r, u, n)
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        gnx[g][0] = *reinterpret_cast<const float4*>(gi_p + g * 64);
+        gnx[g][1] = *reinterpret_cast<const float4*>(gi_p + g * 64 + 4);
+      }
+
+      for (int64_t t = 0; t < T; ++t) {
+        const bool has_next = t + 1 < T;
+        // ---------------- layer 0 ----------------
+        mbar_wait(&bars->d0, ph_d0);
+        ph_d0 ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < kUPT / 8; ++c) {
+          const int j0 = u0 + c * 8;
+          uint32_t dr[8], du[8], dn[8];
+          tmem_ld8_nowait(tl + D0_COL + j0, dr);
+          tmem_ld8_nowait(tl + D0_COL + 64 + j0, du);
+          tmem_ld8_nowait(tl + D0_COL + 128 + j0, dn);
+          float gcur[3][8];
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            gcur[g][0] = gnx[g][0].x; gcur[g][1] = gnx[g][0].y; gcur[g][2] = gnx[g][0].z; gcur[g][3] = gnx[g][0].w;
+            gcur[g][4] = gnx[g][1].x; gcur[g][5] = gnx[g][1].y; gcur[g][6] = gnx[g][1].z; gcur[g][7] = gnx[g][1].w;
+          }
+          // prefetch the next chunk (of this step, or chunk 0 of the next step)
+          {
+            const bool last = c == kUPT / 8 - 1;
+            const float* nx = last ? gi_p + 192 : gi_p + (c + 1) * 8;
+            if (!last || has_next) {
+#pragma unroll
+              for (int g = 0; g < 3; ++g) {
+                gnx[g][0] = *reinterpret_cast<const float4*>(nx + g * 64);
+                gnx[g][1] = *reinterpret_cast<const float4*>(nx + g * 64 + 4);
+              }
+            }
+          }
+          tmem_ld_wait();
+          float hx[8];
+#pragma unroll
+          for (int h4 = 0; h4 < 2; ++h4) {
+            float sr[4], su[4], sn[4], snh[4], sh[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int jj = h4 * 4 + q, j = j0 + jj;
+              float cc[CS];
+#pragma unroll
+              for (int v = 0; v < CS / 4; ++v) {
+                const float4 w4 = *reinterpret_cast<const float4*>(c0 + j * CS + 4 * v);
+                cc[4 * v] = w4.x; cc[4 * v + 1] = w4.y; cc[4 * v + 2] = w4.z; cc[4 * v + 3] = w4.w;
+              }
+              float pr = fmaf(sc, __uint_as_float(dr[jj]), gcur[0][jj]);
+              float pu = fmaf(sc, __uint_as_float(du[jj]), gcur[1][jj]);
+              float pni = gcur[2][jj];
+              const float pnh = fmaf(sc, __uint_as_float(dn[jj]), cc[3 * S]);
+#pragma unroll
+              for (int s = 0; s < S; ++s) {
+                pr = fmaf(cc[s], z[s], pr);
+                pu = fmaf(cc[S + s], z[s], pu);
+                pni = fmaf(cc[2 * S + s], z[s], pni);
+              }
+              const float r = sigmoid_f(pr);
+              const float n = tanh_f(fmaf(r, pnh, pni));
+              const float u = sigmoid_f(pu);
+              const float hn = fmaf(u, hprev[0][c * 8 + jj] - n, n);
+              hprev[0][c * 8 + jj] = hn;
+              hx[jj] = hn * hs;
+              sr[q] = r; su[q] = u; sn[q] = n; snh[q] = pnh; sh[q] = hn;
+            }
+            if (st_p && ok) {
+              float* st = st_p + c * 8 + h4 * 4;
+              *reinterpret_cast<float4*>(st + kStashR * 64) = make_float4(sr[0], sr[1], sr[2], sr[3]);
+              *reinterpret_cast<float4*>(st + kStashU * 64) = make_float4(su[0], su[1], su[2], su[3]);
+              *reinterpret_cast<float4*>(st + kStashN * 64) = make_float4(sn[0], sn[1], sn[2], sn[3]);
+              *reinterpret_cast<float4*>(st + kStashNhh * 64) = make_float4(snh[0], snh[1], snh[2], snh[3]);
+              *reinterpret_cast<float4*>(st + kStashH * 64) = make_float4(sh[0], sh[1], sh[2], sh[3]);
+            }
+          }
+          uint4 hi, lo;
+          split8(hx, hi, lo);
+          const uint32_t off = sw128(row, j0 >> 3);
+          *reinterpret_cast<uint4*>(a_tiles + off) = hi;
+          *reinterpret_cast<uint4*>(a_tiles + kATileBytes + off) = lo;
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(&bars->a0);
+        gi_p += 192;
+
+        // ---------------- layer 1 ----------------
+        if (NL == 2) {
+          mbar_wait(&bars->d1, ph_d1);
+          ph_d1 ^= 1;
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < kUPT / 8; ++c) {
+            const int j0 = u0 + c * 8;
+            uint32_t dr[8], du[8], di[8], dn[8];
+            tmem_ld8_nowait(tl + D1_COL + j0, dr);
+            tmem_ld8_nowait(tl + D1_COL + 64 + j0, du);
+            tmem_ld8_nowait(tl + D1_COL + 128 + j0, di);
+            tmem_ld8_nowait(tl + D1_COL + 192 + j0, dn);
+            tmem_ld_wait();
+            float hx[8];
+#pragma unroll
+            for (int h4 = 0; h4 < 2; ++h4) {
+              float sr[4], su[4], sn[4], snh[4], sh[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int jj = h4 * 4 + q, j = j0 + jj;
+                const float4 cb = *reinterpret_cast<const float4*>(c1 + j * 4);
+                const float pr = fmaf(sc, __uint_as_float(dr[jj]), cb.x);
+                const float pu = fmaf(sc, __uint_as_float(du[jj]), cb.y);
+                const float pni = fmaf(sc, __uint_as_float(di[jj]), cb.z);
+                const float pnh = fmaf(sc, __uint_as_float(dn[jj]), cb.w);
+                const float r = sigmoid_f(pr);
+                const float n = tanh_f(fmaf(r, pnh, pni));
+                const float u = sigmoid_f(pu);
+                const float hn = fmaf(u, hprev[NL - 1][c * 8 + jj] - n, n);
+                hprev[NL - 1][c * 8 + jj] = hn;
+                hx[jj] = hn * hs;
+                sr[q] = r; su[q] = u; sn[q] = n; snh[q] = pnh; sh[q] = hn;
+              }
+              if (st_p && ok) {
+                float* st = st_p + kStashSlots * 64 + c * 8 + h4 * 4;
+                *reinterpret_cast<float4*>(st + kStashR * 64) = make_float4(sr[0], sr[1], sr[2], sr[3]);
+                *reinterpret_cast<float4*>(st + kStashU * 64) = make_float4(su[0], su[1], su[2], su[3]);
+                *reinterpret_cast<float4*>(st + kStashN * 64) = make_float4(sn[0], sn[1], sn[2], sn[3]);
+                *reinterpret_cast<float4*>(st + kStashNhh * 64) = make_float4(snh[0], snh[1], snh[2], snh[3]);
+                *reinterpret_cast<float4*>(st + kStashH * 64) = make_float4(sh[0], sh[1], sh[2], sh[3]);
+              }
+            }
+            uint4 hi, lo;
+            split8(hx, hi, lo);
+            const uint32_t off = sw128(row, j0 >> 3);
+            *reinterpret_cast<uint4*>(a_tiles + 2 * kATileBytes + off) = hi;
+            *reinterpret_cast<uint4*>(a_tiles + 3 * kATileBytes + off) = lo;
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(&bars->a1);
+        }
+        if (st_p) st_p += NL * kStashSlots * 64;
+
+        // ---------------- output projection + reparameterised Euler-Maruyama update ----------------
+        float eps_nxt[S];
+        eps_p += S;
+#pragma unroll
+        for (int s = 0; s < S; ++s) eps_nxt[s] = has_next ? eps_p[s] : 0.f;
+        mbar_wait(&bars->out, ph_out);
+        ph_out ^= 1;
+        tc_fence_after();
+        float o[NOUT];
+        {
+          uint32_t ov[16];
+          tmem_ld16_nowait(tl + DOUT_COL, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int m = 0; m < NOUT; ++m) o[m] = fmaf(sco, __uint_as_float(ov[m]), outb[m]);
+        }
+        tc_fence_before();
+        float zn[S], Lm[NTRIL];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j <= s; ++j) {
+            const int ti = s * (s + 1) / 2 + j;
+            const float raw = o[S + ti];
+            const float Lv = (j == s) ? fmaxf(raw, VISDE_DIAG_MIN) : raw;
+            Lm[ti] = Lv;
+            acc = fmaf(Lv, eps_cur[j], acc);
+          }
+          zn[s] = z[s] + o[s] * p.dt + acc * p.sqrt_dt;
+        }
+        if (writer) {
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            paths_o[s] = zn[s];
+            means_o[s] = o[s];
+#pragma unroll
+            for (int j = 0; j < S; ++j) chol_o[s * S + j] = j <= s ? Lm[s * (s + 1) / 2 + j] : 0.f;
+          }
+          if (raw_o) {
+#pragma unroll
+            for (int ti = 0; ti < NTRIL; ++ti) raw_o[ti] = o[S + ti];
+          }
+        }
+        paths_o += S;
+        means_o += S;
+        chol_o += S * S;
+        if (raw_o) raw_o += NTRIL;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          z[s] = zn[s];
+          eps_cur[s] = eps_nxt[s];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// gth[b, n] = b_ih_l0[n] + (n < 2H ? b_hh_l0[n] : 0) + sum_p theta[b, p] W_ih_l0[n, S + C + p]: the part of the
+// layer-0 pre-activations that is constant along a trajectory; K0 adds it to gi_ctx as a per-row bias
+__global__ void gth_kernel(const float* __restrict__ theta, const float* __restrict__ w_ih0, const float* __restrict__ b_ih0,
+                           const float* __restrict__ b_hh0, int64_t B, int S, int C, int P, int H, float* __restrict__ gth) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int G = 3 * H;
+  if (idx >= B * G) return;
+  const int64_t b = idx / G;
+  const int n = (int)(idx % G);
+  float v = b_ih0[n] + (n < 2 * H ? b_hh0[n] : 0.f);
+  const float* w = w_ih0 + (int64_t)n * (S + C + P) + S + C;
+  for (int q = 0; q < P; ++q) v = fmaf(theta[b * P + q], w[q], v);
+  gth[idx] = v;
+}
+
+template <int NL, int S>
+int launch_fwd_tc(const PathParams& p, cudaStream_t st) {
+  const size_t smem = TcFwdSmem<NL, S>::bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_fwd_tc_kernel<NL, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t ntiles = (p.B + kTileRows - 1) / kTileRows;
+  path_fwd_tc_kernel<NL, S><<<(unsigned)(ntiles < sms ? ntiles : sms), kTcRecThreads, smem, st>>>(p);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  return VISDE_OK;
+}
+
+template <int NL>
+int dispatch_s_tc(const PathParams& p, cudaStream_t st) {
+  switch (p.S) {
+    case 1: return launch_fwd_tc<NL, 1>(p, st);
+    case 2: return launch_fwd_tc<NL, 2>(p, st);
+    case 3: return launch_fwd_tc<NL, 3>(p, st);
+    case 4: return launch_fwd_tc<NL, 4>(p, st);
+  }
+  set_error("tensor-core recurrence: unsupported state dim %d", p.S);
+  return VISDE_EINVAL;
+}
+
+}  // namespace
+
+bool tc_rec_supported(const PathParams& p) {
+  return p.H == 64 && p.NL >= 1 && p.NL <= 2 && p.S >= 1 && p.S <= 4 && p.T >= 1 && p.B >= 1 &&
+         p.T * (int64_t)(p.NL * kStashSlots * p.H) < (int64_t(1) << 31);
+}
+
+int launch_gth(const PathParams& p, float* gth, cudaStream_t st) {
+  const int64_t n = p.B * 3 * p.H;
+  gth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.theta, p.w_ih[0], p.b_ih[0], p.b_hh[0], p.B, p.S, p.C, p.P, p.H, gth);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  return VISDE_OK;
+}
+
+int launch_path_fwd_tc(const PathParams& p, cudaStream_t st) {
+  if (p.NL == 1) return dispatch_s_tc<1>(p, st);
+  if (p.NL == 2) return dispatch_s_tc<2>(p, st);
+  set_error("tensor-core recurrence: unsupported num_layers %d", p.NL);
+  return VISDE_EINVAL;
+}
+
+}  // namespace visde

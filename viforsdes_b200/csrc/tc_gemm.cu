@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tc.cuh"
 
 namespace visde {
 namespace {
@@ -27,64 +28,6 @@ namespace {
 constexpr int kTcThreads = 192;
 constexpr int kStages = 2;
 constexpr uint32_t kTf32Mask = 0xffffe000u;  // keep sign, exponent and the 10 tf32 mantissa bits
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives on the mbarrier once all previously issued MMAs of this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane = row)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// UMMA shared-memory matrix descriptor, 128-byte swizzle (cute/arch/mma_sm100_desc.hpp bit layout):
-// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout=2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
-}
-// K-major tile [rows][32 tf32] (128-byte rows, 8-row groups 1024 B apart), SWIZZLE_128B (layout 2);
-// K slice j of 8 -> +32 B
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int j) { return umma_desc(tile + j * 32, 16, 1024, 2); }
-// MN-major tf32 tile: the only legal layout is SWIZZLE_128B_BASE32B (layout 1; TMA's
-// SWIZZLE_128B_ATOM_32B): slabs of [32 k-rows][32 tf32 along MN] (4 KB apart = LBO), swizzle atoms of
-// 4 k-rows (512 B apart = SBO); K slice j of 8 rows -> +1024 B
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int j) { return umma_desc(tile + j * 1024, 4096, 512, 1); }
 
 // instruction descriptor: D fp32, A/B tf32, M = 128
 __host__ __device__ constexpr uint32_t make_idesc(int N, bool a_mn, bool b_mn) {
@@ -128,6 +71,7 @@ struct RowsArgs {
   int num_kblocks;  // K / 32
   int n0;           // first output column handled (K3 with C > 256 launches several column chunks)
   const float* bias;
+  const float* rowbias;  // [B][N] added per trajectory (K0 for the tensor-core recurrence), or nullptr
   void* out;
   int64_t out_bstride, out_tstride;
   int out_dtype;
@@ -279,32 +223,34 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int t = t0 + row;
       const bool row_ok = t < a.T;
       const int64_t obase = (int64_t)b * a.out_bstride + (int64_t)t * a.out_tstride + a.n0;
+      const float* rb = a.rowbias ? a.rowbias + (int64_t)b * N : nullptr;
 #pragma unroll 1
       for (int c = 0; c < N / 32; ++c) {
         float v[32];
         tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + acc * N + c * 32, v);
+        if (a.bias) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] += a.bias[a.n0 + c * 32 + q];
+        }
+        if (rb) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] += rb[c * 32 + q];
+        }
         if (row_ok) {
           if (a.out_dtype == VISDE_BF16) {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + obase + c * 32;
 #pragma unroll
             for (int q = 0; q < 32; ++q)
-              if (c * 32 + q < a.out_cols) o[q] = __float2bfloat16(v[q] + (a.bias ? a.bias[a.n0 + c * 32 + q] : 0.f));
+              if (c * 32 + q < a.out_cols) o[q] = __float2bfloat16(v[q]);
           } else {
             float* o = reinterpret_cast<float*>(a.out) + obase + c * 32;
             if (c * 32 + 32 <= a.out_cols && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
-              for (int q = 0; q < 32; q += 4) {
-                float4 w;
-                w.x = v[q] + (a.bias ? a.bias[a.n0 + c * 32 + q] : 0.f);
-                w.y = v[q + 1] + (a.bias ? a.bias[a.n0 + c * 32 + q + 1] : 0.f);
-                w.z = v[q + 2] + (a.bias ? a.bias[a.n0 + c * 32 + q + 2] : 0.f);
-                w.w = v[q + 3] + (a.bias ? a.bias[a.n0 + c * 32 + q + 3] : 0.f);
-                *reinterpret_cast<float4*>(o + q) = w;
-              }
+              for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(o + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
             } else {
 #pragma unroll
               for (int q = 0; q < 32; ++q)
-                if (c * 32 + q < a.out_cols) o[q] = v[q] + (a.bias ? a.bias[a.n0 + c * 32 + q] : 0.f);
+                if (c * 32 + q < a.out_cols) o[q] = v[q];
             }
           }
         }
@@ -577,7 +523,7 @@ int tc_split_weights(const float* w_ih0, int ld0, int S, int H, int C, float* sc
 
 // K0: gi_ctx[B,T,192] = ctx . Wc^T + b_ih0
 int tc_ctx_proj(const visde_ctx_view* ctx, int64_t B, int64_t T, int C, int H, const float* wsplit, const float* bias,
-                float* gi_ctx, cudaStream_t st) {
+                const float* rowbias, float* gi_ctx, cudaStream_t st) {
   CUtensorMap mA, mBh, mBl;
   const int64_t dA[3] = {C, T, B}, sA[2] = {ctx->time_stride, ctx->batch_stride};
   const int boxA[3] = {32, 128, 1};
@@ -593,6 +539,7 @@ int tc_ctx_proj(const visde_ctx_view* ctx, int64_t B, int64_t T, int C, int H, c
   a.num_kblocks = C / 32;
   a.n0 = 0;
   a.bias = bias;
+  a.rowbias = rowbias;
   a.out = gi_ctx;
   a.out_bstride = T * (int64_t)(3 * H);
   a.out_tstride = 3 * H;
