@@ -63,13 +63,22 @@ int check_dims(const visde_dims* d) {
 struct StashLayout {
   size_t h_floats, raw_floats;
 };
+// B rounded up to the 128-trajectory tile of the tensor-core recurrence (its stash / gi_ctx layouts are tiled)
+size_t padded_B(const visde_dims* d) { return ((size_t)d->B + 127) / 128 * 128; }
+
 StashLayout stash_layout(const visde_dims* d) {
-  size_t bt = (size_t)d->B * d->T;
-  return {bt * d->NL * kStashSlots * d->H, bt * (size_t)(d->S * (d->S + 1) / 2)};
+  return {padded_B(d) * d->T * d->NL * kStashSlots * d->H, (size_t)d->B * d->T * (size_t)(d->S * (d->S + 1) / 2)};
+}
+
+// dims-only version of use_tc_rec (workspace sizing; the run-time decision also looks at the context view)
+bool tc_rec_possible(const visde_dims* d) {
+  const int fam = d->variant & 0xff;
+  return (fam == VISDE_VARIANT_TC || (fam == VISDE_VARIANT_AUTO && d->B >= 1024)) && d->H == 64 && d->NL <= 2 &&
+         d->S <= 4 && (d->C == 128 || d->C == 256) && !(d->variant & VISDE_FLAG_NO_TENSOR_CORES);
 }
 
 struct BwdWs {
-  size_t dg, dout, sdg, partials, wsplit, cta_part, total, partial_floats;
+  size_t dg, dout, sdg, partials, wsplit, cta_part, stash_std, total, partial_floats;
 };
 BwdWs bwd_ws(const visde_dims* d) {
   BwdWs w{};
@@ -100,6 +109,8 @@ BwdWs bwd_ws(const visde_dims* d) {
   off += align_up(sizeof(float) * tc_weight_scratch_floats(d->H, d->C));
   w.cta_part = off;
   off += align_up(sizeof(float) * fast_partials_floats(d->NL, d->H, d->S));
+  w.stash_std = off;  // per-trajectory copy of a tiled stash for the kernels that read [B, T, NL, 5, H]
+  if (tc_rec_possible(d)) off += align_up(sizeof(float) * (size_t)d->B * d->T * d->NL * kStashSlots * d->H);
   w.total = off;
   return w;
 }
@@ -142,16 +153,13 @@ bool use_tc(const visde_dims* d, const visde_ctx_view* ctx) {
 
 // tensor-core recurrence: explicit request, or AUTO once the batch is large enough that 128-trajectory tiles
 // beat the fp32 SIMT families (needs the tcgen05 K0, which folds the per-trajectory constants into gi_ctx)
-constexpr int64_t kTcRecMinBatch = 1024;
 bool use_tc_rec(const visde_dims* d, const PathParams& p, const visde_ctx_view* ctx) {
-  const int fam = d->variant & 0xff;
-  if (fam != VISDE_VARIANT_TC && !(fam == VISDE_VARIANT_AUTO && d->B >= kTcRecMinBatch)) return false;
-  return tc_rec_supported(p) && use_tc(d, ctx);
+  return tc_rec_possible(d) && tc_rec_supported(p) && use_tc(d, ctx);
 }
 
-size_t fwd_gi_bytes(const visde_dims* d) { return align_up(sizeof(float) * (size_t)d->B * d->T * 3 * d->H); }
+size_t fwd_gi_bytes(const visde_dims* d) { return align_up(sizeof(float) * padded_B(d) * d->T * 3 * d->H); }
 size_t fwd_wsplit_bytes(const visde_dims* d) { return align_up(sizeof(float) * tc_weight_scratch_floats(d->H, d->C)); }
-size_t fwd_gth_bytes(const visde_dims* d) { return align_up(sizeof(float) * (size_t)d->B * 3 * d->H); }
+size_t fwd_gth_bytes(const visde_dims* d) { return align_up(sizeof(float) * padded_B(d) * 3 * d->H); }
 
 bool use_fast(const visde_dims* d, const PathParams& p) {
   if ((d->variant & 0xff) == VISDE_VARIANT_GENERIC) return false;
@@ -248,9 +256,9 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
         float* gth = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + fwd_gi_bytes(d) + fwd_wsplit_bytes(d));
         rc = launch_gth(p, gth, st);
         if (rc) return rc;
-        rc = tc_ctx_proj(ctx, d->B, d->T, d->C, d->H, wsplit, nullptr, gth, gi, st);
+        rc = tc_ctx_proj(ctx, d->B, d->T, d->C, d->H, wsplit, nullptr, gth, gi, true, st);
       } else {
-        rc = tc_ctx_proj(ctx, d->B, d->T, d->C, d->H, wsplit, w->b_ih[0], nullptr, gi, st);
+        rc = tc_ctx_proj(ctx, d->B, d->T, d->C, d->H, wsplit, w->b_ih[0], nullptr, gi, false, st);
       }
     } else {
       RowSrc A{ctx->ptr, ctx->batch_stride, ctx->time_stride, 0, d->C, ctx->dtype};
@@ -311,6 +319,14 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
   p.dout = reinterpret_cast<float*>(wsb + ws.dout);
   p.sdg = reinterpret_cast<float*>(wsb + ws.sdg);
   p.paths = const_cast<float*>(paths);
+  if (d->T > 0 && use_tc_rec(d, p, ctx)) {
+    // the tensor-core forward wrote the stash row-fastest tiled; the kernels below read per-trajectory rows
+    float* std_stash = reinterpret_cast<float*>(wsb + ws.stash_std);
+    StageTimer tmu(VISDE_STAGE_K2_PATH_BWD, 1, st);
+    rc = launch_untile(p.stash, std_stash, d->B, d->T, d->NL * kStashSlots * d->H, st);
+    if (rc) return rc;
+    p.stash = std_stash;
+  }
   const bool fastk = use_fast(d, p);
   p.cta_part = fastk ? reinterpret_cast<float*>(wsb + ws.cta_part) : nullptr;
   float* partials = reinterpret_cast<float*>(wsb + ws.partials);

@@ -116,7 +116,9 @@ int launch_path_fwd_tiled(const PathParams& p, int NB, cudaStream_t st);
 // tensor-core recurrence family for large batches (path_tc.cu): 128 trajectories per CTA, tcgen05 gate GEMMs
 bool tc_rec_supported(const PathParams& p);
 int launch_gth(const PathParams& p, float* gth, cudaStream_t st);  // per-trajectory constant part of the layer-0 gates
-int launch_path_fwd_tc(const PathParams& p, cudaStream_t st);      // expects gi_ctx to already include gth
+int launch_path_fwd_tc(const PathParams& p, cudaStream_t st);      // expects tiled gi_ctx that already includes gth
+// [ceil(B/128)][T][F][128] row-fastest -> [B][T][F]
+int launch_untile(const float* in, float* out, int64_t B, int64_t T, int F, cudaStream_t st);
 size_t fast_partials_floats(int NL, int H, int S);
 // biases, dW_ih_l0[:, :S], dW_out, db_out from the per-CTA partials written by path_bwd_fast
 int launch_fast_partials_reduce(const PathParams& p, const visde_weight_grads* gw, cudaStream_t st);
@@ -158,9 +160,10 @@ bool tc_supported(int H, int NL, int C, const visde_ctx_view* ctx);
 size_t tc_weight_scratch_floats(int H, int C);
 size_t tc_wgrad_partial_floats(int NL, int C);
 int tc_split_weights(const float* w_ih0, int ld0, int S, int H, int C, float* scratch, cudaStream_t st);
-// bias: per-column [3H] or nullptr; rowbias: per-trajectory [B,3H] or nullptr (both are added)
+// bias: per-column [3H] or nullptr.  tiled: row tiles are 128 trajectories at one grid step and gi_ctx is written
+// row-fastest, [ceil(B/128)][T][3H][128] (+ rowbias_tiled [ceil(B/128)][3H][128] per trajectory), for path_tc.cu
 int tc_ctx_proj(const visde_ctx_view* ctx, int64_t B, int64_t T, int C, int H, const float* wsplit, const float* bias,
-                const float* rowbias, float* gi_ctx, cudaStream_t st);
+                const float* rowbias_tiled, float* gi_ctx, bool tiled, cudaStream_t st);
 int tc_grad_ctx(const float* dg, int64_t dg_row, int64_t B, int64_t T, int C, int H, const float* wsplit,
                 const visde_ctx_grad_view* out, cudaStream_t st);
 int tc_wgrads(const visde_ctx_view* ctx, const float* dg, const float* stash, int64_t B, int64_t T, int S, int C, int P,

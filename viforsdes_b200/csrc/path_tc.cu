@@ -295,20 +295,22 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
       for (int k = 0; k < NL; ++k)
 #pragma unroll
         for (int j = 0; j < kUPT; ++j) hprev[k][j] = 0.f;
-      const float* gi_p = p.gi_ctx + b * T * 192 + u0;  // this thread's 32 units of gate r; u at +64, n at +128
-      float* st_p = p.stash ? p.stash + b * T * (int64_t)(NL * kStashSlots * 64) + u0 : nullptr;
+      // row-fastest tiled layouts (one coalesced 128-byte line per warp access):
+      //   gi_ctx [tile][t][3H][128], stash [tile][t][NL][5][H][128]
+      const float* gi_p = p.gi_ctx + tile * T * (int64_t)(192 * kTileRows) + (int64_t)u0 * kTileRows + row;
+      float* st_p = p.stash ? p.stash + tile * T * (int64_t)(NL * kStashSlots * 64 * kTileRows) + (int64_t)u0 * kTileRows + row
+                            : nullptr;
       const float* eps_p = p.eps + b * T * S;
       float* paths_o = p.paths + (b * (T + 1) + 1) * S;
       float* means_o = p.means + b * T * S;
       float* chol_o = p.chol + b * T * S * S;
       float* raw_o = p.raw ? p.raw + b * T * NTRIL : nullptr;
 
-      float4 gnx[3][2];  // next 8-unit chunk of gi_ctx (r, u, n)
+      float gnx[3][8];  // next 8-unit chunk of gi_ctx (r, u, n)
 #pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        gnx[g][0] = *reinterpret_cast<const float4*>(gi_p + g * 64);
-        gnx[g][1] = *reinterpret_cast<const float4*>(gi_p + g * 64 + 4);
-      }
+      for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) gnx[g][q] = gi_p[(g * 64 + q) * kTileRows];
 
       for (int64_t t = 0; t < T; ++t) {
         const bool has_next = t + 1 < T;
@@ -325,27 +327,24 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
           tmem_ld8_nowait(tl + D0_COL + 128 + j0, dn);
           float gcur[3][8];
 #pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            gcur[g][0] = gnx[g][0].x; gcur[g][1] = gnx[g][0].y; gcur[g][2] = gnx[g][0].z; gcur[g][3] = gnx[g][0].w;
-            gcur[g][4] = gnx[g][1].x; gcur[g][5] = gnx[g][1].y; gcur[g][6] = gnx[g][1].z; gcur[g][7] = gnx[g][1].w;
-          }
+          for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) gcur[g][q] = gnx[g][q];
           // prefetch the next chunk (of this step, or chunk 0 of the next step)
           {
             const bool last = c == kUPT / 8 - 1;
-            const float* nx = last ? gi_p + 192 : gi_p + (c + 1) * 8;
+            const float* nx = last ? gi_p + 192 * kTileRows : gi_p + (c + 1) * 8 * kTileRows;
             if (!last || has_next) {
 #pragma unroll
-              for (int g = 0; g < 3; ++g) {
-                gnx[g][0] = *reinterpret_cast<const float4*>(nx + g * 64);
-                gnx[g][1] = *reinterpret_cast<const float4*>(nx + g * 64 + 4);
-              }
+              for (int g = 0; g < 3; ++g)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) gnx[g][q] = nx[(g * 64 + q) * kTileRows];
             }
           }
           tmem_ld_wait();
           float hx[8];
 #pragma unroll
           for (int h4 = 0; h4 < 2; ++h4) {
-            float sr[4], su[4], sn[4], snh[4], sh[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int jj = h4 * 4 + q, j = j0 + jj;
@@ -371,15 +370,14 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
               const float hn = fmaf(u, hprev[0][c * 8 + jj] - n, n);
               hprev[0][c * 8 + jj] = hn;
               hx[jj] = hn * hs;
-              sr[q] = r; su[q] = u; sn[q] = n; snh[q] = pnh; sh[q] = hn;
-            }
-            if (st_p && ok) {
-              float* st = st_p + c * 8 + h4 * 4;
-              *reinterpret_cast<float4*>(st + kStashR * 64) = make_float4(sr[0], sr[1], sr[2], sr[3]);
-              *reinterpret_cast<float4*>(st + kStashU * 64) = make_float4(su[0], su[1], su[2], su[3]);
-              *reinterpret_cast<float4*>(st + kStashN * 64) = make_float4(sn[0], sn[1], sn[2], sn[3]);
-              *reinterpret_cast<float4*>(st + kStashNhh * 64) = make_float4(snh[0], snh[1], snh[2], snh[3]);
-              *reinterpret_cast<float4*>(st + kStashH * 64) = make_float4(sh[0], sh[1], sh[2], sh[3]);
+              if (st_p) {
+                float* st = st_p + (c * 8 + jj) * kTileRows;
+                st[kStashR * 64 * kTileRows] = r;
+                st[kStashU * 64 * kTileRows] = u;
+                st[kStashN * 64 * kTileRows] = n;
+                st[kStashNhh * 64 * kTileRows] = pnh;
+                st[kStashH * 64 * kTileRows] = hn;
+              }
             }
           }
           uint4 hi, lo;
@@ -391,7 +389,7 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(&bars->a0);
-        gi_p += 192;
+        gi_p += 192 * kTileRows;
 
         // ---------------- layer 1 ----------------
         if (NL == 2) {
@@ -410,7 +408,6 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
             float hx[8];
 #pragma unroll
             for (int h4 = 0; h4 < 2; ++h4) {
-              float sr[4], su[4], sn[4], snh[4], sh[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const int jj = h4 * 4 + q, j = j0 + jj;
@@ -425,15 +422,14 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
                 const float hn = fmaf(u, hprev[NL - 1][c * 8 + jj] - n, n);
                 hprev[NL - 1][c * 8 + jj] = hn;
                 hx[jj] = hn * hs;
-                sr[q] = r; su[q] = u; sn[q] = n; snh[q] = pnh; sh[q] = hn;
-              }
-              if (st_p && ok) {
-                float* st = st_p + kStashSlots * 64 + c * 8 + h4 * 4;
-                *reinterpret_cast<float4*>(st + kStashR * 64) = make_float4(sr[0], sr[1], sr[2], sr[3]);
-                *reinterpret_cast<float4*>(st + kStashU * 64) = make_float4(su[0], su[1], su[2], su[3]);
-                *reinterpret_cast<float4*>(st + kStashN * 64) = make_float4(sn[0], sn[1], sn[2], sn[3]);
-                *reinterpret_cast<float4*>(st + kStashNhh * 64) = make_float4(snh[0], snh[1], snh[2], snh[3]);
-                *reinterpret_cast<float4*>(st + kStashH * 64) = make_float4(sh[0], sh[1], sh[2], sh[3]);
+                if (st_p) {
+                  float* st = st_p + (kStashSlots * 64 + c * 8 + jj) * kTileRows;
+                  st[kStashR * 64 * kTileRows] = r;
+                  st[kStashU * 64 * kTileRows] = u;
+                  st[kStashN * 64 * kTileRows] = n;
+                  st[kStashNhh * 64 * kTileRows] = pnh;
+                  st[kStashH * 64 * kTileRows] = hn;
+                }
               }
             }
             uint4 hi, lo;
@@ -446,7 +442,7 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
           tc_fence_before();
           mbar_arrive(&bars->a1);
         }
-        if (st_p) st_p += NL * kStashSlots * 64;
+        if (st_p) st_p += NL * kStashSlots * 64 * kTileRows;
 
         // ---------------- output projection + reparameterised Euler-Maruyama update ----------------
         float eps_nxt[S];
@@ -510,18 +506,40 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
 }
 
 // gth[b, n] = b_ih_l0[n] + (n < 2H ? b_hh_l0[n] : 0) + sum_p theta[b, p] W_ih_l0[n, S + C + p]: the part of the
-// layer-0 pre-activations that is constant along a trajectory; K0 adds it to gi_ctx as a per-row bias
+// layer-0 pre-activations that is constant along a trajectory; K0 adds it to gi_ctx as a per-row bias.
+// Row-fastest tiled layout [ceil(B/128)][3H][128]; pad rows are zero.
 __global__ void gth_kernel(const float* __restrict__ theta, const float* __restrict__ w_ih0, const float* __restrict__ b_ih0,
                            const float* __restrict__ b_hh0, int64_t B, int S, int C, int P, int H, float* __restrict__ gth) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int G = 3 * H;
-  if (idx >= B * G) return;
-  const int64_t b = idx / G;
-  const int n = (int)(idx % G);
-  float v = b_ih0[n] + (n < 2 * H ? b_hh0[n] : 0.f);
-  const float* w = w_ih0 + (int64_t)n * (S + C + P) + S + C;
-  for (int q = 0; q < P; ++q) v = fmaf(theta[b * P + q], w[q], v);
+  const int64_t ntile = (B + kTileRows - 1) / kTileRows;
+  if (idx >= ntile * G * kTileRows) return;
+  const int r = (int)(idx % kTileRows);
+  const int n = (int)((idx / kTileRows) % G);
+  const int64_t b = (idx / ((int64_t)kTileRows * G)) * kTileRows + r;
+  float v = 0.f;
+  if (b < B) {
+    v = b_ih0[n] + (n < 2 * H ? b_hh0[n] : 0.f);
+    const float* w = w_ih0 + (int64_t)n * (S + C + P) + S + C;
+    for (int q = 0; q < P; ++q) v = fmaf(theta[b * P + q], w[q], v);
+  }
   gth[idx] = v;
+}
+
+// out[b][t][f] = in[tile][t][f][row]: row-fastest tiled -> per-trajectory rows (bridge to the kernels that still
+// read the [B, T, F] layouts)
+__global__ void untile_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t B, int64_t T, int F) {
+  __shared__ float tile[32][kTileRows + 1];
+  const int f0 = blockIdx.x * 32;
+  const int64_t t = blockIdx.y, tb = blockIdx.z;
+  const float* src = in + ((tb * T + t) * F + f0) * (int64_t)kTileRows;
+  for (int idx = threadIdx.x; idx < 32 * kTileRows; idx += blockDim.x) tile[idx / kTileRows][idx % kTileRows] = src[idx];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * kTileRows; idx += blockDim.x) {
+    const int r = idx / 32, f = idx % 32;
+    const int64_t b = tb * kTileRows + r;
+    if (b < B && f0 + f < F) out[(b * T + t) * F + f0 + f] = tile[f][r];
+  }
 }
 
 template <int NL, int S>
@@ -561,8 +579,19 @@ bool tc_rec_supported(const PathParams& p) {
 }
 
 int launch_gth(const PathParams& p, float* gth, cudaStream_t st) {
-  const int64_t n = p.B * 3 * p.H;
+  const int64_t n = ((p.B + kTileRows - 1) / kTileRows) * kTileRows * 3 * p.H;
   gth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.theta, p.w_ih[0], p.b_ih[0], p.b_hh[0], p.B, p.S, p.C, p.P, p.H, gth);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  return VISDE_OK;
+}
+
+int launch_untile(const float* in, float* out, int64_t B, int64_t T, int F, cudaStream_t st) {
+  if (F % 32 != 0 || T > 65535) {
+    set_error("untile: unsupported shape (F=%d, T=%lld)", F, (long long)T);
+    return VISDE_EINVAL;
+  }
+  const int64_t ntile = (B + kTileRows - 1) / kTileRows;
+  untile_kernel<<<dim3(F / 32, (unsigned)T, (unsigned)ntile), 256, 0, st>>>(in, out, B, T, F);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }

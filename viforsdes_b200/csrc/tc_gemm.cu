@@ -71,7 +71,10 @@ struct RowsArgs {
   int num_kblocks;  // K / 32
   int n0;           // first output column handled (K3 with C > 256 launches several column chunks)
   const float* bias;
-  const float* rowbias;  // [B][N] added per trajectory (K0 for the tensor-core recurrence), or nullptr
+  const float* rowbias;  // tiled mode: [ceil(B/128)][N][128] added per trajectory, or nullptr
+  int tiled;             // 1: a row tile is 128 TRAJECTORIES at one grid step t (tile = tb * T + t) and the output is
+                         // written row-fastest, out[((tb * T + t) * N + col) * 128 + row]: the layout the tensor-core
+                         // recurrence reads with one coalesced line per warp
   void* out;
   int64_t out_bstride, out_tstride;
   int out_dtype;
@@ -141,7 +144,10 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = g % NA;
           if (g >= NA) mbar_wait(&bars->emptyA[sa], ((g / NA) - 1) & 1);
           mbar_expect_tx(&bars->fullA[sa], A_BYTES);
-          tma_load_3d(smem + sa * A_BYTES, &tmA, &bars->fullA[sa], kb * 32, t0, b);
+          if (a.tiled)
+            tma_load_3d(smem + sa * A_BYTES, &tmA, &bars->fullA[sa], kb * 32, (int)(tile % a.T), (int)(tile / a.T) * 128);
+          else
+            tma_load_3d(smem + sa * A_BYTES, &tmA, &bars->fullA[sa], kb * 32, t0, b);
         }
       }
     }
@@ -223,7 +229,26 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int t = t0 + row;
       const bool row_ok = t < a.T;
       const int64_t obase = (int64_t)b * a.out_bstride + (int64_t)t * a.out_tstride + a.n0;
-      const float* rb = a.rowbias ? a.rowbias + (int64_t)b * N : nullptr;
+      if (a.tiled) {
+        // rows are trajectories tb * 128 + row at grid step t; fp32 row-fastest output, always in bounds (padded)
+        const int64_t tb = tile / a.T;
+        float* o = reinterpret_cast<float*>(a.out) + (int64_t)tile * N * 128 + row;
+        const float* rbt = a.rowbias ? a.rowbias + tb * N * 128 + row : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < N / 32; ++c) {
+          float v[32];
+          tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + acc * N + c * 32, v);
+          if (rbt) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] += rbt[(c * 32 + q) * 128];
+          }
+#pragma unroll
+          for (int q = 0; q < 32; ++q) o[(c * 32 + q) * 128] = v[q];
+        }
+        tc_fence_before();
+        mbar_arrive(&bars->tmemEmpty[acc]);
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < N / 32; ++c) {
         float v[32];
@@ -231,10 +256,6 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (a.bias) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) v[q] += a.bias[a.n0 + c * 32 + q];
-        }
-        if (rb) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] += rb[c * 32 + q];
         }
         if (row_ok) {
           if (a.out_dtype == VISDE_BF16) {
@@ -484,7 +505,7 @@ int launch_rows(const CUtensorMap& mA, const CUtensorMap& mBh, const CUtensorMap
     VISDE_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_kernel<N, B_MN, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  a.num_tiles = (int)(B * a.tiles_per_b);
+  a.num_tiles = a.tiled ? (int)(((B + 127) / 128) * a.T) : (int)(B * a.tiles_per_b);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -523,10 +544,10 @@ int tc_split_weights(const float* w_ih0, int ld0, int S, int H, int C, float* sc
 
 // K0: gi_ctx[B,T,192] = ctx . Wc^T + b_ih0
 int tc_ctx_proj(const visde_ctx_view* ctx, int64_t B, int64_t T, int C, int H, const float* wsplit, const float* bias,
-                const float* rowbias, float* gi_ctx, cudaStream_t st) {
+                const float* rowbias_tiled, float* gi_ctx, bool tiled, cudaStream_t st) {
   CUtensorMap mA, mBh, mBl;
   const int64_t dA[3] = {C, T, B}, sA[2] = {ctx->time_stride, ctx->batch_stride};
-  const int boxA[3] = {32, 128, 1};
+  const int boxA[3] = {32, tiled ? 1 : 128, tiled ? 128 : 1};
   int rc = make_map(&mA, ctx->ptr, 3, dA, sA, boxA);
   if (rc) return rc;
   const int64_t dB[2] = {C, 3 * H}, sB[1] = {C};
@@ -539,7 +560,8 @@ int tc_ctx_proj(const visde_ctx_view* ctx, int64_t B, int64_t T, int C, int H, c
   a.num_kblocks = C / 32;
   a.n0 = 0;
   a.bias = bias;
-  a.rowbias = rowbias;
+  a.rowbias = rowbias_tiled;
+  a.tiled = tiled ? 1 : 0;
   a.out = gi_ctx;
   a.out_bstride = T * (int64_t)(3 * H);
   a.out_tstride = 3 * H;
