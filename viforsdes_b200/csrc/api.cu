@@ -78,7 +78,7 @@ bool tc_rec_possible(const visde_dims* d) {
 }
 
 struct BwdWs {
-  size_t dg, dout, sdg, partials, wsplit, cta_part, stash_std, total, partial_floats;
+  size_t dg, dout, sdg, partials, wsplit, cta_part, stash_std, dg_tiled, total, partial_floats;
 };
 BwdWs bwd_ws(const visde_dims* d) {
   BwdWs w{};
@@ -111,6 +111,8 @@ BwdWs bwd_ws(const visde_dims* d) {
   off += align_up(sizeof(float) * fast_partials_floats(d->NL, d->H, d->S));
   w.stash_std = off;  // per-trajectory copy of a tiled stash for the kernels that read [B, T, NL, 5, H]
   if (tc_rec_possible(d)) off += align_up(sizeof(float) * (size_t)d->B * d->T * d->NL * kStashSlots * d->H);
+  w.dg_tiled = off;   // d_pre of the tensor-core backward, row-fastest tiled
+  if (tc_rec_possible(d)) off += align_up(sizeof(float) * padded_B(d) * d->T * d->NL * kDgSlots * d->H);
   w.total = off;
   return w;
 }
@@ -319,20 +321,28 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
   p.dout = reinterpret_cast<float*>(wsb + ws.dout);
   p.sdg = reinterpret_cast<float*>(wsb + ws.sdg);
   p.paths = const_cast<float*>(paths);
-  if (d->T > 0 && use_tc_rec(d, p, ctx)) {
-    // the tensor-core forward wrote the stash row-fastest tiled; the kernels below read per-trajectory rows
-    float* std_stash = reinterpret_cast<float*>(wsb + ws.stash_std);
-    StageTimer tmu(VISDE_STAGE_K2_PATH_BWD, 1, st);
-    rc = launch_untile(p.stash, std_stash, d->B, d->T, d->NL * kStashSlots * d->H, st);
-    if (rc) return rc;
-    p.stash = std_stash;
-  }
-  const bool fastk = use_fast(d, p);
+  const bool tcrec = d->T > 0 && use_tc_rec(d, p, ctx);
+  const bool fastk = !tcrec && use_fast(d, p);
   p.cta_part = fastk ? reinterpret_cast<float*>(wsb + ws.cta_part) : nullptr;
   float* partials = reinterpret_cast<float*>(wsb + ws.partials);
 
   // K2: reverse-time recurrence
-  {
+  if (tcrec) {
+    // tensor-core family: reads the tiled stash the forward wrote, emits d_pre tiled; the time-parallel kernels
+    // below still read per-trajectory rows, so both are converted (bridge until K3 / K4 read the tiled layouts)
+    StageTimer tm(VISDE_STAGE_K2_PATH_BWD, 4, st);
+    float* dg_std = p.dg;
+    float* std_stash = reinterpret_cast<float*>(wsb + ws.stash_std);
+    p.dg = reinterpret_cast<float*>(wsb + ws.dg_tiled);
+    rc = launch_path_bwd_tc(p, st);
+    if (rc) return rc;
+    rc = launch_untile(p.dg, dg_std, d->B, d->T, d->NL * kDgSlots * d->H, st);
+    if (rc) return rc;
+    rc = launch_untile(p.stash, std_stash, d->B, d->T, d->NL * kStashSlots * d->H, st);
+    if (rc) return rc;
+    p.dg = dg_std;
+    p.stash = std_stash;
+  } else {
     StageTimer tm(VISDE_STAGE_K2_PATH_BWD, 1, st);
     rc = fastk ? launch_path_bwd_fast(p, st) : launch_path_bwd_generic(p, st);
     if (rc) return rc;

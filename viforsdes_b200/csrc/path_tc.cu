@@ -20,53 +20,10 @@
 // written and accumulator drained), init (tile start).  The state-column and theta terms of layer 0
 // and the biases do not go through the tensor cores: theta and bias terms are folded into gi_ctx by
 // K0 (per-trajectory row bias), the S state columns are S FMAs per gate in the epilogue.
-#include <cuda_fp16.h>
-
-#include "common.cuh"
-#include "ptx.cuh"
-#include "tc.cuh"
+#include "path_tc.cuh"
 
 namespace visde {
 namespace {
-
-constexpr int kTileRows = 128;
-constexpr int kWTileBytes = 192 * 128;  // one weight tile: 192 gate rows x 64 fp16
-constexpr int kATileBytes = 128 * 128;  // one operand tile: 128 trajectories x 64 fp16
-constexpr int kOutTileBytes = 16 * 128;
-constexpr int kEpiThreads = 256, kTcRecThreads = 288;
-constexpr int kUPT = 32;    // hidden units per epilogue thread
-constexpr int kHExp = 14;   // hidden states are scaled by 2^14 before the fp16 split
-
-// instruction descriptor: D fp32, A/B fp16 K-major, M = 128
-__host__ __device__ constexpr uint32_t idesc_f16(int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-// byte offset of 16-byte chunk c (8 fp16) of row r in a K-major SWIZZLE_128B tile with 128-byte rows
-__device__ __forceinline__ uint32_t sw128(int r, int c) {
-  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-}
-// fp16 hi / lo halves of 8 (already scaled) floats, packed in K order
-__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const __half2 hh = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
-    const float2 back = __half22float2(hh);
-    const __half2 ll = __floats2half2_rn(x[2 * q] - back.x, x[2 * q + 1] - back.y);
-    h[q] = *reinterpret_cast<const uint32_t*>(&hh);
-    l[q] = *reinterpret_cast<const uint32_t*>(&ll);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-// power-of-two exponent a with amax * 2^a in [2^13, 2^14)
-__device__ __forceinline__ int scale_exp(uint32_t amax_bits) {
-  if (amax_bits == 0) return 0;
-  const int e = (int)(amax_bits >> 23) - 127;
-  const int a = 13 - e;
-  return a > 100 ? 100 : a;
-}
-__device__ __forceinline__ float exp2i(int a) { return __uint_as_float((uint32_t)(a + 127) << 23); }
 
 template <int NL, int S>
 struct TcFwdSmem {

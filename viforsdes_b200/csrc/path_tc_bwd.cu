@@ -1,0 +1,452 @@
+// Tensor-core BPTT for large batches (B >> #SM, H = 64): K2c path_bwd_tc.
+//
+// Mirror of path_tc.cu in reverse time.  A CTA owns 128 trajectories (MMA M = TMEM lanes); per layer
+// and step the gate cotangents d_pre = (d r_pre, d u_pre, d n_pre, d n_hh) [128, 4 x 64] are the A
+// operand of
+//     dhc_k  [128,64] = d_gh_k . W_hh_k      (carried to step t-1, ping-pong accumulators)
+//     dh_in0 [128,64] = d_gi_1 . W_ih_1      (handed to layer 0 of the same step)
+// issued as tcgen05.mma kind::f16 (M = 128, N = 64, K = 16 per instruction) from shared-memory tiles,
+// with the same fp16 hi/lo 3-pass split as the forward.  Gradients have no fixed range, so every
+// trajectory row is scaled by its own power of two per layer-step, 2^e with max|dh| 2^e in
+// [2^9, 2^10): the two epilogue threads of a row agree on it through a 64-thread named barrier, and
+// the accumulator is read back with 2^-(e + a_w).  d_pre is produced in chunks of 16 hidden units
+// (a 2-slot ring of [128 x 64] fp16 hi/lo tiles: 4 K-groups = the 4 slots of the chunk's units), so
+// the MMAs of chunk c run while the epilogue computes chunk c+1 and the A operand never needs more
+// than 64 KB next to the 144 KB of resident transposed weights.  The direct term dh * u of the GRU
+// cell is parked in TMEM next to the accumulators (tcgen05.st) instead of registers.
+//
+// Inputs / outputs use the row-fastest tiled layouts of the forward: stash [tile][t][NL][5][H][128]
+// is read with one coalesced line per warp access, d_pre is written as dg [tile][t][NL][4][H][128].
+// The reductions over (b, t) (biases, state columns of W_ih_l0, W_out, sum_t d_gi for theta) are
+// left to the time-parallel kernels that read dg.
+#include "path_tc.cuh"
+
+namespace visde {
+namespace {
+
+constexpr int kRowExp = 9;  // rows are scaled so that max|dh| 2^e is in [2^9, 2^10)
+
+template <int NL, int S>
+struct TcBwdSmem {
+  static constexpr int NMAT = 2 * NL - 1;  // W_hh_l0^T, W_ih_l1^T, W_hh_l1^T
+  static constexpr int CZ = (3 * S <= 4) ? 4 : (3 * S <= 8 ? 8 : 12);
+  static constexpr int OFF_W = 0;                               // [NMAT][hi, lo][3 K-blocks][64][128 B]
+  static constexpr int OFF_A = OFF_W + NMAT * 2 * kWTileBytes;  // ring [2][hi, lo][128][128 B]
+  static constexpr int OFF_WOUT = OFF_A + 4 * kATileBytes;      // float [64][16]: W_out[m][i] at [i][m]
+  static constexpr int OFF_WZ = OFF_WOUT + 64 * 16 * 4;         // float [64][CZ]: W_ih_l0[g*64+i][s] at [i][g*S+s]
+  static constexpr int OFF_MAX = OFF_WZ + 64 * CZ * 4;          // float [2 buffers][2 cg][128]
+  static constexpr int OFF_DZX = OFF_MAX + 2 * 2 * 128 * 4;     // float [2 cg][128][S]
+  static constexpr int OFF_BAR = OFF_DZX + 2 * 128 * S * 4;
+  struct Bars {
+    uint64_t full[2], empty[2], in0, done;
+    uint32_t tmem_base;
+    uint32_t amax;
+  };
+  static constexpr size_t bytes = OFF_BAR + sizeof(Bars) + 1024;
+};
+
+__device__ __forceinline__ int row_exp(float mx) {
+  const uint32_t bits = __float_as_uint(mx);
+  if (bits == 0u) return 0;
+  int e = kRowExp - ((int)(bits >> 23) - 127);
+  e = e > 100 ? 100 : e;
+  return e < -100 ? -100 : e;
+}
+
+template <int NL, int S>
+__global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParams p) {
+  using L = TcBwdSmem<NL, S>;
+  constexpr int NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL, CZ = L::CZ, NMAT = L::NMAT;
+  static_assert(NOUT <= 16, "W_out columns are staged as 16 floats per unit");
+  constexpr uint32_t TMEM_COLS = NL == 2 ? 512 : 256;
+  // accumulators: dhc_k ping-pong [k][parity] (64 columns each), dh_in0; then the parked direct terms
+  constexpr uint32_t IN0_COL = NL == 2 ? 256 : 0, DIR_COL = NL == 2 ? 320 : 128;
+  constexpr int SLOT_BYTES = 2 * kATileBytes;
+  extern __shared__ __align__(1024) uint8_t smem_raw_tcb[];
+  uint8_t* smem = smem_raw_tcb + ((1024u - (smem_u32(smem_raw_tcb) & 1023u)) & 1023u);
+  typename L::Bars* bars = reinterpret_cast<typename L::Bars*>(smem + L::OFF_BAR);
+  float* woutc = reinterpret_cast<float*>(smem + L::OFF_WOUT);
+  float* wzc = reinterpret_cast<float*>(smem + L::OFF_WZ);
+  float* maxb = reinterpret_cast<float*>(smem + L::OFF_MAX);
+  float* dzx = reinterpret_cast<float*>(smem + L::OFF_DZX);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ld0 = S + p.C + p.P;
+  const int T = (int)p.T;
+
+  // ---- weight scaling exponent (shared by the three matrices: their products meet in dh)
+  if (tid == 0) bars->amax = 0u;
+  __syncthreads();
+  {
+    float mx = 0.f;
+    for (int m = 0; m < NMAT; ++m) {
+      const float* src = m == 0 ? p.w_hh[0] : (m == 1 ? p.w_ih[1] : p.w_hh[1]);
+      for (int idx = tid; idx < 192 * 64; idx += kTcRecThreads) mx = fmaxf(mx, fabsf(src[idx]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) atomicMax(&bars->amax, __float_as_uint(mx));
+  }
+  __syncthreads();
+  const int ew = scale_exp(bars->amax);
+  const float w_scale = exp2i(ew);
+
+  // ---- resident transposed weight tiles.  B operand rows = input / hidden index i (N = 64); K runs over
+  // (chunk c of 16 units, gate g, unit in chunk): K-group gB = c * 3 + g sits in K-block gB / 4 at byte
+  // column (gB % 4) * 32 of the 128-byte swizzled row
+  for (int m = 0; m < NMAT; ++m) {
+    const float* src = m == 0 ? p.w_hh[0] : (m == 1 ? p.w_ih[1] : p.w_hh[1]);
+    uint8_t* thi = smem + L::OFF_W + (m * 2) * kWTileBytes;
+    uint8_t* tlo = thi + kWTileBytes;
+    for (int idx = tid; idx < 64 * 24; idx += kTcRecThreads) {
+      const int i = idx & 63, hg = idx >> 6;  // hg = gB * 2 + half
+      const int gB = hg >> 1, half = hg & 1, c = gB / 3, g = gB % 3;
+      float x[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) x[q] = src[(g * 64 + c * 16 + half * 8 + q) * 64 + i] * w_scale;
+      uint4 hi, lo;
+      split8(x, hi, lo);
+      const uint32_t off = (uint32_t)(gB >> 2) * 8192u + sw128(i, (gB & 3) * 2 + half);
+      *reinterpret_cast<uint4*>(thi + off) = hi;
+      *reinterpret_cast<uint4*>(tlo + off) = lo;
+    }
+  }
+  for (int idx = tid; idx < 64 * 16; idx += kTcRecThreads) {
+    const int i = idx >> 4, m = idx & 15;
+    woutc[idx] = m < NOUT ? p.out_w[m * 64 + i] : 0.f;
+  }
+  for (int idx = tid; idx < 64 * CZ; idx += kTcRecThreads) {
+    const int i = idx / CZ, q = idx % CZ;
+    wzc[idx] = q < 3 * S ? p.w_ih[0][(int64_t)((q / S) * 64 + i) * ld0 + (q % S)] : 0.f;
+  }
+  if (tid == 0) {
+    mbar_init(&bars->full[0], kEpiThreads);
+    mbar_init(&bars->full[1], kEpiThreads);
+    mbar_init(&bars->empty[0], 1);
+    mbar_init(&bars->empty[1], 1);
+    mbar_init(&bars->in0, 1);
+    mbar_init(&bars->done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const int64_t ntiles = (p.B + kTileRows - 1) / kTileRows;
+
+  if (warp == 8) {
+    // ======================= MMA issuer ==========================================================
+    if (lane == 0) {
+      const uint32_t w0 = smem_u32(smem + L::OFF_W), a0 = smem_u32(smem + L::OFF_A);
+      constexpr uint32_t ID64 = idesc_f16(64);
+      // 9 MMAs: acc[128,64] (+)= A_chunk[slots] . W^T[K-groups of chunk c]
+      auto issue = [&](uint32_t acc, uint32_t slot_base, int m, int c, bool n_is_nh, bool fresh) {
+        const uint32_t a_hi = slot_base, a_lo = slot_base + kATileBytes;
+        const uint32_t b_hi = w0 + (uint32_t)(m * 2) * kWTileBytes, b_lo = b_hi + kWTileBytes;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const int aslot = g < 2 ? g : (n_is_nh ? 3 : 2);
+          const int gB = c * 3 + g;
+          const uint32_t boff = (uint32_t)(gB >> 2) * 8192u + (uint32_t)(gB & 3) * 32u;
+          const uint64_t dah = umma_desc(a_hi + aslot * 32, 16, 1024, 2), dal = umma_desc(a_lo + aslot * 32, 16, 1024, 2);
+          const uint64_t dbh = umma_desc(b_hi + boff, 16, 1024, 2), dbl = umma_desc(b_lo + boff, 16, 1024, 2);
+          umma_f16(acc, dal, dbh, ID64, (fresh && g == 0) ? 0u : 1u);
+          umma_f16(acc, dah, dbl, ID64, 1u);
+          umma_f16(acc, dah, dbh, ID64, 1u);
+        }
+      };
+      uint32_t gc = 0;  // chunks consumed so far (ring position / phases)
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int t = T - 1; t >= 0; --t) {
+          const uint32_t wpar = (uint32_t)((t & 1) ^ 1);  // accumulators written at step t are read at step t-1
+#pragma unroll
+          for (int k = NL - 1; k >= 0; --k) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c, ++gc) {
+              const uint32_t slot = gc & 1;
+              mbar_wait(&bars->full[slot], (gc >> 1) & 1);
+              tc_fence_after();
+              const uint32_t sb = a0 + slot * SLOT_BYTES;
+              if (t > 0) issue(tmem + (uint32_t)(k * 2 + wpar) * 64, sb, k == 0 ? 0 : 2, c, true, c == 0);
+              if (NL == 2 && k == 1) issue(tmem + IN0_COL, sb, 1, c, false, c == 0);
+              umma_commit(&bars->empty[slot]);
+            }
+            if (NL == 2 && k == 1) umma_commit(&bars->in0);
+          }
+        }
+      }
+      umma_commit(&bars->done);
+      mbar_wait(&bars->done, 0);
+    }
+    __syncwarp();
+  } else {
+    // ======================= gate-cotangent epilogue =============================================
+    const int quad = warp & 3, cg = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
+    uint8_t* a_ring = smem + L::OFF_A;
+    uint32_t gc = 0, ph_in0 = 0, xb = 0;
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t b_raw = tile * kTileRows + row;
+      const bool ok = b_raw < p.B;
+      const float okf = ok ? 1.f : 0.f;
+      const int64_t b = ok ? b_raw : p.B - 1;
+      const float* st_tile = p.stash + tile * T * (int64_t)(NL * kStashSlots * 64 * kTileRows) + row;
+      float* dg_tile = p.dg + tile * T * (int64_t)(NL * kDgSlots * 64 * kTileRows) + row;
+      const float* gp_p = p.g_paths + b * (T + 1) * S;
+      const float* gm_p = p.g_means + b * (int64_t)T * S;
+      const float* ep_p = p.eps + b * (int64_t)T * S;
+      const float* raw_p = p.raw + b * (int64_t)T * NTRIL;
+      const float* gl_p = p.g_chol + b * (int64_t)T * S * S;
+
+      float dz[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) dz[s] = 0.f;
+      float sc_prev[NL];  // 2^-(e + a_w) of the row scale used by step t+1 (per layer)
+#pragma unroll
+      for (int k = 0; k < NL; ++k) sc_prev[k] = 0.f;
+
+      for (int t = T - 1; t >= 0; --t) {
+        const bool first = t == T - 1;
+        const uint32_t rpar = (uint32_t)(t & 1);
+        // ---- cotangent of z_{t+1}: both threads of a row add the two partial sums in the same order
+        if (!first) {
+          named_bar_sync(1 + quad, 64);
+#pragma unroll
+          for (int s = 0; s < S; ++s) dz[s] += dzx[(0 * 128 + row) * S + s] + dzx[(1 * 128 + row) * S + s];
+        }
+        // ---- cotangent of the output projection (kernels/backward.py:300-334)
+        float dout[NOUT];
+        {
+          float gP[S], gM[S], ev[S], rd[S], gL[S * S];
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            gP[s] = gp_p[(t + 1) * S + s] * okf;
+            gM[s] = gm_p[t * S + s] * okf;
+            ev[s] = ep_p[t * S + s];
+            rd[s] = raw_p[t * NTRIL + s * (s + 1) / 2 + s];
+          }
+#pragma unroll
+          for (int q = 0; q < S * S; ++q) gL[q] = gl_p[t * S * S + q] * okf;
+#pragma unroll
+          for (int s = 0; s < S; ++s) dz[s] += gP[s];
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            dout[s] = fmaf(dz[s], p.dt, gM[s]);
+#pragma unroll
+            for (int j = 0; j <= s; ++j) {
+              float d = fmaf(dz[s] * ev[j], p.sqrt_dt, gL[s * S + j]);
+              if (j == s) d = (rd[s] >= VISDE_DIAG_MIN || d < 0.f) ? d : 0.f;  // primitives/bounds.py:20
+              dout[S + s * (s + 1) / 2 + j] = d;
+            }
+          }
+          if (ok && cg == 0) {
+            float* o = p.dout + (b * T + t) * NOUT;
+#pragma unroll
+            for (int m = 0; m < NOUT; ++m) o[m] = dout[m];
+          }
+        }
+        float dzp[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) dzp[s] = 0.f;
+        float sc_in = 0.f;  // scale of dh_in0 (written by layer 1 of this step)
+
+#pragma unroll
+        for (int k = NL - 1; k >= 0; --k) {
+          if (NL == 2 && k == 0) {
+            mbar_wait(&bars->in0, ph_in0);
+            ph_in0 ^= 1;
+            tc_fence_after();
+          }
+          if (NL == 1 && !first) {
+            // dhc_0 of the previous step comes from its last chunk's MMAs (with two layers the ring waits of
+            // layer 1 already cover them)
+            mbar_wait(&bars->empty[(gc - 1) & 1], ((gc - 1) >> 1) & 1);
+            tc_fence_after();
+          }
+          // ---------- pass 1: dh of this thread's 32 units, row maximum ----------
+          float dh[kUPT];
+          float mx = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int j0 = c * 16 + cg * 8;
+            uint32_t va[8], vd[8], vi[8];
+            if (!first) {
+              tmem_ld8_nowait(tl + (uint32_t)(k * 2 + rpar) * 64 + j0, va);
+              tmem_ld8_nowait(tl + DIR_COL + (uint32_t)k * 64 + j0, vd);
+            }
+            if (NL == 2 && k == 0) tmem_ld8_nowait(tl + IN0_COL + j0, vi);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float v = first ? 0.f : fmaf(sc_prev[k], __uint_as_float(va[q]), __uint_as_float(vd[q]));
+              if (NL == 2 && k == 0) v = fmaf(sc_in, __uint_as_float(vi[q]), v);
+              if (k == NL - 1) {
+                const float* wc = woutc + (j0 + q) * 16;
+#pragma unroll
+                for (int m4 = 0; m4 < (NOUT + 3) / 4; ++m4) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(wc + 4 * m4);
+                  v = fmaf(w4.x, dout[4 * m4], v);
+                  if (4 * m4 + 1 < NOUT) v = fmaf(w4.y, dout[4 * m4 + 1 < NOUT ? 4 * m4 + 1 : 0], v);
+                  if (4 * m4 + 2 < NOUT) v = fmaf(w4.z, dout[4 * m4 + 2 < NOUT ? 4 * m4 + 2 : 0], v);
+                  if (4 * m4 + 3 < NOUT) v = fmaf(w4.w, dout[4 * m4 + 3 < NOUT ? 4 * m4 + 3 : 0], v);
+                }
+              }
+              dh[c * 8 + q] = v;
+              mx = fmaxf(mx, fabsf(v));
+            }
+          }
+          // ---------- the two threads of the row agree on the power-of-two scale ----------
+          maxb[(xb * 2 + cg) * 128 + row] = mx;
+          named_bar_sync(1 + quad, 64);
+          mx = fmaxf(mx, maxb[(xb * 2 + (cg ^ 1)) * 128 + row]);
+          xb ^= 1;
+          const int er = row_exp(mx);
+          const float rs = exp2i(er);
+          const float sc_this = exp2i(-(er + ew));
+
+          // ---------- pass 2: gate cotangents, dg, direct term, A-operand chunks ----------
+          const float* st_k = st_tile + ((int64_t)t * NL + k) * (kStashSlots * 64 * kTileRows);
+          const float* hp_k = st_k - (int64_t)NL * (kStashSlots * 64 * kTileRows) + kStashH * 64 * kTileRows;  // step t-1
+          float* dg_k = dg_tile + ((int64_t)t * NL + k) * (kDgSlots * 64 * kTileRows);
+#pragma unroll
+          for (int c = 0; c < 4; ++c, ++gc) {
+            const int j0 = c * 16 + cg * 8;
+            float dr_[8], du_[8], dn_[8], dnh_[8];
+            uint32_t dirv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int i = j0 + q;
+              const float r = st_k[(kStashR * 64 + i) * kTileRows];
+              const float u = st_k[(kStashU * 64 + i) * kTileRows];
+              const float n = st_k[(kStashN * 64 + i) * kTileRows];
+              const float nhh = st_k[(kStashNhh * 64 + i) * kTileRows];
+              const float hp = t > 0 ? hp_k[i * kTileRows] : 0.f;
+              const float dhv = dh[c * 8 + q];
+              const float dnp = dhv * (1.f - u) * (1.f - n * n);
+              const float dup = dhv * (hp - n) * u * (1.f - u);
+              const float drp = dnp * nhh * r * (1.f - r);
+              const float dnh = dnp * r;
+              dirv[q] = __float_as_uint(dhv * u);
+              dg_k[(0 * 64 + i) * kTileRows] = drp;
+              dg_k[(1 * 64 + i) * kTileRows] = dup;
+              dg_k[(2 * 64 + i) * kTileRows] = dnp;
+              dg_k[(3 * 64 + i) * kTileRows] = dnh;
+              if (k == 0) {
+                const float* wz = wzc + i * CZ;
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                  dzp[s] = fmaf(wz[s], drp, fmaf(wz[S + s], dup, fmaf(wz[2 * S + s], dnp, dzp[s])));
+              }
+              dr_[q] = drp * rs; du_[q] = dup * rs; dn_[q] = dnp * rs; dnh_[q] = dnh * rs;
+            }
+            tmem_st8(tl + DIR_COL + (uint32_t)k * 64 + j0, dirv);
+            // ring slot: the MMAs that read its previous content (chunk gc - 2) must have completed
+            const uint32_t slot = gc & 1;
+            if (gc >= 2) mbar_wait(&bars->empty[slot], ((gc >> 1) - 1) & 1);
+            uint8_t* ahi = a_ring + slot * SLOT_BYTES;
+            uint4 hi, lo;
+            split8(dr_, hi, lo);
+            *reinterpret_cast<uint4*>(ahi + sw128(row, 0 + cg)) = hi;
+            *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 0 + cg)) = lo;
+            split8(du_, hi, lo);
+            *reinterpret_cast<uint4*>(ahi + sw128(row, 2 + cg)) = hi;
+            *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 2 + cg)) = lo;
+            split8(dn_, hi, lo);
+            *reinterpret_cast<uint4*>(ahi + sw128(row, 4 + cg)) = hi;
+            *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 4 + cg)) = lo;
+            split8(dnh_, hi, lo);
+            *reinterpret_cast<uint4*>(ahi + sw128(row, 6 + cg)) = hi;
+            *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 6 + cg)) = lo;
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(&bars->full[slot]);
+          }
+          tmem_st_wait();
+          sc_prev[k] = sc_this;
+          if (NL == 2 && k == 1) sc_in = sc_this;
+        }
+        // ---- this thread's share of d z_t through the state columns of W_ih_l0
+#pragma unroll
+        for (int s = 0; s < S; ++s) dzx[(cg * 128 + row) * S + s] = dzp[s];
+      }
+      // grad_x0 = d z_0 + g_paths[:, 0]
+      named_bar_sync(1 + quad, 64);
+      if (ok && cg == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          p.grad_x0[b * S + s] = dz[s] + dzx[(0 * 128 + row) * S + s] + dzx[(1 * 128 + row) * S + s] + gp_p[s];
+      }
+      named_bar_sync(1 + quad, 64);  // dzx is rewritten by the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// sdg[b][g*H + i] = sum_t d_gi_l0[b, t, g, i] from the tiled dg (slots r, u, n of layer 0)
+__global__ void sdg_tiled_kernel(const float* __restrict__ dg, int64_t B, int64_t T, int NL, float* __restrict__ sdg) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (tile, f, row), row fastest
+  const int64_t ntile = (B + kTileRows - 1) / kTileRows;
+  if (idx >= ntile * 192 * kTileRows) return;
+  const int r = (int)(idx % kTileRows), f = (int)((idx / kTileRows) % 192);
+  const int64_t tb = idx / (192 * kTileRows), b = tb * kTileRows + r;
+  if (b >= B) return;
+  const int64_t tstride = (int64_t)NL * kDgSlots * 64 * kTileRows;
+  const float* src = dg + tb * T * tstride + (int64_t)f * kTileRows + r;
+  float acc = 0.f;
+  for (int64_t t = 0; t < T; ++t) acc += src[t * tstride];
+  sdg[b * 192 + f] = acc;
+}
+
+template <int NL, int S>
+int launch_bwd_tc(const PathParams& p, cudaStream_t st) {
+  const size_t smem = TcBwdSmem<NL, S>::bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_bwd_tc_kernel<NL, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t ntiles = (p.B + kTileRows - 1) / kTileRows;
+  path_bwd_tc_kernel<NL, S><<<(unsigned)(ntiles < sms ? ntiles : sms), kTcRecThreads, smem, st>>>(p);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  return VISDE_OK;
+}
+
+template <int NL>
+int dispatch_s_tcb(const PathParams& p, cudaStream_t st) {
+  switch (p.S) {
+    case 1: return launch_bwd_tc<NL, 1>(p, st);
+    case 2: return launch_bwd_tc<NL, 2>(p, st);
+    case 3: return launch_bwd_tc<NL, 3>(p, st);
+    case 4: return launch_bwd_tc<NL, 4>(p, st);
+  }
+  set_error("tensor-core recurrence: unsupported state dim %d", p.S);
+  return VISDE_EINVAL;
+}
+
+}  // namespace
+
+// p.stash and p.dg are the row-fastest tiled buffers; p.dout / p.grad_x0 / p.sdg per-trajectory
+int launch_path_bwd_tc(const PathParams& p, cudaStream_t st) {
+  int rc;
+  if (p.NL == 1) rc = dispatch_s_tcb<1>(p, st);
+  else if (p.NL == 2) rc = dispatch_s_tcb<2>(p, st);
+  else {
+    set_error("tensor-core recurrence: unsupported num_layers %d", p.NL);
+    return VISDE_EINVAL;
+  }
+  if (rc) return rc;
+  const int64_t n = ((p.B + kTileRows - 1) / kTileRows) * 192 * kTileRows;
+  sdg_tiled_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.dg, p.B, p.T, p.NL, p.sdg);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  return VISDE_OK;
+}
+
+}  // namespace visde
