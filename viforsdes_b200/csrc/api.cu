@@ -89,7 +89,11 @@ BwdWs bwd_ws(const visde_dims* d) {
   w.dg = off;
   off += align_up(sizeof(float) * bt * d->NL * kDgSlots * d->H);
   w.dout = off;
-  off += align_up(sizeof(float) * bt * n_out);
+  {
+    size_t fl = bt * n_out;
+    if (tc_rec_possible(d) && padded_B(d) * d->T * 16 > fl) fl = padded_B(d) * d->T * 16;  // tiled [tile][t][16][128]
+    off += align_up(sizeof(float) * fl);
+  }
   w.sdg = off;
   off += align_up(sizeof(float) * (size_t)d->B * G);
   int64_t K = d->B * d->T;
@@ -100,6 +104,10 @@ BwdWs bwd_ws(const visde_dims* d) {
   if (pf3 > pf) pf = pf3;
   if (d->H == 64 && d->NL <= 2 && (d->C == 128 || d->C == 256)) {
     size_t pt = tc_wgrad_partial_floats(d->NL, d->C);
+    if (pt > pf) pf = pt;
+  }
+  if (tc_rec_possible(d)) {
+    size_t pt = tc_thin_partial_floats(d->B, d->NL, d->S);
     if (pt > pf) pf = pt;
   }
   w.partial_floats = pf;
@@ -330,11 +338,13 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
   if (tcrec) {
     // tensor-core family: reads the tiled stash the forward wrote, emits d_pre tiled; the time-parallel kernels
     // below still read per-trajectory rows, so both are converted (bridge until K3 / K4 read the tiled layouts)
-    StageTimer tm(VISDE_STAGE_K2_PATH_BWD, 4, st);
+    StageTimer tm(VISDE_STAGE_K2_PATH_BWD, 5, st);
     float* dg_std = p.dg;
     float* std_stash = reinterpret_cast<float*>(wsb + ws.stash_std);
     p.dg = reinterpret_cast<float*>(wsb + ws.dg_tiled);
     rc = launch_path_bwd_tc(p, st);
+    if (rc) return rc;
+    rc = launch_tc_thin_grads(p, p.dout, gw, partials, ws.partial_floats, st);
     if (rc) return rc;
     rc = launch_untile(p.dg, dg_std, d->B, d->T, d->NL * kDgSlots * d->H, st);
     if (rc) return rc;
@@ -393,11 +403,14 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
     }
   }
   // K4: weight gradients
-  StageTimer tm4(VISDE_STAGE_K4_WGRAD, fastk ? (tc ? 5 : 3 + 2 * (2 * NL)) : (tc ? 2 + 2 * (2 * NL + 1) : 2 * (2 * NL + 1)), st);
-  if (fastk) {
-    // fast family: biases, dW_ih_l0[:, :S], dW_out, db_out were accumulated inside K2 (per-CTA partials)
-    rc = launch_fast_partials_reduce(p, gw, st);
-    if (rc) return rc;
+  StageTimer tm4(VISDE_STAGE_K4_WGRAD, (fastk || tcrec) ? (tc ? 5 : 3 + 2 * (2 * NL)) : (tc ? 2 + 2 * (2 * NL + 1) : 2 * (2 * NL + 1)), st);
+  if (fastk || tcrec) {
+    // fast family: biases, dW_ih_l0[:, :S], dW_out, db_out were accumulated inside K2 (per-CTA partials);
+    // tensor-core family: launch_tc_thin_grads above already wrote them
+    if (fastk) {
+      rc = launch_fast_partials_reduce(p, gw, st);
+      if (rc) return rc;
+    }
     if (P > 0) {  // theta columns of dW_ih_l0 = (sum_t d_gi_l0)^T theta: only B rows
       RowSrc A{p.sdg, G, 0, 0, G, VISDE_F32};
       RowSrc bs[1] = {RowSrc{theta, P, 0, 0, P, VISDE_F32}};

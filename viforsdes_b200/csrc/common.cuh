@@ -117,8 +117,12 @@ int launch_path_fwd_tiled(const PathParams& p, int NB, cudaStream_t st);
 bool tc_rec_supported(const PathParams& p);
 int launch_gth(const PathParams& p, float* gth, cudaStream_t st);  // per-trajectory constant part of the layer-0 gates
 int launch_path_fwd_tc(const PathParams& p, cudaStream_t st);      // expects tiled gi_ctx that already includes gth
-// BPTT on tensor cores: p.stash / p.dg are the tiled buffers, p.dout / p.grad_x0 / p.sdg per-trajectory
+// BPTT on tensor cores: p.stash / p.dg / p.dout ([tile][t][16][128]) are tiled buffers, p.grad_x0 per-trajectory
 int launch_path_bwd_tc(const PathParams& p, cudaStream_t st);
+// biases, dW_ih_l0[:, :S], dW_out, db_out and p.sdg from the tiled dg / dout / stash (per-tile partials + fixed-order sum)
+size_t tc_thin_partial_floats(int64_t B, int NL, int S);
+int launch_tc_thin_grads(const PathParams& p, const float* dout_tiled, const visde_weight_grads* gw, float* partials,
+                         size_t partial_floats, cudaStream_t st);
 // [ceil(B/128)][T][F][128] row-fastest -> [B][T][F]
 int launch_untile(const float* in, float* out, int64_t B, int64_t T, int F, cudaStream_t st);
 size_t fast_partials_floats(int NL, int H, int S);

@@ -201,6 +201,36 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
       const float* raw_p = p.raw + b * (int64_t)T * NTRIL;
       const float* gl_p = p.g_chol + b * (int64_t)T * S * S;
 
+      // software pipeline: the stashed gates of the NEXT chunk (8 units x 5 values) and the per-step row inputs of
+      // the NEXT step are loaded while the current ones are being processed
+      float nr[8], nu[8], nn[8], nnh[8], nhp[8];
+      auto load_chunk = [&](int tt, int kk, int cc) {
+        const float* sk = st_tile + ((int64_t)tt * NL + kk) * (kStashSlots * 64 * kTileRows) + (cc * 16 + cg * 8) * kTileRows;
+        const float* hk = sk - (int64_t)NL * (kStashSlots * 64 * kTileRows) + kStashH * 64 * kTileRows;  // step tt - 1
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          nr[q] = sk[(kStashR * 64 + q) * kTileRows];
+          nu[q] = sk[(kStashU * 64 + q) * kTileRows];
+          nn[q] = sk[(kStashN * 64 + q) * kTileRows];
+          nnh[q] = sk[(kStashNhh * 64 + q) * kTileRows];
+          nhp[q] = tt > 0 ? hk[q * kTileRows] : 0.f;
+        }
+      };
+      float n_gP[S], n_gM[S], n_ev[S], n_rd[S], n_gL[S * S];
+      auto load_small = [&](int tt) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          n_gP[s] = gp_p[(tt + 1) * S + s];
+          n_gM[s] = gm_p[tt * S + s];
+          n_ev[s] = ep_p[tt * S + s];
+          n_rd[s] = raw_p[tt * NTRIL + s * (s + 1) / 2 + s];
+        }
+#pragma unroll
+        for (int q = 0; q < S * S; ++q) n_gL[q] = gl_p[tt * S * S + q];
+      };
+      load_small(T - 1);
+      load_chunk(T - 1, NL - 1, 0);
+
       float dz[S];
 #pragma unroll
       for (int s = 0; s < S; ++s) dz[s] = 0.f;
@@ -223,13 +253,14 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
           float gP[S], gM[S], ev[S], rd[S], gL[S * S];
 #pragma unroll
           for (int s = 0; s < S; ++s) {
-            gP[s] = gp_p[(t + 1) * S + s] * okf;
-            gM[s] = gm_p[t * S + s] * okf;
-            ev[s] = ep_p[t * S + s];
-            rd[s] = raw_p[t * NTRIL + s * (s + 1) / 2 + s];
+            gP[s] = n_gP[s] * okf;
+            gM[s] = n_gM[s] * okf;
+            ev[s] = n_ev[s];
+            rd[s] = n_rd[s];
           }
 #pragma unroll
-          for (int q = 0; q < S * S; ++q) gL[q] = gl_p[t * S * S + q] * okf;
+          for (int q = 0; q < S * S; ++q) gL[q] = n_gL[q] * okf;
+          if (t > 0) load_small(t - 1);
 #pragma unroll
           for (int s = 0; s < S; ++s) dz[s] += gP[s];
 #pragma unroll
@@ -242,10 +273,10 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
               dout[S + s * (s + 1) / 2 + j] = d;
             }
           }
-          if (ok && cg == 0) {
-            float* o = p.dout + (b * T + t) * NOUT;
+          if (cg == 0) {  // tiled [tile][t][16][128]; pad rows hold zeros
+            float* o = p.dout + (tile * T + t) * (int64_t)(16 * kTileRows) + row;
 #pragma unroll
-            for (int m = 0; m < NOUT; ++m) o[m] = dout[m];
+            for (int m = 0; m < NOUT; ++m) o[m * kTileRows] = dout[m];
           }
         }
         float dzp[S];
@@ -308,22 +339,25 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
           const float sc_this = exp2i(-(er + ew));
 
           // ---------- pass 2: gate cotangents, dg, direct term, A-operand chunks ----------
-          const float* st_k = st_tile + ((int64_t)t * NL + k) * (kStashSlots * 64 * kTileRows);
-          const float* hp_k = st_k - (int64_t)NL * (kStashSlots * 64 * kTileRows) + kStashH * 64 * kTileRows;  // step t-1
           float* dg_k = dg_tile + ((int64_t)t * NL + k) * (kDgSlots * 64 * kTileRows);
 #pragma unroll
           for (int c = 0; c < 4; ++c, ++gc) {
             const int j0 = c * 16 + cg * 8;
+            float cr[8], cu[8], cn[8], cnh[8], chp[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              cr[q] = nr[q]; cu[q] = nu[q]; cn[q] = nn[q]; cnh[q] = nnh[q]; chp[q] = nhp[q];
+            }
+            // next chunk in processing order: (t, k, c+1) | (t, k-1, 0) | (t-1, NL-1, 0)
+            if (c < 3) load_chunk(t, k, c + 1);
+            else if (k > 0) load_chunk(t, k - 1, 0);
+            else if (t > 0) load_chunk(t - 1, NL - 1, 0);
             float dr_[8], du_[8], dn_[8], dnh_[8];
             uint32_t dirv[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const int i = j0 + q;
-              const float r = st_k[(kStashR * 64 + i) * kTileRows];
-              const float u = st_k[(kStashU * 64 + i) * kTileRows];
-              const float n = st_k[(kStashN * 64 + i) * kTileRows];
-              const float nhh = st_k[(kStashNhh * 64 + i) * kTileRows];
-              const float hp = t > 0 ? hp_k[i * kTileRows] : 0.f;
+              const float r = cr[q], u = cu[q], n = cn[q], nhh = cnh[q], hp = chp[q];
               const float dhv = dh[c * 8 + q];
               const float dnp = dhv * (1.f - u) * (1.f - n * n);
               const float dup = dhv * (hp - n) * u * (1.f - u);
@@ -387,21 +421,6 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
   if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// sdg[b][g*H + i] = sum_t d_gi_l0[b, t, g, i] from the tiled dg (slots r, u, n of layer 0)
-__global__ void sdg_tiled_kernel(const float* __restrict__ dg, int64_t B, int64_t T, int NL, float* __restrict__ sdg) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (tile, f, row), row fastest
-  const int64_t ntile = (B + kTileRows - 1) / kTileRows;
-  if (idx >= ntile * 192 * kTileRows) return;
-  const int r = (int)(idx % kTileRows), f = (int)((idx / kTileRows) % 192);
-  const int64_t tb = idx / (192 * kTileRows), b = tb * kTileRows + r;
-  if (b >= B) return;
-  const int64_t tstride = (int64_t)NL * kDgSlots * 64 * kTileRows;
-  const float* src = dg + tb * T * tstride + (int64_t)f * kTileRows + r;
-  float acc = 0.f;
-  for (int64_t t = 0; t < T; ++t) acc += src[t * tstride];
-  sdg[b * 192 + f] = acc;
-}
-
 template <int NL, int S>
 int launch_bwd_tc(const PathParams& p, cudaStream_t st) {
   const size_t smem = TcBwdSmem<NL, S>::bytes;
@@ -433,18 +452,242 @@ int dispatch_s_tcb(const PathParams& p, cudaStream_t st) {
 
 }  // namespace
 
-// p.stash and p.dg are the row-fastest tiled buffers; p.dout / p.grad_x0 / p.sdg per-trajectory
+// p.stash, p.dg and p.dout are the row-fastest tiled buffers; p.grad_x0 per-trajectory
 int launch_path_bwd_tc(const PathParams& p, cudaStream_t st) {
-  int rc;
-  if (p.NL == 1) rc = dispatch_s_tcb<1>(p, st);
-  else if (p.NL == 2) rc = dispatch_s_tcb<2>(p, st);
-  else {
-    set_error("tensor-core recurrence: unsupported num_layers %d", p.NL);
-    return VISDE_EINVAL;
+  if (p.NL == 1) return dispatch_s_tcb<1>(p, st);
+  if (p.NL == 2) return dispatch_s_tcb<2>(p, st);
+  set_error("tensor-core recurrence: unsupported num_layers %d", p.NL);
+  return VISDE_EINVAL;
+}
+
+}  // namespace visde
+
+// ------------------------------------------------------------------------------------------------
+// Thin gradient pieces of the tensor-core family: everything that is a plain reduction of d_pre over
+// (b, t) -- the bias gradients, the state columns of dW_ih_l0, dW_out / db_out and sum_t d_gi_l0 for the
+// theta columns -- from the tiled dg / dout / stash in one coalesced pass (thread = trajectory row),
+// per-tile partials, then a fixed-order sum over tiles (deterministic, no atomics).
+// ------------------------------------------------------------------------------------------------
+namespace visde {
+namespace {
+
+constexpr int kThinFPB = 32;  // dg features per block
+
+// partial record of one tile: [F] bias sums, [192][S] dW_z, [NOUT][64] dW_out, [NOUT] db_out
+__host__ __device__ inline int thin_part_floats(int NL, int S) {
+  const int nout = S + S * (S + 1) / 2;
+  return NL * kDgSlots * 64 + 192 * S + nout * 64 + nout;
+}
+
+template <int S>
+__global__ void __launch_bounds__(256) tc_thin_kernel(const float* __restrict__ dg, const float* __restrict__ dout,
+                                                      const float* __restrict__ stash, const float* __restrict__ paths,
+                                                      int64_t B, int T, int NL, float* __restrict__ sdg,
+                                                      float* __restrict__ part) {
+  constexpr int NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL;
+  const int F = NL * kDgSlots * 64;
+  const int nfg = F / kThinFPB;
+  const int64_t tb = blockIdx.x;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, rq = w & 3, par = w >> 2;
+  const int row = rq * 32 + lane;
+  const int64_t b_raw = tb * kTileRows + row;
+  const bool ok = b_raw < B;
+  const int64_t b = ok ? b_raw : B - 1;
+  float* prec = part + tb * thin_part_floats(NL, S);
+  __shared__ float red[2][4][16 * (1 + S)];
+
+  if ((int)blockIdx.y < nfg) {
+    // ---- bias sums, dW_z, sum_t d_gi_l0: 16 features per thread, lanes = rows
+    const int f0 = blockIdx.y * kThinFPB + par * 16;
+    const int64_t tstride = (int64_t)F * kTileRows;
+    const float* src = dg + tb * T * tstride + (int64_t)f0 * kTileRows + row;
+    const bool wz = f0 < 192;  // layer-0 slots r, u, n feed the state columns of W_ih_l0
+    const float* zp = paths + b * (int64_t)(T + 1) * S;
+    float acc[16], accz[16][S];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      acc[j] = 0.f;
+#pragma unroll
+      for (int s = 0; s < S; ++s) accz[j][s] = 0.f;
+    }
+    for (int t = 0; t < T; ++t) {
+      float z[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) z[s] = wz ? zp[t * S + s] : 0.f;
+      const float* st = src + t * tstride;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = st[j * kTileRows];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        acc[j] += v[j];
+#pragma unroll
+        for (int s = 0; s < S; ++s) accz[j][s] = fmaf(v[j], z[s], accz[j][s]);
+      }
+    }
+    if (wz && ok) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sdg[b * 192 + f0 + j] = acc[j];
+    }
+    // sum over the 128 rows of the tile (pad rows hold exact zeros)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float a = acc[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) red[par][rq][j] = a;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float c = accz[j][s];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) red[par][rq][16 + j * S + s] = c;
+      }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * 16 * (1 + S); idx += blockDim.x) {
+      const int pp = idx / (16 * (1 + S)), q = idx % (16 * (1 + S));
+      const float a = (red[pp][0][q] + red[pp][1][q]) + (red[pp][2][q] + red[pp][3][q]);
+      const int fb = blockIdx.y * kThinFPB + pp * 16;
+      if (q < 16) prec[fb + q] = a;
+      else if (fb < 192) prec[F + (fb + (q - 16) / S) * S + (q - 16) % S] = a;
+    }
+  } else {
+    // ---- dW_out[m][i] = sum dout[m] h_top[i], db_out[m] = sum dout[m]: 8 units per block, 4 per thread
+    const int ig = blockIdx.y - nfg;  // 0..7
+    const int i0 = ig * 8 + par * 4;
+    const int64_t sstride = (int64_t)NL * kStashSlots * 64 * kTileRows;
+    const float* hsrc = stash + tb * T * sstride + ((int64_t)((NL - 1) * kStashSlots + kStashH) * 64 + i0) * kTileRows + row;
+    const float* dsrc = dout + tb * T * (int64_t)(16 * kTileRows) + row;
+    float acc[4][NOUT], accd[NOUT];
+#pragma unroll
+    for (int m = 0; m < NOUT; ++m) {
+      accd[m] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j][m] = 0.f;
+    }
+    for (int t = 0; t < T; ++t) {
+      float dv[NOUT], h[4];
+#pragma unroll
+      for (int m = 0; m < NOUT; ++m) dv[m] = dsrc[((int64_t)t * 16 + m) * kTileRows];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = hsrc[t * sstride + j * kTileRows];
+#pragma unroll
+      for (int m = 0; m < NOUT; ++m) {
+        accd[m] += dv[m];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j][m] = fmaf(dv[m], h[j], acc[j][m]);
+      }
+    }
+    float* pw = prec + F + 192 * S;
+    float* red2 = &red[0][0][0];  // [8 warps][4 * NOUT + NOUT]
+    static_assert(8 * 5 * NOUT <= 2 * 4 * 16 * (1 + S), "reduction scratch too small");
+#pragma unroll
+    for (int m = 0; m < NOUT; ++m) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = acc[j][m];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) red2[w * 5 * NOUT + j * NOUT + m] = a;
+      }
+      float d = accd[m];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (lane == 0) red2[w * 5 * NOUT + 4 * NOUT + m] = d;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * 5 * NOUT; idx += blockDim.x) {
+      const int pp = idx / (5 * NOUT), q = idx % (5 * NOUT);
+      const float* r0 = red2 + (pp * 4) * 5 * NOUT + q;
+      const float a = (r0[0] + r0[5 * NOUT]) + (r0[2 * 5 * NOUT] + r0[3 * 5 * NOUT]);
+      if (q < 4 * NOUT) pw[(q % NOUT) * 64 + ig * 8 + pp * 4 + q / NOUT] = a;
+      else if (ig == 0 && pp == 0) pw[NOUT * 64 + (q - 4 * NOUT)] = a;
+    }
   }
-  if (rc) return rc;
-  const int64_t n = ((p.B + kTileRows - 1) / kTileRows) * 192 * kTileRows;
-  sdg_tiled_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.dg, p.B, p.T, p.NL, p.sdg);
+}
+
+struct ThinReduceArgs {
+  const float* part;
+  int ntile, NL, S, n_out, ld0;
+  float* b_ih[VISDE_MAX_LAYERS];
+  float* b_hh[VISDE_MAX_LAYERS];
+  float* w_ih0;
+  float* out_w;
+  float* out_b;
+};
+__global__ void tc_thin_reduce_kernel(ThinReduceArgs a) {
+  const int total = thin_part_floats(a.NL, a.S);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  float acc = 0.f;
+  for (int c = 0; c < a.ntile; ++c) acc += a.part[(int64_t)c * total + idx];
+  const int F = a.NL * kDgSlots * 64;
+  int off = idx;
+  if (off < F) {
+    const int k = off / (kDgSlots * 64), slot = (off / 64) % kDgSlots, i = off % 64;
+    if (slot < 2) {
+      a.b_ih[k][slot * 64 + i] = acc;
+      a.b_hh[k][slot * 64 + i] = acc;
+    } else if (slot == 2) {
+      a.b_ih[k][128 + i] = acc;
+    } else {
+      a.b_hh[k][128 + i] = acc;
+    }
+    return;
+  }
+  off -= F;
+  if (off < 192 * a.S) {
+    a.w_ih0[(int64_t)(off / a.S) * a.ld0 + off % a.S] = acc;  // row g*64+i, state column s
+    return;
+  }
+  off -= 192 * a.S;
+  if (off < a.n_out * 64) {
+    a.out_w[off] = acc;
+    return;
+  }
+  a.out_b[off - a.n_out * 64] = acc;
+}
+
+}  // namespace
+
+size_t tc_thin_partial_floats(int64_t B, int NL, int S) {
+  return (size_t)((B + kTileRows - 1) / kTileRows) * thin_part_floats(NL, S);
+}
+
+// dg / dout_tiled / stash: row-fastest tiled buffers of the tensor-core backward
+int launch_tc_thin_grads(const PathParams& p, const float* dout_tiled, const visde_weight_grads* gw, float* partials,
+                         size_t partial_floats, cudaStream_t st) {
+  if (tc_thin_partial_floats(p.B, p.NL, p.S) > partial_floats) {
+    set_error("tc thin gradients: workspace too small");
+    return VISDE_EWORKSPACE;
+  }
+  const int64_t ntile = (p.B + kTileRows - 1) / kTileRows;
+  const dim3 grid((unsigned)ntile, p.NL * kDgSlots * 64 / kThinFPB + 8);
+  switch (p.S) {
+    case 1: tc_thin_kernel<1><<<grid, 256, 0, st>>>(p.dg, dout_tiled, p.stash, p.paths, p.B, (int)p.T, p.NL, p.sdg, partials); break;
+    case 2: tc_thin_kernel<2><<<grid, 256, 0, st>>>(p.dg, dout_tiled, p.stash, p.paths, p.B, (int)p.T, p.NL, p.sdg, partials); break;
+    case 3: tc_thin_kernel<3><<<grid, 256, 0, st>>>(p.dg, dout_tiled, p.stash, p.paths, p.B, (int)p.T, p.NL, p.sdg, partials); break;
+    case 4: tc_thin_kernel<4><<<grid, 256, 0, st>>>(p.dg, dout_tiled, p.stash, p.paths, p.B, (int)p.T, p.NL, p.sdg, partials); break;
+    default: set_error("tc thin gradients: unsupported state dim %d", p.S); return VISDE_EINVAL;
+  }
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  ThinReduceArgs a{};
+  a.part = partials;
+  a.ntile = (int)ntile;
+  a.NL = p.NL;
+  a.S = p.S;
+  a.n_out = p.n_out;
+  a.ld0 = p.S + p.C + p.P;
+  for (int k = 0; k < p.NL; ++k) {
+    a.b_ih[k] = gw->b_ih[k];
+    a.b_hh[k] = gw->b_hh[k];
+  }
+  a.w_ih0 = gw->w_ih[0];
+  a.out_w = gw->out_w;
+  a.out_b = gw->out_b;
+  const int total = thin_part_floats(p.NL, p.S);
+  tc_thin_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(a);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
