@@ -70,15 +70,20 @@ StashLayout stash_layout(const visde_dims* d) {
   return {padded_B(d) * d->T * d->NL * kStashSlots * d->H, (size_t)d->B * d->T * (size_t)(d->S * (d->S + 1) / 2)};
 }
 
+// AUTO switches to the tensor-core recurrence family from this batch size on: below it the 128-trajectory tiles
+// leave most SMs idle and the fp32 SIMT families (one / eight trajectories per CTA) finish sooner (measured
+// break-even for fwd + bwd on 148 SMs is B ~ 2 600)
+constexpr int64_t kTcRecMinBatch = 3072;
+
 // dims-only version of use_tc_rec (workspace sizing; the run-time decision also looks at the context view)
 bool tc_rec_possible(const visde_dims* d) {
   const int fam = d->variant & 0xff;
-  return (fam == VISDE_VARIANT_TC || (fam == VISDE_VARIANT_AUTO && d->B >= 1024)) && d->H == 64 && d->NL <= 2 &&
+  return (fam == VISDE_VARIANT_TC || (fam == VISDE_VARIANT_AUTO && d->B >= kTcRecMinBatch)) && d->H == 64 && d->NL <= 2 &&
          d->S <= 4 && (d->C == 128 || d->C == 256) && !(d->variant & VISDE_FLAG_NO_TENSOR_CORES);
 }
 
 struct BwdWs {
-  size_t dg, dout, sdg, partials, wsplit, cta_part, stash_std, dg_tiled, total, partial_floats;
+  size_t dg, dout, sdg, partials, wsplit, cta_part, dg_tiled, total, partial_floats;
 };
 BwdWs bwd_ws(const visde_dims* d) {
   BwdWs w{};
@@ -117,8 +122,6 @@ BwdWs bwd_ws(const visde_dims* d) {
   off += align_up(sizeof(float) * tc_weight_scratch_floats(d->H, d->C));
   w.cta_part = off;
   off += align_up(sizeof(float) * fast_partials_floats(d->NL, d->H, d->S));
-  w.stash_std = off;  // per-trajectory copy of a tiled stash for the kernels that read [B, T, NL, 5, H]
-  if (tc_rec_possible(d)) off += align_up(sizeof(float) * (size_t)d->B * d->T * d->NL * kStashSlots * d->H);
   w.dg_tiled = off;   // d_pre of the tensor-core backward, row-fastest tiled
   if (tc_rec_possible(d)) off += align_up(sizeof(float) * padded_B(d) * d->T * d->NL * kDgSlots * d->H);
   w.total = off;
@@ -335,23 +338,17 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
   float* partials = reinterpret_cast<float*>(wsb + ws.partials);
 
   // K2: reverse-time recurrence
+  const float* dg_tiled = nullptr;
   if (tcrec) {
-    // tensor-core family: reads the tiled stash the forward wrote, emits d_pre tiled; the time-parallel kernels
-    // below still read per-trajectory rows, so both are converted (bridge until K3 / K4 read the tiled layouts)
-    StageTimer tm(VISDE_STAGE_K2_PATH_BWD, 5, st);
-    float* dg_std = p.dg;
-    float* std_stash = reinterpret_cast<float*>(wsb + ws.stash_std);
+    // tensor-core family: reads the tiled stash the forward wrote and emits d_pre / d_out row-fastest tiled; the
+    // thin reductions over (b, t) run right behind it, K3 / K4 below read the tiled buffers directly
+    StageTimer tm(VISDE_STAGE_K2_PATH_BWD, 3, st);
     p.dg = reinterpret_cast<float*>(wsb + ws.dg_tiled);
+    dg_tiled = p.dg;
     rc = launch_path_bwd_tc(p, st);
     if (rc) return rc;
     rc = launch_tc_thin_grads(p, p.dout, gw, partials, ws.partial_floats, st);
     if (rc) return rc;
-    rc = launch_untile(p.dg, dg_std, d->B, d->T, d->NL * kDgSlots * d->H, st);
-    if (rc) return rc;
-    rc = launch_untile(p.stash, std_stash, d->B, d->T, d->NL * kStashSlots * d->H, st);
-    if (rc) return rc;
-    p.dg = dg_std;
-    p.stash = std_stash;
   } else {
     StageTimer tm(VISDE_STAGE_K2_PATH_BWD, 1, st);
     rc = fastk ? launch_path_bwd_fast(p, st) : launch_path_bwd_generic(p, st);
@@ -388,7 +385,8 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
     if (tc) {
       rc = tc_split_weights(w->w_ih[0], ld0, S, H, C, wsplit, st);
       if (rc) return rc;
-      rc = tc_grad_ctx(p.dg, dg_t, d->B, d->T, C, H, wsplit, grad_ctx, st);
+      rc = tcrec ? tc_grad_ctx(dg_tiled, dg_t, d->B, d->T, C, H, wsplit, grad_ctx, true, st)
+                 : tc_grad_ctx(p.dg, dg_t, d->B, d->T, C, H, wsplit, grad_ctx, false, st);
       if (rc) return rc;
     } else if (C > 0) {
       rc = launch_gemm_nn(dg_src(0), d->B, d->T, G, w->w_ih[0] + S, ld0, C, grad_ctx->ptr, grad_ctx->batch_stride,
@@ -418,6 +416,7 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
       rc = launch_gemm_tn(A, G, G, 0, bs, 1, d->B, 1, &o, 1, partials, ws.partial_floats, st);
       if (rc) return rc;
     }
+    if (tcrec) return tc_wgrads_tiled(ctx, dg_tiled, p.stash, d->B, d->T, S, C, P, H, NL, gw, partials, ws.partial_floats, st);
     if (tc) return tc_wgrads(ctx, p.dg, p.stash, d->B, d->T, S, C, P, H, NL, gw, partials, ws.partial_floats, st);
     if (C > 0) {
       RowSrc bs[1] = {RowSrc{ctx->ptr, ctx->batch_stride, ctx->time_stride, 0, C, ctx->dtype}};

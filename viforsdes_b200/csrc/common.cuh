@@ -171,9 +171,14 @@ int tc_split_weights(const float* w_ih0, int ld0, int S, int H, int C, float* sc
 int tc_ctx_proj(const visde_ctx_view* ctx, int64_t B, int64_t T, int C, int H, const float* wsplit, const float* bias,
                 const float* rowbias_tiled, float* gi_ctx, bool tiled, cudaStream_t st);
 int tc_grad_ctx(const float* dg, int64_t dg_row, int64_t B, int64_t T, int C, int H, const float* wsplit,
-                const visde_ctx_grad_view* out, cudaStream_t st);
+                const visde_ctx_grad_view* out, bool dg_tiled, cudaStream_t st);
 int tc_wgrads(const visde_ctx_view* ctx, const float* dg, const float* stash, int64_t B, int64_t T, int S, int C, int P,
               int H, int NL, const visde_weight_grads* gw, float* partials, size_t partial_floats, cudaStream_t st);
+
+// same products from the row-fastest tiled dg / stash of the tensor-core family
+int tc_wgrads_tiled(const visde_ctx_view* ctx, const float* dg, const float* stash, int64_t B, int64_t T, int S, int C,
+                    int P, int H, int NL, const visde_weight_grads* gw, float* partials, size_t partial_floats,
+                    cudaStream_t st);
 
 // --- ELBO ---------------------------------------------------------------------------------
 struct ElboParams {

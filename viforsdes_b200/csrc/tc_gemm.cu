@@ -75,6 +75,11 @@ struct RowsArgs {
   int tiled;             // 1: a row tile is 128 TRAJECTORIES at one grid step t (tile = tb * T + t) and the output is
                          // written row-fastest, out[((tb * T + t) * N + col) * 128 + row]: the layout the tensor-core
                          // recurrence reads with one coalesced line per warp
+  int a_tiled;           // 1 (K3 of the tensor-core family): A is MN-major, read from the row-fastest tiled dg
+                         // [tile][t][F][128]: a row tile is 128 trajectories at one grid step (tile = tb * T + t),
+                         // A slabs are [32 features][32 rows]; output rows are (b = tb * 128 + row, t)
+  int a_feat_rows;       // a_tiled: features per (tile, t) block of the tiled buffer (F)
+  int64_t B;             // a_tiled: trajectories (rows >= B are not stored)
   void* out;
   int64_t out_bstride, out_tstride;
   int out_dtype;
@@ -100,14 +105,14 @@ struct RowsSmem {
   static constexpr size_t bytes = OFF_BAR + sizeof(Bars) + 1024;
 };
 
-template <int N, bool B_MN, int NA>
+template <int N, bool B_MN, int NA, bool A_MN = false>
 __global__ void __launch_bounds__(kRowsThreads, 1)
 tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, RowsArgs a) {
   using L = RowsSmem<N, NA>;
   constexpr int A_BYTES = L::A_BYTES, B_BYTES = L::B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * N <= 256 ? 256 : 512;
-  constexpr uint32_t IDESC = make_idesc(N, false, B_MN);
+  constexpr uint32_t IDESC = make_idesc(N, A_MN, B_MN);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   typename L::Bars* bars = reinterpret_cast<typename L::Bars*>(smem + L::OFF_BAR);
@@ -144,7 +149,11 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = g % NA;
           if (g >= NA) mbar_wait(&bars->emptyA[sa], ((g / NA) - 1) & 1);
           mbar_expect_tx(&bars->fullA[sa], A_BYTES);
-          if (a.tiled)
+          if (A_MN) {
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl)
+              tma_load_2d(smem + sa * A_BYTES + sl * 4096, &tmA, &bars->fullA[sa], sl * 32, tile * a.a_feat_rows + kb * 32);
+          } else if (a.tiled)
             tma_load_3d(smem + sa * A_BYTES, &tmA, &bars->fullA[sa], kb * 32, (int)(tile % a.T), (int)(tile / a.T) * 128);
           else
             tma_load_3d(smem + sa * A_BYTES, &tmA, &bars->fullA[sa], kb * 32, t0, b);
@@ -190,7 +199,8 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t b_hi = smem_u32(smem + L::OFF_B + sb * 2 * B_BYTES), b_lo = b_hi + B_BYTES;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint64_t dah = desc_kmajor(a_hi, j), dal = desc_kmajor(a_lo, j);
+            const uint64_t dah = A_MN ? desc_mnmajor(a_hi, j) : desc_kmajor(a_hi, j);
+            const uint64_t dal = A_MN ? desc_mnmajor(a_lo, j) : desc_kmajor(a_lo, j);
             const uint64_t dbh = B_MN ? desc_mnmajor(b_hi, j) : desc_kmajor(b_hi, j);
             const uint64_t dbl = B_MN ? desc_mnmajor(b_lo, j) : desc_kmajor(b_lo, j);
             umma_tf32(dcol, dal, dbh, IDESC, (kb | j) != 0);  // small terms first
@@ -226,9 +236,15 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t acc = lt & 1;
       mbar_wait(&bars->tmemFull[acc], (lt >> 1) & 1);
       tc_fence_after();
-      const int t = t0 + row;
-      const bool row_ok = t < a.T;
-      const int64_t obase = (int64_t)b * a.out_bstride + (int64_t)t * a.out_tstride + a.n0;
+      int t = t0 + row;
+      bool row_ok = t < a.T;
+      int64_t obase = (int64_t)b * a.out_bstride + (int64_t)t * a.out_tstride + a.n0;
+      if (A_MN) {
+        const int64_t bb = (int64_t)(tile / a.T) * 128 + row;
+        t = (int)(tile % a.T);
+        row_ok = bb < a.B;
+        obase = bb * a.out_bstride + (int64_t)t * a.out_tstride + a.n0;
+      }
       if (a.tiled) {
         // rows are trajectories tb * 128 + row at grid step t; fp32 row-fastest output, always in bounds (padded)
         const int64_t tb = tile / a.T;
@@ -412,6 +428,138 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
+// K4 of the tensor-core family: the same split-K products read from the row-fastest tiled buffers
+// dg [tile][t][F][128] / stash [tile][t][Fs][128] (K = trajectories of a tile: both operands K-major, 4-D tensor
+// maps so that the t-1 shift of h(t-1) is an out-of-bounds zero fill) and from the caller's ctx [B,T,C]
+// (MN-major slabs, K = 32 trajectories at one grid step).  One k-block = 32 trajectories of one (tile, t).
+struct WgtProblem {
+  int a_ctx;       // 1: A = 128 ctx columns (MN-major), 0: A = [h_l0 | h_l1] from the tiled stash (K-major)
+  int a_cols[4];   // ctx: column of each 32-wide slab; stash: feature row of h_l0, h_l1
+  int a_tshift;
+  int b_feat[3];   // feature rows of the three 64-wide gate groups in dg
+};
+struct WgtArgs {
+  WgtProblem prob[5];
+  int nprob, nsplit;
+  int64_t total_kblocks;  // ntile * T * 4
+  int T;
+  float* partials;        // [nprob][nsplit][128][192]
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CUtensorMap tmDg,
+                      const __grid_constant__ CUtensorMap tmSt, WgtArgs a) {
+  constexpr int N = 192;
+  constexpr int A_BYTES = 128 * 128, B_BYTES = N * 128;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr uint32_t TMEM_COLS = 256;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + kStages * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pi = blockIdx.y, split = blockIdx.x;
+  const WgtProblem& pr = a.prob[pi];
+  const int64_t per = (a.total_kblocks + a.nsplit - 1) / a.nsplit;
+  const int64_t kb0 = split * per;
+  const int64_t kb1 = kb0 + per < a.total_kblocks ? kb0 + per : a.total_kblocks;
+  const int nk = kb1 > kb0 ? (int)(kb1 - kb0) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->split[s], 128);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % kStages;
+        if (kb >= kStages) mbar_wait(&bars->empty[s], ((kb / kStages) - 1) & 1);
+        const int64_t g = kb0 + kb;
+        const int kq = (int)(g & 3), t = (int)((g >> 2) % a.T), tb = (int)((g >> 2) / a.T);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        mbar_expect_tx(&bars->full[s], A_BYTES + B_BYTES);
+        if (pr.a_ctx) {
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl)
+            tma_load_3d(st + sl * 4096, &tmCtx, &bars->full[s], pr.a_cols[sl], t, tb * 128 + kq * 32);
+        } else {
+          tma_load_4d(st, &tmSt, &bars->full[s], kq * 32, pr.a_cols[0], t + pr.a_tshift, tb);
+          tma_load_4d(st + 8192, &tmSt, &bars->full[s], kq * 32, pr.a_cols[1], t + pr.a_tshift, tb);
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          tma_load_4d(st + 2 * A_BYTES + q * 8192, &tmDg, &bars->full[s], kq * 32, pr.b_feat[q], t, tb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(N, pr.a_ctx != 0, false);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&bars->split[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t dah = pr.a_ctx ? desc_mnmajor(a_hi, j) : desc_kmajor(a_hi, j);
+          const uint64_t dal = pr.a_ctx ? desc_mnmajor(a_lo, j) : desc_kmajor(a_lo, j);
+          const uint64_t dbh = desc_kmajor(b_hi, j), dbl = desc_kmajor(b_lo, j);
+          umma_tf32(tmem_d, dal, dbh, idesc, (kb | j) != 0);
+          umma_tf32(tmem_d, dah, dbl, idesc, 1);
+          umma_tf32(tmem_d, dah, dbh, idesc, 1);
+        }
+        umma_commit(&bars->empty[s]);
+      }
+      if (nk > 0) umma_commit(&bars->accum); else mbar_arrive(&bars->accum);
+    }
+  } else {
+    const int tid128 = threadIdx.x - 64;
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % kStages;
+      mbar_wait(&bars->full[s], (kb / kStages) & 1);
+      uint8_t* st = smem + s * STAGE_BYTES;
+      split_tile(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + A_BYTES), A_BYTES / 16, tid128);
+      split_tile(reinterpret_cast<float4*>(st + 2 * A_BYTES), reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES),
+                 B_BYTES / 16, tid128);
+      fence_proxy_async();
+      mbar_arrive(&bars->split[s]);
+    }
+    mbar_wait(&bars->accum, 0);
+    tc_fence_after();
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    float* out = a.partials + (((int64_t)pi * a.nsplit + split) * 128 + row) * N;
+#pragma unroll 1
+    for (int c = 0; c < N / 32; ++c) {
+      float v[32];
+      if (nk > 0) {
+        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + c * 32, v);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 32; q += 4)
+        *reinterpret_cast<float4*>(out + c * 32 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
 // fixed-order sum over splits + scatter (transposed) into the gradient tensors
 struct WgScatter {
   float* dst;      // dst[n * ld + col0 + (row - row0)] = sum_split partial[row][n]
@@ -475,8 +623,8 @@ int make_map(CUtensorMap* m, const void* base, int rank, const int64_t* dims, co
     set_error("cuTensorMapEncodeTiled unavailable");
     return VISDE_ECUDA;
   }
-  cuuint64_t gdim[3], gstr[2];
-  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) {
     gdim[i] = (cuuint64_t)dims[i];
     bx[i] = (cuuint32_t)box[i];
@@ -496,21 +644,21 @@ int make_map(CUtensorMap* m, const void* base, int rank, const int64_t* dims, co
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int N, bool B_MN, int NA>
+template <int N, bool B_MN, int NA, bool A_MN = false>
 int launch_rows(const CUtensorMap& mA, const CUtensorMap& mBh, const CUtensorMap& mBl, RowsArgs a, int64_t B,
                 cudaStream_t st) {
   const size_t smem = RowsSmem<N, NA>::bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    VISDE_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_kernel<N, B_MN, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VISDE_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_kernel<N, B_MN, NA, A_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  a.num_tiles = a.tiled ? (int)(((B + 127) / 128) * a.T) : (int)(B * a.tiles_per_b);
+  a.num_tiles = (a.tiled || a.a_tiled) ? (int)(((B + 127) / 128) * a.T) : (int)(B * a.tiles_per_b);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-  tc_rows_kernel<N, B_MN, NA><<<grid, kRowsThreads, smem, st>>>(mA, mBh, mBl, a);
+  tc_rows_kernel<N, B_MN, NA, A_MN><<<grid, kRowsThreads, smem, st>>>(mA, mBh, mBl, a);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
@@ -570,13 +718,21 @@ int tc_ctx_proj(const visde_ctx_view* ctx, int64_t B, int64_t T, int C, int H, c
   return launch_rows<192, false, 4>(mA, mBh, mBl, a, B, st);
 }
 
-// K3: grad_ctx[b,t,:] = d_gi_l0[(b,t), :192] . Wc   (dg rows have `dg_row` floats)
+// K3: grad_ctx[b,t,:] = d_gi_l0[(b,t), :192] . Wc   (dg rows have `dg_row` floats).  dg_tiled: dg is the row-fastest
+// tiled buffer [ceil(B/128)][T][dg_row][128] of the tensor-core backward (A operand MN-major)
 int tc_grad_ctx(const float* dg, int64_t dg_row, int64_t B, int64_t T, int C, int H, const float* wsplit,
-                const visde_ctx_grad_view* out, cudaStream_t st) {
+                const visde_ctx_grad_view* out, bool dg_tiled, cudaStream_t st) {
   CUtensorMap mA, mBh, mBl;
-  const int64_t dA[3] = {3 * H, T, B}, sA[2] = {dg_row, T * dg_row};
-  const int boxA[3] = {32, 128, 1};
-  int rc = make_map(&mA, dg, 3, dA, sA, boxA);
+  int rc;
+  if (dg_tiled) {
+    const int64_t dA[2] = {128, ((B + 127) / 128) * T * dg_row}, sA[1] = {128};
+    const int boxA[2] = {32, 32};
+    rc = make_map(&mA, dg, 2, dA, sA, boxA, true);
+  } else {
+    const int64_t dA[3] = {3 * H, T, B}, sA[2] = {dg_row, T * dg_row};
+    const int boxA[3] = {32, 128, 1};
+    rc = make_map(&mA, dg, 3, dA, sA, boxA);
+  }
   if (rc) return rc;
   const int64_t dB[2] = {C, 3 * H}, sB[1] = {C};
   const int boxB[2] = {32, 32};
@@ -589,15 +745,20 @@ int tc_grad_ctx(const float* dg, int64_t dg_row, int64_t B, int64_t T, int C, in
     a.num_kblocks = 3 * H / 32;
     a.n0 = n0;
     a.bias = nullptr;
+    a.a_tiled = dg_tiled ? 1 : 0;
+    a.a_feat_rows = (int)dg_row;
+    a.B = B;
     a.out = out->ptr;
     a.out_bstride = out->batch_stride;
     a.out_tstride = out->time_stride;
     a.out_dtype = out->dtype;
     a.out_cols = C - n0 < 256 ? C - n0 : 256;
-    if (a.out_cols == 256)
-      rc = launch_rows<256, true, 3>(mA, mBh, mBl, a, B, st);
+    if (dg_tiled)
+      rc = a.out_cols == 256 ? launch_rows<256, true, 3, true>(mA, mBh, mBl, a, B, st)
+                             : launch_rows<128, true, 4, true>(mA, mBh, mBl, a, B, st);
     else
-      rc = launch_rows<128, true, 4>(mA, mBh, mBl, a, B, st);
+      rc = a.out_cols == 256 ? launch_rows<256, true, 3>(mA, mBh, mBl, a, B, st)
+                             : launch_rows<128, true, 4>(mA, mBh, mBl, a, B, st);
     if (rc) return rc;
   }
   return VISDE_OK;
@@ -697,6 +858,105 @@ int tc_wgrads(const visde_ctx_view* ctx, const float* dg, const float* stash, in
     attr_set = true;
   }
   tc_wgrad_kernel<<<dim3(a.nsplit, np), kTcThreads, smem, st>>>(m0, m1, m2, a);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  r.partials = partials;
+  r.nsplit = a.nsplit;
+  r.nprob = np;
+  tc_wgrad_reduce_kernel<<<dim3((128 * 192 + 255) / 256, np), 256, 0, st>>>(r);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  return VISDE_OK;
+}
+
+// K4 (big part) of the tensor-core family: dg / stash are the row-fastest tiled buffers
+int tc_wgrads_tiled(const visde_ctx_view* ctx, const float* dg, const float* stash, int64_t B, int64_t T, int S, int C,
+                    int P, int H, int NL, const visde_weight_grads* gw, float* partials, size_t partial_floats,
+                    cudaStream_t st) {
+  const int64_t F = (int64_t)NL * kDgSlots * H, Fs = stash_row_floats(NL, H), ntile = (B + 127) / 128;
+  CUtensorMap m0, m1, m2;
+  {
+    const int64_t d[3] = {C, T, B}, s[2] = {ctx->time_stride, ctx->batch_stride};
+    const int box[3] = {32, 1, 32};
+    int rc = make_map(&m0, ctx->ptr, 3, d, s, box, true);
+    if (rc) return rc;
+  }
+  {
+    const int64_t d[4] = {128, F, T, ntile}, s[3] = {128, F * 128, T * F * 128};
+    const int box[4] = {32, 64, 1, 1};
+    int rc = make_map(&m1, dg, 4, d, s, box);
+    if (rc) return rc;
+  }
+  {
+    const int64_t d[4] = {128, Fs, T, ntile}, s[3] = {128, Fs * 128, T * Fs * 128};
+    const int box[4] = {32, 64, 1, 1};
+    int rc = make_map(&m2, stash, 4, d, s, box);
+    if (rc) return rc;
+  }
+  WgtArgs a{};
+  WgReduceArgs r{};
+  int np = 0;
+  const int ld0 = S + C + P;
+  auto set_b = [&](WgtProblem& p, int layer, bool gh) {
+    const int base = layer * kDgSlots * H;
+    p.b_feat[0] = base;
+    p.b_feat[1] = base + H;
+    p.b_feat[2] = base + (gh ? 3 * H : 2 * H);  // (r, u, n_hh) or (r, u, n)
+  };
+  auto hcat = [&](WgtProblem& p, int tshift) {
+    p.a_ctx = 0;
+    p.a_cols[0] = kStashH * H;
+    p.a_cols[1] = (NL > 1 ? kStashSlots + kStashH : kStashH) * H;
+    p.a_tshift = tshift;
+  };
+  for (int c0 = 0; c0 < C; c0 += 128) {  // dW_ih0[:, S + c0 : S + c0 + 128]
+    WgtProblem& p = a.prob[np];
+    p.a_ctx = 1;
+    for (int sl = 0; sl < 4; ++sl) p.a_cols[sl] = c0 + sl * 32;
+    p.a_tshift = 0;
+    set_b(p, 0, false);
+    r.sc[np] = WgScatter{gw->w_ih[0], ld0, S + c0, 0, 128};
+    ++np;
+  }
+  {  // dW_hh0 = d_gh0^T h0(t-1)
+    WgtProblem& p = a.prob[np];
+    hcat(p, -1);
+    set_b(p, 0, true);
+    r.sc[np] = WgScatter{gw->w_hh[0], H, 0, 0, H};
+    ++np;
+  }
+  if (NL > 1) {
+    {  // dW_ih1 = d_gi1^T h0(t)
+      WgtProblem& p = a.prob[np];
+      hcat(p, 0);
+      set_b(p, 1, false);
+      r.sc[np] = WgScatter{gw->w_ih[1], H, 0, 0, H};
+      ++np;
+    }
+    {  // dW_hh1 = d_gh1^T h1(t-1)
+      WgtProblem& p = a.prob[np];
+      hcat(p, -1);
+      set_b(p, 1, true);
+      r.sc[np] = WgScatter{gw->w_hh[1], H, 0, H, H};
+      ++np;
+    }
+  }
+  a.nprob = np;
+  a.nsplit = 148 / np;
+  a.T = (int)T;
+  a.total_kblocks = ntile * T * 4;
+  if (a.total_kblocks < a.nsplit) a.nsplit = (int)a.total_kblocks;
+  a.partials = partials;
+  if ((size_t)np * a.nsplit * 128 * 192 > partial_floats) {
+    set_error("tc_wgrads_tiled: workspace too small");
+    return VISDE_EWORKSPACE;
+  }
+  constexpr int STAGE_BYTES = 2 * 128 * 128 + 2 * 192 * 128;
+  const size_t smem = kStages * STAGE_BYTES + sizeof(TcBarriers) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VISDE_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  tc_wgrad_tiled_kernel<<<dim3(a.nsplit, np), kTcThreads, smem, st>>>(m0, m1, m2, a);
   VISDE_CUDA_CHECK(cudaGetLastError());
   r.partials = partials;
   r.nsplit = a.nsplit;
