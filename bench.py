@@ -315,8 +315,10 @@ def main() -> None:
                 "frac": (d["achieved_gbs"] / hbm_peak) if d["achieved_gbs"] else None, "traffic": traffic,
                 "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback 6.65 TB/s",
                 "kernel_ms": dur * 1e3, "share_of_step": d["ms_per_step"] / ms_per_step,
-                "note": "B=128 trajectories on 148 SMs with T serial steps: latency-bound, see DESIGN.md §5; "
-                        "whole-path figures in step_roofline"}
+                "note": ("B=128 trajectories on 148 SMs with T serial steps: latency-bound, see DESIGN.md §5; "
+                         "whole-path figures in step_roofline") if B <= 148 else
+                        ("large-batch family: gate GEMMs on tcgen05, HBM-bound by the stash / d_pre streams "
+                         "(DESIGN.md §5); whole-path figures in step_roofline")}
     fl = path_flops_per_unit(S, Cd, H, NL)
     step_roofline = {"path_bytes_per_unit": path_bytes_per_unit(S, Cd), "path_flops_per_unit": fl,
                      "achieved_gbs": path_bytes_per_unit(S, Cd) * units / (ms_per_step * 1e-3) / 1e9,
