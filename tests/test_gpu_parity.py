@@ -346,3 +346,51 @@ def test_full_size_properties():
                          p64.eps[:2].double(), p64.dt)
     for a, r, nm in zip(o1, ref, ("paths", "means", "chol")):
         assert normwise(a[:2], r) < 1e-4, f"{nm} vs fp64 oracle: {normwise(a[:2], r)}"
+
+
+def test_tc_family_large_batch_properties():
+    """Large batch (B = 3 200 = 25 tiles of 128 trajectories): AUTO must pick the tensor-core recurrence
+    family; size-independent properties -- bit-determinism (fixed-order reductions, no atomics), agreement
+    with the FP32 register-resident family on every output and gradient, linearity of the backward, and
+    fp64-oracle agreement on a slice of the batch."""
+    from viforsdes_b200 import _lib, ops
+
+    p = O.make_problem("lv", 3200, 40, context_dim=128, hidden_dim=64, num_layers=2)
+    head = build_head(p)
+
+    def run(scale=1.0):
+        for q in head.parameters():
+            q.grad = None
+        x0, full, view, theta, eps = cuda_inputs(p)
+        out = head.sample_diffusion_paths(x0, view, theta, eps, p.dt)
+        g = torch.Generator(device="cuda").manual_seed(3)
+        cts = [torch.randn(o.shape, device="cuda", generator=g) * scale for o in out]
+        torch.autograd.backward(list(out), cts)
+        return [o.detach() for o in out], {"x0": x0.grad, "context": full.grad, "theta": theta.grad, **head_grads(head)}
+
+    ops.set_variant(_lib.VARIANT_AUTO)
+    o1, g1 = run()
+    o2, g2 = run()
+    for a, b in zip(o1, o2):
+        assert torch.equal(a, b), "forward must be bit-deterministic"
+    for k in g1:
+        assert torch.equal(g1[k], g2[k]), f"backward must be bit-deterministic ({k})"
+    _, g3 = run(scale=2.0)
+    for k in g1:
+        assert normwise(g3[k], 2.0 * g1[k]) < 1e-5, f"backward must be linear in the cotangents ({k})"
+    ops.set_variant(_lib.VARIANT_TC)
+    o5, _ = run()
+    for a, b in zip(o1, o5):
+        assert torch.equal(a, b), "AUTO at B = 3200 must be the tensor-core family"
+    ops.set_variant(_lib.VARIANT_FAST)
+    o4, g4 = run()
+    for a, b, nm in zip(o1, o4, ("paths", "means", "chol")):
+        assert normwise(a, b) < 1e-4, f"tc vs fast {nm}: {normwise(a, b)}"
+    for k in g1:
+        assert normwise(g1[k], g4[k]) < 2e-4, f"tc vs fast grad {k}: {normwise(g1[k], g4[k])}"
+    ops.set_variant(_lib.VARIANT_AUTO)
+    w64 = p.weights.map(lambda t: t.double())
+    sl = slice(3197, 3200)  # last rows of the last (full) tile
+    ref = O.sample_paths(w64, p.x0[sl].double(), p.context[sl].double(), p.theta[sl].double(), p.eps[sl].double(), p.dt)
+    for a, r, nm in zip(o1, ref, ("paths", "means", "chol")):
+        assert normwise(a[sl], r) < 1e-4, f"{nm} vs fp64 oracle: {normwise(a[sl], r)}"

@@ -31,17 +31,38 @@ struct GenericSmem {
     z = out + n_out;
     eps = z + S;
   }
-  static size_t bytes(int NL, int H, int n_out, int S) {
+  __host__ __device__ static size_t bytes(int NL, int H, int n_out, int S) {
     return sizeof(float) * (size_t)(NL * H + 9 * H + n_out + 2 * S);
   }
 };
 
+// SW: the recurrent, output and state-column weights are staged once per CTA in shared memory, transposed
+// ([k][row], padded row pitch) so that thread `row` walks its dot product with conflict-free LDS instead of a
+// strided L2 stream (18 ms -> ~1 ms per launch at B = 1024, T = 100, S = 10).  Used whenever they fit (H = 64, NL = 2,
+// S = 10: 171 KB); larger shapes stream from L2 as before.
+template <bool SW, int HT>
 __global__ void __launch_bounds__(kThreads) path_fwd_generic_kernel(PathParams p) {
   extern __shared__ float smem_f[];
-  const int H = p.H, S = p.S, NL = p.NL, G = 3 * p.H;
+  const int H = HT > 0 ? HT : p.H, S = p.S, NL = p.NL, G = 3 * H;  // HT > 0: compile-time trip counts
   const int ld0 = p.S + p.C + p.P;
   GenericSmem sm(smem_f, NL, H, p.n_out, S);
   const int tid = threadIdx.x;
+  const int GP = G + 1, OP = p.n_out + 1;  // padded pitches of the transposed copies
+  float* wt_hh = smem_f + GenericSmem::bytes(NL, H, p.n_out, S) / sizeof(float);  // [NL][H][GP]
+  float* wt_ih = wt_hh + (size_t)NL * H * GP;                                      // [NL-1][H][GP]
+  float* wt_out = wt_ih + (size_t)(NL - 1) * H * GP;                               // [H][OP]
+  float* wt_z = wt_out + (size_t)H * OP;                                           // [S][GP]
+  if (SW) {
+    for (int k = 0; k < NL; ++k)
+      for (int idx = tid; idx < G * H; idx += kThreads) {
+        const int j = idx / H, q = idx % H;
+        wt_hh[((size_t)k * H + q) * GP + j] = p.w_hh[k][idx];
+        if (k > 0) wt_ih[((size_t)(k - 1) * H + q) * GP + j] = p.w_ih[k][idx];
+      }
+    for (int idx = tid; idx < p.n_out * H; idx += kThreads) wt_out[(size_t)(idx % H) * OP + idx / H] = p.out_w[idx];
+    for (int idx = tid; idx < G * S; idx += kThreads) wt_z[(size_t)(idx % S) * GP + idx / S] = p.w_ih[0][(int64_t)(idx / S) * ld0 + idx % S];
+    __syncthreads();
+  }
 
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     for (int i = tid; i < NL * H; i += kThreads) sm.h[i] = 0.f;
@@ -57,24 +78,57 @@ __global__ void __launch_bounds__(kThreads) path_fwd_generic_kernel(PathParams p
     }
     __syncthreads();
 
+    // one gate row per thread when 3H <= kThreads: the layer-0 input of the next step is prefetched a step ahead
+    const bool pre = G <= kThreads;
+    float gi_pre = (pre && tid < G && p.T > 0) ? p.gi_ctx[b * p.T * G + tid] : 0.f;
     for (int64_t t = 0; t < p.T; ++t) {
       const int64_t row = b * p.T + t;
+      const float gi_now = gi_pre;
+      if (pre && tid < G && t + 1 < p.T) gi_pre = p.gi_ctx[(row + 1) * G + tid];
       for (int k = 0; k < NL; ++k) {
         // gate pre-activations, one row per thread
         for (int j = tid; j < G; j += kThreads) {
           float gi, gh = p.b_hh[k][j];
-          const float* whh = p.w_hh[k] + (int64_t)j * H;
           const float* hk = sm.h + k * H;
-          for (int q = 0; q < H; ++q) gh += whh[q] * hk[q];
+          if (SW) {
+            const float* w = wt_hh + (size_t)k * H * GP + j;
+            float g2 = 0.f;
+#pragma unroll 8
+            for (int q = 0; q + 1 < H; q += 2) {
+              gh = fmaf(w[q * GP], hk[q], gh);
+              g2 = fmaf(w[(q + 1) * GP], hk[q + 1], g2);
+            }
+            if (H & 1) g2 = fmaf(w[(H - 1) * GP], hk[H - 1], g2);
+            gh += g2;
+          } else {
+            const float* whh = p.w_hh[k] + (int64_t)j * H;
+            for (int q = 0; q < H; ++q) gh += whh[q] * hk[q];
+          }
           if (k == 0) {
-            gi = p.gi_ctx[row * G + j] + sm.gth[j];
-            const float* wz = p.w_ih[0] + (int64_t)j * ld0;
-            for (int s = 0; s < S; ++s) gi += wz[s] * sm.z[s];
+            gi = (pre ? gi_now : p.gi_ctx[row * G + j]) + sm.gth[j];
+            if (SW) {
+              for (int s = 0; s < S; ++s) gi = fmaf(wt_z[(size_t)s * GP + j], sm.z[s], gi);
+            } else {
+              const float* wz = p.w_ih[0] + (int64_t)j * ld0;
+              for (int s = 0; s < S; ++s) gi += wz[s] * sm.z[s];
+            }
           } else {
             gi = p.b_ih[k][j];
-            const float* wih = p.w_ih[k] + (int64_t)j * H;
             const float* hb = sm.h + (k - 1) * H;
-            for (int q = 0; q < H; ++q) gi += wih[q] * hb[q];
+            if (SW) {
+              const float* w = wt_ih + (size_t)(k - 1) * H * GP + j;
+              float g2 = 0.f;
+#pragma unroll 8
+              for (int q = 0; q + 1 < H; q += 2) {
+                gi = fmaf(w[q * GP], hb[q], gi);
+                g2 = fmaf(w[(q + 1) * GP], hb[q + 1], g2);
+              }
+              if (H & 1) g2 = fmaf(w[(H - 1) * GP], hb[H - 1], g2);
+              gi += g2;
+            } else {
+              const float* wih = p.w_ih[k] + (int64_t)j * H;
+              for (int q = 0; q < H; ++q) gi += wih[q] * hb[q];
+            }
           }
           sm.gi[j] = gi;
           sm.gh[j] = gh;
@@ -101,9 +155,20 @@ __global__ void __launch_bounds__(kThreads) path_fwd_generic_kernel(PathParams p
       // output projection
       for (int m = tid; m < p.n_out; m += kThreads) {
         float acc = p.out_b[m];
-        const float* wo = p.out_w + (int64_t)m * H;
         const float* ht = sm.h + (NL - 1) * H;
-        for (int q = 0; q < H; ++q) acc += wo[q] * ht[q];
+        if (SW) {
+          float a2 = 0.f;
+#pragma unroll 8
+          for (int q = 0; q + 1 < H; q += 2) {
+            acc = fmaf(wt_out[q * OP + m], ht[q], acc);
+            a2 = fmaf(wt_out[(q + 1) * OP + m], ht[q + 1], a2);
+          }
+          if (H & 1) a2 = fmaf(wt_out[(H - 1) * OP + m], ht[H - 1], a2);
+          acc += a2;
+        } else {
+          const float* wo = p.out_w + (int64_t)m * H;
+          for (int q = 0; q < H; ++q) acc += wo[q] * ht[q];
+        }
         sm.out[m] = acc;
       }
       if (tid < S) sm.eps[tid] = p.eps[row * S + tid];
@@ -152,18 +217,38 @@ struct GenericBwdSmem {
     dz = dout + n_out;
     eps = dz + S;
   }
-  static size_t bytes(int NL, int H, int n_out, int S) {
+  __host__ __device__ static size_t bytes(int NL, int H, int n_out, int S) {
     return sizeof(float) * (size_t)(NL * H + 8 * H + n_out + 2 * S);
   }
 };
 
+// SW: weights staged once per CTA in shared memory (native row-major: thread i reads column i, conflict-free).
+// In both modes the transposed products are split over kThreads / H row ranges and summed through shared memory.
+template <bool SW, int HT>
 __global__ void __launch_bounds__(kThreads) path_bwd_generic_kernel(PathParams p) {
   extern __shared__ float smem_f[];
-  const int H = p.H, S = p.S, NL = p.NL, G = 3 * p.H;
+  const int H = HT > 0 ? HT : p.H, S = p.S, NL = p.NL, G = 3 * H;
   const int ld0 = p.S + p.C + p.P;
   GenericBwdSmem sm(smem_f, NL, H, p.n_out, S);
   const int tid = threadIdx.x;
   const int64_t srow = stash_row_floats(NL, H);
+  const int nparts = kThreads / H > 0 ? kThreads / H : 1;  // row ranges of the transposed products (H <= 256)
+  float* red = smem_f + GenericBwdSmem::bytes(NL, H, p.n_out, S) / sizeof(float);  // [2][nparts][H] + [16 parts][S]
+  float* redz = red + 2 * nparts * H;
+  float* s_whh = redz + 16 * S;                        // [NL][G][H]
+  float* s_wih = s_whh + (size_t)NL * G * H;           // [NL-1][G][H]
+  float* s_wout = s_wih + (size_t)(NL - 1) * G * H;    // [n_out][H]
+  float* s_wz = s_wout + (size_t)p.n_out * H;          // [G][S]
+  if (SW) {
+    for (int k = 0; k < NL; ++k)
+      for (int idx = tid; idx < G * H; idx += kThreads) {
+        s_whh[(size_t)k * G * H + idx] = p.w_hh[k][idx];
+        if (k > 0) s_wih[(size_t)(k - 1) * G * H + idx] = p.w_ih[k][idx];
+      }
+    for (int idx = tid; idx < p.n_out * H; idx += kThreads) s_wout[idx] = p.out_w[idx];
+    for (int idx = tid; idx < G * S; idx += kThreads) s_wz[idx] = p.w_ih[0][(int64_t)(idx / S) * ld0 + idx % S];
+    __syncthreads();
+  }
 
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     for (int i = tid; i < NL * H; i += kThreads) sm.dhc[i] = 0.f;
@@ -199,9 +284,19 @@ __global__ void __launch_bounds__(kThreads) path_bwd_generic_kernel(PathParams p
         p.dout[row * p.n_out + m] = d;
       }
       __syncthreads();
+      if (tid < nparts * H) {
+        // W_out^T d_out, split over row ranges like the recurrent products
+        const int i = tid % H, part = tid / H;
+        const int m0 = part * p.n_out / nparts, m1 = (part + 1) * p.n_out / nparts;
+        const float* wo = SW ? s_wout : p.out_w;
+        float acc = 0.f;
+        for (int m = m0; m < m1; ++m) acc += wo[(int64_t)m * H + i] * sm.dout[m];
+        red[part * H + i] = acc;
+      }
+      __syncthreads();
       for (int i = tid; i < H; i += kThreads) {
         float acc = sm.dhc[(NL - 1) * H + i];
-        for (int m = 0; m < p.n_out; ++m) acc += p.out_w[(int64_t)m * H + i] * sm.dout[m];
+        for (int q = 0; q < nparts; ++q) acc += red[q * H + i];
         sm.dh[i] = acc;
       }
       for (int k = NL - 1; k >= 0; --k) {
@@ -227,29 +322,59 @@ __global__ void __launch_bounds__(kThreads) path_bwd_generic_kernel(PathParams p
           dgo[3 * H + i] = dnh;
         }
         __syncthreads();
-        for (int i = tid; i < H; i += kThreads) {
-          const float* whh = p.w_hh[k];
-          float acc = 0.f;
-          for (int j = 0; j < H; ++j) {
+        if (tid < nparts * H) {
+          // partial transposed products over this thread's range of gate rows
+          const int i = tid % H, part = tid / H;
+          const int j0 = part * H / nparts, j1 = (part + 1) * H / nparts;
+          const float* whh = SW ? s_whh + (size_t)k * G * H : p.w_hh[k];
+          float acc = 0.f, accb = 0.f;
+#pragma unroll 4
+          for (int j = j0; j < j1; ++j) {
             acc += whh[(int64_t)(j)*H + i] * sm.dg[j];
             acc += whh[(int64_t)(H + j) * H + i] * sm.dg[H + j];
             acc += whh[(int64_t)(2 * H + j) * H + i] * sm.dg[3 * H + j];
           }
-          sm.dhc[k * H + i] += acc;
           if (k > 0) {
-            const float* wih = p.w_ih[k];
-            float accb = sm.dhc[(k - 1) * H + i];
-            for (int j = 0; j < G; ++j) accb += wih[(int64_t)j * H + i] * sm.dg[j];
-            sm.dh[i] = accb;
+            const float* wih = SW ? s_wih + (size_t)(k - 1) * G * H : p.w_ih[k];
+#pragma unroll 4
+            for (int j = j0; j < j1; ++j) {
+              accb += wih[(int64_t)j * H + i] * sm.dg[j];
+              accb += wih[(int64_t)(H + j) * H + i] * sm.dg[H + j];
+              accb += wih[(int64_t)(2 * H + j) * H + i] * sm.dg[2 * H + j];
+            }
           }
+          red[part * H + i] = acc;
+          red[(nparts + part) * H + i] = accb;
         }
         if (k == 0) {
-          if (tid < S) {
+          // d z_t += W_ih_l0[:, :S]^T d_gi: 16 row ranges x S columns
+          const int s = tid % 16, part = tid / 16;
+          if (s < S) {
+            const int j0 = part * G / 16, j1 = (part + 1) * G / 16;
             float acc = 0.f;
-            for (int j = 0; j < G; ++j) acc += p.w_ih[0][(int64_t)j * ld0 + tid] * sm.dg[j];
-            sm.dz[tid] += acc;
+            if (SW) {
+              for (int j = j0; j < j1; ++j) acc += s_wz[j * S + s] * sm.dg[j];
+            } else {
+              for (int j = j0; j < j1; ++j) acc += p.w_ih[0][(int64_t)j * ld0 + s] * sm.dg[j];
+            }
+            redz[part * S + s] = acc;
           }
           for (int j = tid; j < G; j += kThreads) sm.sdgi[j] += sm.dg[j];
+        }
+        __syncthreads();
+        for (int i = tid; i < H; i += kThreads) {
+          float acc = 0.f, accb = 0.f;
+          for (int q = 0; q < nparts; ++q) {
+            acc += red[q * H + i];
+            accb += red[(nparts + q) * H + i];
+          }
+          sm.dhc[k * H + i] += acc;
+          if (k > 0) sm.dh[i] = sm.dhc[(k - 1) * H + i] + accb;
+        }
+        if (k == 0 && tid < S) {
+          float acc = 0.f;
+          for (int q = 0; q < 16; ++q) acc += redz[q * S + tid];
+          sm.dz[tid] += acc;
         }
         __syncthreads();
       }
@@ -271,15 +396,57 @@ int grid_for(int64_t B) {
 }  // namespace
 
 int launch_path_fwd_generic(const PathParams& p, cudaStream_t st) {
-  size_t smem = GenericSmem::bytes(p.NL, p.H, p.n_out, p.S);
-  path_fwd_generic_kernel<<<grid_for(p.B), kThreads, smem, st>>>(p);
+  const size_t base = GenericSmem::bytes(p.NL, p.H, p.n_out, p.S);
+  const int G = 3 * p.H;
+  const size_t wfl = (size_t)p.NL * p.H * (G + 1) + (size_t)(p.NL - 1) * p.H * (G + 1) + (size_t)p.H * (p.n_out + 1) +
+                     (size_t)p.S * (G + 1);
+  const size_t smem_w = base + sizeof(float) * wfl;
+  if (smem_w <= 227 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_fwd_generic_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_fwd_generic_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(p.B < sms ? p.B : sms);
+    if (p.H == 64)
+      path_fwd_generic_kernel<true, 64><<<grid, kThreads, smem_w, st>>>(p);
+    else
+      path_fwd_generic_kernel<true, 0><<<grid, kThreads, smem_w, st>>>(p);
+  } else {
+    path_fwd_generic_kernel<false, 0><<<grid_for(p.B), kThreads, base, st>>>(p);
+  }
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
 
 int launch_path_bwd_generic(const PathParams& p, cudaStream_t st) {
-  size_t smem = GenericBwdSmem::bytes(p.NL, p.H, p.n_out, p.S);
-  path_bwd_generic_kernel<<<grid_for(p.B), kThreads, smem, st>>>(p);
+  const int G = 3 * p.H;
+  const int nparts = kThreads / p.H > 0 ? kThreads / p.H : 1;
+  const size_t base = GenericBwdSmem::bytes(p.NL, p.H, p.n_out, p.S) + sizeof(float) * ((size_t)2 * nparts * p.H + 16 * p.S);
+  const size_t wfl = (size_t)p.NL * G * p.H + (size_t)(p.NL - 1) * G * p.H + (size_t)p.n_out * p.H + (size_t)G * p.S;
+  const size_t smem_w = base + sizeof(float) * wfl;
+  if (smem_w <= 227 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_bwd_generic_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_bwd_generic_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(p.B < sms ? p.B : sms);
+    if (p.H == 64)
+      path_bwd_generic_kernel<true, 64><<<grid, kThreads, smem_w, st>>>(p);
+    else
+      path_bwd_generic_kernel<true, 0><<<grid, kThreads, smem_w, st>>>(p);
+  } else {
+    path_bwd_generic_kernel<false, 0><<<grid_for(p.B), kThreads, base, st>>>(p);
+  }
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
