@@ -51,10 +51,18 @@ FAST_OK = {"lv_h64_b37_ragged_tile", "ou_h32_b13_ragged_tile", "ou_h32_l2", "lv_
            "l96s4_h64_c128_l2"}
 
 
+# wide-state register-resident family (4 < S <= 16, H <= 64, NL <= 2)
+CASES["l96s16_h32_l1"] = ("l96", 3, 9, dict(context_dim=8, hidden_dim=32, num_layers=1, state_dim=16))
+CASES["l96s5_h64_l2_b150"] = ("l96", 150, 5, dict(context_dim=16, hidden_dim=64, num_layers=2, state_dim=5))
+FASTS_OK = {"l96s10_h64_l2", "l96s6_h64_c128_l2", "l96s16_h32_l1", "l96s5_h64_l2_b150"}
+
+
 def _variants(name):
     from viforsdes_b200 import _lib
 
     v = [_lib.VARIANT_GENERIC, _lib.VARIANT_FAST, _lib.VARIANT_TILED] if name in FAST_OK else [_lib.VARIANT_GENERIC]
+    if name in FASTS_OK:
+        v.append(_lib.VARIANT_FAST)
     if name in TC_OK:  # the same kernels with the GEMM stages forced onto the fp32 SIMT path
         v += [x | NO_TC for x in v]
     if name in TC_REC_OK:  # gate GEMMs of the recurrence on tcgen05 (fp16 hi/lo 3-pass split)

@@ -178,6 +178,11 @@ bool use_fast(const visde_dims* d, const PathParams& p) {
   if ((d->variant & 0xff) == VISDE_VARIANT_GENERIC) return false;
   return fast_supported(p);
 }
+// wide-state version of the register-resident family (4 < S <= 16)
+bool use_fasts(const visde_dims* d, const PathParams& p) {
+  const int fam = d->variant & 0xff;
+  return (fam == VISDE_VARIANT_AUTO || fam == VISDE_VARIANT_FAST) && fasts_supported(p);
+}
 
 __global__ void fill_loss_cotangent_kernel(float* g_terms, int64_t B) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,7 +235,7 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
   VISDE_REQUIRE(d->T == 0 || (ctx && ctx->ptr && eps && means && chol), "NULL tensor argument");
   VISDE_REQUIRE(d->P == 0 || theta, "theta is NULL");
   VISDE_REQUIRE(((d->variant & 0xff) != VISDE_VARIANT_FAST && (d->variant & 0xff) != VISDE_VARIANT_TILED) ||
-                    (d->H <= 64 && d->H % 4 == 0 && d->NL <= 2 && d->S <= 4),
+                    (d->H <= 64 && d->H % 4 == 0 && d->NL <= 2 && d->S <= ((d->variant & 0xff) == VISDE_VARIANT_FAST ? 16 : 4)),
                 "fast variant requested for an unsupported shape (H=%d NL=%d S=%d)", d->H, d->NL, d->S);
   VISDE_REQUIRE((d->variant & 0xff) != VISDE_VARIANT_TC || (d->H == 64 && d->NL <= 2 && d->S <= 4 && use_tc(d, ctx)),
                 "tensor-core recurrence requested for an unsupported shape (needs H=64, NL<=2, S<=4, fp32 16-byte "
@@ -282,6 +287,7 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
   }
   StageTimer tm(VISDE_STAGE_K1_PATH_FWD, 1, st);
   if (tcrec) return launch_path_fwd_tc(p, st);
+  if (use_fasts(d, p)) return launch_path_fwd_fasts(p, st);
   if (use_fast(d, p)) {
     const int fam = d->variant & 0xff;
     const int nb = (fam == VISDE_VARIANT_FAST || fam == VISDE_VARIANT_TC) ? 0 : tiled_batch_tile(d->B, fam == VISDE_VARIANT_TILED);
@@ -333,8 +339,9 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
   p.sdg = reinterpret_cast<float*>(wsb + ws.sdg);
   p.paths = const_cast<float*>(paths);
   const bool tcrec = d->T > 0 && use_tc_rec(d, p, ctx);
-  const bool fastk = !tcrec && use_fast(d, p);
-  p.cta_part = fastk ? reinterpret_cast<float*>(wsb + ws.cta_part) : nullptr;
+  const bool fastsk = !tcrec && use_fasts(d, p);
+  const bool fastk = !tcrec && !fastsk && use_fast(d, p);
+  p.cta_part = (fastk || fastsk) ? reinterpret_cast<float*>(wsb + ws.cta_part) : nullptr;
   float* partials = reinterpret_cast<float*>(wsb + ws.partials);
 
   // K2: reverse-time recurrence
@@ -350,8 +357,8 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
     rc = launch_tc_thin_grads(p, p.dout, gw, partials, ws.partial_floats, st);
     if (rc) return rc;
   } else {
-    StageTimer tm(VISDE_STAGE_K2_PATH_BWD, 1, st);
-    rc = fastk ? launch_path_bwd_fast(p, st) : launch_path_bwd_generic(p, st);
+    StageTimer tm(VISDE_STAGE_K2_PATH_BWD, fastsk ? 2 : 1, st);
+    rc = fastsk ? launch_path_bwd_fasts(p, gw, st) : fastk ? launch_path_bwd_fast(p, st) : launch_path_bwd_generic(p, st);
     if (rc) return rc;
   }
   if (d->T == 0) {
@@ -401,8 +408,8 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
     }
   }
   // K4: weight gradients
-  StageTimer tm4(VISDE_STAGE_K4_WGRAD, (fastk || tcrec) ? (tc ? 5 : 3 + 2 * (2 * NL)) : (tc ? 2 + 2 * (2 * NL + 1) : 2 * (2 * NL + 1)), st);
-  if (fastk || tcrec) {
+  StageTimer tm4(VISDE_STAGE_K4_WGRAD, (fastk || tcrec || fastsk) ? (tc ? 5 : 3 + 2 * (2 * NL)) : (tc ? 2 + 2 * (2 * NL + 1) : 2 * (2 * NL + 1)), st);
+  if (fastk || tcrec || fastsk) {
     // fast family: biases, dW_ih_l0[:, :S], dW_out, db_out were accumulated inside K2 (per-CTA partials);
     // tensor-core family: launch_tc_thin_grads above already wrote them
     if (fastk) {
@@ -414,6 +421,18 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
       RowSrc bs[1] = {RowSrc{theta, P, 0, 0, P, VISDE_F32}};
       TnOut o{gw->w_ih[0] + S + C, ld0, 0, P};
       rc = launch_gemm_tn(A, G, G, 0, bs, 1, d->B, 1, &o, 1, partials, ws.partial_floats, st);
+      if (rc) return rc;
+    }
+    if (fastsk && d->T > 0) {
+      // wide-state family: the S-sized reductions are time-parallel GEMMs over (b, t)
+      RowSrc bz[1] = {RowSrc{paths, (int64_t)(d->T + 1) * S, S, 0, S, VISDE_F32}};
+      TnOut oz{gw->w_ih[0], ld0, 0, S};
+      rc = launch_gemm_tn(dg_src(0), G, G, 0, bz, 1, d->B, d->T, &oz, 1, partials, ws.partial_floats, st);
+      if (rc) return rc;
+      RowSrc A{p.dout, d->T * (int64_t)p.n_out, p.n_out, 0, p.n_out, VISDE_F32};
+      RowSrc bo[2] = {h_src(NL - 1, 0), ones};
+      TnOut oo[2] = {{gw->out_w, H, 0, H}, {gw->out_b, 1, H, 1}};
+      rc = launch_gemm_tn(A, p.n_out, p.n_out, 0, bo, 2, d->B, d->T, oo, 2, partials, ws.partial_floats, st);
       if (rc) return rc;
     }
     if (tcrec) return tc_wgrads_tiled(ctx, dg_tiled, p.stash, d->B, d->T, S, C, P, H, NL, gw, partials, ws.partial_floats, st);

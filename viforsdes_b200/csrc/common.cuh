@@ -113,6 +113,12 @@ int launch_path_bwd_fast(const PathParams& p, cudaStream_t st);
 // batch-tiled family for B > #SM (path_tiled.cu): NB trajectories per CTA, weights in shared memory
 int tiled_batch_tile(int64_t B, bool force);
 int launch_path_fwd_tiled(const PathParams& p, int NB, cudaStream_t st);
+// register-resident family for wide state spaces, 4 < S <= 16 (path_fast_s.cu); the backward also writes the bias
+// gradients (p.cta_part: fasts_partials_floats()); dW_ih_l0[:, :S], dW_out, db_out are left to the GEMM stage
+bool fasts_supported(const PathParams& p);
+size_t fasts_partials_floats(int NL, int H);
+int launch_path_fwd_fasts(const PathParams& p, cudaStream_t st);
+int launch_path_bwd_fasts(const PathParams& p, const visde_weight_grads* gw, cudaStream_t st);
 // tensor-core recurrence family for large batches (path_tc.cu): 128 trajectories per CTA, tcgen05 gate GEMMs
 bool tc_rec_supported(const PathParams& p);
 int launch_gth(const PathParams& p, float* gth, cudaStream_t st);  // per-trajectory constant part of the layer-0 gates
