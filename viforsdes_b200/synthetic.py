@@ -28,6 +28,21 @@ WORKLOADS = {
 }
 
 
+class _Workloads(dict):
+    """Named configurations plus the pattern `<ou|lv>_b<B>_t<T>` (dt = 0.05) for the batch sweep of config 3."""
+
+    def __missing__(self, name: str):
+        import re
+
+        m = re.fullmatch(r"(ou|lv)_b(\d+)_t(\d+)", name)
+        if not m:
+            raise KeyError(name)
+        return (m.group(1), int(m.group(2)), int(m.group(3)), 0.05)
+
+
+WORKLOADS = _Workloads(WORKLOADS)
+
+
 @dataclass
 class Inputs:
     kind: str
