@@ -178,6 +178,8 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", default="auto", choices=["auto", "generic", "fast", "tiled", "tc"],
                     help="recurrence kernel family (ad-hoc comparisons; production is auto)")
+    ap.add_argument("--context-dtype", default="f32", choices=["f32", "bf16"],
+                    help="dtype of context / grad_context in the device-resident leg (bf16 = the reference's AMP mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -209,7 +211,8 @@ def main() -> None:
         inp.w_ih, inp.w_hh, inp.b_ih, inp.b_hh, inp.out_w, inp.out_b = ref.w_ih, ref.w_hh, ref.b_ih, ref.b_hh, ref.out_w, ref.out_b
     variant = {"auto": _lib.VARIANT_AUTO, "generic": _lib.VARIANT_GENERIC, "fast": _lib.VARIANT_FAST,
                "tiled": _lib.VARIANT_TILED, "tc": _lib.VARIANT_TC}[args.variant]
-    it = PathIteration(inp, dev, variant=variant)
+    it = PathIteration(inp, dev, variant=variant,
+                       context_dtype=torch.bfloat16 if args.context_dtype == "bf16" else torch.float32)
     S, Cd, H, NL = it.S, it.C, it.H, it.NL
     units = B * T
     flush = torch.empty(512 << 20, device=dev, dtype=torch.uint8)
@@ -335,7 +338,7 @@ def main() -> None:
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": args.workload, "sde": kind, "batch_per_gpu": B, "n_steps": T, "dt": dt, "state_dim": S,
-                   "context_dim": Cd, "hidden_dim": H, "num_layers": NL, "parallelism": f"dp{world}", "variant": args.variant,
+                   "context_dim": Cd, "hidden_dim": H, "num_layers": NL, "parallelism": f"dp{world}", "variant": args.variant, "context_dtype": args.context_dtype,
                    "l2": "512 MB flush write between timed steps; per-step working set ~0.9 GB > 126 MB L2"},
         "e2e": e2e, "gpu_launches": int(sum(cnt)),
         "roofline": roofline, "step_roofline": step_roofline, "stages": stages, "cpu_baseline": cb,

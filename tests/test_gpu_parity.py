@@ -233,6 +233,29 @@ def test_bf16_and_contiguous_context():
     assert torch.equal(a[0], b[0]) and torch.equal(a[4]["w_ih_l0"], b[4]["w_ih_l0"])
 
 
+def test_bf16_context_takes_the_tensor_core_gemms():
+    """bf16 context on shapes eligible for the tcgen05 GEMM stages (what the reference's autocast encoder feeds the
+    head): widened once to fp32 in the workspace, then the same tensor-core K0 / K3 / K4 as for fp32 context -- both
+    with the register-resident and with the tensor-core recurrence family.  Same numbers as the fp32 SIMT stages on
+    the bf16-rounded values."""
+    from viforsdes_b200 import _lib, ops
+
+    p = O.make_problem("lv", 130, 21, context_dim=128, hidden_dim=64, num_layers=2)
+    pb = O.make_problem("lv", 130, 21, context_dim=128, hidden_dim=64, num_layers=2)
+    pb.context = p.context.to(torch.bfloat16).to(torch.float32)
+    r32, r64 = oracle_refs(pb)
+    for v in (_lib.VARIANT_AUTO, _lib.VARIANT_TC, _lib.VARIANT_FAST | NO_TC):
+        ops.set_variant(v)
+        paths, means, chol, terms, grads = run_cuda_fwd_bwd(p, ctx_dtype=torch.bfloat16)
+        assert grads["context"].dtype == torch.bfloat16
+        for a, b32, b64, nm in zip((paths, means, chol), r32[:3], r64[:3], ("paths", "means", "chol")):
+            assert_parity(a, b32, b64, name=f"v{v}/{nm}")
+        assert_close(grads["context"].float(), r64[4]["context"], rtol=1e-2, atol_scale=1e-2, name=f"v{v}/grad_context(bf16)")
+        for nm in r64[4]:
+            if nm != "context":
+                assert_parity(grads[nm], r32[4][nm], r64[4][nm], name=f"v{v}/grad_{nm}")
+
+
 def test_edge_shapes():
     """B = 1, T = 1, and empty inputs (B = 0 / T = 0) do not crash and match the oracle."""
     for B, T in ((1, 1), (1, 5), (3, 1)):

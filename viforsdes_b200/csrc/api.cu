@@ -48,6 +48,12 @@ namespace {
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// fp32 copy of a bf16 context (reserved whenever the dims are eligible for the tcgen05 GEMM stages)
+size_t ctx_f32_bytes(const visde_dims* d) {
+  const bool dims_ok = d->H == 64 && d->NL <= 2 && (d->C == 128 || d->C == 256);
+  return dims_ok ? align_up(sizeof(float) * (size_t)d->B * d->T * d->C) : 0;
+}
+
 int check_dims(const visde_dims* d) {
   VISDE_REQUIRE(d != nullptr, "dims is NULL");
   VISDE_REQUIRE(d->B >= 0 && d->T >= 0, "B and T must be non-negative (got %lld, %lld)", (long long)d->B,
@@ -83,7 +89,7 @@ bool tc_rec_possible(const visde_dims* d) {
 }
 
 struct BwdWs {
-  size_t dg, dout, sdg, partials, wsplit, cta_part, dg_tiled, total, partial_floats;
+  size_t dg, dout, sdg, partials, wsplit, cta_part, dg_tiled, ctx_f32, total, partial_floats;
 };
 BwdWs bwd_ws(const visde_dims* d) {
   BwdWs w{};
@@ -124,6 +130,8 @@ BwdWs bwd_ws(const visde_dims* d) {
   off += align_up(sizeof(float) * fast_partials_floats(d->NL, d->H, d->S));
   w.dg_tiled = off;   // d_pre of the tensor-core backward, row-fastest tiled
   if (tc_rec_possible(d)) off += align_up(sizeof(float) * padded_B(d) * d->T * d->NL * kDgSlots * d->H);
+  w.ctx_f32 = off;    // fp32 copy of a bf16 context for the tcgen05 GEMM stages
+  off += ctx_f32_bytes(d);
   w.total = off;
   return w;
 }
@@ -184,6 +192,33 @@ bool use_fasts(const visde_dims* d, const PathParams& p) {
   return (fam == VISDE_VARIANT_AUTO || fam == VISDE_VARIANT_FAST) && fasts_supported(p);
 }
 
+// bf16 context (what the reference's autocast encoder emits, inference/training_context.py:104) -> dense fp32
+// [B,T,C] in the workspace, so that the tcgen05 GEMM stages (fp32 TMA tiles, 3xTF32) serve it too; bf16 values are
+// exact in fp32, so this is the arithmetic of kernels/forward.py (load, widen, fp32 math)
+__global__ void ctx_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int64_t bstride, int64_t tstride, int64_t B,
+                                       int64_t T, int C, float* __restrict__ dst) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*T*C/2 pairs
+  const int64_t half_c = C / 2;
+  if (idx >= B * T * half_c) return;
+  const int64_t c2 = idx % half_c, bt = idx / half_c, t = bt % T, b = bt / T;
+  const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + b * bstride + t * tstride + 2 * c2);
+  *reinterpret_cast<float2*>(dst + bt * C + 2 * c2) = __bfloat1622float2(v);
+}
+bool ctx_convertible(const visde_dims* d, const visde_ctx_view* ctx) {
+  if (!ctx || ctx->dtype != VISDE_BF16 || (d->variant & VISDE_FLAG_NO_TENSOR_CORES)) return false;
+  if ((reinterpret_cast<uintptr_t>(ctx->ptr) & 3) || (ctx->batch_stride & 1) || (ctx->time_stride & 1)) return false;
+  visde_ctx_view probe{reinterpret_cast<const void*>(uintptr_t(256)), d->T * (int64_t)d->C, d->C, VISDE_F32};
+  return tc_supported(d->H, d->NL, d->C, &probe);
+}
+int convert_ctx(const visde_dims* d, const visde_ctx_view* ctx, float* buf, visde_ctx_view* out, cudaStream_t st) {
+  const int64_t n = d->B * d->T * (d->C / 2);
+  ctx_bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(ctx->ptr),
+                                                                       ctx->batch_stride, ctx->time_stride, d->B, d->T, d->C, buf);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  *out = visde_ctx_view{buf, d->T * (int64_t)d->C, d->C, VISDE_F32};
+  return VISDE_OK;
+}
+
 __global__ void fill_loss_cotangent_kernel(float* g_terms, int64_t B) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -218,7 +253,7 @@ size_t visde_stash_bytes(const visde_dims* d) {
 
 size_t visde_workspace_bytes(const visde_dims* d, int backward) {
   if (check_dims(d) != VISDE_OK) return 0;
-  if (!backward) return fwd_gi_bytes(d) + fwd_wsplit_bytes(d) + fwd_gth_bytes(d) + 256;
+  if (!backward) return fwd_gi_bytes(d) + fwd_wsplit_bytes(d) + fwd_gth_bytes(d) + ctx_f32_bytes(d) + 256;
   return bwd_ws(d).total + 256;
 }
 
@@ -237,7 +272,7 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
   VISDE_REQUIRE(((d->variant & 0xff) != VISDE_VARIANT_FAST && (d->variant & 0xff) != VISDE_VARIANT_TILED) ||
                     (d->H <= 64 && d->H % 4 == 0 && d->NL <= 2 && d->S <= ((d->variant & 0xff) == VISDE_VARIANT_FAST ? 16 : 4)),
                 "fast variant requested for an unsupported shape (H=%d NL=%d S=%d)", d->H, d->NL, d->S);
-  VISDE_REQUIRE((d->variant & 0xff) != VISDE_VARIANT_TC || (d->H == 64 && d->NL <= 2 && d->S <= 4 && use_tc(d, ctx)),
+  VISDE_REQUIRE((d->variant & 0xff) != VISDE_VARIANT_TC || (d->H == 64 && d->NL <= 2 && d->S <= 4 && (use_tc(d, ctx) || ctx_convertible(d, ctx))),
                 "tensor-core recurrence requested for an unsupported shape (needs H=64, NL<=2, S<=4, fp32 16-byte "
                 "aligned context with C in {128, 256}; got H=%d NL=%d S=%d C=%d)", d->H, d->NL, d->S, d->C);
   if (workspace_bytes < visde_workspace_bytes(d, 0) - 256 || (!workspace && d->T > 0)) {
@@ -245,6 +280,12 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
     return VISDE_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  visde_ctx_view ctx_f32;
+  if (d->T > 0 && ctx_convertible(d, ctx)) {
+    float* buf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + fwd_gi_bytes(d) + fwd_wsplit_bytes(d) + fwd_gth_bytes(d));
+    if ((rc = convert_ctx(d, ctx, buf, &ctx_f32, st))) return rc;
+    ctx = &ctx_f32;
+  }
   PathParams p;
   fill_common(p, d, dt, w);
   p.x0 = x0;
@@ -321,6 +362,11 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
   const int H = d->H, S = d->S, C = d->C, P = d->P, NL = d->NL, G = 3 * d->H;
   const int ld0 = S + C + P;
   char* wsb = reinterpret_cast<char*>(workspace);
+  visde_ctx_view ctx_f32;
+  if (d->T > 0 && ctx_convertible(d, ctx)) {
+    if ((rc = convert_ctx(d, ctx, reinterpret_cast<float*>(wsb + ws.ctx_f32), &ctx_f32, st))) return rc;
+    ctx = &ctx_f32;
+  }
   PathParams p;
   fill_common(p, d, dt, w);
   p.x0 = nullptr;
@@ -383,8 +429,11 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
   };
   const RowSrc ones{nullptr, 0, 0, 0, 1, VISDE_F32};
 
-  const bool tc = use_tc(d, ctx) && (grad_ctx->batch_stride % 4 == 0) && (grad_ctx->time_stride % 4 == 0) &&
-                  ((reinterpret_cast<uintptr_t>(grad_ctx->ptr) & 15) == 0);
+  // the tcgen05 K3 writes fp32 rows with 16-byte stores (needs alignment) or bf16 element-wise
+  const bool tc = use_tc(d, ctx) &&
+                  (grad_ctx->dtype == VISDE_BF16 ||
+                   ((grad_ctx->batch_stride % 4 == 0) && (grad_ctx->time_stride % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(grad_ctx->ptr) & 15) == 0)));
   float* wsplit = reinterpret_cast<float*>(wsb + ws.wsplit);
   // K3: grad_context = d_gi_l0 . W_ih_l0[:, S:S+C]
   {

@@ -15,7 +15,8 @@ from viforsdes_b200.synthetic import Inputs
 
 
 class PathIteration:
-    def __init__(self, inp: Inputs, device: torch.device | str = "cuda", variant: int = _lib.VARIANT_AUTO) -> None:
+    def __init__(self, inp: Inputs, device: torch.device | str = "cuda", variant: int = _lib.VARIANT_AUTO,
+                 context_dtype: torch.dtype = torch.float32) -> None:
         if inp.sde_kind == _lib.SDE_GENERIC:
             raise ValueError("PathIteration covers the built-in OU / LV functors; user SDEs go through "
                              "viforsdes_b200.elbo.compute_evidence_lower_bound")
@@ -30,7 +31,10 @@ class PathIteration:
         self.dims = _lib.Dims(B, T, S, Cd, P, H, NL, variant)
         self.dt, self.sde_kind, self.mask = float(inp.dt), inp.sde_kind, inp.positive_mask
         to = lambda t: t.to(dev).contiguous()  # noqa: E731
-        self.x0, self.ctx, self.theta, self.eps = to(inp.x0), to(inp.context_full), to(inp.theta), to(inp.eps)
+        self.x0, self.theta, self.eps = to(inp.x0), to(inp.theta), to(inp.eps)
+        # bf16 = what the reference's autocast encoder hands to the head (grad_context comes back in the same dtype)
+        self.ctx = inp.context_full.to(dev).to(context_dtype).contiguous()
+        cdt = _lib.BF16 if context_dtype == torch.bfloat16 else _lib.F32
         self.w = [[to(t) for t in ws] for ws in (inp.w_ih, inp.w_hh, inp.b_ih, inp.b_hh)]
         self.out_w, self.out_b = to(inp.out_w), to(inp.out_b)
         # all 4*NL+2 weight gradients are views of ONE flat buffer: it is the all-reduce bucket
@@ -48,7 +52,7 @@ class PathIteration:
         self.g_z, self.g_means, self.g_chol = torch.empty_like(self.paths), torch.empty_like(self.means), torch.empty_like(self.chol)
         self.g_theta_elbo = torch.empty(B, P, **f)
         self.grad_x0, self.grad_theta = torch.empty(B, S, **f), torch.empty(B, P, **f)
-        self.grad_ctx = torch.zeros(B, T + 1, Cd, **f)
+        self.grad_ctx = torch.zeros(B, T + 1, Cd, device=dev, dtype=context_dtype)
         u8 = dict(device=dev, dtype=torch.uint8)
         self.stash = torch.empty(self.lib.visde_stash_bytes(C.byref(self.dims)), **u8)
         self.ws_f = torch.empty(self.lib.visde_workspace_bytes(C.byref(self.dims), 0), **u8)
@@ -57,8 +61,8 @@ class PathIteration:
         self.obs_values = to(inp.obs_values)
         self.obs = _lib.Obs(self.obs_idx.shape[0], self.obs_values.shape[1], self.obs_idx.data_ptr(),
                             self.obs_values.data_ptr(), None, float(inp.obs_variance))
-        self.cv = _lib.CtxView(self.ctx.data_ptr(), (T + 1) * Cd, Cd, _lib.F32)
-        self.gv = _lib.CtxView(self.grad_ctx.data_ptr(), (T + 1) * Cd, Cd, _lib.F32)
+        self.cv = _lib.CtxView(self.ctx.data_ptr(), (T + 1) * Cd, Cd, cdt)
+        self.gv = _lib.CtxView(self.grad_ctx.data_ptr(), (T + 1) * Cd, Cd, cdt)
         self.ws_struct = self._wstruct(self.w, self.out_w, self.out_b)
         self.gw_struct = self._wstruct(self.gw, self.g_out_w, self.g_out_b)
         # K0, K1, K5, K6, K2, grad_ctx, grad_theta, (2 NL + 1) x (split-K GEMM + reduce), theta-grad add
