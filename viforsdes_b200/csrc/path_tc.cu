@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
   constexpr uint32_t TMEM_COLS = NL == 2 ? 512 : 256;
   constexpr uint32_t D0_COL = 0, D1_COL = 192, DOUT_COL = NL == 2 ? 448 : 192;
   extern __shared__ __align__(1024) uint8_t smem_raw_tc[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023));
+  // offset arithmetic on the __shared__ array (not a uintptr_t round trip) keeps the address space known: LDS / STS
+  uint8_t* smem = smem_raw_tc + ((1024u - (smem_u32(smem_raw_tc) & 1023u)) & 1023u);
   typename L::Bars* bars = reinterpret_cast<typename L::Bars*>(smem + L::OFF_BAR);
   float* c0 = reinterpret_cast<float*>(smem + L::OFF_C0);
   float* c1 = reinterpret_cast<float*>(smem + L::OFF_C1);

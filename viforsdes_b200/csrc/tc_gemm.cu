@@ -276,9 +276,20 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (row_ok) {
           if (a.out_dtype == VISDE_BF16) {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + obase + c * 32;
+            if (c * 32 + 32 <= a.out_cols && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
-            for (int q = 0; q < 32; ++q)
-              if (c * 32 + q < a.out_cols) o[q] = __float2bfloat16(v[q]);
+              for (int q = 0; q < 32; q += 8) {
+                const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[q], v[q + 1]), p1 = __floats2bfloat162_rn(v[q + 2], v[q + 3]);
+                const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[q + 4], v[q + 5]), p3 = __floats2bfloat162_rn(v[q + 6], v[q + 7]);
+                *reinterpret_cast<uint4*>(o + q) =
+                    make_uint4(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1),
+                               *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; ++q)
+                if (c * 32 + q < a.out_cols) o[q] = __float2bfloat16(v[q]);
+            }
           } else {
             float* o = reinterpret_cast<float*>(a.out) + obase + c * 32;
             if (c * 32 + 32 <= a.out_cols && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
