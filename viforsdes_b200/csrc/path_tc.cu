@@ -25,6 +25,8 @@
 namespace visde {
 namespace {
 
+constexpr int kFwdThreads = 256;  // 8 warps = 255 registers per thread; warp 0 doubles as the MMA issuer
+
 template <int NL, int S>
 struct TcFwdSmem {
   static constexpr int NMAT = 2 * NL - 1;
@@ -58,7 +60,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t dcol, uint32_t a_hi, uint32_
 }
 
 template <int NL, int S>
-__global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tc_kernel(PathParams p) {
   using L = TcFwdSmem<NL, S>;
   constexpr int NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL, CS = L::CS, NMAT = L::NMAT;
   static_assert(NOUT <= 16, "output projection tile holds 16 rows");
@@ -82,9 +84,9 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
     float mx = 0.f, mo = 0.f;
     for (int m = 0; m < NMAT; ++m) {
       const float* src = m == 0 ? p.w_hh[0] : (m == 1 ? p.w_ih[1] : p.w_hh[1]);
-      for (int idx = tid; idx < 192 * 64; idx += kTcRecThreads) mx = fmaxf(mx, fabsf(src[idx]));
+      for (int idx = tid; idx < 192 * 64; idx += kFwdThreads) mx = fmaxf(mx, fabsf(src[idx]));
     }
-    for (int idx = tid; idx < NOUT * 64; idx += kTcRecThreads) mo = fmaxf(mo, fabsf(p.out_w[idx]));
+    for (int idx = tid; idx < NOUT * 64; idx += kFwdThreads) mo = fmaxf(mo, fabsf(p.out_w[idx]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
     const float* src = m == 0 ? p.w_hh[0] : (m == 1 ? p.w_ih[1] : p.w_hh[1]);
     uint8_t* thi = smem + L::OFF_W + (m * 2) * kWTileBytes;
     uint8_t* tlo = thi + kWTileBytes;
-    for (int idx = tid; idx < 192 * 8; idx += kTcRecThreads) {
+    for (int idx = tid; idx < 192 * 8; idx += kFwdThreads) {
       const int n = idx >> 3, c = idx & 7;
       float x[8];
 #pragma unroll
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
       *reinterpret_cast<uint4*>(tlo + sw128(n, c)) = lo;
     }
   }
-  for (int idx = tid; idx < 16 * 8; idx += kTcRecThreads) {
+  for (int idx = tid; idx < 16 * 8; idx += kFwdThreads) {
     const int n = idx >> 3, c = idx & 7;
     float x[8];
 #pragma unroll
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
     *reinterpret_cast<uint4*>(smem + L::OFF_WOUT + sw128(n, c)) = hi;
     *reinterpret_cast<uint4*>(smem + L::OFF_WOUT + kOutTileBytes + sw128(n, c)) = lo;
   }
-  for (int idx = tid; idx < 64 * CS; idx += kTcRecThreads) {
+  for (int idx = tid; idx < 64 * CS; idx += kFwdThreads) {
     const int j = idx / CS, q = idx % CS;
     float v = 0.f;
     if (q < 3 * S) v = p.w_ih[0][(int64_t)((q / S) * 64 + j) * ld0 + (q % S)];
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
     c0[idx] = v;
   }
   if (NL == 2) {
-    for (int j = tid; j < 64; j += kTcRecThreads) {
+    for (int j = tid; j < 64; j += kFwdThreads) {
       c1[j * 4 + 0] = p.b_ih[1][j] + p.b_hh[1][j];
       c1[j * 4 + 1] = p.b_ih[1][64 + j] + p.b_hh[1][64 + j];
       c1[j * 4 + 2] = p.b_ih[1][128 + j];
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
     mbar_init(&bars->out, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  if (warp == 0) tmem_alloc(&bars->tmem_base, TMEM_COLS);
   fence_proxy_async();  // the weight tiles were written through the generic proxy
   tc_fence_before();
   __syncthreads();
@@ -160,62 +162,43 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
   const uint32_t tmem = bars->tmem_base;
   const int64_t ntiles = (p.B + kTileRows - 1) / kTileRows;
 
-  if (warp == 8) {
-    // ======================= MMA issuer ==========================================================
-    if (lane == 0) {
-      const uint32_t w0 = smem_u32(smem + L::OFF_W);
-      auto whi = [&](int m) { return w0 + (uint32_t)(m * 2) * kWTileBytes; };
-      auto wlo = [&](int m) { return w0 + (uint32_t)(m * 2 + 1) * kWTileBytes; };
-      const uint32_t a0h = smem_u32(smem + L::OFF_A), a0l = a0h + kATileBytes;
-      const uint32_t a1h = a0h + 2 * kATileBytes, a1l = a1h + kATileBytes;
-      const uint32_t woh = smem_u32(smem + L::OFF_WOUT), wol = woh + kOutTileBytes;
-      constexpr uint32_t ID192 = idesc_f16(192), ID128 = idesc_f16(128), ID64 = idesc_f16(64), ID16 = idesc_f16(16);
-      constexpr uint32_t NROWS = 128 * 128;  // byte offset of gate rows 128.. (the n block) in a weight tile
-      uint32_t ph_init = 0, ph_a0 = 0, ph_a1 = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        mbar_wait(&bars->init, ph_init);
-        ph_init ^= 1;
-        tc_fence_after();
-        // h(-1) = 0: the A tiles are zero, so these just clear the accumulators
-        issue_gemm(tmem + D0_COL, a0h, a0l, whi(0), wlo(0), ID192, false);
-        umma_commit(&bars->d0);
-        if (NL == 2) {
-          issue_gemm(tmem + D1_COL, a1h, a1l, whi(2), wlo(2), ID128, false);
-          issue_gemm(tmem + D1_COL + 192, a1h, a1l, whi(2) + NROWS, wlo(2) + NROWS, ID64, false);
-        }
-        for (int64_t t = 0; t < T; ++t) {
-          mbar_wait(&bars->a0, ph_a0);
-          ph_a0 ^= 1;
-          tc_fence_after();
-          if (NL == 2) {
-            // layer 1 input part: r, u accumulate onto the recurrent part, n_i has its own columns
-            issue_gemm(tmem + D1_COL, a0h, a0l, whi(1), wlo(1), ID128, true);
-            issue_gemm(tmem + D1_COL + 128, a0h, a0l, whi(1) + NROWS, wlo(1) + NROWS, ID64, false);
-            umma_commit(&bars->d1);
-          } else {
-            issue_gemm(tmem + DOUT_COL, a0h, a0l, woh, wol, ID16, false);
-            umma_commit(&bars->out);
-          }
-          if (t + 1 < T) {
-            issue_gemm(tmem + D0_COL, a0h, a0l, whi(0), wlo(0), ID192, false);  // W_hh_l0 h0(t) for step t+1
-            umma_commit(&bars->d0);
-          }
-          if (NL == 2) {
-            mbar_wait(&bars->a1, ph_a1);
-            ph_a1 ^= 1;
-            tc_fence_after();
-            issue_gemm(tmem + DOUT_COL, a1h, a1l, woh, wol, ID16, false);
-            umma_commit(&bars->out);
-            if (t + 1 < T) {
-              issue_gemm(tmem + D1_COL, a1h, a1l, whi(2), wlo(2), ID128, false);
-              issue_gemm(tmem + D1_COL + 192, a1h, a1l, whi(2) + NROWS, wlo(2) + NROWS, ID64, false);
-            }
-          }
-        }
-      }
+  // ---- MMA issue (lane 0 of warp 0, between its epilogue phases) ---------------------------------
+  const uint32_t w0 = smem_u32(smem + L::OFF_W);
+  auto whi = [&](int m) { return w0 + (uint32_t)(m * 2) * kWTileBytes; };
+  auto wlo = [&](int m) { return w0 + (uint32_t)(m * 2 + 1) * kWTileBytes; };
+  const uint32_t a0h = smem_u32(smem + L::OFF_A), a0l = a0h + kATileBytes;
+  const uint32_t a1h = a0h + 2 * kATileBytes, a1l = a1h + kATileBytes;
+  const uint32_t woh = smem_u32(smem + L::OFF_WOUT), wol = woh + kOutTileBytes;
+  constexpr uint32_t ID192 = idesc_f16(192), ID128 = idesc_f16(128), ID64 = idesc_f16(64), ID16 = idesc_f16(16);
+  constexpr uint32_t NROWS = 128 * 128;  // byte offset of gate rows 128.. (the n block) in a weight tile
+  auto issue_recurrent_l0 = [&]() {  // D0 = h0 . W_hh_l0^T (for the next step)
+    issue_gemm(tmem + D0_COL, a0h, a0l, whi(0), wlo(0), ID192, false);
+    umma_commit(&bars->d0);
+  };
+  auto issue_recurrent_l1 = [&]() {  // D1[r, u] = h1 . W_hh_l1[r, u]^T, D1[n_h] = h1 . W_hh_l1[n]^T
+    issue_gemm(tmem + D1_COL, a1h, a1l, whi(2), wlo(2), ID128, false);
+    issue_gemm(tmem + D1_COL + 192, a1h, a1l, whi(2) + NROWS, wlo(2) + NROWS, ID64, false);
+  };
+  auto issue_after_layer0 = [&](bool has_next) {
+    if (NL == 2) {
+      // layer 1 input part: r, u accumulate onto the recurrent part, n_i has its own columns
+      issue_gemm(tmem + D1_COL, a0h, a0l, whi(1), wlo(1), ID128, true);
+      issue_gemm(tmem + D1_COL + 128, a0h, a0l, whi(1) + NROWS, wlo(1) + NROWS, ID64, false);
+      umma_commit(&bars->d1);
+    } else {
+      issue_gemm(tmem + DOUT_COL, a0h, a0l, woh, wol, ID16, false);
+      umma_commit(&bars->out);
     }
-    __syncwarp();
-  } else {
+    if (has_next) issue_recurrent_l0();
+  };
+  auto issue_after_layer1 = [&](bool has_next) {
+    issue_gemm(tmem + DOUT_COL, a1h, a1l, woh, wol, ID16, false);
+    umma_commit(&bars->out);
+    if (has_next) issue_recurrent_l1();
+  };
+  uint32_t ph_init = 0, ph_a0 = 0, ph_a1 = 0;  // issuer-side phases (warp 0)
+
+  {
     // ======================= gate epilogue =======================================================
     const int quad = warp & 3, cg = warp >> 2;
     const int row = quad * 32 + lane;
@@ -241,6 +224,16 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
         }
       fence_proxy_async();
       mbar_arrive(&bars->init);
+      if (warp == 0) {
+        mbar_wait(&bars->init, ph_init);
+        ph_init ^= 1;
+        tc_fence_after();
+        if (lane == 0) {  // h(-1) = 0: the A tiles are zero, so these just clear the accumulators
+          issue_recurrent_l0();
+          if (NL == 2) issue_recurrent_l1();
+        }
+        __syncwarp();
+      }
 
       float z[S], eps_cur[S], hprev[NL][kUPT];
 #pragma unroll
@@ -264,15 +257,21 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
       float* chol_o = p.chol + b * T * S * S;
       float* raw_o = p.raw ? p.raw + b * T * NTRIL : nullptr;
 
-      float gnx[3][8];  // next 8-unit chunk of gi_ctx (r, u, n)
+      // gi_ctx of this thread's 32 units, two register sets: units 0..15 of step t+1 are loaded while layer 1 of
+      // step t runs, units 16..31 at the top of layer 0 (two 8-unit chunks before their first use)
+      float g01[3][16], g23[3][16];
 #pragma unroll
       for (int g = 0; g < 3; ++g)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) gnx[g][q] = gi_p[(g * 64 + q) * kTileRows];
+        for (int q = 0; q < 16; ++q) g01[g][q] = gi_p[(g * 64 + q) * kTileRows];
 
       for (int64_t t = 0; t < T; ++t) {
         const bool has_next = t + 1 < T;
         // ---------------- layer 0 ----------------
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+          for (int q = 0; q < 16; ++q) g23[g][q] = gi_p[(g * 64 + 16 + q) * kTileRows];
         mbar_wait(&bars->d0, ph_d0);
         ph_d0 ^= 1;
         tc_fence_after();
@@ -287,18 +286,7 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
 #pragma unroll
           for (int g = 0; g < 3; ++g)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) gcur[g][q] = gnx[g][q];
-          // prefetch the next chunk (of this step, or chunk 0 of the next step)
-          {
-            const bool last = c == kUPT / 8 - 1;
-            const float* nx = last ? gi_p + 192 * kTileRows : gi_p + (c + 1) * 8 * kTileRows;
-            if (!last || has_next) {
-#pragma unroll
-              for (int g = 0; g < 3; ++g)
-#pragma unroll
-                for (int q = 0; q < 8; ++q) gnx[g][q] = nx[(g * 64 + q) * kTileRows];
-            }
-          }
+            for (int q = 0; q < 8; ++q) gcur[g][q] = c < 2 ? g01[g][(c & 1) * 8 + q] : g23[g][(c & 1) * 8 + q];
           tmem_ld_wait();
           float hx[8];
 #pragma unroll
@@ -348,6 +336,19 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
         tc_fence_before();
         mbar_arrive(&bars->a0);
         gi_p += 192 * kTileRows;
+        if (warp == 0) {
+          mbar_wait(&bars->a0, ph_a0);
+          ph_a0 ^= 1;
+          tc_fence_after();
+          if (lane == 0) issue_after_layer0(has_next);
+          __syncwarp();
+        }
+        if (has_next) {
+#pragma unroll
+          for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int q = 0; q < 16; ++q) g01[g][q] = gi_p[(g * 64 + q) * kTileRows];
+        }
 
         // ---------------- layer 1 ----------------
         if (NL == 2) {
@@ -399,6 +400,13 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(&bars->a1);
+          if (warp == 0) {
+            mbar_wait(&bars->a1, ph_a1);
+            ph_a1 ^= 1;
+            tc_fence_after();
+            if (lane == 0) issue_after_layer1(has_next);
+            __syncwarp();
+          }
         }
         if (st_p) st_p += NL * kStashSlots * 64 * kTileRows;
 
@@ -460,7 +468,7 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_fwd_tc_kernel(PathParam
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // gth[b, n] = b_ih_l0[n] + (n < 2H ? b_hh_l0[n] : 0) + sum_p theta[b, p] W_ih_l0[n, S + C + p]: the part of the
@@ -512,7 +520,7 @@ int launch_fwd_tc(const PathParams& p, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ntiles = (p.B + kTileRows - 1) / kTileRows;
-  path_fwd_tc_kernel<NL, S><<<(unsigned)(ntiles < sms ? ntiles : sms), kTcRecThreads, smem, st>>>(p);
+  path_fwd_tc_kernel<NL, S><<<(unsigned)(ntiles < sms ? ntiles : sms), kFwdThreads, smem, st>>>(p);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
