@@ -24,6 +24,7 @@
 namespace visde {
 namespace {
 
+constexpr int kBwdThreads = 256;  // 8 warps = 255 registers per thread; the warps take turns as MMA issuer
 constexpr int kRowExp = 9;  // rows are scaled so that max|dh| 2^e is in [2^9, 2^10)
 
 template <int NL, int S>
@@ -38,7 +39,7 @@ struct TcBwdSmem {
   static constexpr int OFF_DZX = OFF_MAX + 2 * 2 * 128 * 4;     // float [2 cg][128][S]
   static constexpr int OFF_BAR = OFF_DZX + 2 * 128 * S * 4;
   struct Bars {
-    uint64_t full[2], empty[2], in0, done;
+    uint64_t full[2], empty[2], in0;
     uint32_t tmem_base;
     uint32_t amax;
   };
@@ -54,7 +55,7 @@ __device__ __forceinline__ int row_exp(float mx) {
 }
 
 template <int NL, int S>
-__global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParams p) {
+__global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tc_kernel(PathParams p) {
   using L = TcBwdSmem<NL, S>;
   constexpr int NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL, CZ = L::CZ, NMAT = L::NMAT;
   static_assert(NOUT <= 16, "W_out columns are staged as 16 floats per unit");
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
     float mx = 0.f;
     for (int m = 0; m < NMAT; ++m) {
       const float* src = m == 0 ? p.w_hh[0] : (m == 1 ? p.w_ih[1] : p.w_hh[1]);
-      for (int idx = tid; idx < 192 * 64; idx += kTcRecThreads) mx = fmaxf(mx, fabsf(src[idx]));
+      for (int idx = tid; idx < 192 * 64; idx += kBwdThreads) mx = fmaxf(mx, fabsf(src[idx]));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
     const float* src = m == 0 ? p.w_hh[0] : (m == 1 ? p.w_ih[1] : p.w_hh[1]);
     uint8_t* thi = smem + L::OFF_W + (m * 2) * kWTileBytes;
     uint8_t* tlo = thi + kWTileBytes;
-    for (int idx = tid; idx < 64 * 24; idx += kTcRecThreads) {
+    for (int idx = tid; idx < 64 * 24; idx += kBwdThreads) {
       const int i = idx & 63, hg = idx >> 6;  // hg = gB * 2 + half
       const int gB = hg >> 1, half = hg & 1, c = gB / 3, g = gB % 3;
       float x[8];
@@ -110,11 +111,11 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
       *reinterpret_cast<uint4*>(tlo + off) = lo;
     }
   }
-  for (int idx = tid; idx < 64 * 16; idx += kTcRecThreads) {
+  for (int idx = tid; idx < 64 * 16; idx += kBwdThreads) {
     const int i = idx >> 4, m = idx & 15;
     woutc[idx] = m < NOUT ? p.out_w[m * 64 + i] : 0.f;
   }
-  for (int idx = tid; idx < 64 * CZ; idx += kTcRecThreads) {
+  for (int idx = tid; idx < 64 * CZ; idx += kBwdThreads) {
     const int i = idx / CZ, q = idx % CZ;
     wzc[idx] = q < 3 * S ? p.w_ih[0][(int64_t)((q / S) * 64 + i) * ld0 + (q % S)] : 0.f;
   }
@@ -124,10 +125,9 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
     mbar_init(&bars->empty[0], 1);
     mbar_init(&bars->empty[1], 1);
     mbar_init(&bars->in0, 1);
-    mbar_init(&bars->done, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  if (warp == 0) tmem_alloc(&bars->tmem_base, TMEM_COLS);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -135,58 +135,36 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
   const uint32_t tmem = bars->tmem_base;
   const int64_t ntiles = (p.B + kTileRows - 1) / kTileRows;
 
-  if (warp == 8) {
-    // ======================= MMA issuer ==========================================================
-    if (lane == 0) {
-      const uint32_t w0 = smem_u32(smem + L::OFF_W), a0 = smem_u32(smem + L::OFF_A);
-      constexpr uint32_t ID64 = idesc_f16(64);
-      // 9 MMAs: acc[128,64] (+)= A_chunk[slots] . W^T[K-groups of chunk c]
-      auto issue = [&](uint32_t acc, uint32_t slot_base, int m, int c, bool n_is_nh, bool fresh) {
-        const uint32_t a_hi = slot_base, a_lo = slot_base + kATileBytes;
-        const uint32_t b_hi = w0 + (uint32_t)(m * 2) * kWTileBytes, b_lo = b_hi + kWTileBytes;
+  // ---- MMA issue: chunk gc is issued by lane 0 of warp gc % 8 once all 256 threads have written it (the issue
+  // order across warps is chained through the `full` barriers; the tensor pipe executes in issue order, so the
+  // commit of a later chunk also covers the earlier ones)
+  const uint32_t w0 = smem_u32(smem + L::OFF_W), a0 = smem_u32(smem + L::OFF_A);
+  constexpr uint32_t ID64 = idesc_f16(64);
+  // 9 MMAs: acc[128,64] (+)= A_chunk[slots] . W^T[K-groups of chunk c]
+  auto issue = [&](uint32_t acc, uint32_t slot_base, int m, int c, bool n_is_nh, bool fresh) {
+    const uint32_t a_hi = slot_base, a_lo = slot_base + kATileBytes;
+    const uint32_t b_hi = w0 + (uint32_t)(m * 2) * kWTileBytes, b_lo = b_hi + kWTileBytes;
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {
-          const int aslot = g < 2 ? g : (n_is_nh ? 3 : 2);
-          const int gB = c * 3 + g;
-          const uint32_t boff = (uint32_t)(gB >> 2) * 8192u + (uint32_t)(gB & 3) * 32u;
-          const uint64_t dah = umma_desc(a_hi + aslot * 32, 16, 1024, 2), dal = umma_desc(a_lo + aslot * 32, 16, 1024, 2);
-          const uint64_t dbh = umma_desc(b_hi + boff, 16, 1024, 2), dbl = umma_desc(b_lo + boff, 16, 1024, 2);
-          umma_f16(acc, dal, dbh, ID64, (fresh && g == 0) ? 0u : 1u);
-          umma_f16(acc, dah, dbl, ID64, 1u);
-          umma_f16(acc, dah, dbh, ID64, 1u);
-        }
-      };
-      uint32_t gc = 0;  // chunks consumed so far (ring position / phases)
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int t = T - 1; t >= 0; --t) {
-          const uint32_t wpar = (uint32_t)((t & 1) ^ 1);  // accumulators written at step t are read at step t-1
-#pragma unroll
-          for (int k = NL - 1; k >= 0; --k) {
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c, ++gc) {
-              const uint32_t slot = gc & 1;
-              mbar_wait(&bars->full[slot], (gc >> 1) & 1);
-              tc_fence_after();
-              const uint32_t sb = a0 + slot * SLOT_BYTES;
-              if (t > 0) issue(tmem + (uint32_t)(k * 2 + wpar) * 64, sb, k == 0 ? 0 : 2, c, true, c == 0);
-              if (NL == 2 && k == 1) issue(tmem + IN0_COL, sb, 1, c, false, c == 0);
-              umma_commit(&bars->empty[slot]);
-            }
-            if (NL == 2 && k == 1) umma_commit(&bars->in0);
-          }
-        }
-      }
-      umma_commit(&bars->done);
-      mbar_wait(&bars->done, 0);
+    for (int g = 0; g < 3; ++g) {
+      const int aslot = g < 2 ? g : (n_is_nh ? 3 : 2);
+      const int gB = c * 3 + g;
+      const uint32_t boff = (uint32_t)(gB >> 2) * 8192u + (uint32_t)(gB & 3) * 32u;
+      const uint64_t dah = umma_desc(a_hi + aslot * 32, 16, 1024, 2), dal = umma_desc(a_lo + aslot * 32, 16, 1024, 2);
+      const uint64_t dbh = umma_desc(b_hi + boff, 16, 1024, 2), dbl = umma_desc(b_lo + boff, 16, 1024, 2);
+      umma_f16(acc, dal, dbh, ID64, (fresh && g == 0) ? 0u : 1u);
+      umma_f16(acc, dah, dbl, ID64, 1u);
+      umma_f16(acc, dah, dbh, ID64, 1u);
     }
-    __syncwarp();
-  } else {
+  };
+  uint32_t gc = 0;  // chunks produced so far (ring position / phases); uniform over the CTA
+
+  {
     // ======================= gate-cotangent epilogue =============================================
     const int quad = warp & 3, cg = warp >> 2;
     const int row = quad * 32 + lane;
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     uint8_t* a_ring = smem + L::OFF_A;
-    uint32_t gc = 0, ph_in0 = 0, xb = 0;
+    uint32_t ph_in0 = 0, xb = 0;
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t b_raw = tile * kTileRows + row;
@@ -203,18 +181,25 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
 
       // software pipeline: the stashed gates of the NEXT chunk (8 units x 5 values) and the per-step row inputs of
       // the NEXT step are loaded while the current ones are being processed
-      float nr[8], nu[8], nn[8], nnh[8], nhp[8];
-      auto load_chunk = [&](int tt, int kk, int cc) {
+      // two register sets (even / odd chunks): a chunk's values are requested TWO chunks before they are used
+      float pv[2][5][8];
+      auto load_chunk = [&](float (&dst)[5][8], int tt, int kk, int cc) {
         const float* sk = st_tile + ((int64_t)tt * NL + kk) * (kStashSlots * 64 * kTileRows) + (cc * 16 + cg * 8) * kTileRows;
         const float* hk = sk - (int64_t)NL * (kStashSlots * 64 * kTileRows) + kStashH * 64 * kTileRows;  // step tt - 1
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          nr[q] = sk[(kStashR * 64 + q) * kTileRows];
-          nu[q] = sk[(kStashU * 64 + q) * kTileRows];
-          nn[q] = sk[(kStashN * 64 + q) * kTileRows];
-          nnh[q] = sk[(kStashNhh * 64 + q) * kTileRows];
-          nhp[q] = tt > 0 ? hk[q * kTileRows] : 0.f;
+          dst[0][q] = sk[(kStashR * 64 + q) * kTileRows];
+          dst[1][q] = sk[(kStashU * 64 + q) * kTileRows];
+          dst[2][q] = sk[(kStashN * 64 + q) * kTileRows];
+          dst[3][q] = sk[(kStashNhh * 64 + q) * kTileRows];
+          dst[4][q] = tt > 0 ? hk[q * kTileRows] : 0.f;
         }
+      };
+      // the chunk `ahead` positions after (tt, kk, cc) in processing order (c fastest, then layers down, then t-1)
+      auto load_ahead = [&](float (&dst)[5][8], int tt, int kk, int cc, int ahead) {
+        int lin = ((T - 1 - tt) * NL + (NL - 1 - kk)) * 4 + cc + ahead;
+        const int t2 = T - 1 - lin / (4 * NL), k2 = NL - 1 - (lin / 4) % NL, c2 = lin % 4;
+        if (t2 >= 0) load_chunk(dst, t2, k2, c2);
       };
       float n_gP[S], n_gM[S], n_ev[S], n_rd[S], n_gL[S * S];
       auto load_small = [&](int tt) {
@@ -229,7 +214,8 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
         for (int q = 0; q < S * S; ++q) n_gL[q] = gl_p[tt * S * S + q];
       };
       load_small(T - 1);
-      load_chunk(T - 1, NL - 1, 0);
+      load_ahead(pv[0], T - 1, NL - 1, 0, 0);
+      load_ahead(pv[1], T - 1, NL - 1, 0, 1);
 
       float dz[S];
 #pragma unroll
@@ -346,12 +332,10 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
             float cr[8], cu[8], cn[8], cnh[8], chp[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              cr[q] = nr[q]; cu[q] = nu[q]; cn[q] = nn[q]; cnh[q] = nnh[q]; chp[q] = nhp[q];
+              cr[q] = pv[c & 1][0][q]; cu[q] = pv[c & 1][1][q]; cn[q] = pv[c & 1][2][q];
+              cnh[q] = pv[c & 1][3][q]; chp[q] = pv[c & 1][4][q];
             }
-            // next chunk in processing order: (t, k, c+1) | (t, k-1, 0) | (t-1, NL-1, 0)
-            if (c < 3) load_chunk(t, k, c + 1);
-            else if (k > 0) load_chunk(t, k - 1, 0);
-            else if (t > 0) load_chunk(t - 1, NL - 1, 0);
+            load_ahead(pv[c & 1], t, k, c, 2);
             float dr_[8], du_[8], dn_[8], dnh_[8];
             uint32_t dirv[8];
 #pragma unroll
@@ -397,6 +381,19 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(&bars->full[slot]);
+            if (warp == (int)(gc & 7)) {
+              mbar_wait(&bars->full[slot], (gc >> 1) & 1);
+              tc_fence_after();
+              if (lane == 0) {
+                const uint32_t sb = a0 + slot * SLOT_BYTES;
+                // accumulators written at step t are read at step t-1 (ping-pong by step parity)
+                if (t > 0) issue(tmem + (uint32_t)(k * 2 + ((t & 1) ^ 1)) * 64, sb, k == 0 ? 0 : 2, c, true, c == 0);
+                if (NL == 2 && k == 1) issue(tmem + IN0_COL, sb, 1, c, false, c == 0);
+                umma_commit(&bars->empty[slot]);
+                if (NL == 2 && k == 1 && c == 3) umma_commit(&bars->in0);
+              }
+              __syncwarp();
+            }
           }
           tmem_st_wait();
           sc_prev[k] = sc_this;
@@ -415,10 +412,13 @@ __global__ void __launch_bounds__(kTcRecThreads, 1) path_bwd_tc_kernel(PathParam
       }
       named_bar_sync(1 + quad, 64);  // dzx is rewritten by the next tile
     }
+    // every MMA has completed before TMEM is released (in-order pipe: the last two commits cover all)
+    if (gc >= 2) mbar_wait(&bars->empty[(gc - 2) & 1], ((gc - 2) >> 1) & 1);
+    if (gc >= 1) mbar_wait(&bars->empty[(gc - 1) & 1], ((gc - 1) >> 1) & 1);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 template <int NL, int S>
@@ -433,7 +433,7 @@ int launch_bwd_tc(const PathParams& p, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ntiles = (p.B + kTileRows - 1) / kTileRows;
-  path_bwd_tc_kernel<NL, S><<<(unsigned)(ntiles < sms ? ntiles : sms), kTcRecThreads, smem, st>>>(p);
+  path_bwd_tc_kernel<NL, S><<<(unsigned)(ntiles < sms ? ntiles : sms), kBwdThreads, smem, st>>>(p);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
