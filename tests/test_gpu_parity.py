@@ -39,8 +39,10 @@ CASES = {
 CASES["lv_h64_c128_b150_two_tiles"] = ("lv", 150, 12, dict(context_dim=128, hidden_dim=64, num_layers=2))
 CASES["ou_h64_c128_l1_b130"] = ("ou", 130, 9, dict(context_dim=128, hidden_dim=64, num_layers=1))
 CASES["l96s4_h64_c128_l2"] = ("l96", 5, 21, dict(context_dim=128, hidden_dim=64, num_layers=2, state_dim=4))
+CASES["lv_h64_c128_t1"] = ("lv", 4, 1, dict(context_dim=128, hidden_dim=64, num_layers=2))   # single step: no carried state
+CASES["ou_h64_c128_l1_t2"] = ("ou", 3, 2, dict(context_dim=128, hidden_dim=64, num_layers=1))
 TC_OK = {"lv_h64_c128_l2", "ou_h64_c256_l1", "lv_h64_c256_l2", "l96s6_h64_c128_l2", "lv_h64_c128_b150_two_tiles",
-         "ou_h64_c128_l1_b130", "l96s4_h64_c128_l2"}
+         "ou_h64_c128_l1_b130", "l96s4_h64_c128_l2", "lv_h64_c128_t1", "ou_h64_c128_l1_t2"}
 TC_REC_OK = TC_OK - {"l96s6_h64_c128_l2"}
 NO_TC = 0x100  # VISDE_FLAG_NO_TENSOR_CORES
 # batch sizes that do not divide the tile of the batch-tiled family
@@ -48,7 +50,7 @@ CASES["lv_h64_b37_ragged_tile"] = ("lv", 37, 9, dict(context_dim=16, hidden_dim=
 CASES["ou_h32_b13_ragged_tile"] = ("ou", 13, 7, dict(context_dim=8, hidden_dim=32, num_layers=1))
 FAST_OK = {"lv_h64_b37_ragged_tile", "ou_h32_b13_ragged_tile", "ou_h32_l2", "lv_h16_l1", "ou_h64_l2", "lv_h64_l2", "lv_h48_l2", "ou_h20_l1", "l96s3_h64_l2",
            "lv_h64_c128_l2", "ou_h64_c256_l1", "lv_h64_c256_l2", "lv_h64_c128_b150_two_tiles", "ou_h64_c128_l1_b130",
-           "l96s4_h64_c128_l2"}
+           "l96s4_h64_c128_l2", "lv_h64_c128_t1", "ou_h64_c128_l1_t2"}
 
 
 # wide-state register-resident family (4 < S <= 16, H <= 64, NL <= 2)

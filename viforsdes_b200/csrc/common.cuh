@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/visde.h"
 
 namespace visde {
@@ -28,6 +30,21 @@ void set_error(const char* fmt, ...);
       return VISDE_EINVAL;                                                                \
     }                                                                                     \
   } while (0)
+
+// "Done once per device" flag for per-kernel attributes (cudaFuncSetAttribute is per device: a process that drives
+// several GPUs must opt every one of them into > 48 KB of dynamic shared memory).
+struct DeviceOnce {
+  std::atomic<uint64_t> mask{0};
+  bool needed(int* dev_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *dev_out = dev;
+    return dev >= 64 || !((mask.load(std::memory_order_acquire) >> dev) & 1ull);
+  }
+  void done(int dev) {
+    if (dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release);
+  }
+};
 
 constexpr int kGateR = 0, kGateU = 1, kGateN = 2;  // nn.GRU row-block order r, z(update), n
 // stash slots per (b, t, layer): r, u, n, n_hh (= W_hn h + b_hn), h_new

@@ -542,11 +542,12 @@ bool fasts_supported(const PathParams& p) {
 
 int launch_path_fwd_fasts(const PathParams& p, cudaStream_t st) {
   const size_t smem = fasts_fwd_smem(p);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  int attr_dev = 0;
+  if (attr_once.needed(&attr_dev)) {
     VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_fwd_fasts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_fwd_fasts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   if (p.NL == 1) path_fwd_fasts_kernel<1><<<fasts_grid(p.B), kThr, smem, st>>>(p);
   else path_fwd_fasts_kernel<2><<<fasts_grid(p.B), kThr, smem, st>>>(p);
@@ -559,11 +560,12 @@ size_t fasts_partials_floats(int NL, int H) { return (size_t)256 * fasts_part_fl
 // p.cta_part must hold fasts_partials_floats(); writes the bias gradients
 int launch_path_bwd_fasts(const PathParams& p, const visde_weight_grads* gw, cudaStream_t st) {
   const size_t smem = fasts_bwd_smem(p);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  int attr_dev = 0;
+  if (attr_once.needed(&attr_dev)) {
     VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_bwd_fasts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_bwd_fasts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   const int grid = fasts_grid(p.B);
   if (p.NL == 1) path_bwd_fasts_kernel<1><<<grid, kThr, smem, st>>>(p);

@@ -402,11 +402,12 @@ int launch_path_fwd_generic(const PathParams& p, cudaStream_t st) {
                      (size_t)p.S * (G + 1);
   const size_t smem_w = base + sizeof(float) * wfl;
   if (smem_w <= 227 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    int attr_dev = 0;
+    if (attr_once.needed(&attr_dev)) {
       VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_fwd_generic_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_fwd_generic_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
+      attr_once.done(attr_dev);
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -430,11 +431,12 @@ int launch_path_bwd_generic(const PathParams& p, cudaStream_t st) {
   const size_t wfl = (size_t)p.NL * G * p.H + (size_t)(p.NL - 1) * G * p.H + (size_t)p.n_out * p.H + (size_t)G * p.S;
   const size_t smem_w = base + sizeof(float) * wfl;
   if (smem_w <= 227 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    int attr_dev = 0;
+    if (attr_once.needed(&attr_dev)) {
       VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_bwd_generic_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_bwd_generic_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
+      attr_once.done(attr_dev);
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

@@ -511,10 +511,11 @@ __global__ void untile_kernel(const float* __restrict__ in, float* __restrict__ 
 template <int NL, int S>
 int launch_fwd_tc(const PathParams& p, cudaStream_t st) {
   const size_t smem = TcFwdSmem<NL, S>::bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  int attr_dev = 0;
+  if (attr_once.needed(&attr_dev)) {
     VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_fwd_tc_kernel<NL, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -424,10 +424,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tc_kernel(PathParams 
 template <int NL, int S>
 int launch_bwd_tc(const PathParams& p, cudaStream_t st) {
   const size_t smem = TcBwdSmem<NL, S>::bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  int attr_dev = 0;
+  if (attr_once.needed(&attr_dev)) {
     VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_bwd_tc_kernel<NL, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

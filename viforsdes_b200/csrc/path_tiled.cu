@@ -400,10 +400,11 @@ int tiled_grid(int64_t B, int NB) {
 template <int NL, int S, int NB>
 int launch_tiled(const PathParams& p, cudaStream_t st) {
   const size_t smem = tiled_smem_bytes(NL, NB);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  int attr_dev = 0;
+  if (attr_once.needed(&attr_dev)) {
     VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_fwd_tiled_kernel<NL, S, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   path_fwd_tiled_kernel<NL, S, NB><<<tiled_grid(p.B, NB), kTiledThreads, smem, st>>>(p);
   VISDE_CUDA_CHECK(cudaGetLastError());

@@ -659,10 +659,11 @@ template <int N, bool B_MN, int NA, bool A_MN = false>
 int launch_rows(const CUtensorMap& mA, const CUtensorMap& mBh, const CUtensorMap& mBl, RowsArgs a, int64_t B,
                 cudaStream_t st) {
   const size_t smem = RowsSmem<N, NA>::bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  int attr_dev = 0;
+  if (attr_once.needed(&attr_dev)) {
     VISDE_CUDA_CHECK(cudaFuncSetAttribute(tc_rows_kernel<N, B_MN, NA, A_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   a.num_tiles = (a.tiled || a.a_tiled) ? (int)(((B + 127) / 128) * a.T) : (int)(B * a.tiles_per_b);
   int dev = 0, sms = 148;
@@ -863,10 +864,11 @@ int tc_wgrads(const visde_ctx_view* ctx, const float* dg, const float* stash, in
   }
   constexpr int STAGE_BYTES = 2 * 128 * 128 + 2 * 192 * 128;
   const size_t smem = kStages * STAGE_BYTES + sizeof(TcBarriers) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  int attr_dev = 0;
+  if (attr_once.needed(&attr_dev)) {
     VISDE_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   tc_wgrad_kernel<<<dim3(a.nsplit, np), kTcThreads, smem, st>>>(m0, m1, m2, a);
   VISDE_CUDA_CHECK(cudaGetLastError());
@@ -962,10 +964,11 @@ int tc_wgrads_tiled(const visde_ctx_view* ctx, const float* dg, const float* sta
   }
   constexpr int STAGE_BYTES = 2 * 128 * 128 + 2 * 192 * 128;
   const size_t smem = kStages * STAGE_BYTES + sizeof(TcBarriers) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  int attr_dev = 0;
+  if (attr_once.needed(&attr_dev)) {
     VISDE_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_once.done(attr_dev);
   }
   tc_wgrad_tiled_kernel<<<dim3(a.nsplit, np), kTcThreads, smem, st>>>(m0, m1, m2, a);
   VISDE_CUDA_CHECK(cudaGetLastError());
