@@ -26,7 +26,6 @@ namespace visde {
 namespace {
 
 constexpr int kTcThreads = 192;
-constexpr int kStages = 2;
 constexpr uint32_t kTf32Mask = 0xffffe000u;  // keep sign, exponent and the 10 tf32 mantissa bits
 
 // instruction descriptor: D fp32, A/B tf32, M = 128
@@ -53,13 +52,6 @@ __device__ __forceinline__ void split_tile(float4* hi, float4* lo, int nvec, int
   }
 }
 
-struct TcBarriers {
-  uint64_t full[kStages];   // TMA bytes landed
-  uint64_t split[kStages];  // hi/lo tiles written (128 arrivals)
-  uint64_t empty[kStages];  // MMAs that read the stage have completed
-  uint64_t accum;           // all MMAs of the tile done
-  uint32_t tmem_base;
-};
 
 // ------------------------------------------------------------------------------------------
 // K0 / K3: rows kernel
@@ -329,17 +321,27 @@ struct WgArgs {
   float* partials;        // [nprob][nsplit][128][192]
 };
 
+// Pipeline (both K4 kernels): raw fp32 tiles land in a 3-deep ring (TMA runs two k-blocks ahead of the MMAs); the split
+// warps turn a raw stage into its hi part in place and write the lo part into a 2-deep ring; the MMA warp frees both.
+constexpr int kWgtRaw = 3, kWgtLo = 2;
+struct WgtBarriers {
+  uint64_t full[kWgtRaw], emptyRaw[kWgtRaw], split[kWgtLo], emptyLo[kWgtLo], accum;
+  uint32_t tmem_base;
+};
+constexpr int kWgtStageBytes = 128 * 128 + 192 * 128;  // A [128 x 32 fp32] + B [192 x 32 fp32] = 40 KB
+constexpr size_t kWgtSmemBytes = (size_t)(kWgtRaw + kWgtLo) * kWgtStageBytes + sizeof(WgtBarriers) + 1024;
+
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                 const __grid_constant__ CUtensorMap tm2, WgArgs a) {
   constexpr int N = 192;
   constexpr int A_BYTES = 128 * 128, B_BYTES = N * 128;
-  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   constexpr uint32_t TMEM_COLS = 256;
   constexpr uint32_t IDESC = make_idesc(N, true, true);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + kStages * STAGE_BYTES);
+  uint8_t* lo_ring = smem + kWgtRaw * kWgtStageBytes;
+  WgtBarriers* bars = reinterpret_cast<WgtBarriers*>(smem + (kWgtRaw + kWgtLo) * kWgtStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pi = blockIdx.y, split = blockIdx.x;
   const WgProblem& pr = a.prob[pi];
@@ -349,10 +351,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
   const int nk = kb1 > kb0 ? (int)(kb1 - kb0) : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kWgtRaw; ++s) {
       mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->emptyRaw[s], 1);
+    }
+    for (int s = 0; s < kWgtLo; ++s) {
       mbar_init(&bars->split[s], 128);
-      mbar_init(&bars->empty[s], 1);
+      mbar_init(&bars->emptyLo[s], 1);
     }
     mbar_init(&bars->accum, 1);
     fence_barrier_init();
@@ -368,29 +373,28 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
       const CUtensorMap* mA = pr.a_map == 0 ? &tm0 : pr.a_map == 1 ? &tm1 : &tm2;
       const CUtensorMap* mB = pr.b_map == 0 ? &tm0 : pr.b_map == 1 ? &tm1 : &tm2;
       for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % kStages;
-        if (kb >= kStages) mbar_wait(&bars->empty[s], ((kb / kStages) - 1) & 1);
+        const int s = kb % kWgtRaw;
+        if (kb >= kWgtRaw) mbar_wait(&bars->emptyRaw[s], ((kb / kWgtRaw) - 1) & 1);
         const int64_t g = kb0 + kb;
         const int b = (int)(g / a.kb_per_b), t32 = (int)(g % a.kb_per_b) * 32;
-        uint8_t* st = smem + s * STAGE_BYTES;
+        uint8_t* st = smem + s * kWgtStageBytes;
         mbar_expect_tx(&bars->full[s], A_BYTES + B_BYTES);
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl)
           tma_load_3d(st + sl * 4096, mA, &bars->full[s], pr.a_cols[sl], t32 + pr.a_tshift, b);
 #pragma unroll
         for (int sl = 0; sl < 6; ++sl)
-          tma_load_3d(st + 2 * A_BYTES + sl * 4096, mB, &bars->full[s], pr.b_cols[sl], t32 + pr.b_tshift, b);
+          tma_load_3d(st + A_BYTES + sl * 4096, mB, &bars->full[s], pr.b_cols[sl], t32 + pr.b_tshift, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&bars->split[s], ph);
+        const int s = kb % kWgtRaw, sl = kb % kWgtLo;
+        mbar_wait(&bars->split[sl], (kb / kWgtLo) & 1);
         tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+        const uint32_t hi = smem_u32(smem + s * kWgtStageBytes), lo = smem_u32(lo_ring + sl * kWgtStageBytes);
+        const uint32_t a_hi = hi, a_lo = lo, b_hi = hi + A_BYTES, b_lo = lo + A_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint64_t dah = desc_mnmajor(a_hi, j), dal = desc_mnmajor(a_lo, j);
@@ -399,21 +403,21 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
           umma_tf32(tmem_d, dah, dbl, IDESC, 1);
           umma_tf32(tmem_d, dah, dbh, IDESC, 1);
         }
-        umma_commit(&bars->empty[s]);
+        umma_commit(&bars->emptyRaw[s]);
+        umma_commit(&bars->emptyLo[sl]);
       }
       if (nk > 0) umma_commit(&bars->accum); else mbar_arrive(&bars->accum);
     }
   } else {
     const int tid128 = threadIdx.x - 64;
     for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % kStages;
-      mbar_wait(&bars->full[s], (kb / kStages) & 1);
-      uint8_t* st = smem + s * STAGE_BYTES;
-      split_tile(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + A_BYTES), A_BYTES / 16, tid128);
-      split_tile(reinterpret_cast<float4*>(st + 2 * A_BYTES), reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES),
-                 B_BYTES / 16, tid128);
+      const int s = kb % kWgtRaw, sl = kb % kWgtLo;
+      mbar_wait(&bars->full[s], (kb / kWgtRaw) & 1);
+      if (kb >= kWgtLo) mbar_wait(&bars->emptyLo[sl], ((kb / kWgtLo) - 1) & 1);
+      split_tile(reinterpret_cast<float4*>(smem + s * kWgtStageBytes), reinterpret_cast<float4*>(lo_ring + sl * kWgtStageBytes),
+                 kWgtStageBytes / 16, tid128);
       fence_proxy_async();
-      mbar_arrive(&bars->split[s]);
+      mbar_arrive(&bars->split[sl]);
     }
     mbar_wait(&bars->accum, 0);
     tc_fence_after();
@@ -462,11 +466,11 @@ tc_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_co
                       const __grid_constant__ CUtensorMap tmSt, WgtArgs a) {
   constexpr int N = 192;
   constexpr int A_BYTES = 128 * 128, B_BYTES = N * 128;
-  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   constexpr uint32_t TMEM_COLS = 256;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + kStages * STAGE_BYTES);
+  uint8_t* lo_ring = smem + kWgtRaw * kWgtStageBytes;
+  WgtBarriers* bars = reinterpret_cast<WgtBarriers*>(smem + (kWgtRaw + kWgtLo) * kWgtStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pi = blockIdx.y, split = blockIdx.x;
   const WgtProblem& pr = a.prob[pi];
@@ -476,10 +480,13 @@ tc_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_co
   const int nk = kb1 > kb0 ? (int)(kb1 - kb0) : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kWgtRaw; ++s) {
       mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->emptyRaw[s], 1);
+    }
+    for (int s = 0; s < kWgtLo; ++s) {
       mbar_init(&bars->split[s], 128);
-      mbar_init(&bars->empty[s], 1);
+      mbar_init(&bars->emptyLo[s], 1);
     }
     mbar_init(&bars->accum, 1);
     fence_barrier_init();
@@ -493,11 +500,11 @@ tc_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_co
   if (warp == 0) {
     if (lane == 0) {
       for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % kStages;
-        if (kb >= kStages) mbar_wait(&bars->empty[s], ((kb / kStages) - 1) & 1);
+        const int s = kb % kWgtRaw;
+        if (kb >= kWgtRaw) mbar_wait(&bars->emptyRaw[s], ((kb / kWgtRaw) - 1) & 1);
         const int64_t g = kb0 + kb;
         const int kq = (int)(g & 3), t = (int)((g >> 2) % a.T), tb = (int)((g >> 2) / a.T);
-        uint8_t* st = smem + s * STAGE_BYTES;
+        uint8_t* st = smem + s * kWgtStageBytes;
         mbar_expect_tx(&bars->full[s], A_BYTES + B_BYTES);
         if (pr.a_ctx) {
 #pragma unroll
@@ -509,19 +516,18 @@ tc_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_co
         }
 #pragma unroll
         for (int q = 0; q < 3; ++q)
-          tma_load_4d(st + 2 * A_BYTES + q * 8192, &tmDg, &bars->full[s], kq * 32, pr.b_feat[q], t, tb);
+          tma_load_4d(st + A_BYTES + q * 8192, &tmDg, &bars->full[s], kq * 32, pr.b_feat[q], t, tb);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(N, pr.a_ctx != 0, false);
       for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&bars->split[s], ph);
+        const int s = kb % kWgtRaw, sl = kb % kWgtLo;
+        mbar_wait(&bars->split[sl], (kb / kWgtLo) & 1);
         tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+        const uint32_t hi = smem_u32(smem + s * kWgtStageBytes), lo = smem_u32(lo_ring + sl * kWgtStageBytes);
+        const uint32_t a_hi = hi, a_lo = lo, b_hi = hi + A_BYTES, b_lo = lo + A_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint64_t dah = pr.a_ctx ? desc_mnmajor(a_hi, j) : desc_kmajor(a_hi, j);
@@ -531,21 +537,21 @@ tc_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_co
           umma_tf32(tmem_d, dah, dbl, idesc, 1);
           umma_tf32(tmem_d, dah, dbh, idesc, 1);
         }
-        umma_commit(&bars->empty[s]);
+        umma_commit(&bars->emptyRaw[s]);
+        umma_commit(&bars->emptyLo[sl]);
       }
       if (nk > 0) umma_commit(&bars->accum); else mbar_arrive(&bars->accum);
     }
   } else {
     const int tid128 = threadIdx.x - 64;
     for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % kStages;
-      mbar_wait(&bars->full[s], (kb / kStages) & 1);
-      uint8_t* st = smem + s * STAGE_BYTES;
-      split_tile(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + A_BYTES), A_BYTES / 16, tid128);
-      split_tile(reinterpret_cast<float4*>(st + 2 * A_BYTES), reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES),
-                 B_BYTES / 16, tid128);
+      const int s = kb % kWgtRaw, sl = kb % kWgtLo;
+      mbar_wait(&bars->full[s], (kb / kWgtRaw) & 1);
+      if (kb >= kWgtLo) mbar_wait(&bars->emptyLo[sl], ((kb / kWgtLo) - 1) & 1);
+      split_tile(reinterpret_cast<float4*>(smem + s * kWgtStageBytes), reinterpret_cast<float4*>(lo_ring + sl * kWgtStageBytes),
+                 kWgtStageBytes / 16, tid128);
       fence_proxy_async();
-      mbar_arrive(&bars->split[s]);
+      mbar_arrive(&bars->split[sl]);
     }
     mbar_wait(&bars->accum, 0);
     tc_fence_after();
@@ -862,8 +868,7 @@ int tc_wgrads(const visde_ctx_view* ctx, const float* dg, const float* stash, in
     set_error("tc_wgrads: workspace too small");
     return VISDE_EWORKSPACE;
   }
-  constexpr int STAGE_BYTES = 2 * 128 * 128 + 2 * 192 * 128;
-  const size_t smem = kStages * STAGE_BYTES + sizeof(TcBarriers) + 1024;
+  const size_t smem = kWgtSmemBytes;
   static DeviceOnce attr_once;
   int attr_dev = 0;
   if (attr_once.needed(&attr_dev)) {
@@ -962,8 +967,7 @@ int tc_wgrads_tiled(const visde_ctx_view* ctx, const float* dg, const float* sta
     set_error("tc_wgrads_tiled: workspace too small");
     return VISDE_EWORKSPACE;
   }
-  constexpr int STAGE_BYTES = 2 * 128 * 128 + 2 * 192 * 128;
-  const size_t smem = kStages * STAGE_BYTES + sizeof(TcBarriers) + 1024;
+  const size_t smem = kWgtSmemBytes;
   static DeviceOnce attr_once;
   int attr_dev = 0;
   if (attr_once.needed(&attr_dev)) {
