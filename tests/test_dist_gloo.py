@@ -33,6 +33,14 @@ def _worker(rank: int, world: int, port: int) -> None:
         for i, v in enumerate(b.views):
             assert torch.allclose(v, torch.full_like(v, 1.5 * (i + 1)))
         assert all(v.data_ptr() >= b.flat.data_ptr() for v in b.views)
+        # extra tail slot: the ELBO scalar rides in the same collective as the gradients
+        b2 = FlatBucket([(4, 3), (5,)], "cpu", extra=1)
+        for v in b2.views:
+            v.fill_(float(rank))
+        torch.sum(torch.full((6,), float(rank + 1)), dim=0, keepdim=True, out=b2.extra)
+        b2.allreduce_mean_()
+        assert b2.extra.shape == (1,) and b2.extra.item() == 9.0  # mean of 6 and 12
+        assert all(torch.allclose(v, torch.full_like(v, 0.5)) for v in b2.views)
         # sum of shard gradients == single-process gradient on the concatenated batch (local loss is a batch mean)
         torch.manual_seed(0)
         lin = torch.nn.Linear(4, 3)

@@ -44,14 +44,17 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
 class FlatBucket:
     """One contiguous fp32 buffer whose slices ARE the gradient tensors (no pack / unpack copies)."""
 
-    def __init__(self, shapes: Sequence[Sequence[int]], device: torch.device | str) -> None:
+    def __init__(self, shapes: Sequence[Sequence[int]], device: torch.device | str, extra: int = 0) -> None:
+        """`extra` scalars ride at the tail of the bucket (the ELBO value: one collective per iteration instead
+        of two)."""
         sizes = [int(torch.Size(s).numel()) for s in shapes]
         offs, total = [], 0
         for n in sizes:
             offs.append(total)
             total += (n + 3) // 4 * 4  # keep every view 16-byte aligned
-        self.flat = torch.zeros(total, device=device, dtype=torch.float32)
+        self.flat = torch.zeros(total + extra, device=device, dtype=torch.float32)
         self.views: List[Tensor] = [self.flat[o:o + n].view(*s) for o, n, s in zip(offs, sizes, shapes)]
+        self.extra: Tensor = self.flat[total:total + extra]
 
     def allreduce_mean_(self, group=None) -> None:
         allreduce_mean_(self.flat, group)

@@ -39,7 +39,8 @@ class PathIteration:
         self.out_w, self.out_b = to(inp.out_w), to(inp.out_b)
         # all 4*NL+2 weight gradients are views of ONE flat buffer: it is the all-reduce bucket
         shapes = [tuple(t.shape) for ws in self.w for t in ws] + [tuple(self.out_w.shape), tuple(self.out_b.shape)]
-        self.bucket = FlatBucket(shapes, dev)
+        self.bucket = FlatBucket(shapes, dev, extra=1)  # + the ELBO scalar: one all-reduce per iteration
+        self.elbo_sign = torch.tensor([1.0, 1.0, -1.0, 1.0], **f) / B  # mean_b(obs + sde - gen + jac)
         v = self.bucket.views
         self.gw = [v[i * NL:(i + 1) * NL] for i in range(4)]
         self.g_out_w, self.g_out_b = v[4 * NL], v[4 * NL + 1]
@@ -106,6 +107,10 @@ class PathIteration:
         with torch.cuda.device(self.dev):
             self.forward()
             self.backward()
+
+    def stage_elbo(self) -> None:
+        """Write the batch-mean ELBO of this rank into the bucket's tail slot (two tiny kernels)."""
+        torch.sum(torch.mv(self.terms, self.elbo_sign), dim=0, keepdim=True, out=self.bucket.extra)
 
     def results(self) -> Dict[str, object]:
         grads = {"x0": self.grad_x0, "context": self.grad_ctx[:, : self.T], "theta": self.grad_theta,
