@@ -22,6 +22,7 @@ namespace {
 
 constexpr int kHP = 64, kKS = 4, kSL = 16, kSLP = kSL + 4, kHB = kKS * kSLP;  // padded H-vector: 80 floats
 constexpr int kThr = kHP * kKS;
+constexpr int kWzPitch = 3 * kHP + 8;  // forward W_z copy: state column s at s * kWzPitch (4 consecutive s: disjoint banks)
 constexpr int kWoPitch = 72;  // W_out^T rows in the backward: 4 consecutive rows hit 4 disjoint bank octets
 
 __device__ __forceinline__ float ks_allreduce4(float v) {
@@ -63,8 +64,8 @@ __global__ void __launch_bounds__(kThr, 1) path_fwd_fasts_kernel(PathParams p) {
   extern __shared__ __align__(16) float smem_fs[];
   float* hbuf = smem_fs;                        // [2][NL][kHB]
   float* wout_s = hbuf + 2 * NL * kHB;          // [npass * 64][kHB] rows of W_out as padded K-slices
-  float* wz_s = wout_s + npass * kHP * kHB;     // [S][3][kHP]
-  float* bout_s = wz_s + S * 3 * kHP;           // [NOUT]
+  float* wz_s = wout_s + npass * kHP * kHB;     // [S][kWzPitch]: (g, unit) at g * kHP + unit
+  float* bout_s = wz_s + S * kWzPitch;          // [NOUT]
   float* obuf = bout_s + NOUT;                  // [NOUT]
   float* zbuf = obuf + NOUT;                    // [S]
   float* epsbuf = zbuf + S;                     // [2][S]
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(kThr, 1) path_fwd_fasts_kernel(PathParams p) {
   }
   for (int idx = tid; idx < S * 3 * kHP; idx += kThr) {
     const int u = idx % kHP, g = (idx / kHP) % 3, s = idx / (3 * kHP);
-    wz_s[idx] = u < H ? p.w_ih[0][(int64_t)(g * H + u) * ld0 + s] : 0.f;
+    wz_s[s * kWzPitch + g * kHP + u] = u < H ? p.w_ih[0][(int64_t)(g * H + u) * ld0 + s] : 0.f;
   }
   for (int m = tid; m < NOUT; m += kThr) bout_s[m] = p.out_b[m];
 
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(kThr, 1) path_fwd_fasts_kernel(PathParams p) {
           float er = lead * (gi_cur[0] + gth[0]), eu = lead * (gi_cur[1] + gth[1]), en = lead * (gi_cur[2] + gth[2]);
           for (int s = ks; s < S; s += kKS) {
             const float zs = zbuf[s];
-            const float* wz = wz_s + s * 3 * kHP + i;
+            const float* wz = wz_s + s * kWzPitch + i;
             er = fmaf(wz[0], zs, er);
             eu = fmaf(wz[kHP], zs, eu);
             en = fmaf(wz[2 * kHP], zs, en);
@@ -218,36 +219,43 @@ __global__ void __launch_bounds__(kThr, 1) path_fwd_fasts_kernel(PathParams p) {
         if (ks == 0 && m < NOUT) obuf[m] = v + bout_s[m];
       }
       __syncthreads();
-      // ---- reparameterised Euler-Maruyama update, one state dimension per thread
+      // ---- reparameterised Euler-Maruyama update: one state dimension per thread computes z_{t+1} (the only part on
+      // the critical path); means / chol / raw leave after the barrier, one element per thread, straight from obuf
+      float zn_keep = 0.f;
       if (tid < S) {
         const int s = tid;
-        const int64_t row = b * p.T + t;
-        const float mu = obuf[s];
         float acc = 0.f;
-        float* Lrow = p.chol + (row * S + s) * S;
         const float* ev = epsbuf + par * S;
-        for (int j = 0; j < S; ++j) {
-          float L = 0.f;
-          if (j <= s) {
-            const int ti = s * (s + 1) / 2 + j;
-            const float raw = obuf[S + ti];
-            L = (j == s) ? fmaxf(raw, VISDE_DIAG_MIN) : raw;
-            acc = fmaf(L, ev[j], acc);
-            if (p.raw) p.raw[row * NTRIL + ti] = raw;
-          }
-          Lrow[j] = L;
-        }
-        const float zn = zbuf[s] + mu * p.dt + acc * p.sqrt_dt;
-        p.means[row * S + s] = mu;
-        p.paths[(b * (p.T + 1) + t + 1) * S + s] = zn;
-        zbuf[s] = zn;
+        const float* Lr = obuf + S + s * (s + 1) / 2;
+        for (int j = 0; j < s; ++j) acc = fmaf(Lr[j], ev[j], acc);
+        acc = fmaf(fmaxf(Lr[s], VISDE_DIAG_MIN), ev[s], acc);
+        zn_keep = zbuf[s] + obuf[s] * p.dt + acc * p.sqrt_dt;
+        zbuf[s] = zn_keep;
         epsbuf[(par ^ 1) * S + s] = eps_next;
+      }
+      __syncthreads();
+      {
+        const int64_t row = b * p.T + t;
+        if (tid < S) {
+          p.paths[(b * (p.T + 1) + t + 1) * S + tid] = zn_keep;
+          p.means[row * S + tid] = obuf[tid];
+        }
+        if (tid < S * S) {  // S <= 16: one element of the S x S factor per thread
+          const int r = tid / S, c = tid % S;
+          float L = 0.f;
+          if (c <= r) {
+            const float raw = obuf[S + r * (r + 1) / 2 + c];
+            L = (c == r) ? fmaxf(raw, VISDE_DIAG_MIN) : raw;
+          }
+          p.chol[row * S * S + tid] = L;
+        }
+        if (p.raw && tid < NTRIL) p.raw[row * NTRIL + tid] = obuf[S + tid];
       }
       if (st_lane) st_lane += NL * kStashSlots * H;
 #pragma unroll
       for (int g = 0; g < 3; ++g) gi_cur[g] = gi_nxt[g];
-      __syncthreads();
     }
+    __syncthreads();  // obuf / zbuf reuse by the next trajectory
   }
 }
 
@@ -525,7 +533,7 @@ int fasts_grid(int64_t B) {
 
 size_t fasts_fwd_smem(const PathParams& p) {
   const int npass = (p.n_out + kHP - 1) / kHP;
-  return sizeof(float) * ((size_t)2 * p.NL * kHB + (size_t)npass * kHP * kHB + (size_t)p.S * 3 * kHP + 2 * (size_t)p.n_out + 3 * (size_t)p.S + 8);
+  return sizeof(float) * ((size_t)2 * p.NL * kHB + (size_t)npass * kHP * kHB + (size_t)p.S * kWzPitch + 2 * (size_t)p.n_out + 3 * (size_t)p.S + 8);
 }
 size_t fasts_bwd_smem(const PathParams& p) {
   const int SMALL = 4 * p.S + p.S * p.S, SMALLP = (SMALL + 3) / 4 * 4;
