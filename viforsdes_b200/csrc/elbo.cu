@@ -17,7 +17,8 @@
 namespace visde {
 namespace {
 
-constexpr int kElboThreads = 128;
+constexpr int kElboThreads = 128;     // block size when there are many trajectories
+constexpr int kElboMaxThreads = 512;  // few trajectories, long grids: more threads per trajectory (fewer serial round trips)
 constexpr float kHalfLog2Pi = 0.91893853320467274178f;
 
 __device__ __forceinline__ float softplus_f(float z) { return z > 20.f ? z : log1pf(expf(z)); }
@@ -189,20 +190,20 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   __syncthreads();
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kElboThreads / 32; ++i) s += red[i];
+  for (int i = 0; i < kElboMaxThreads / 32; ++i) s += (i < (int)(blockDim.x >> 5)) ? red[i] : 0.f;
   return s;
 }
 
 template <int SMAX>
-__global__ void __launch_bounds__(kElboThreads) elbo_fwd_kernel(ElboParams p) {
-  __shared__ float red[kElboThreads / 32];
+__global__ void __launch_bounds__(kElboMaxThreads) elbo_fwd_kernel(ElboParams p) {
+  __shared__ float red[kElboMaxThreads / 32];
   const int S = p.S;
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     float th[4] = {0.f, 0.f, 0.f, 0.f};
     if (p.sde_kind != VISDE_SDE_GENERIC)
       for (int q = 0; q < 3; ++q) th[q] = p.theta[b * p.P + q];
     float s_obs = 0.f, s_sde = 0.f, s_gen = 0.f, s_jac = 0.f;
-    for (int64_t tau = threadIdx.x; tau <= p.T; tau += kElboThreads) {
+    for (int64_t tau = threadIdx.x; tau <= p.T; tau += blockDim.x) {
       float zt[SMAX], xt[SMAX];
       load_vec<SMAX>(p.z + (b * (p.T + 1) + tau) * S, S, zt);
       to_state_vec<SMAX>(S, p.pos_mask, zt, xt);
@@ -238,8 +239,8 @@ __global__ void __launch_bounds__(kElboThreads) elbo_fwd_kernel(ElboParams p) {
 }
 
 template <int SMAX>
-__global__ void __launch_bounds__(kElboThreads) elbo_bwd_kernel(ElboParams p) {
-  __shared__ float red[kElboThreads / 32];
+__global__ void __launch_bounds__(kElboMaxThreads) elbo_bwd_kernel(ElboParams p) {
+  __shared__ float red[kElboMaxThreads / 32];
   const int S = p.S;
   const float sq = sqrtf(p.dt);
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kElboThreads) elbo_bwd_kernel(ElboParams p) {
     const float g_obs = p.g_terms[b * 4 + 0], g_sde = p.g_terms[b * 4 + 1];
     const float g_gen = p.g_terms[b * 4 + 2], g_jac = p.g_terms[b * 4 + 3];
     float gth[3] = {0.f, 0.f, 0.f};
-    for (int64_t tau = threadIdx.x; tau <= p.T; tau += kElboThreads) {
+    for (int64_t tau = threadIdx.x; tau <= p.T; tau += blockDim.x) {
       float zt[SMAX], xt[SMAX], spg[SMAX], gz[SMAX], gx[SMAX];
       load_vec<SMAX>(p.z + (b * (p.T + 1) + tau) * S, S, zt);
       to_state_vec<SMAX>(S, p.pos_mask, zt, xt);
@@ -377,12 +378,19 @@ int elbo_grid(int64_t B) {
   return (int)(B < cap ? B : cap);
 }
 
+// one block per trajectory: with few trajectories every extra pass over tau is a serial HBM round trip
+int elbo_threads(int64_t B, int64_t T) {
+  if (B > 148 * 4) return kElboThreads;
+  int64_t t = (T + 1 + 31) / 32 * 32;
+  return (int)(t < kElboThreads ? kElboThreads : (t > kElboMaxThreads ? kElboMaxThreads : t));
+}
+
 template <int SMAX>
 int launch_both(const ElboParams& p, cudaStream_t st, bool bwd) {
   if (bwd)
-    elbo_bwd_kernel<SMAX><<<elbo_grid(p.B), kElboThreads, 0, st>>>(p);
+    elbo_bwd_kernel<SMAX><<<elbo_grid(p.B), elbo_threads(p.B, p.T), 0, st>>>(p);
   else
-    elbo_fwd_kernel<SMAX><<<elbo_grid(p.B), kElboThreads, 0, st>>>(p);
+    elbo_fwd_kernel<SMAX><<<elbo_grid(p.B), elbo_threads(p.B, p.T), 0, st>>>(p);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
