@@ -12,14 +12,16 @@
 // 2^-(a+14) in the epilogue.  fp16 rather than tf32 because the three recurrent matrices then fit in
 // shared memory as resident hi/lo tiles (144 KB instead of 288 KB) and the MMA rate doubles.
 //
-// Warp roles (288 threads): warps 0..7 are the gate epilogue -- warp w reads TMEM lane quadrant w % 4
-// (32 trajectories) and hidden units [32 * (w / 4), +32): tcgen05.ld -> gates (raw MUFU) -> h(t) kept
-// in registers for the next step's update, written as fp16 hi/lo into the K-major SWIZZLE_128B A
-// tiles, and stashed for the backward; warp 8 allocates TMEM and one of its lanes issues every MMA.
-// mbarriers: d0 / d1 / out (tcgen05.commit: accumulators ready), a0 / a1 (256 arrivals: A tile
-// written and accumulator drained), init (tile start).  The state-column and theta terms of layer 0
-// and the biases do not go through the tensor cores: theta and bias terms are folded into gi_ctx by
-// K0 (per-trajectory row bias), the S state columns are S FMAs per gate in the epilogue.
+// Warp roles (256 threads = 8 warps, 255 registers each): every warp is a gate-epilogue warp -- warp w reads TMEM
+// lane quadrant w % 4 (32 trajectories) and hidden units [32 * (w / 4), +32): tcgen05.ld -> gates (raw MUFU) -> h(t)
+// kept in registers for the next step's update, written as fp16 hi/lo into the K-major SWIZZLE_128B A tiles, and
+// stashed for the backward.  Warp 0 also allocates TMEM and its lane 0 issues every MMA between its own epilogue
+// phases (a dedicated ninth warp would cap the kernel at 168 registers per thread).
+// mbarriers: d0 / d1 / out (tcgen05.commit: accumulators ready), a0 / a1 (256 arrivals: A tile written and
+// accumulator drained), init (tile start).  The state-column and theta terms of layer 0 and the biases do not go
+// through the tensor cores: theta and bias terms are folded into gi_ctx by K0 (per-trajectory row bias), the S state
+// columns are S FMAs per gate in the epilogue.  gi_ctx and the stash use the row-fastest tiled layouts
+// [tile][t][feature][128 rows]: a thread owns a trajectory row, so every warp access is one full 128-byte line.
 #include "path_tc.cuh"
 
 namespace visde {

@@ -13,7 +13,7 @@ constexpr int kTileRows = 128;
 constexpr int kWTileBytes = 192 * 128;  // one weight tile: 192 gate rows x 64 fp16
 constexpr int kATileBytes = 128 * 128;  // one operand tile: 128 trajectories x 64 fp16
 constexpr int kOutTileBytes = 16 * 128;
-constexpr int kEpiThreads = 256, kTcRecThreads = 288;
+constexpr int kEpiThreads = 256;  // all 8 warps of the recurrence kernels are epilogue warps
 constexpr int kUPT = 32;    // hidden units per epilogue thread
 constexpr int kHExp = 14;   // hidden states are scaled by 2^14 before the fp16 split
 
