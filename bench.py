@@ -180,6 +180,7 @@ def main() -> None:
                     help="recurrence kernel family (ad-hoc comparisons; production is auto)")
     ap.add_argument("--context-dtype", default="f32", choices=["f32", "bf16"],
                     help="dtype of context / grad_context in the device-resident leg (bf16 = the reference's AMP mode)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the iteration kernel by kernel in the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -217,8 +218,13 @@ def main() -> None:
     units = B * T
     flush = torch.empty(512 << 20, device=dev, dtype=torch.uint8)
 
-    def step() -> None:
-        it.step()
+    use_graph = not args.no_graph
+
+    def step(graph: bool = False) -> None:
+        if graph:
+            it.replay()  # the whole iteration as one CUDA-graph launch (the NCCL exchange stays outside the graph)
+        else:
+            it.step()
         if world > 1:  # the path's one exchange step
             it.stage_elbo()               # the ELBO scalar rides in the tail slot of the gradient bucket:
             it.bucket.allreduce_mean_()   # ONE NCCL all-reduce (AVG) of 351 KB per iteration
@@ -230,22 +236,39 @@ def main() -> None:
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        _lib.check(lib.visde_profile_begin(K * 8 + 8))
+        if use_graph:
+            it.capture()
+            for _ in range(2):
+                step(graph=True)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+        # ---- timed region: K iterations, CUDA events per step on the launching stream ----
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         t_wall = time.perf_counter()
         for i in range(K):
             flush.zero_()  # L2 flush between timed iterations (outside the event bracket)
             ev[i][0].record()
-            step()
+            step(graph=use_graph)
             ev[i][1].record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t_wall = time.perf_counter() - t_wall
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        # ---- per-stage breakdown: the same K iterations kernel by kernel with the library's stage timer ----
+        _lib.check(lib.visde_profile_begin(K * 8 + 8))
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for i in range(K):
+            flush.zero_()
+            ev2[i][0].record()
+            step()
+            ev2[i][1].record()
+        torch.cuda.synchronize()
         ms = (C.c_double * len(_lib.STAGES))()
         cnt = (C.c_int * len(_lib.STAGES))()
         _lib.check(lib.visde_profile_end(ms, cnt))
-        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        eager_ms_per_step = sum(a.elapsed_time(b) for a, b in ev2) / K
         tt = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -315,7 +338,9 @@ def main() -> None:
     roofline = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": (d["achieved_gbs"] / hbm_peak) if d["achieved_gbs"] else None, "traffic": traffic,
                 "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback 6.65 TB/s",
-                "kernel_ms": dur * 1e3, "share_of_step": d["ms_per_step"] / ms_per_step,
+                "kernel_ms": dur * 1e3, "share_of_step": d["ms_per_step"] / eager_ms_per_step,
+                "timing": "CUDA events of the library's stage timer around this stage, same K iterations launched kernel by "
+                          "kernel right after the timed region (the timed region itself is one graph replay per iteration)",
                 "note": ("B=128 trajectories on 148 SMs with T serial steps: latency-bound, see DESIGN.md §5; "
                          "whole-path figures in step_roofline") if B <= 148 else
                         ("large-batch family: gate GEMMs on tcgen05, HBM-bound by the stash / d_pre streams "
@@ -337,12 +362,13 @@ def main() -> None:
         "data": "synthetic",
         "config": {"workload": args.workload, "sde": kind, "batch_per_gpu": B, "n_steps": T, "dt": dt, "state_dim": S,
                    "context_dim": Cd, "hidden_dim": H, "num_layers": NL, "parallelism": f"dp{world}", "variant": args.variant, "context_dtype": args.context_dtype,
+                   "launch": "one CUDA-graph replay per iteration" if use_graph else "kernel by kernel",
                    "l2": "512 MB flush write between timed steps; per-step working set ~0.9 GB > 126 MB L2"},
         "e2e": e2e, "gpu_launches": int(sum(cnt)),
         "roofline": roofline, "step_roofline": step_roofline, "stages": stages, "cpu_baseline": cb,
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                    "samples": clocks["samples"]},
-        "wall_ms_per_step_incl_flush": t_wall / K * 1e3,
+        "wall_ms_per_step_incl_flush": t_wall / K * 1e3, "eager_ms_per_step": eager_ms_per_step,
     }
     print(json.dumps(line))
     if world > 1:

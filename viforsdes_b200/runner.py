@@ -108,6 +108,24 @@ class PathIteration:
             self.forward()
             self.backward()
 
+    def capture(self) -> None:
+        """Capture one iteration (every kernel of K0..K4 + the ELBO kernels, all buffers static) into a CUDA graph:
+        `replay()` then costs one launch instead of ~14 and leaves no gaps between the dependent kernels."""
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):  # warm-up on the capture side: per-kernel attributes, tensor-map encoders
+            for _ in range(2):
+                self.step()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.step()
+
+    def replay(self) -> None:
+        self.graph.replay()
+
     def stage_elbo(self) -> None:
         """Write the batch-mean ELBO of this rank into the bucket's tail slot (two tiny kernels)."""
         torch.sum(torch.mv(self.terms, self.elbo_sign), dim=0, keepdim=True, out=self.bucket.extra)
