@@ -692,6 +692,12 @@ struct visde_session_inputs {
   cudaEvent_t loaded;    // copy stream: this set's H2D copies are complete
   cudaEvent_t consumed;  // compute stream: the kernels that read this set are complete
   cudaEvent_t done;      // compute stream: kernels + D2H of the iteration that used this set
+  // the kernel sequence of one iteration on this input set, captured once as a CUDA graph (one launch per iteration,
+  // no gaps between the dependent kernels); re-captured when a scalar baked into the kernel parameters changes
+  cudaGraphExec_t graph;
+  float graph_dt, graph_var;
+  bool graph_obsmat;
+  uint32_t uses;
 };
 
 struct visde_session {
@@ -822,6 +828,7 @@ void visde_session_destroy(visde_session* s) {
     if (s->in[q].loaded) cudaEventDestroy(s->in[q].loaded);
     if (s->in[q].consumed) cudaEventDestroy(s->in[q].consumed);
     if (s->in[q].done) cudaEventDestroy(s->in[q].done);
+    if (s->in[q].graph) cudaGraphExecDestroy(s->in[q].graph);
   }
   if (s->st) cudaStreamDestroy(s->st);
   if (s->copy_st) cudaStreamDestroy(s->copy_st);
@@ -831,6 +838,32 @@ void visde_session_destroy(visde_session* s) {
 size_t visde_session_h2d_bytes(const visde_session* s) { return s ? s->h2d : 0; }
 size_t visde_session_d2h_bytes(const visde_session* s) { return s ? s->d2h : 0; }
 int visde_session_launches(const visde_session* s) { return s ? s->launches : 0; }
+
+// kernel sequence of one iteration on input set `in` (everything between the H2D and the D2H copies)
+static int session_enqueue(visde_session* s, visde_session_inputs& in, float dt, const visde_obs* od_p, cudaStream_t st) {
+  const visde_dims& d = s->d;
+  const size_t B = d.B, T = d.T, C = d.C, P = d.P;
+  const visde_obs& od = *od_p;
+  visde_ctx_view cv{in.ctx, (int64_t)((T + 1) * C), (int64_t)C, VISDE_F32};
+  visde_ctx_grad_view gv{s->grad_ctx, (int64_t)((T + 1) * C), (int64_t)C, VISDE_F32};
+  int rc = visde_path_fwd(&d, dt, in.x0, &cv, in.theta, in.eps, &in.w, s->paths, s->means, s->chol, s->stash, s->ws_f,
+                          s->ws_f_bytes, st);
+  if (rc) return rc;
+  rc = visde_elbo_fwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, in.theta, nullptr, nullptr, &od,
+                      s->terms, st);
+  if (rc) return rc;
+  fill_loss_cotangent_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(s->g_terms, (int64_t)B);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  rc = visde_elbo_bwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, in.theta, nullptr, nullptr, &od,
+                      s->g_terms, s->g_z, s->g_means, s->g_chol, s->g_theta_elbo, nullptr, nullptr, st);
+  if (rc) return rc;
+  rc = visde_path_bwd(&d, dt, s->g_z, s->g_means, s->g_chol, &cv, in.theta, in.eps, &in.w, s->paths, s->stash,
+                      s->grad_x0, &gv, s->grad_theta, &s->gw, s->ws_b, s->ws_b_bytes, st);
+  if (rc) return rc;
+  add_inplace_kernel<<<(unsigned)((B * P + 255) / 256), 256, 0, st>>>(s->grad_theta, s->g_theta_elbo, (int64_t)(B * P));
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  return VISDE_OK;
+}
 
 int visde_session_submit(visde_session* s, float dt, const float* x0, const float* context,
                          const float* theta, const float* eps, const visde_weights* w_host,
@@ -873,24 +906,44 @@ int visde_session_submit(visde_session* s, float dt, const float* x0, const floa
   VISDE_CUDA_CHECK(cudaEventRecord(in.loaded, cs));
   VISDE_CUDA_CHECK(cudaStreamWaitEvent(st, in.loaded, 0));
 
-  visde_ctx_view cv{in.ctx, (int64_t)((T + 1) * C), (int64_t)C, VISDE_F32};
-  visde_ctx_grad_view gv{s->grad_ctx, (int64_t)((T + 1) * C), (int64_t)C, VISDE_F32};
-  int rc = visde_path_fwd(&d, dt, in.x0, &cv, in.theta, in.eps, &in.w, s->paths, s->means, s->chol, s->stash, s->ws_f,
-                          s->ws_f_bytes, st);
-  if (rc) return rc;
-  rc = visde_elbo_fwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, in.theta, nullptr, nullptr, &od,
-                      s->terms, st);
-  if (rc) return rc;
-  fill_loss_cotangent_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(s->g_terms, (int64_t)B);
-  VISDE_CUDA_CHECK(cudaGetLastError());
-  rc = visde_elbo_bwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, in.theta, nullptr, nullptr, &od,
-                      s->g_terms, s->g_z, s->g_means, s->g_chol, s->g_theta_elbo, nullptr, nullptr, st);
-  if (rc) return rc;
-  rc = visde_path_bwd(&d, dt, s->g_z, s->g_means, s->g_chol, &cv, in.theta, in.eps, &in.w, s->paths, s->stash,
-                      s->grad_x0, &gv, s->grad_theta, &s->gw, s->ws_b, s->ws_b_bytes, st);
-  if (rc) return rc;
-  add_inplace_kernel<<<(unsigned)((B * P + 255) / 256), 256, 0, st>>>(s->grad_theta, s->g_theta_elbo, (int64_t)(B * P));
-  VISDE_CUDA_CHECK(cudaGetLastError());
+  // first use of an input set runs kernel by kernel (per-kernel attributes, tensor-map encoders); from the second use
+  // on the same sequence is replayed as one CUDA graph
+  int rc;
+  const bool obs_mat = obs_host->obs_matrix != nullptr;
+  if (in.graph && (in.graph_dt != dt || in.graph_var != od.variance || in.graph_obsmat != obs_mat)) {
+    cudaGraphExecDestroy(in.graph);
+    in.graph = nullptr;
+  }
+  if (in.graph) {
+    VISDE_CUDA_CHECK(cudaGraphLaunch(in.graph, st));
+  } else if (in.uses >= 1 && !g_prof_on) {
+    cudaGraph_t g = nullptr;
+    VISDE_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = session_enqueue(s, in, dt, &od, st);
+    const cudaError_t ce = cudaStreamEndCapture(st, &g);
+    if (rc || ce != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      if (!rc) rc = session_enqueue(s, in, dt, &od, st);  // capture unavailable: plain launches
+      if (rc) return rc;
+    } else {
+      const cudaError_t ie = cudaGraphInstantiate(&in.graph, g, 0);
+      cudaGraphDestroy(g);
+      if (ie != cudaSuccess) {
+        in.graph = nullptr;
+        cudaGetLastError();
+        if ((rc = session_enqueue(s, in, dt, &od, st))) return rc;
+      } else {
+        in.graph_dt = dt;
+        in.graph_var = od.variance;
+        in.graph_obsmat = obs_mat;
+        VISDE_CUDA_CHECK(cudaGraphLaunch(in.graph, st));
+      }
+    }
+  } else {
+    if ((rc = session_enqueue(s, in, dt, &od, st))) return rc;
+  }
+  ++in.uses;
   VISDE_CUDA_CHECK(cudaEventRecord(in.consumed, st));
 
   D2H(terms, s->terms, B * 4);
