@@ -450,7 +450,12 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
       if (rc) return rc;
     }
     // grad_theta (through the GRU input) = (sum_t d_gi_l0) . W_ih_l0[:, S+C:]
-    if (P > 0) {
+    const bool thin_family = fastk || tcrec || fastsk;  // these families take the theta columns of dW_ih_l0 from sdg
+    if (P > 0 && theta_grads_supported(P)) {
+      rc = launch_theta_grads(p.sdg, theta, w->w_ih[0], d->B, G, P, ld0, S + C, grad_theta,
+                              thin_family ? gw->w_ih[0] : nullptr, st);
+      if (rc) return rc;
+    } else if (P > 0) {
       RowSrc A{p.sdg, G, 0, 0, G, VISDE_F32};
       rc = launch_gemm_nn(A, d->B, 1, G, w->w_ih[0] + S + C, ld0, P, grad_theta, P, 0, VISDE_F32, st);
       if (rc) return rc;
@@ -465,7 +470,7 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
       rc = launch_fast_partials_reduce(p, gw, st);
       if (rc) return rc;
     }
-    if (P > 0) {  // theta columns of dW_ih_l0 = (sum_t d_gi_l0)^T theta: only B rows
+    if (P > 0 && !theta_grads_supported(P)) {  // theta columns of dW_ih_l0 = (sum_t d_gi_l0)^T theta: only B rows
       RowSrc A{p.sdg, G, 0, 0, G, VISDE_F32};
       RowSrc bs[1] = {RowSrc{theta, P, 0, 0, P, VISDE_F32}};
       TnOut o{gw->w_ih[0] + S + C, ld0, 0, P};

@@ -183,6 +183,10 @@ int launch_gemm_tn(const RowSrc& A, int M, int a_split, int a_skip, const RowSrc
                    int64_t B, int64_t T, const TnOut* outs, int nouts, float* partials,
                    size_t partial_floats, cudaStream_t st);
 size_t gemm_tn_partial_floats(int M, int N, int64_t K);
+// grad_theta = sdg . W_ih_l0[:, col0:col0+P] and (dw != nullptr) dW_ih_l0[:, col0:col0+P] = sdg^T theta in one small launch
+bool theta_grads_supported(int P);
+int launch_theta_grads(const float* sdg, const float* theta, const float* w_ih0, int64_t B, int G, int P, int ld0, int col0,
+                       float* grad_theta, float* dw, cudaStream_t st);
 
 // --- tensor-core (tcgen05, 3xTF32) versions of K0 / K3 / K4 (tc_gemm.cu) ------------------------
 bool tc_supported(int H, int NL, int C, const visde_ctx_view* ctx);

@@ -296,4 +296,91 @@ int launch_gemm_tn(const RowSrc& A, int M, int a_split, int a_skip, const RowSrc
   return VISDE_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// theta pieces from sdg[b][g] = sum_t d_gi_l0[b, t, g] (both are B-row problems: two generic GEMM launches cost 60 us
+// at B = 128, this one kernel ~5 us):
+//   grad_theta[b][p]            = sum_g sdg[b][g] W_ih_l0[g][col0 + p]          (blocks >= G: 8 threads per b)
+//   dW_ih_l0[g][col0 + p]       = sum_b sdg[b][g] theta[b][p]                   (block g: fixed-order tree over b)
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kThetaMaxP = 16;
+__global__ void __launch_bounds__(256) theta_grads_kernel(const float* __restrict__ sdg, const float* __restrict__ theta,
+                                                          const float* __restrict__ w_ih0, int64_t B, int G, int P, int ld0,
+                                                          int col0, float* __restrict__ grad_theta, float* __restrict__ dw) {
+  const int tid = threadIdx.x;
+  float acc[kThetaMaxP];
+#pragma unroll
+  for (int q = 0; q < kThetaMaxP; ++q) acc[q] = 0.f;
+  const int nrow_blocks = dw ? G : 0;
+  if ((int)blockIdx.x < nrow_blocks) {
+    const int g = blockIdx.x;
+    for (int64_t b = tid; b < B; b += 256) {
+      const float v = sdg[b * G + g];
+#pragma unroll
+      for (int q = 0; q < kThetaMaxP; ++q)
+        if (q < P) acc[q] = fmaf(v, theta[b * P + q], acc[q]);
+    }
+    __shared__ float red[8][kThetaMaxP];
+#pragma unroll
+    for (int q = 0; q < kThetaMaxP; ++q) {
+      float a = acc[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if ((tid & 31) == 0) red[tid >> 5][q] = a;
+    }
+    __syncthreads();
+    if (tid < P) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) a += red[w][tid];
+      dw[(int64_t)g * ld0 + col0 + tid] = a;
+    }
+  } else {
+    // 32 trajectories per block; thread = (trajectory tid / 8, eighth tid % 8 of the 3H rows); W_theta staged in smem
+    __shared__ float wth[768 * 2];  // [G][P] for G * P <= 1536, else read from global
+    const bool staged = G * P <= 768 * 2;
+    if (staged) {
+      for (int idx = tid; idx < G * P; idx += 256) wth[idx] = w_ih0[(int64_t)(idx / P) * ld0 + col0 + idx % P];
+    }
+    __syncthreads();
+    const int64_t b = (int64_t)(blockIdx.x - nrow_blocks) * 32 + (tid >> 3);
+    const int part = tid & 7;
+    const int g0 = part * G / 8, g1 = (part + 1) * G / 8;
+    if (b < B) {
+      const float* row = sdg + b * G;
+#pragma unroll 8
+      for (int g = g0; g < g1; ++g) {
+        const float v = row[g];
+        const float* w = staged ? wth + g * P : w_ih0 + (int64_t)g * ld0 + col0;
+#pragma unroll
+        for (int q = 0; q < kThetaMaxP; ++q)
+          if (q < P) acc[q] = fmaf(v, w[q], acc[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kThetaMaxP; ++q) {
+      if (q < P) {  // uniform branch: P is a kernel argument
+        float a = acc[q];
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        if (part == 0 && b < B) grad_theta[b * P + q] = a;
+      }
+    }
+  }
+}
+}  // namespace
+
+bool theta_grads_supported(int P) { return P >= 1 && P <= kThetaMaxP; }
+
+// dw == nullptr: grad_theta only
+int launch_theta_grads(const float* sdg, const float* theta, const float* w_ih0, int64_t B, int G, int P, int ld0, int col0,
+                       float* grad_theta, float* dw, cudaStream_t st) {
+  const unsigned blocks = (unsigned)((dw ? G : 0) + (B + 31) / 32);
+  theta_grads_kernel<<<blocks, 256, 0, st>>>(sdg, theta, w_ih0, B, G, P, ld0, col0, grad_theta, dw);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  return VISDE_OK;
+}
+
 }  // namespace visde
