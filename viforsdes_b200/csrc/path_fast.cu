@@ -614,11 +614,15 @@ struct FastReduceArgs {
   float* out_b;
 };
 __global__ void fast_partials_reduce_kernel(FastReduceArgs a) {
+  // one warp per output: lane l sums CTAs l, l+32, ... then a fixed-order shuffle tree (deterministic)
   const int total = fast_part_floats(a.NL, a.H, a.S);
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (idx >= total) return;
   float acc = 0.f;
-  for (int c = 0; c < a.ncta; ++c) acc += a.part[(int64_t)c * total + idx];
+  for (int c = threadIdx.x & 31; c < a.ncta; c += 32) acc += a.part[(int64_t)c * total + idx];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) != 0) return;
   const int H = a.H;
   int off = idx;
   if (off < a.NL * kDgSlots * H) {
@@ -726,7 +730,7 @@ int launch_fast_partials_reduce(const PathParams& p, const visde_weight_grads* g
   a.out_w = gw->out_w;
   a.out_b = gw->out_b;
   const int total = fast_part_floats(p.NL, p.H, p.S);
-  fast_partials_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(a);
+  fast_partials_reduce_kernel<<<(total + 7) / 8, 256, 0, st>>>(a);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }

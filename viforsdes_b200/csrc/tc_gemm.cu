@@ -25,7 +25,8 @@
 namespace visde {
 namespace {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;  // K4 kernels: warp 0 TMA, warp 1 MMA, warps 2..9 hi/lo split (2..5 also epilogue)
+constexpr int kWgtSplitThreads = 256;
 constexpr uint32_t kTf32Mask = 0xffffe000u;  // keep sign, exponent and the 10 tf32 mantissa bits
 
 // instruction descriptor: D fp32, A/B tf32, M = 128
@@ -35,23 +36,39 @@ __host__ __device__ constexpr uint32_t make_idesc(int N, bool a_mn, bool b_mn) {
 }
 
 // in place hi = trunc_tf32(x); lo = trunc_tf32(x - hi), for `nvec` float4 handled by 128 threads
-__device__ __forceinline__ void split_tile(float4* hi, float4* lo, int nvec, int tid128) {
-  for (int v = tid128; v < nvec; v += 128) {
-    float4 x = hi[v];
+__device__ __forceinline__ void split_one(const float4 x, float4& h, float4& l) {
+  h.x = __uint_as_float(__float_as_uint(x.x) & kTf32Mask);
+  h.y = __uint_as_float(__float_as_uint(x.y) & kTf32Mask);
+  h.z = __uint_as_float(__float_as_uint(x.z) & kTf32Mask);
+  h.w = __uint_as_float(__float_as_uint(x.w) & kTf32Mask);
+  l.x = __uint_as_float(__float_as_uint(x.x - h.x) & kTf32Mask);
+  l.y = __uint_as_float(__float_as_uint(x.y - h.y) & kTf32Mask);
+  l.z = __uint_as_float(__float_as_uint(x.z - h.z) & kTf32Mask);
+  l.w = __uint_as_float(__float_as_uint(x.w - h.w) & kTf32Mask);
+}
+// NT threads split `nvec` float4 (four independent elements in flight per thread per pass)
+template <int NT = 128>
+__device__ __forceinline__ void split_tile(float4* hi, float4* lo, int nvec, int tid) {
+  int v = tid;
+  for (; v + 3 * NT < nvec; v += 4 * NT) {
+    const float4 x0 = hi[v], x1 = hi[v + NT], x2 = hi[v + 2 * NT], x3 = hi[v + 3 * NT];
+    float4 h0, l0, h1, l1, h2, l2, h3, l3;
+    split_one(x0, h0, l0);
+    split_one(x1, h1, l1);
+    split_one(x2, h2, l2);
+    split_one(x3, h3, l3);
+    hi[v] = h0; lo[v] = l0;
+    hi[v + NT] = h1; lo[v + NT] = l1;
+    hi[v + 2 * NT] = h2; lo[v + 2 * NT] = l2;
+    hi[v + 3 * NT] = h3; lo[v + 3 * NT] = l3;
+  }
+  for (; v < nvec; v += NT) {
     float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(x.x) & kTf32Mask);
-    h.y = __uint_as_float(__float_as_uint(x.y) & kTf32Mask);
-    h.z = __uint_as_float(__float_as_uint(x.z) & kTf32Mask);
-    h.w = __uint_as_float(__float_as_uint(x.w) & kTf32Mask);
-    l.x = __uint_as_float(__float_as_uint(x.x - h.x) & kTf32Mask);
-    l.y = __uint_as_float(__float_as_uint(x.y - h.y) & kTf32Mask);
-    l.z = __uint_as_float(__float_as_uint(x.z - h.z) & kTf32Mask);
-    l.w = __uint_as_float(__float_as_uint(x.w - h.w) & kTf32Mask);
+    split_one(hi[v], h, l);
     hi[v] = h;
     lo[v] = l;
   }
 }
-
 
 // ------------------------------------------------------------------------------------------
 // K0 / K3: rows kernel
@@ -356,7 +373,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
       mbar_init(&bars->emptyRaw[s], 1);
     }
     for (int s = 0; s < kWgtLo; ++s) {
-      mbar_init(&bars->split[s], 128);
+      mbar_init(&bars->split[s], kWgtSplitThreads);
       mbar_init(&bars->emptyLo[s], 1);
     }
     mbar_init(&bars->accum, 1);
@@ -414,11 +431,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
       const int s = kb % kWgtRaw, sl = kb % kWgtLo;
       mbar_wait(&bars->full[s], (kb / kWgtRaw) & 1);
       if (kb >= kWgtLo) mbar_wait(&bars->emptyLo[sl], ((kb / kWgtLo) - 1) & 1);
-      split_tile(reinterpret_cast<float4*>(smem + s * kWgtStageBytes), reinterpret_cast<float4*>(lo_ring + sl * kWgtStageBytes),
-                 kWgtStageBytes / 16, tid128);
+      split_tile<kWgtSplitThreads>(reinterpret_cast<float4*>(smem + s * kWgtStageBytes),
+                                   reinterpret_cast<float4*>(lo_ring + sl * kWgtStageBytes), kWgtStageBytes / 16, tid128);
       fence_proxy_async();
       mbar_arrive(&bars->split[sl]);
     }
+    if (warp <= 5) {
     mbar_wait(&bars->accum, 0);
     tc_fence_after();
     const int quad = warp & 3;
@@ -436,6 +454,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
 #pragma unroll
       for (int q = 0; q < 32; q += 4)
         *reinterpret_cast<float4*>(out + c * 32 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+    }
     }
   }
   tc_fence_before();
@@ -485,7 +504,7 @@ tc_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_co
       mbar_init(&bars->emptyRaw[s], 1);
     }
     for (int s = 0; s < kWgtLo; ++s) {
-      mbar_init(&bars->split[s], 128);
+      mbar_init(&bars->split[s], kWgtSplitThreads);
       mbar_init(&bars->emptyLo[s], 1);
     }
     mbar_init(&bars->accum, 1);
@@ -548,11 +567,12 @@ tc_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_co
       const int s = kb % kWgtRaw, sl = kb % kWgtLo;
       mbar_wait(&bars->full[s], (kb / kWgtRaw) & 1);
       if (kb >= kWgtLo) mbar_wait(&bars->emptyLo[sl], ((kb / kWgtLo) - 1) & 1);
-      split_tile(reinterpret_cast<float4*>(smem + s * kWgtStageBytes), reinterpret_cast<float4*>(lo_ring + sl * kWgtStageBytes),
-                 kWgtStageBytes / 16, tid128);
+      split_tile<kWgtSplitThreads>(reinterpret_cast<float4*>(smem + s * kWgtStageBytes),
+                                   reinterpret_cast<float4*>(lo_ring + sl * kWgtStageBytes), kWgtStageBytes / 16, tid128);
       fence_proxy_async();
       mbar_arrive(&bars->split[sl]);
     }
+    if (warp <= 5) {
     mbar_wait(&bars->accum, 0);
     tc_fence_after();
     const int quad = warp & 3;
@@ -570,6 +590,7 @@ tc_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap tmCtx, const __grid_co
 #pragma unroll
       for (int q = 0; q < 32; q += 4)
         *reinterpret_cast<float4*>(out + c * 32 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+    }
     }
   }
   tc_fence_before();
