@@ -101,7 +101,7 @@ struct RowsArgs {
 //   warps 2..5  split       : A raw -> hi (in place) + lo (2-deep ring shared with the B slot)
 //   warp 1      MMA issuer  : 3xTF32 into one of two TMEM accumulators (tile i+1 overlaps the epilogue of i)
 //   warps 6..9  epilogue    : tcgen05.ld -> (+bias) -> global
-constexpr int kRowsThreads = 352;
+constexpr int kRowsThreads = 480;  // + warps 11..14: four more hi/lo split warps
 
 template <int N, int NA>
 struct RowsSmem {
@@ -137,7 +137,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->fullB[s], 1);
       mbar_init(&bars->emptyB[s], 1);
-      mbar_init(&bars->split[s], 128);
+      mbar_init(&bars->split[s], 256);
       mbar_init(&bars->tmemFull[s], 1);
       mbar_init(&bars->tmemEmpty[s], 128);
     }
@@ -222,16 +222,16 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(&bars->tmemFull[acc]);
       }
     }
-  } else if (warp >= 2 && warp <= 5) {
-    const int tid128 = threadIdx.x - 64;
+  } else if ((warp >= 2 && warp <= 5) || warp >= 11) {
+    const int tid128 = warp <= 5 ? threadIdx.x - 64 : threadIdx.x - 352 + 128;  // 0..255
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int kb = 0; kb < nk; ++kb, ++g) {
         const uint32_t sa = g % NA, sb = g & 1;
         mbar_wait(&bars->fullA[sa], (g / NA) & 1);
         if (g >= 2) mbar_wait(&bars->emptyB[sb], ((g >> 1) - 1) & 1);  // lo slot released by the MMAs of g-2
-        split_tile(reinterpret_cast<float4*>(smem + sa * A_BYTES),
-                   reinterpret_cast<float4*>(smem + L::OFF_ALO + sb * A_BYTES), A_BYTES / 16, tid128);
+        split_tile<256>(reinterpret_cast<float4*>(smem + sa * A_BYTES),
+                        reinterpret_cast<float4*>(smem + L::OFF_ALO + sb * A_BYTES), A_BYTES / 16, tid128);
         fence_proxy_async();
         mbar_arrive(&bars->split[sb]);
       }
