@@ -89,6 +89,7 @@ struct RowsArgs {
                          // A slabs are [32 features][32 rows]; output rows are (b = tb * 128 + row, t)
   int a_feat_rows;       // a_tiled: features per (tile, t) block of the tiled buffer (F)
   int64_t B;             // a_tiled: trajectories (rows >= B are not stored)
+  int out_tma;           // 1: fp32 output through TMA stores of swizzled [128 x 32] staging tiles (tmOut)
   void* out;
   int64_t out_bstride, out_tstride;
   int out_dtype;
@@ -106,7 +107,10 @@ constexpr int kRowsThreads = 480;  // + warps 11..14: four more hi/lo split warp
 template <int N, int NA>
 struct RowsSmem {
   static constexpr int A_BYTES = 128 * 128, B_BYTES = N * 128;
-  static constexpr int OFF_ALO = NA * A_BYTES, OFF_B = OFF_ALO + 2 * A_BYTES, OFF_BAR = OFF_B + 2 * 2 * B_BYTES;
+  static constexpr int OFF_ALO = NA * A_BYTES, OFF_B = OFF_ALO + 2 * A_BYTES, OFF_STG = OFF_B + 2 * 2 * B_BYTES;
+  // epilogue staging tile [128 rows][32 fp32], SWIZZLE_128B: the accumulator chunk leaves through one TMA store
+  // (full 128-byte row segments, rows clipped by the tensor map) instead of per-thread row-strided stores
+  static constexpr int OFF_BAR = OFF_STG + A_BYTES;
   struct Bars {
     uint64_t fullA[NA], emptyA[NA], fullB[2], emptyB[2], split[2], tmemFull[2], tmemEmpty[2];
     uint32_t tmem_base;
@@ -117,7 +121,7 @@ struct RowsSmem {
 template <int N, bool B_MN, int NA, bool A_MN = false>
 __global__ void __launch_bounds__(kRowsThreads, 1)
 tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-               const __grid_constant__ CUtensorMap tmBlo, RowsArgs a) {
+               const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut, RowsArgs a) {
   using L = RowsSmem<N, NA>;
   constexpr int A_BYTES = L::A_BYTES, B_BYTES = L::B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * N <= 256 ? 256 : 512;
@@ -274,6 +278,33 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_arrive(&bars->tmemEmpty[acc]);
         continue;
       }
+      if (a.out_tma) {
+        uint8_t* stg = smem + L::OFF_STG;
+#pragma unroll 1
+        for (int c = 0; c < a.out_cols / 32; ++c) {
+          float v[32];
+          tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + acc * N + c * 32, v);
+          if (a.bias) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] += a.bias[a.n0 + c * 32 + q];
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)  // 16-byte chunk j of row `row` lives at chunk j ^ (row % 8): conflict-free
+            *reinterpret_cast<float4*>(stg + row * 128 + ((j ^ (row & 7)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (warp == 6 && lane == 0) {
+            if (A_MN) tma_store_3d(&tmOut, stg, a.n0 + c * 32, (int)(tile % a.T), (int)(tile / a.T) * 128);
+            else tma_store_3d(&tmOut, stg, a.n0 + c * 32, t0, b);
+            tma_store_commit_and_wait_read();
+          }
+          named_bar_sync(1, 128);  // staging tile reusable
+        }
+        tc_fence_before();
+        mbar_arrive(&bars->tmemEmpty[acc]);
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < N / 32; ++c) {
         float v[32];
@@ -315,6 +346,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       mbar_arrive(&bars->tmemEmpty[acc]);
     }
+    if (a.out_tma && warp == 6 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -683,8 +715,8 @@ int make_map(CUtensorMap* m, const void* base, int rank, const int64_t* dims, co
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int N, bool B_MN, int NA, bool A_MN = false>
-int launch_rows(const CUtensorMap& mA, const CUtensorMap& mBh, const CUtensorMap& mBl, RowsArgs a, int64_t B,
-                cudaStream_t st) {
+int launch_rows(const CUtensorMap& mA, const CUtensorMap& mBh, const CUtensorMap& mBl, const CUtensorMap& mOut, RowsArgs a,
+                int64_t B, cudaStream_t st) {
   const size_t smem = RowsSmem<N, NA>::bytes;
   static DeviceOnce attr_once;
   int attr_dev = 0;
@@ -697,7 +729,7 @@ int launch_rows(const CUtensorMap& mA, const CUtensorMap& mBh, const CUtensorMap
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-  tc_rows_kernel<N, B_MN, NA, A_MN><<<grid, kRowsThreads, smem, st>>>(mA, mBh, mBl, a);
+  tc_rows_kernel<N, B_MN, NA, A_MN><<<grid, kRowsThreads, smem, st>>>(mA, mBh, mBl, mOut, a);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
@@ -754,7 +786,14 @@ int tc_ctx_proj(const visde_ctx_view* ctx, int64_t B, int64_t T, int C, int H, c
   a.out_tstride = 3 * H;
   a.out_dtype = VISDE_F32;
   a.out_cols = 3 * H;
-  return launch_rows<192, false, 4>(mA, mBh, mBl, a, B, st);
+  CUtensorMap mOut = mA;  // placeholder when the TMA-store epilogue is off
+  if (!tiled) {
+    const int64_t dO[3] = {3 * H, T, B}, sO[2] = {3 * H, T * (int64_t)(3 * H)};
+    const int boxO[3] = {32, 128, 1};
+    if ((rc = make_map(&mOut, gi_ctx, 3, dO, sO, boxO))) return rc;
+    a.out_tma = 1;
+  }
+  return launch_rows<192, false, 4>(mA, mBh, mBl, mOut, a, B, st);
 }
 
 // K3: grad_ctx[b,t,:] = d_gi_l0[(b,t), :192] . Wc   (dg rows have `dg_row` floats).  dg_tiled: dg is the row-fastest
@@ -777,9 +816,19 @@ int tc_grad_ctx(const float* dg, int64_t dg_row, int64_t B, int64_t T, int C, in
   const int boxB[2] = {32, 32};
   if ((rc = make_map(&mBh, wsplit, 2, dB, sB, boxB, true))) return rc;
   if ((rc = make_map(&mBl, wsplit + (size_t)3 * H * C, 2, dB, sB, boxB, true))) return rc;
+  // fp32 grad_ctx with 16-byte aligned strides leaves through TMA stores (rows beyond T / B are clipped by the map)
+  CUtensorMap mOut = mA;
+  const bool out_tma = out->dtype == VISDE_F32 && aligned16(out->ptr) && out->batch_stride % 4 == 0 &&
+                       out->time_stride % 4 == 0 && C % 32 == 0;
+  if (out_tma) {
+    const int64_t dO[3] = {C, T, B}, sO[2] = {out->time_stride, out->batch_stride};
+    const int boxT[3] = {32, 1, 128}, boxS[3] = {32, 128, 1};
+    if ((rc = make_map(&mOut, out->ptr, 3, dO, sO, dg_tiled ? boxT : boxS))) return rc;
+  }
   for (int n0 = 0; n0 < C; n0 += 256) {
     RowsArgs a{};
     a.T = T;
+    a.out_tma = out_tma ? 1 : 0;
     a.tiles_per_b = (int)((T + 127) / 128);
     a.num_kblocks = 3 * H / 32;
     a.n0 = n0;
@@ -793,11 +842,11 @@ int tc_grad_ctx(const float* dg, int64_t dg_row, int64_t B, int64_t T, int C, in
     a.out_dtype = out->dtype;
     a.out_cols = C - n0 < 256 ? C - n0 : 256;
     if (dg_tiled)
-      rc = a.out_cols == 256 ? launch_rows<256, true, 3, true>(mA, mBh, mBl, a, B, st)
-                             : launch_rows<128, true, 4, true>(mA, mBh, mBl, a, B, st);
+      rc = a.out_cols == 256 ? launch_rows<256, true, 3, true>(mA, mBh, mBl, mOut, a, B, st)
+                             : launch_rows<128, true, 4, true>(mA, mBh, mBl, mOut, a, B, st);
     else
-      rc = a.out_cols == 256 ? launch_rows<256, true, 3>(mA, mBh, mBl, a, B, st)
-                             : launch_rows<128, true, 4>(mA, mBh, mBl, a, B, st);
+      rc = a.out_cols == 256 ? launch_rows<256, true, 3>(mA, mBh, mBl, mOut, a, B, st)
+                             : launch_rows<128, true, 4>(mA, mBh, mBl, mOut, a, B, st);
     if (rc) return rc;
   }
   return VISDE_OK;
