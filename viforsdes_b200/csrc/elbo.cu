@@ -195,7 +195,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 template <int SMAX>
-__global__ void __launch_bounds__(kElboMaxThreads) elbo_fwd_kernel(ElboParams p) {
+__global__ void __launch_bounds__(SMAX <= 4 ? kElboMaxThreads : kElboThreads) elbo_fwd_kernel(ElboParams p) {
   __shared__ float red[kElboMaxThreads / 32];
   const int S = p.S;
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kElboMaxThreads) elbo_fwd_kernel(ElboParams p)
 }
 
 template <int SMAX>
-__global__ void __launch_bounds__(kElboMaxThreads) elbo_bwd_kernel(ElboParams p) {
+__global__ void __launch_bounds__(SMAX <= 4 ? kElboMaxThreads : kElboThreads) elbo_bwd_kernel(ElboParams p) {
   __shared__ float red[kElboMaxThreads / 32];
   const int S = p.S;
   const float sq = sqrtf(p.dt);
@@ -379,8 +379,8 @@ int elbo_grid(int64_t B) {
 }
 
 // one block per trajectory: with few trajectories every extra pass over tau is a serial HBM round trip
-int elbo_threads(int64_t B, int64_t T) {
-  if (B > 148 * 4) return kElboThreads;
+int elbo_threads(int64_t B, int64_t T, int smax) {
+  if (B > 148 * 4 || smax > 4) return kElboThreads;  // wide-state instantiations keep the 128-thread register budget
   int64_t t = (T + 1 + 31) / 32 * 32;
   return (int)(t < kElboThreads ? kElboThreads : (t > kElboMaxThreads ? kElboMaxThreads : t));
 }
@@ -388,9 +388,9 @@ int elbo_threads(int64_t B, int64_t T) {
 template <int SMAX>
 int launch_both(const ElboParams& p, cudaStream_t st, bool bwd) {
   if (bwd)
-    elbo_bwd_kernel<SMAX><<<elbo_grid(p.B), elbo_threads(p.B, p.T), 0, st>>>(p);
+    elbo_bwd_kernel<SMAX><<<elbo_grid(p.B), elbo_threads(p.B, p.T, SMAX), 0, st>>>(p);
   else
-    elbo_fwd_kernel<SMAX><<<elbo_grid(p.B), elbo_threads(p.B, p.T), 0, st>>>(p);
+    elbo_fwd_kernel<SMAX><<<elbo_grid(p.B), elbo_threads(p.B, p.T, SMAX), 0, st>>>(p);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
