@@ -72,7 +72,9 @@ __device__ __forceinline__ int padded(int j) {
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int HP, int KS, int NL, int S>
+// HEX: the hidden size equals the padded size HP (the common H = 64 / 32 case): H becomes a compile-time constant and
+// the per-step index arithmetic folds away
+template <int HP, int KS, int NL, int S, bool HEX>
 __global__ void __launch_bounds__(HP* KS, 1) path_fwd_fast_kernel(PathParams p) {
   constexpr int SL = HP / KS, NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL;
   constexpr int HB = KS * (SL + 4);        // padded H-vector length
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(HP* KS, 1) path_fwd_fast_kernel(PathParams p) 
   constexpr int NP = (NOUT + RPP - 1) / RPP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i = tid / KS, ks = tid % KS, grp = lane / KS;
-  const int H = p.H, G = 3 * p.H, ld0 = p.S + p.C + p.P;
+  const int H = HEX ? HP : p.H, G = 3 * H, ld0 = p.S + p.C + p.P;
   const bool unit_ok = i < H;
   const float lead = ks == 0 ? 1.f : 0.f;  // lane that adds the non-sliced terms before the reduce
 
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(HP* KS, 1) path_fwd_fast_kernel(PathParams p) 
 // ---------------------------------------------------------------------------------------------
 // backward (BPTT)
 // ---------------------------------------------------------------------------------------------
-template <int HP, int KS, int NL, int S>
+template <int HP, int KS, int NL, int S, bool HEX>
 __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) {
   constexpr int SL = HP / KS, NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL;
   constexpr int HB = KS * (SL + 4);
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
   constexpr int NZ = 3 * S, NPZ = (NZ + RPP - 1) / RPP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i = tid / KS, ks = tid % KS, grp = lane / KS;
-  const int H = p.H, G = 3 * p.H, ld0 = p.S + p.C + p.P;
+  const int H = HEX ? HP : p.H, G = 3 * H, ld0 = p.S + p.C + p.P;
   const bool unit_ok = i < H;
   const int srow = (int)stash_row_floats(NL, H);
 
@@ -662,9 +664,12 @@ int fast_grid(int64_t B) {
 template <int HP, int KS, int NL, int S>
 int launch_fast(const PathParams& p, cudaStream_t st, bool bwd) {
   if (bwd)
-    path_bwd_fast_kernel<HP, KS, NL, S><<<fast_grid(p.B), HP * KS, 0, st>>>(p);
+    if (p.H == HP) path_bwd_fast_kernel<HP, KS, NL, S, true><<<fast_grid(p.B), HP * KS, 0, st>>>(p);
+    else path_bwd_fast_kernel<HP, KS, NL, S, false><<<fast_grid(p.B), HP * KS, 0, st>>>(p);
+  else if (p.H == HP)
+    path_fwd_fast_kernel<HP, KS, NL, S, true><<<fast_grid(p.B), HP * KS, 0, st>>>(p);
   else
-    path_fwd_fast_kernel<HP, KS, NL, S><<<fast_grid(p.B), HP * KS, 0, st>>>(p);
+    path_fwd_fast_kernel<HP, KS, NL, S, false><<<fast_grid(p.B), HP * KS, 0, st>>>(p);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
