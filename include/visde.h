@@ -15,6 +15,10 @@
  *                          evidence_lower_bound.py:37-40, only the Gaussian algebra :77-83 runs here)
  *   visde_session_*     <- one trainer iteration's path part (inference/trainer.py:176-198) with
  *                          HOST buffers: H2D, path fwd, ELBO fwd+bwd, path bwd, D2H.
+ *   visde_em_fwd/_bwd   <- core/euler_maruyama.py:11-45 (pre-training simulator, trainer.py:208-259)
+ *   visde_path_summary  <- posterior/variational_posterior.py:93-135 (sample / summary)
+ *   visde_grad_sqnorm, visde_adamw_ema_step <- trainer.py:199-203 (unscale, clip_grad_norm_, AdamW.step) and
+ *                          exponential_moving_average.py:25-28 (EMA update)
  *
  * Conventions
  *   - plain pointers and sizes only; every device buffer is allocated by the caller; the library
@@ -220,6 +224,44 @@ int visde_session_submit(visde_session* s, float dt, const float* x0, const floa
                          const visde_obs* obs_host, float* terms, float* grad_x0, float* grad_theta,
                          const visde_weight_grads* gw_host, float* grad_context);
 int visde_session_wait(visde_session* s);
+
+/* ---- callers either side of the path ----------------------------------------- */
+
+/* core/euler_maruyama.py:11-45 for the built-in OU / LV functors (the theta pre-training simulator,
+ * inference/trainer.py:208-259): x0 [B,S], theta [B,P] -> paths [B,T+1,S] with
+ * x_{t+1} = x_t + f dt + D eps_t sqrt(dt), dims in positive_mask clamped to >= 1e-6 after every step (:41-42).
+ * S, P follow sde_kind (OU 1/3, LV 2/3); VISDE_SDE_GENERIC -> VISDE_EINVAL (user SDEs are stepped in PyTorch).
+ * noise [B,T,S] standard normals, or NULL: drawn in the kernel (Philox4x32-10, key = seed, counter = (t, b),
+ * Box-Muller; visde_philox_normal writes the same draws), so pre-training never materialises the noise. */
+int visde_em_fwd(int64_t B, int64_t T, int sde_kind, uint32_t positive_mask, float dt, const float* x0,
+                 const float* theta, const float* noise, uint64_t seed, float* paths, void* stream);
+/* reverse mode of visde_em_fwd (what autograd does through the reference's Python loop): g_paths [B,T+1,S] ->
+ * grad_theta [B,P], grad_x0 [B,S] (may be NULL).  `paths` is the forward's output; noise / seed as in the forward. */
+int visde_em_bwd(int64_t B, int64_t T, int sde_kind, uint32_t positive_mask, float dt, const float* theta,
+                 const float* noise, uint64_t seed, const float* paths, const float* g_paths, float* grad_x0,
+                 float* grad_theta, void* stream);
+/* out [B,T,S] (S <= 4): the standard normals visde_em_fwd / _bwd draw for (seed, b, t) */
+int visde_philox_normal(uint64_t seed, int64_t B, int64_t T, int32_t S, float* out, void* stream);
+
+/* posterior/variational_posterior.py:93-135 (sample / summary): z [n,T1,S] latent paths of the stash-less forward
+ * -> x = from_latent(z) [n,T1,S] (may be NULL), mean [T1,S], std [T1,S] over the n samples (Bessel-corrected like
+ * torch.std; nan for n == 1).  Fixed-order two-stage reduction. */
+size_t visde_path_summary_workspace_bytes(int64_t n, int64_t T1, int32_t S);
+int visde_path_summary(int64_t n, int64_t T1, int32_t S, uint32_t positive_mask, const float* z, float* x,
+                       float* mean, float* std, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Optimiser tail of inference/trainer.py:199-203,126 over flat fp32 buffers (the all-reduce bucket):
+ * visde_grad_sqnorm: sqnorm (device scalar) = [accumulate ? sqnorm : 0] + inv_scale^2 * sum g^2   (inv_scale: device
+ *   scalar of GradScaler.unscale_, or NULL); deterministic.
+ * visde_adamw_ema_step: g *= inv_scale * min(1, max_norm / (sqrt(sqnorm) + 1e-6)) (clip_grad_norm_; skipped when
+ *   sqnorm == NULL or max_norm <= 0), torch.optim.AdamW update (decoupled weight decay, `step` counts from 1), then
+ *   ema = lerp(ema, param, 1 - ema_decay) (exponential_moving_average.py:25-28; ema may be NULL).  No host sync. */
+size_t visde_grad_sqnorm_workspace_bytes(void);
+int visde_grad_sqnorm(int64_t n, const float* grads, const float* inv_scale, int accumulate, float* sqnorm,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int visde_adamw_ema_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema,
+                         float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                         float max_norm, const float* sqnorm, const float* inv_scale, float ema_decay, void* stream);
 
 #ifdef __cplusplus
 }

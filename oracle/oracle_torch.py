@@ -489,3 +489,83 @@ def run_fwd_bwd(p: Problem, dtype: torch.dtype | None = None):
     grads["out_w"] = w.out_w.grad
     grads["out_b"] = w.out_b.grad
     return paths.detach(), means.detach(), chol.detach(), terms, grads
+
+
+# --------------------------------------------------------------------------------------
+# Callers either side of the path: prior simulator, posterior summary, optimiser tail
+# --------------------------------------------------------------------------------------
+def euler_maruyama(sde, x0: Tensor, theta: Tensor, n_steps: int, dt: float, positive_dims: Sequence[int] = (),
+                   noise: Tensor | None = None) -> Tensor:
+    """core/euler_maruyama.py:27-45: explicit Euler-Maruyama with a clamp of the positive dims after every step."""
+    sqrt_dt = dt**0.5
+    traj = [x0]
+    x = x0
+    pos = list(positive_dims)
+    for step in range(n_steps):
+        x = x + sde.drift(x, theta) * dt + torch.einsum("bij,bj->bi", sde.diffusion(x, theta), noise[:, step]) * sqrt_dt
+        if pos:
+            keep = torch.ones(x.shape[-1], dtype=torch.bool)
+            keep[pos] = False
+            x = torch.where(keep, x, x.clamp(min=1e-6))  # out-of-place form of x[:, pos] = x[:, pos].clamp(min=1e-6)
+        traj.append(x)
+    return torch.stack(traj, dim=1)
+
+
+def pretrain_mse(sde, theta: Tensor, obs_times: Tensor, obs_values: Tensor, n_steps: int, dt: float,
+                 positive_dims: Sequence[int], noise: Tensor) -> Tensor:
+    """inference/trainer.py:253-259."""
+    n = theta.shape[0]
+    x0 = obs_values[0].unsqueeze(0).expand(n, -1).to(theta.dtype)
+    paths = euler_maruyama(sde, x0, theta, n_steps, dt, positive_dims, noise)
+    obs_idx = (obs_times / dt).round().long()
+    return ((paths[:, obs_idx] - obs_values.to(theta.dtype)) ** 2).mean()
+
+
+def philox_normal(seed: int, B: int, T: int, S: int):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011: multipliers 0xD2511F53 / 0xCD9E8D57, Weyl key increments
+    0x9E3779B9 / 0xBB67AE85) with counter (t_lo, t_hi, b_lo, b_hi) and key = seed, then Box-Muller on
+    u = (top 24 bits + 0.5) 2^-24: the in-kernel noise of csrc/em.cu, restated in numpy (float64 transcendental part)."""
+    import numpy as np
+
+    b, t = np.meshgrid(np.arange(B, dtype=np.uint64), np.arange(T, dtype=np.uint64), indexing="ij")
+    m32 = np.uint64(0xFFFFFFFF)
+    c = [t & m32, t >> np.uint64(32), b & m32, b >> np.uint64(32)]
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]  # 32 x 32 -> 64-bit products (no overflow in uint64)
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & m32, p1 >> np.uint64(32), p1 & m32
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & m32, (k1 + np.uint64(0xBB67AE85)) & m32
+    u = [((x >> np.uint64(8)).astype(np.float64) + 0.5) * 2.0**-24 for x in c]
+    ra, rb = np.sqrt(-2.0 * np.log(u[0])), np.sqrt(-2.0 * np.log(u[2]))
+    n = np.stack([ra * np.cos(2 * np.pi * u[1]), ra * np.sin(2 * np.pi * u[1]),
+                  rb * np.cos(2 * np.pi * u[3]), rb * np.sin(2 * np.pi * u[3])], axis=-1)
+    return torch.from_numpy(n[..., :S].copy())
+
+
+def path_summary(z: Tensor, positive_dims: Sequence[int]):
+    """posterior/variational_posterior.py:116-135: x = from_latent(z); mean / std (Bessel) over the samples."""
+    x = to_state(z, positive_dims)
+    return x, x.mean(dim=0), x.std(dim=0)
+
+
+def adamw_ema_steps(params: list[Tensor], grads_per_step: list[list[Tensor]], lrs_by_param: list[float], max_norm: float,
+                    ema_decay: float, inv_scale: float = 1.0):
+    """inference/trainer.py:199-203 + :126 with the third-party pieces they call: ``GradScaler.unscale_`` (grad *= 1/scale),
+    ``nn.utils.clip_grad_norm_``, ``torch.optim.AdamW`` (torch defaults, one param group per learning rate) and
+    ``ExponentialMovingAverage.update`` (shadow.lerp_(param, 1 - decay), exponential_moving_average.py:25-28)."""
+    ps = [torch.nn.Parameter(p.clone()) for p in params]
+    opt = torch.optim.AdamW([{"params": [p], "lr": lr} for p, lr in zip(ps, lrs_by_param)])
+    shadow = [p.detach().clone() for p in ps]
+    norms = []
+    for grads in grads_per_step:
+        for p, g in zip(ps, grads):
+            p.grad = g.clone() * inv_scale
+        norms.append(torch.nn.utils.clip_grad_norm_(ps, max_norm) if max_norm > 0 else
+                     torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(p.grad) for p in ps])))
+        opt.step()
+        with torch.no_grad():
+            for s, p in zip(shadow, ps):
+                s.lerp_(p.detach(), 1 - ema_decay)
+    return [p.detach() for p in ps], shadow, torch.stack(norms)

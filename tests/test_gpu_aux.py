@@ -1,0 +1,326 @@
+"""GPU parity tests for the callers either side of the path: the fused Euler-Maruyama prior simulator
+(forward + reverse-mode), the posterior-sample summary, the fused clip + AdamW + EMA step and the context-producer
+fold, each against the CPU oracle and the committed reference outputs (tests/golden/*.pt)."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import pytest
+import torch
+from torch import nn
+
+from oracle import oracle_torch as O
+from tests._util import assert_close, assert_parity, build_head
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+def _sdes(kind):
+    from viforsdes_b200 import sde as vs
+
+    return (vs.OrnsteinUhlenbeck(), O.OrnsteinUhlenbeck()) if kind == "ou" else (vs.LotkaVolterra(), O.LotkaVolterra())
+
+
+def _em_inputs(kind, B, T, seed, near_clamp=False):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "ou":
+        theta = torch.stack([torch.exp(0.3 * torch.randn(B, generator=g)), 1 + 0.3 * torch.randn(B, generator=g),
+                             torch.exp(-1 + 0.3 * torch.randn(B, generator=g))], 1)
+        x0 = 0.5 + 0.2 * torch.randn(B, 1, generator=g)
+        pos = []
+    else:
+        theta = torch.exp(torch.log(torch.tensor([0.5, 0.0025, 0.3])) + 0.1 * torch.randn(B, 3, generator=g))
+        x0 = torch.tensor([71.0, 79.0]).expand(B, 2) * torch.exp(0.1 * torch.randn(B, 2, generator=g))
+        pos = [0, 1]
+    noise = torch.randn(B, T, x0.shape[1], generator=g)
+    if near_clamp and kind == "lv" and B >= 4:
+        x0[:4] = torch.tensor([[2e-6, 3.0], [1.5, 1e-6], [1e-5, 1e-5], [4e-6, 40.0]])
+        noise[:4, : min(T, 4)] = -2.5
+    return x0.contiguous(), theta, noise, pos
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Euler-Maruyama simulator
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["em_ou", "em_lv"])
+def test_em_matches_reference_golden(name):
+    from viforsdes_b200.euler_maruyama import euler_maruyama
+
+    g = torch.load(GOLD / f"{name}.pt")
+    sde, _ = _sdes(g["kind"])
+    x0 = g["x0"].cuda().requires_grad_(True)
+    theta = g["theta"].cuda().requires_grad_(True)
+    paths = euler_maruyama(sde, x0, theta, g["horizon"], g["dt"], g["positive_dims"], noise=g["noise"].cuda())
+    assert_close(paths, g["paths"], name="paths")
+    if g["kind"] == "lv":
+        assert (paths == 1e-6).any()
+    obs_idx = (g["obs_times"] / g["dt"]).round().long().cuda()
+    mse = ((paths[:, obs_idx] - g["obs_values"].cuda()) ** 2).mean()
+    assert_close(mse, g["mse"], name="mse")
+    mse.backward()
+    assert_close(theta.grad, g["g_theta"], name="g_theta")
+    assert_close(x0.grad, g["g_x0"], name="g_x0")
+
+
+@pytest.mark.parametrize("kind,B,T", [("ou", 70, 37), ("lv", 70, 45), ("lv", 1, 1), ("ou", 33, 32), ("lv", 5, 16),
+                                      ("lv", 64, 200)])
+def test_em_fwd_bwd_vs_oracle(kind, B, T):
+    """Ragged warps (B % 32 != 0), step counts that do not divide the 32/S-step chunk, clamp hits; random cotangents on the
+    whole trajectory (not only the observation points)."""
+    x0, theta, noise, pos = _em_inputs(kind, B, T, seed=B * 1000 + T, near_clamp=True)
+    gsde, osde = _sdes(kind)
+    gp = torch.randn(B, T + 1, x0.shape[1], generator=torch.Generator().manual_seed(1))
+    refs = []
+    for dt_ in (torch.float32, torch.float64):
+        a, th = x0.detach().clone().to(dt_).requires_grad_(True), theta.detach().clone().to(dt_).requires_grad_(True)
+        p = O.euler_maruyama(osde, a, th, T, 0.05, pos, noise.to(dt_))
+        p.backward(gp.to(dt_))
+        refs.append((p.detach(), th.grad, a.grad))
+    a, th = x0.cuda().requires_grad_(True), theta.cuda().requires_grad_(True)
+    from viforsdes_b200 import _lib
+    from viforsdes_b200.euler_maruyama import _mask
+
+    p = torch.ops.visde.em_fwd(a, th, noise.cuda(), 0, T, 0.05, gsde.device_kind, _mask(pos))
+    p.backward(gp.cuda())
+    assert _lib.load() is not None
+    for got, i, nm in ((p, 0, "paths"), (th.grad, 1, "g_theta"), (a.grad, 2, "g_x0")):
+        assert_parity(got, refs[0][i], refs[1][i], name=f"{kind} B={B} T={T} {nm}")
+
+
+def test_em_philox_noise():
+    from viforsdes_b200.euler_maruyama import euler_maruyama, philox_normal
+    from viforsdes_b200.sde import LotkaVolterra
+
+    seed, B, T = 0x1234_5678_9ABC_DEF0, 77, 53
+    n = philox_normal(seed, B, T, 2)
+    ref = O.philox_normal(seed, B, T, 2)
+    assert (n.cpu().double() - ref).abs().max().item() < 2e-5
+    x0, theta, _, pos = _em_inputs("lv", B, T, seed=3)
+    a, th = x0.cuda(), theta.cuda().requires_grad_(True)
+    p1 = euler_maruyama(LotkaVolterra(), a, th, T * 0.05, 0.05, pos, noise=None, seed=seed)
+    th2 = theta.cuda().requires_grad_(True)
+    p2 = euler_maruyama(LotkaVolterra(), a, th2, T * 0.05, 0.05, pos, noise=n)
+    assert torch.equal(p1, p2), "in-kernel Philox draws differ from visde_philox_normal"
+    gp = torch.randn_like(p1)
+    p1.backward(gp)
+    p2.backward(gp)
+    assert torch.equal(th.grad, th2.grad), "backward must regenerate the forward's draws"
+    p3 = euler_maruyama(LotkaVolterra(), a, th, T * 0.05, 0.05, pos, noise=None, seed=seed + 1)
+    assert not torch.equal(p1, p3)
+    # S = 1 uses the first normal of the same block
+    assert torch.equal(philox_normal(seed, B, T, 1)[..., 0], n[..., 0])
+
+
+def test_em_pretraining_size_properties():
+    """inference/trainer.py:208-259 sizes (4096 simulations, LV horizon 40 at dt 0.05 = 800 steps): bit-determinism, finite
+    values, linearity of the reverse mode in the cotangent, fp64 oracle on a slice, and the fused objective."""
+    from viforsdes_b200.euler_maruyama import _mask, pretrain_mse
+    from viforsdes_b200.sde import LotkaVolterra
+
+    B, T = 4096, 800
+    x0, theta, _, pos = _em_inputs("lv", B, T, seed=9)
+    x0[:] = torch.tensor([71.0, 79.0])
+    a, seed = x0.cuda(), 2024
+    kind, mask = LotkaVolterra.device_kind, _mask(pos)
+    th = theta.cuda().requires_grad_(True)
+    p = torch.ops.visde.em_fwd(a, th, None, seed, T, 0.05, kind, mask)
+    assert torch.isfinite(p).all() and (p >= 1e-6).all()
+    assert torch.equal(p, torch.ops.visde.em_fwd(a, th, None, seed, T, 0.05, kind, mask))
+    g1, g2 = torch.randn_like(p) * 1e-3, torch.randn_like(p) * 1e-3
+    outs = [torch.autograd.grad(p, th, g, retain_graph=True)[0] for g in (g1, g2, 2.0 * g1 - 0.5 * g2)]
+    assert torch.equal(outs[0], torch.autograd.grad(p, th, g1, retain_graph=True)[0])
+    lin = 2.0 * outs[0] - 0.5 * outs[1]
+    assert (outs[2] - lin).abs().max().item() <= 1e-4 * lin.abs().max().item()
+    # slice against the fp64 oracle with the same draws
+    from viforsdes_b200.euler_maruyama import philox_normal
+
+    sl = slice(100, 108)
+    noise = philox_normal(seed, B, T, 2)[sl].cpu()
+    refs = []
+    for dt_ in (torch.float32, torch.float64):
+        t_ = theta[sl].detach().clone().to(dt_).requires_grad_(True)
+        pr = O.euler_maruyama(O.LotkaVolterra(), x0[sl].to(dt_), t_, T, 0.05, pos, noise.to(dt_))
+        pr.backward(g1[sl].cpu().to(dt_))
+        refs.append((pr.detach(), t_.grad))
+    assert_parity(p[sl], refs[0][0], refs[1][0], name="paths slice")
+    assert_parity(outs[0][sl], refs[0][1], refs[1][1], name="g_theta slice")
+    obs_t = torch.tensor([0.0, 10.0, 20.0, 30.0, 40.0]).cuda()
+    obs_v = torch.tensor([[71.0, 79.0], [120.0, 60.0], [160.0, 140.0], [60.0, 200.0], [50.0, 90.0]]).cuda()
+    mse = pretrain_mse(LotkaVolterra(), th, obs_t, obs_v, 40.0, 0.05, pos, seed=seed)
+    idx = (obs_t / 0.05).round().long()
+    assert torch.allclose(mse, ((p[:, idx] - obs_v) ** 2).mean())
+    mse.backward()
+    assert torch.isfinite(th.grad).all()
+
+
+def test_em_user_sde_steps_in_pytorch_and_errors():
+    from viforsdes_b200 import _lib
+    from viforsdes_b200.euler_maruyama import euler_maruyama
+
+    sde = O.Lorenz96(6)
+    g = torch.Generator().manual_seed(0)
+    x0, theta = torch.randn(5, 6, generator=g), torch.stack([8 + torch.randn(5, generator=g), 0.3 * torch.ones(5)], 1)
+    noise = torch.randn(5, 12, 6, generator=g)
+    ref = O.euler_maruyama(sde, x0, theta, 12, 0.05, [], noise)
+    got = euler_maruyama(sde, x0.cuda(), theta.cuda(), 0.6, 0.05, [], noise=noise.cuda())
+    assert_close(got, ref, name="l96 paths")
+    with pytest.raises(ValueError):
+        euler_maruyama(sde, x0.cuda(), theta.cuda(), 0.6, -0.05)
+    with pytest.raises(ValueError):
+        euler_maruyama(sde, x0.cuda(), theta.cuda(), 0.0, 0.05)
+    lib = _lib.load()
+    assert lib.visde_em_fwd(4, 4, _lib.SDE_GENERIC, 0, 0.05, None, None, None, 0, None, None) == _lib.EINVAL
+    assert lib.visde_em_fwd(0, 4, _lib.SDE_OU, 0, 0.05, None, None, None, 0, None, None) == _lib.OK  # empty batch
+    assert lib.visde_em_fwd(4, 4, _lib.SDE_OU, 0, 0.0, None, None, None, 0, None, None) == _lib.EINVAL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# posterior summary
+# ---------------------------------------------------------------------------------------------------------------
+def test_summary_matches_reference_golden():
+    from viforsdes_b200.posterior import summarise_paths
+    from viforsdes_b200.state_space import StateSpace
+
+    g = torch.load(GOLD / "summary_lv.pt")
+    x, mean, std = summarise_paths(g["z"].cuda(), StateSpace(2, g["positive_dims"]))
+    assert_close(x, g["x"], rtol=1e-6, name="x")
+    assert_close(mean, g["mean"], rtol=1e-5, name="mean")
+    assert_close(std, g["std"], rtol=1e-5, name="std")
+
+
+@pytest.mark.parametrize("n,T1,S,pos", [(1000, 801, 2, [0, 1]), (1, 5, 1, []), (33, 7, 3, [1]), (5000, 101, 10, [])])
+def test_summary_vs_oracle(n, T1, S, pos):
+    from viforsdes_b200.posterior import summarise_paths
+    from viforsdes_b200.state_space import StateSpace
+
+    z = 4.0 * torch.randn(n, T1, S, generator=torch.Generator().manual_seed(n)) + 2.0
+    x64, m64, s64 = O.path_summary(z.double(), pos)
+    x, mean, std = summarise_paths(z.cuda(), StateSpace(S, pos))
+    assert_close(x, x64, rtol=1e-6, name="x")
+    assert_close(mean, m64, rtol=1e-5, name="mean")
+    if n == 1:
+        assert torch.isnan(std).all()  # torch.std of one sample
+    else:
+        assert_close(std, s64, rtol=1e-5, name="std")
+    _, mean2, std2 = summarise_paths(z.cuda(), StateSpace(S, pos), want_x=False)
+    assert torch.equal(mean, mean2) and torch.equal(std.nan_to_num(), std2.nan_to_num())
+
+
+def test_posterior_sample_and_summary_through_the_head():
+    """VariationalPosterior.sample / summary flow (variational_posterior.py:93-135) with a stub encoder: eval-mode,
+    stash-less forward, x = from_latent(z), mean / std over the samples."""
+    from viforsdes_b200.observations import Observations
+    from viforsdes_b200.posterior import sample_posterior, summarise_posterior
+    from viforsdes_b200.state_space import StateSpace
+
+    p = O.make_problem("lv", 48, 30, context_dim=16, hidden_dim=32, num_layers=2)
+    head = build_head(p)
+    ctx_full = torch.zeros(48, 31, 16)
+    ctx_full[:, :-1] = p.context
+
+    class Post:
+        def rsample(self, n):
+            return p.theta.cuda()[:n]
+
+    enc = lambda *a: ctx_full.cuda()  # noqa: E731
+    obs = Observations(times=p.obs_times.cuda(), values=p.obs_values.cuda())
+    ss = StateSpace(2, [0, 1])
+    s = sample_posterior(enc, head, Post(), obs, 48, 30 * p.dt, p.dt, ss, noise=p.eps.cuda())
+    assert head.training, "sampling must restore the training flag"
+    x0 = p.obs_values[0].unsqueeze(0).expand(48, -1)
+    zref, _, _ = O.sample_paths(p.weights, O.to_latent(x0, [0, 1]), p.context, p.theta, p.eps, p.dt)
+    xref = O.to_state(zref, [0, 1])
+    assert_close(s.diffusion_paths, xref.detach(), name="posterior x")
+    summ = summarise_posterior(enc, head, Post(), obs, 30 * p.dt, p.dt, ss, n_samples=48, noise=p.eps.cuda())
+    assert_close(summ.diffusion_path_mean, xref.mean(0).detach(), name="path mean")
+    assert_close(summ.diffusion_path_std, xref.std(0).detach(), rtol=1e-3, name="path std")
+    assert_close(summ.sde_parameter_mean, p.theta.mean(0), name="theta mean")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused clip + AdamW + EMA
+# ---------------------------------------------------------------------------------------------------------------
+def _golden_module(g):
+    model = nn.Sequential(nn.Linear(5, 7), nn.Tanh(), nn.Linear(7, 3))
+    with torch.no_grad():
+        for p, v in zip(model.parameters(), g["init"]):
+            p.copy_(v)
+    return model.cuda()
+
+
+def test_fused_adamw_ema_matches_reference_golden():
+    from viforsdes_b200.optim import FlatParameters, FusedAdamWEma
+
+    g = torch.load(GOLD / "ema.pt")
+    model = _golden_module(g)
+    flat = FlatParameters([list(model[0].parameters()), list(model[2].parameters())])
+    opt = FusedAdamWEma(flat, lrs=[1e-2, 3e-3], max_norm=g["max_norm"], ema_decay=g["decay"])
+    for step, gs in enumerate(g["grads"]):
+        flat.zero_grad()
+        for p, gr in zip(model.parameters(), gs):
+            p.grad.copy_(gr)  # gradients land in the flat bucket through the views
+        opt.step()
+        assert abs(opt.grad_norm.item() - g["norms"][step].item()) <= 1e-5 * g["norms"][step].item()
+    for p, ref in zip(model.parameters(), g["params"]):
+        assert_close(p, ref, rtol=1e-5, atol_scale=1e-6, name="param")
+    for s, ref in zip(opt.ema_views(), g["shadow"]):
+        assert_close(s, ref, rtol=1e-5, atol_scale=1e-6, name="ema shadow")
+
+
+@pytest.mark.parametrize("n,max_norm,scale,ema", [(351_000, 1.0, 1.0, 0.999), (1_000_003, 0.0, 1.0, None),
+                                                  (4099, 0.5, 1024.0, 0.9), (3, 10.0, 1.0, 0.5)])
+def test_fused_adamw_ema_vs_oracle(n, max_norm, scale, ema):
+    """Head-sized (351 KB bucket) and encoder-sized buffers, unaligned tails, GradScaler inv_scale, no-clip and no-EMA."""
+    from viforsdes_b200.optim import FlatParameters, FusedAdamWEma
+
+    gen = torch.Generator().manual_seed(n)
+    p0 = torch.randn(n, generator=gen)
+    grads = [[scale * torch.randn(n, generator=gen) * (10.0 if k == 1 else 0.1)] for k in range(4)]
+    rp, rs, rn = O.adamw_ema_steps([p0.double()], [[g[0].double()] for g in grads], [2e-3], max_norm,
+                                   ema if ema is not None else 0.0, inv_scale=1.0 / scale)
+    param = nn.Parameter(p0.clone().cuda())
+    flat = FlatParameters([[param]])
+    opt = FusedAdamWEma(flat, lrs=[2e-3], max_norm=max_norm, ema_decay=ema)
+    inv = torch.tensor([1.0 / scale], device="cuda") if scale != 1.0 else None
+    for k, g in enumerate(grads):
+        param.grad.copy_(g[0])
+        opt.step(inv_scale=inv)
+        if max_norm > 0:
+            assert abs(opt.grad_norm.item() - rn[k].item()) <= 2e-5 * rn[k].item()
+    assert_close(param, rp[0], rtol=2e-5, atol_scale=2e-6, name="param")
+    if ema is not None:
+        assert_close(opt.ema_views()[0], rs[0], rtol=2e-5, atol_scale=2e-6, name="ema")
+    else:
+        assert opt.ema_views() == []
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# context-producer fold
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("E,Cd,B,T", [(24, 16, 5, 13), (128, 128, 3, 40)])
+def test_context_fold_matches_unfused(E, Cd, B, T):
+    """head(tokens . W_op^T + b_op) == head_folded(tokens): outputs and every gradient, including both factors of the fold."""
+    p = O.make_problem("lv", B, T, context_dim=Cd, hidden_dim=64, num_layers=2)
+    g = torch.Generator().manual_seed(E)
+    tokens = 0.3 * torch.randn(B, T, E, generator=g)
+    proj = nn.Linear(E, Cd)
+    outs = []
+    for folded in (False, True):
+        head = build_head(p)
+        pr = nn.Linear(E, Cd).cuda()
+        pr.load_state_dict(proj.state_dict())
+        tk = tokens.cuda().requires_grad_(True)
+        x0, th, eps = p.x0.cuda(), p.theta.cuda().requires_grad_(True), p.eps.cuda()
+        if folded:
+            paths, means, chol = head.sample_diffusion_paths_from_tokens(x0, tk, pr, th, eps, p.dt)
+        else:
+            paths, means, chol = head.sample_diffusion_paths(x0, pr(tk), th, eps, p.dt)
+        gen = torch.Generator().manual_seed(7)
+        loss = sum((o * torch.randn(o.shape, generator=gen).cuda()).sum() for o in (paths, means, chol))
+        loss.backward()
+        outs.append((paths.detach(), means.detach(), chol.detach(), tk.grad, th.grad, pr.weight.grad, pr.bias.grad,
+                     head.gru.weight_ih_l0.grad, head.gru.bias_ih_l0.grad, head.gru.weight_hh_l1.grad, head.out_proj.weight.grad))
+    names = ["paths", "means", "chol", "g_tokens", "g_theta", "g_proj_w", "g_proj_b", "g_w_ih_l0", "g_b_ih_l0", "g_w_hh_l1", "g_out_w"]
+    for a, b, nm in zip(outs[1], outs[0], names):
+        assert_close(a, b, rtol=2e-4, atol_scale=5e-5, name=nm)

@@ -66,6 +66,17 @@ PROTOTYPES = {
     "visde_session_submit": (C.c_int, [_fp, C.c_float, _fp, _fp, _fp, _fp, C.POINTER(Weights), C.POINTER(Obs), _fp, _fp,
                                        _fp, C.POINTER(Weights), _fp]),
     "visde_session_wait": (C.c_int, [_fp]),
+    "visde_em_fwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_uint32, C.c_float, _fp, _fp, _fp, C.c_uint64, _fp, _fp]),
+    "visde_em_bwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_uint32, C.c_float, _fp, _fp, C.c_uint64, _fp, _fp,
+                               _fp, _fp, _fp]),
+    "visde_philox_normal": (C.c_int, [C.c_uint64, C.c_int64, C.c_int64, C.c_int32, _fp, _fp]),
+    "visde_path_summary_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
+    "visde_path_summary": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_uint32, _fp, _fp, _fp, _fp, _fp, C.c_size_t,
+                                     _fp]),
+    "visde_grad_sqnorm_workspace_bytes": (C.c_size_t, []),
+    "visde_grad_sqnorm": (C.c_int, [C.c_int64, _fp, _fp, C.c_int, _fp, _fp, C.c_size_t, _fp]),
+    "visde_adamw_ema_step": (C.c_int, [C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_float, C.c_float,
+                                       C.c_float, C.c_int64, C.c_float, _fp, _fp, C.c_float, _fp]),
 }
 
 _lib: C.CDLL | None = None

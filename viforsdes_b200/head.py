@@ -97,3 +97,32 @@ class DiffusionTransitionHead(nn.Module):
         if x0.dtype != torch.float32:  # autograd.py:117-122
             return paths.to(x0.dtype), means.to(x0.dtype), chol.to(x0.dtype)
         return paths, means, chol
+
+    def sample_diffusion_paths_from_tokens(self, x0: Tensor, tokens: Tensor, output_proj: nn.Linear,
+                                           sde_parameters: Tensor, standard_noise: Tensor,
+                                           time_step: float) -> tuple[Tensor, Tensor, Tensor]:
+        """Context-producer fusion.  The encoder ends in a plain ``output_proj`` Linear
+        (primitives/sit.py:156-158,185) and the head starts with the context columns of ``weight_ih_l0``: two
+        back-to-back linear maps.  Fold them, ``W' = W_ih[:, ctx] . W_op`` and ``b' = b_ih + W_ih[:, ctx] . b_op``
+        (a [3H, C] x [C, E] product per step), and feed the encoder's pre-projection ``tokens`` [B, T, E] to the
+        same kernels with C := E: the [B, T, C] context tensor is never written or read, the encoder's output GEMM
+        and its backward disappear, and autograd distributes the folded gradients to both weight matrices."""
+        S, Cd = self.state_dim, self.context_dim
+        if output_proj.out_features != Cd or tokens.shape[-1] != output_proj.in_features:
+            raise ValueError("output_proj must map the token width to the head's context_dim")
+        w_ih, w_hh, b_ih, b_hh = self._weight_lists()
+        w0 = w_ih[0]
+        w_ctx = w0[:, S:S + Cd]
+        folded = torch.cat([w0[:, :S], w_ctx @ output_proj.weight.to(w0.dtype), w0[:, S + Cd:]], dim=1)
+        b0 = b_ih[0] if output_proj.bias is None else b_ih[0] + w_ctx @ output_proj.bias.to(w0.dtype)
+        save = self.training and torch.is_grad_enabled()
+        args = (x0, tokens, sde_parameters, standard_noise, [folded, *w_ih[1:]], w_hh, [b0, *b_ih[1:]], b_hh,
+                self.out_proj.weight, self.out_proj.bias, float(time_step), save)
+        if save:
+            paths, means, chol, _ = torch.ops.visde.path_fwd(*args)
+        else:
+            with torch.no_grad():
+                paths, means, chol, _ = torch.ops.visde.path_fwd(*args)
+        if x0.dtype != torch.float32:
+            return paths.to(x0.dtype), means.to(x0.dtype), chol.to(x0.dtype)
+        return paths, means, chol

@@ -1,0 +1,100 @@
+"""Fused optimiser tail of a training iteration (inference/trainer.py:199-203 + :126): unscale, global-norm clip,
+AdamW and the EMA update over ONE flat fp32 buffer in two kernel launches and no host sync (csrc/optim.cu).
+
+``FlatParameters`` re-points the parameters (and gradients) of a module at slices of flat buffers, so the gradient
+buffer is at the same time the NCCL all-reduce bucket (``dist.allreduce_mean_(flat.grads)``).  Parameter groups with
+their own learning rate (training_context.py:97-102: ``learning_rate`` / ``sde_param_lr``) are contiguous segments."""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+from torch import Tensor, nn
+
+from viforsdes_b200 import _lib
+from viforsdes_b200.ops import _ptr, _require_cuda, _stream
+
+
+class FlatParameters:
+    def __init__(self, groups: Sequence[Iterable[nn.Parameter]]) -> None:
+        self.groups: List[List[nn.Parameter]] = [list(g) for g in groups]
+        params = [p for g in self.groups for p in g]
+        if not params:
+            raise ValueError("no parameters")
+        dev = params[0].device
+        if any(p.dtype != torch.float32 or p.device != dev for p in params):
+            raise ValueError("FlatParameters needs fp32 parameters on one device (master weights)")
+        total, self.segments = 0, []
+        offs = []
+        for g in self.groups:
+            start = total
+            for p in g:
+                offs.append(total)
+                total += (p.numel() + 3) // 4 * 4  # every tensor 16-byte aligned
+            self.segments.append((start, total))
+        self.data = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grads = torch.zeros(total, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                n = p.numel()
+                self.data[o:o + n].copy_(p.detach().reshape(-1))
+                p.data = self.data[o:o + n].view_as(p)
+                p.grad = self.grads[o:o + n].view_as(p)
+        self.params = params
+
+    def zero_grad(self) -> None:
+        """Keeps the gradient views attached (``set_to_none`` would detach them from the bucket)."""
+        self.grads.zero_()
+
+
+class FusedAdamWEma:
+    """torch.optim.AdamW defaults (betas (0.9, 0.999), eps 1e-8, weight_decay 1e-2) + clip_grad_norm_ + EMA lerp."""
+
+    def __init__(self, flat: FlatParameters, lrs: Sequence[float], betas: tuple[float, float] = (0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 1e-2, max_norm: float = 0.0, ema_decay: Optional[float] = None) -> None:
+        if len(lrs) != len(flat.segments):
+            raise ValueError("one learning rate per parameter group")
+        _require_cuda(flat.data)
+        self.flat, self.lrs, self.betas, self.eps, self.wd = flat, list(lrs), betas, eps, weight_decay
+        self.max_norm, self.ema_decay = max_norm, ema_decay
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(flat.data), torch.zeros_like(flat.data)
+        self.ema = flat.data.clone() if ema_decay is not None else None
+        self.sqnorm = torch.zeros(1, device=flat.data.device, dtype=torch.float32)
+        self.lib = _lib.load()
+        self.ws = torch.empty(self.lib.visde_grad_sqnorm_workspace_bytes(), device=flat.data.device, dtype=torch.uint8)
+        self.step_count = 0
+
+    @property
+    def grad_norm(self) -> Tensor:
+        """Device scalar (pre-clip global norm, what ``clip_grad_norm_`` returns); reading it is the caller's sync."""
+        return self.sqnorm.sqrt().squeeze(0)
+
+    def step(self, inv_scale: Optional[Tensor] = None) -> None:
+        f, lib = self.flat, self.lib
+        self.step_count += 1
+        st = _stream()
+        with torch.cuda.device(f.data.device):
+            clip = self.max_norm > 0
+            if clip:
+                _lib.check(lib.visde_grad_sqnorm(f.grads.numel(), _ptr(f.grads), _ptr(inv_scale), 0, _ptr(self.sqnorm),
+                                                 _ptr(self.ws), self.ws.numel(), st))
+            for (lo, hi), lr in zip(f.segments, self.lrs):
+                if hi == lo:
+                    continue
+                sl = slice(lo, hi)
+                _lib.check(lib.visde_adamw_ema_step(
+                    hi - lo, _ptr(f.data[sl]), _ptr(f.grads[sl]), _ptr(self.exp_avg[sl]), _ptr(self.exp_avg_sq[sl]),
+                    _ptr(self.ema[sl]) if self.ema is not None else None, lr, self.betas[0], self.betas[1], self.eps,
+                    self.wd, self.step_count, self.max_norm if clip else 0.0, _ptr(self.sqnorm) if clip else None,
+                    _ptr(inv_scale), self.ema_decay if self.ema_decay is not None else 0.0, st))
+
+    def ema_views(self) -> List[Tensor]:
+        """EMA shadow tensors shaped like the parameters (``ExponentialMovingAverage.shadow`` values, in order)."""
+        if self.ema is None:
+            return []
+        out, off = [], 0
+        for g in self.flat.groups:
+            for p in g:
+                out.append(self.ema[off:off + p.numel()].view_as(p))
+                off += (p.numel() + 3) // 4 * 4
+        return out
