@@ -7,8 +7,8 @@
 // with f, D the Ornstein-Uhlenbeck / Lotka-Volterra functors of examples/*.py (same algebra as elbo.cu).
 // User SDEs are stepped in PyTorch by the host mirror (viforsdes_b200/euler_maruyama.py), as BASELINE.json asks.
 //
-// Layout: one LANE per trajectory (state, theta and the theta-adjoint stay in registers for all T steps), one warp
-// per CTA so that 4096 trajectories spread over 128 SMs.  The per-step operands of a trajectory are 4-8 bytes at a
+// Layout: one LANE per trajectory (state, theta and the theta-adjoint stay in registers for all T steps), 32 trajectories
+// per CTA so that 4096 trajectories spread over 128 SMs; a second warp per CTA moves the operands (see em_fwd_kernel).  The per-step operands of a trajectory are 4-8 bytes at a
 // stride of T*S floats, so the warp moves them in chunks of 32/S steps through a padded shared-memory tile: every
 // global access is one contiguous <=128-byte row segment of one trajectory, 32 independent rows in flight.
 // noise == NULL draws eps in the kernel: Philox4x32-10 keyed by `seed`, counter (t, b), Box-Muller; the backward
@@ -41,10 +41,12 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, int64_t b, int64_t
   const float s = 5.9604644775390625e-8f;  // 2^-24
   const float u0 = ((float)(r.x >> 8) + 0.5f) * s, u1 = ((float)(r.y >> 8) + 0.5f) * s;
   const float u2 = ((float)(r.z >> 8) + 0.5f) * s, u3 = ((float)(r.w >> 8) + 0.5f) * s;
+  // accurate log (u near 1 needs relative accuracy); fast sin / cos: |error| < 4e-7 in [-pi, pi], i.e. ~2e-6 on a draw
   const float ra = sqrtf(-2.f * logf(u0)), rb = sqrtf(-2.f * logf(u2));
   float sa, ca, sb, cb;
-  sincosf(6.283185307179586f * u1, &sa, &ca);
-  sincosf(6.283185307179586f * u3, &sb, &cb);
+  __sincosf(6.283185307179586f * u1 - 3.14159265358979f, &sa, &ca);  // argument in [-pi, pi): the intrinsic's accurate range
+  __sincosf(6.283185307179586f * u3 - 3.14159265358979f, &sb, &cb);
+  sa = -sa; ca = -ca; sb = -sb; cb = -cb;
   n[0] = ra * ca;
   n[1] = ra * sa;
   n[2] = rb * cb;
@@ -73,31 +75,47 @@ struct OuModel {
 struct LvModel {
   static constexpr int S = 2, P = 3;
   // examples/lotka_volterra.py:18-46 (drift, Cholesky factor of the diffusion matrix with its three clamps)
+  // Cholesky factor through MUFU.RSQ (L = m rsqrt(m), 1 / L = rsqrt(m); ~2 ulp) instead of IEEE sqrt + divisions: the
+  // transition is the serial chain of the kernel.  L00 >= sqrt(1e-6) = 1e-3, so the reference's clamp(L00, 1e-6) never binds.
+  struct Chol {
+    float b11, b12, b22, r00, L00, L10, ee, r11, L11;
+  };
+  __device__ static Chol chol(float u, float v, float uv, const float (&th)[P]) {
+    Chol c;
+    c.b11 = th[0] * u + th[1] * uv;
+    c.b12 = -th[1] * uv;
+    c.b22 = th[2] * v + th[1] * uv;
+    const float m11 = fmaxf(c.b11, 1e-6f);
+    c.r00 = rsqrtf(m11);
+    c.L00 = m11 * c.r00;
+    c.L10 = c.b12 * c.r00;
+    c.ee = c.b22 - c.L10 * c.L10;
+    const float m22 = fmaxf(c.ee, 1e-6f);
+    c.r11 = rsqrtf(m22);
+    c.L11 = m22 * c.r11;
+    return c;
+  }
   __device__ static void step(const float (&x)[S], const float (&th)[P], const float (&e)[S], float dt, float sq,
                               float (&xn)[S]) {
     const float u = x[0], v = x[1], uv = u * v;
     const float f0 = th[0] * u - th[1] * uv, f1 = th[1] * uv - th[2] * v;
-    const float b11 = th[0] * u + th[1] * uv, b12 = -th[1] * uv, b22 = th[2] * v + th[1] * uv;
-    const float L00 = sqrtf(fmaxf(b11, 1e-6f)), d00 = fmaxf(L00, 1e-6f), L10 = b12 / d00;
-    const float L11 = sqrtf(fmaxf(b22 - L10 * L10, 1e-6f));
-    xn[0] = u + f0 * dt + (L00 * e[0]) * sq;
-    xn[1] = v + f1 * dt + (L10 * e[0] + L11 * e[1]) * sq;
+    const Chol c = chol(u, v, uv, th);
+    xn[0] = u + f0 * dt + (c.L00 * e[0]) * sq;
+    xn[1] = v + f1 * dt + (c.L10 * e[0] + c.L11 * e[1]) * sq;
   }
   __device__ static void step_bwd(const float (&x)[S], const float (&th)[P], const float (&e)[S], float dt, float sq,
                                   const float (&a)[S], float (&gth)[P], float (&gx)[S]) {
     const float u = x[0], v = x[1], uv = u * v;
-    const float b11 = th[0] * u + th[1] * uv, b12 = -th[1] * uv, b22 = th[2] * v + th[1] * uv;
-    const float L00 = sqrtf(fmaxf(b11, 1e-6f)), d00 = fmaxf(L00, 1e-6f), L10 = b12 / d00;
-    const float ee = b22 - L10 * L10, L11 = sqrtf(fmaxf(ee, 1e-6f));
+    const Chol c = chol(u, v, uv, th);
     // noise term
     float gL00 = a[0] * e[0] * sq, gL10 = a[1] * e[0] * sq;
     const float gL11 = a[1] * e[1] * sq;
-    const float ge = ee >= 1e-6f ? 0.5f * gL11 / L11 : 0.f;  // torch clamp(min): gradient passes where input >= min
+    const float ge = c.ee >= 1e-6f ? 0.5f * gL11 * c.r11 : 0.f;  // torch clamp(min): gradient passes where input >= min
     const float gb22 = ge;
-    gL10 -= 2.f * L10 * ge;
-    const float gb12 = gL10 / d00, gd00 = -gL10 * L10 / d00;
-    gL00 += L00 >= 1e-6f ? gd00 : 0.f;
-    const float gb11 = b11 >= 1e-6f ? 0.5f * gL00 / L00 : 0.f;
+    gL10 -= 2.f * c.L10 * ge;
+    const float gb12 = gL10 * c.r00;
+    gL00 -= gL10 * c.L10 * c.r00;  // through the denominator of L10 = b12 / L00
+    const float gb11 = c.b11 >= 1e-6f ? 0.5f * gL00 * c.r00 : 0.f;
     // drift
     const float gf0 = a[0] * dt, gf1 = a[1] * dt;
     const float g1 = gf0 + gb11;                         // d / d(th0 u)
@@ -113,10 +131,17 @@ struct LvModel {
 
 // ---- warp tile <-> global rows ---------------------------------------------------------------------------------
 // tile[r][c] <- row r of 32 trajectories, `ncols` contiguous floats starting at base + r * row_stride
-__device__ __forceinline__ void tile_load(float* tile, const float* base, int64_t row_stride, int nrows, int ncols, int lane) {
-#pragma unroll 8
-  for (int r = 0; r < 32; ++r)
-    if (r < nrows && lane < ncols) tile[r * kTileLd + lane] = base[r * row_stride + lane];
+__device__ __forceinline__ void tile_load(float* tile, const float* __restrict__ base, int64_t row_stride, int nrows, int ncols, int lane) {
+  // two passes of 16 rows, every load of a pass issued before its first store: two memory latencies per tile
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 16) {
+    float v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = (r0 + r < nrows && lane < ncols) ? base[(r0 + r) * row_stride + lane] : 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      if (r0 + r < nrows && lane < ncols) tile[(r0 + r) * kTileLd + lane] = v[r];
+  }
 }
 __device__ __forceinline__ void tile_store(const float* tile, float* base, int64_t row_stride, int nrows, int ncols, int lane) {
 #pragma unroll 8
@@ -138,58 +163,95 @@ struct EmParams {
   float* grad_theta;     // bwd out [B,P]
 };
 
+// noise of chunk [t0, t0 + tc) for the 32 trajectories of this CTA -> tile (injected: coalesced row loads; Philox: each lane
+// generates its own trajectory's draws, the tc blocks are independent so the integer rounds of several steps overlap)
+template <int S>
+__device__ __forceinline__ void chunk_noise(const EmParams& p, float* tile, int64_t b0, int nrows, int64_t t0, int tc, int lane) {
+  if (p.noise) {
+    tile_load(tile, p.noise + (b0 * p.T + t0) * S, p.T * S, nrows, tc * S, lane);
+  } else {
+#pragma unroll 4
+    for (int j = 0; j < tc; ++j) {
+      float n4[4];
+      philox_normal4(p.seed, b0 + lane, t0 + j, n4);
+#pragma unroll
+      for (int s = 0; s < S; ++s) tile[lane * kTileLd + j * S + s] = n4[s];
+    }
+  }
+}
+
+// Four warps per CTA.  Warp 0 is the stepper: state in registers, operands and results only through shared-memory tiles, so
+// nothing on its serial chain ever waits on HBM or on the Philox rounds.  The others are movers: while warp 0 steps chunk c,
+// warp 1 prepares the noise tile of chunk c+1 (draws or loads it) and warp 2 stores the path tile of chunk c-1 (backward:
+// warps 1-3 load the x, cotangent and noise tiles of the next chunk).  One barrier per chunk.
+constexpr int kEmThreads = 128;
 template <class M>
-__global__ void __launch_bounds__(32) em_fwd_kernel(EmParams p) {
+__global__ void __launch_bounds__(kEmThreads) em_fwd_kernel(EmParams p) {
   constexpr int S = M::S, P = M::P, TC = 32 / S;
-  __shared__ float tin[32 * kTileLd], tout[32 * kTileLd];
-  const int lane = threadIdx.x;
+  __shared__ float tin[2][32 * kTileLd], tout[2][32 * kTileLd];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b0 = (int64_t)blockIdx.x * 32, b = b0 + lane;
   const int nrows = (int)(p.B - b0 < 32 ? p.B - b0 : 32);
   const bool ok = lane < nrows;
+  const int64_t nchunk = (p.T + TC - 1) / TC;
   float x[S], th[P];
 #pragma unroll
   for (int s = 0; s < S; ++s) x[s] = ok ? p.x0[b * S + s] : 1.f;
 #pragma unroll
   for (int q = 0; q < P; ++q) th[q] = ok ? p.theta[b * P + q] : 1.f;
-  if (ok) {
+  if (warp == 0 && ok) {
 #pragma unroll
     for (int s = 0; s < S; ++s) p.paths[b * (p.T + 1) * S + s] = x[s];
   }
-  for (int64_t t0 = 0; t0 < p.T; t0 += TC) {
+  if (warp == 1 && nchunk > 0) chunk_noise<S>(p, tin[0], b0, nrows, 0, (int)(p.T < TC ? p.T : TC), lane);
+  __syncthreads();
+  for (int64_t c = 0; c < nchunk; ++c) {
+    const int64_t t0 = c * TC;
     const int tc = (int)(p.T - t0 < TC ? p.T - t0 : TC);
-    if (p.noise) {
-      tile_load(tin, p.noise + (b0 * p.T + t0) * S, p.T * S, nrows, tc * S, lane);
-      __syncwarp();
-    }
-    for (int j = 0; j < tc; ++j) {
-      float e[S], xn[S];
-      if (p.noise) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) e[s] = tin[lane * kTileLd + j * S + s];
-      } else {
-        float n4[4];
-        philox_normal4(p.seed, b, t0 + j, n4);
-#pragma unroll
-        for (int s = 0; s < S; ++s) e[s] = n4[s];
+    if (warp == 1) {
+      if (c + 1 < nchunk) {
+        const int64_t t1 = t0 + TC;
+        chunk_noise<S>(p, tin[(c + 1) & 1], b0, nrows, t1, (int)(p.T - t1 < TC ? p.T - t1 : TC), lane);
       }
-      M::step(x, th, e, p.dt, p.sqrt_dt, xn);
+    } else if (warp == 2) {
+      if (c > 0) tile_store(tout[(c - 1) & 1], p.paths + (b0 * (p.T + 1) + t0 - TC + 1) * S, (p.T + 1) * S, nrows, TC * S, lane);
+    } else if (warp == 0) {
+      const float* ti = tin[c & 1];
+      float* to = tout[c & 1];
+      for (int j = 0; j < tc; ++j) {
+        float e[S], xn[S];
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-        x[s] = ((p.pos_mask >> s) & 1u) ? fmaxf(xn[s], kEmClamp) : xn[s];
-        tout[lane * kTileLd + j * S + s] = x[s];
+        for (int s = 0; s < S; ++s) e[s] = ti[lane * kTileLd + j * S + s];
+        M::step(x, th, e, p.dt, p.sqrt_dt, xn);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          x[s] = ((p.pos_mask >> s) & 1u) ? fmaxf(xn[s], kEmClamp) : xn[s];
+          to[lane * kTileLd + j * S + s] = x[s];
+        }
       }
     }
-    __syncwarp();
-    tile_store(tout, p.paths + (b0 * (p.T + 1) + t0 + 1) * S, (p.T + 1) * S, nrows, tc * S, lane);
-    __syncwarp();
+    __syncthreads();
+  }
+  if (warp == 2 && nchunk > 0) {
+    const int64_t t0 = (nchunk - 1) * TC;
+    tile_store(tout[(nchunk - 1) & 1], p.paths + (b0 * (p.T + 1) + t0 + 1) * S, (p.T + 1) * S, nrows, (int)(p.T - t0) * S, lane);
   }
 }
 
+template <int S>
+__device__ __forceinline__ void bwd_chunk_operands(const EmParams& p, float* tx, float* tg, float* tn, int64_t b0, int nrows,
+                                                   int64_t t0, int tc, int lane, int warp) {
+  // x_t for t in the chunk (warp 1), cotangents of x_{t+1} (warp 2), and the noise of the chunk (warp 3)
+  if (warp == 1) tile_load(tx, p.paths + (b0 * (p.T + 1) + t0) * S, (p.T + 1) * S, nrows, tc * S, lane);
+  if (warp == 2) tile_load(tg, p.g_paths + (b0 * (p.T + 1) + t0 + 1) * S, (p.T + 1) * S, nrows, tc * S, lane);
+  if (warp == 3) chunk_noise<S>(p, tn, b0, nrows, t0, tc, lane);
+}
+
 template <class M>
-__global__ void __launch_bounds__(32) em_bwd_kernel(EmParams p) {
+__global__ void __launch_bounds__(kEmThreads) em_bwd_kernel(EmParams p) {
   constexpr int S = M::S, P = M::P, TC = 32 / S;
-  __shared__ float tn[32 * kTileLd], tx[32 * kTileLd], tg[32 * kTileLd];
-  const int lane = threadIdx.x;
+  __shared__ float tn[2][32 * kTileLd], tx[2][32 * kTileLd], tg[2][32 * kTileLd];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b0 = (int64_t)blockIdx.x * 32, b = b0 + lane;
   const int nrows = (int)(p.B - b0 < 32 ? p.B - b0 : 32);
   const bool ok = lane < nrows;
@@ -202,42 +264,38 @@ __global__ void __launch_bounds__(32) em_bwd_kernel(EmParams p) {
 #pragma unroll
   for (int s = 0; s < S; ++s) a[s] = 0.f;
   const int64_t nchunk = (p.T + TC - 1) / TC;
-  for (int64_t c = nchunk - 1; c >= 0; --c) {
-    const int64_t t0 = c * TC;
-    const int tc = (int)(p.T - t0 < TC ? p.T - t0 : TC);
-    // x_t for t in the chunk, cotangents of x_{t+1}, and the noise of the chunk
-    tile_load(tx, p.paths + (b0 * (p.T + 1) + t0) * S, (p.T + 1) * S, nrows, tc * S, lane);
-    tile_load(tg, p.g_paths + (b0 * (p.T + 1) + t0 + 1) * S, (p.T + 1) * S, nrows, tc * S, lane);
-    if (p.noise) tile_load(tn, p.noise + (b0 * p.T + t0) * S, p.T * S, nrows, tc * S, lane);
-    __syncwarp();
-    for (int j = tc - 1; j >= 0; --j) {
-      float x[S], e[S], xn[S], gx[S];
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        x[s] = ok ? tx[lane * kTileLd + j * S + s] : 1.f;
-        a[s] += ok ? tg[lane * kTileLd + j * S + s] : 0.f;
-      }
-      if (p.noise) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) e[s] = ok ? tn[lane * kTileLd + j * S + s] : 0.f;
-      } else {
-        float n4[4];
-        philox_normal4(p.seed, b, t0 + j, n4);
-#pragma unroll
-        for (int s = 0; s < S; ++s) e[s] = n4[s];
-      }
-      // clamp(min=1e-6) passes the gradient where the unclamped value is >= 1e-6: recompute it exactly as the forward did
-      M::step(x, th, e, p.dt, p.sqrt_dt, xn);
-#pragma unroll
-      for (int s = 0; s < S; ++s)
-        if (((p.pos_mask >> s) & 1u) && !(xn[s] >= kEmClamp)) a[s] = 0.f;
-      M::step_bwd(x, th, e, p.dt, p.sqrt_dt, a, gth, gx);
-#pragma unroll
-      for (int s = 0; s < S; ++s) a[s] = gx[s];
-    }
-    __syncwarp();
+  auto chunk_len = [&](int64_t c) { return (int)(p.T - c * TC < TC ? p.T - c * TC : TC); };
+  if (warp >= 1 && nchunk > 0) {
+    const int64_t c = nchunk - 1;
+    bwd_chunk_operands<S>(p, tx[c & 1], tg[c & 1], tn[c & 1], b0, nrows, c * TC, chunk_len(c), lane, warp);
   }
-  if (ok) {
+  __syncthreads();
+  for (int64_t c = nchunk - 1; c >= 0; --c) {
+    if (warp >= 1) {
+      if (c > 0) bwd_chunk_operands<S>(p, tx[(c - 1) & 1], tg[(c - 1) & 1], tn[(c - 1) & 1], b0, nrows, (c - 1) * TC, TC, lane, warp);
+    } else {
+      const float *cx = tx[c & 1], *cg = tg[c & 1], *cn = tn[c & 1];
+      for (int j = chunk_len(c) - 1; j >= 0; --j) {
+        float x[S], e[S], xn[S], gx[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          x[s] = ok ? cx[lane * kTileLd + j * S + s] : 1.f;
+          a[s] += ok ? cg[lane * kTileLd + j * S + s] : 0.f;
+          e[s] = ok ? cn[lane * kTileLd + j * S + s] : 0.f;
+        }
+        // clamp(min=1e-6) passes the gradient where the unclamped value is >= 1e-6: recompute it exactly as the forward did
+        M::step(x, th, e, p.dt, p.sqrt_dt, xn);
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          if (((p.pos_mask >> s) & 1u) && !(xn[s] >= kEmClamp)) a[s] = 0.f;
+        M::step_bwd(x, th, e, p.dt, p.sqrt_dt, a, gth, gx);
+#pragma unroll
+        for (int s = 0; s < S; ++s) a[s] = gx[s];
+      }
+    }
+    __syncthreads();
+  }
+  if (warp == 0 && ok) {
 #pragma unroll
     for (int q = 0; q < P; ++q) p.grad_theta[b * P + q] = gth[q];
     if (p.grad_x0) {
@@ -283,8 +341,8 @@ int visde_em_fwd(int64_t B, int64_t T, int sde_kind, uint32_t positive_mask, flo
   p.x0 = x0; p.theta = theta; p.noise = noise; p.paths = paths;
   const unsigned grid = (unsigned)((B + 31) / 32);
   cudaStream_t st = (cudaStream_t)stream;
-  if (sde_kind == VISDE_SDE_OU) em_fwd_kernel<OuModel><<<grid, 32, 0, st>>>(p);
-  else em_fwd_kernel<LvModel><<<grid, 32, 0, st>>>(p);
+  if (sde_kind == VISDE_SDE_OU) em_fwd_kernel<OuModel><<<grid, kEmThreads, 0, st>>>(p);
+  else em_fwd_kernel<LvModel><<<grid, kEmThreads, 0, st>>>(p);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
@@ -305,8 +363,8 @@ int visde_em_bwd(int64_t B, int64_t T, int sde_kind, uint32_t positive_mask, flo
   p.grad_x0 = grad_x0; p.grad_theta = grad_theta;
   const unsigned grid = (unsigned)((B + 31) / 32);
   cudaStream_t st = (cudaStream_t)stream;
-  if (sde_kind == VISDE_SDE_OU) em_bwd_kernel<OuModel><<<grid, 32, 0, st>>>(p);
-  else em_bwd_kernel<LvModel><<<grid, 32, 0, st>>>(p);
+  if (sde_kind == VISDE_SDE_OU) em_bwd_kernel<OuModel><<<grid, kEmThreads, 0, st>>>(p);
+  else em_bwd_kernel<LvModel><<<grid, kEmThreads, 0, st>>>(p);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
