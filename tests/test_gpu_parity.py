@@ -53,6 +53,12 @@ FAST_OK = {"lv_h64_b37_ragged_tile", "ou_h32_b13_ragged_tile", "ou_h32_l2", "lv_
            "l96s4_h64_c128_l2", "lv_h64_c128_t1", "ou_h64_c128_l1_t2"}
 
 
+# batches above 4 x #SM take the 8-trajectory tiles of the batch-tiled family (forward and backward); ragged last tile
+CASES["lv_h64_b601_tile8"] = ("lv", 601, 6, dict(context_dim=16, hidden_dim=64, num_layers=2))
+CASES["ou_h32_l1_b610_tile8"] = ("ou", 610, 5, dict(context_dim=8, hidden_dim=32, num_layers=1))
+CASES["l96s4_h64_b597_tile8"] = ("l96", 597, 4, dict(context_dim=8, hidden_dim=64, num_layers=2, state_dim=4))
+FAST_OK |= {"lv_h64_b601_tile8", "ou_h32_l1_b610_tile8", "l96s4_h64_b597_tile8"}
+
 # wide-state register-resident family (4 < S <= 16, H <= 64, NL <= 2)
 CASES["l96s16_h32_l1"] = ("l96", 3, 9, dict(context_dim=8, hidden_dim=32, num_layers=1, state_dim=16))
 CASES["l96s5_h64_l2_b150"] = ("l96", 150, 5, dict(context_dim=16, hidden_dim=64, num_layers=2, state_dim=5))

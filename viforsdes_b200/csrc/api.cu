@@ -392,6 +392,7 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
 
   // K2: reverse-time recurrence
   const float* dg_tiled = nullptr;
+  int part_ctas = 0;  // per-CTA partial records written by the batch-tiled backward (0: one record per fast-family CTA)
   if (tcrec) {
     // tensor-core family: reads the tiled stash the forward wrote and emits d_pre / d_out row-fastest tiled; the
     // thin reductions over (b, t) run right behind it, K3 / K4 below read the tiled buffers directly
@@ -404,7 +405,15 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
     if (rc) return rc;
   } else {
     StageTimer tm(VISDE_STAGE_K2_PATH_BWD, fastsk ? 2 : 1, st);
-    rc = fastsk ? launch_path_bwd_fasts(p, gw, st) : fastk ? launch_path_bwd_fast(p, st) : launch_path_bwd_generic(p, st);
+    if (fastk) {
+      // more trajectories than SMs: the batch-tiled kernel carries 4-8 trajectories through every barrier / shuffle round
+      const int fam = d->variant & 0xff;
+      const int nb = (fam == VISDE_VARIANT_FAST || fam == VISDE_VARIANT_TC || p.H > 64 || d->T == 0)
+                         ? 0 : tiled_batch_tile(d->B, fam == VISDE_VARIANT_TILED);
+      rc = nb > 0 ? launch_path_bwd_tiled(p, nb, &part_ctas, st) : launch_path_bwd_fast(p, st);
+    } else {
+      rc = fastsk ? launch_path_bwd_fasts(p, gw, st) : launch_path_bwd_generic(p, st);
+    }
     if (rc) return rc;
   }
   if (d->T == 0) {
@@ -467,7 +476,7 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
     // fast family: biases, dW_ih_l0[:, :S], dW_out, db_out were accumulated inside K2 (per-CTA partials);
     // tensor-core family: launch_tc_thin_grads above already wrote them
     if (fastk) {
-      rc = launch_fast_partials_reduce(p, gw, st);
+      rc = launch_fast_partials_reduce(p, gw, st, part_ctas);
       if (rc) return rc;
     }
     if (P > 0 && !theta_grads_supported(P)) {  // theta columns of dW_ih_l0 = (sum_t d_gi_l0)^T theta: only B rows

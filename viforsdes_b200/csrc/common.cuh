@@ -130,6 +130,7 @@ int launch_path_bwd_fast(const PathParams& p, cudaStream_t st);
 // batch-tiled family for B > #SM (path_tiled.cu): NB trajectories per CTA, weights in shared memory
 int tiled_batch_tile(int64_t B, bool force);
 int launch_path_fwd_tiled(const PathParams& p, int NB, cudaStream_t st);
+int launch_path_bwd_tiled(const PathParams& p, int NB, int* ncta, cudaStream_t st);  // same outputs + partial records as the fast family
 // register-resident family for wide state spaces, 4 < S <= 16 (path_fast_s.cu); the backward also writes the bias
 // gradients (p.cta_part: fasts_partials_floats()); dW_ih_l0[:, :S], dW_out, db_out are left to the GEMM stage
 bool fasts_supported(const PathParams& p);
@@ -150,7 +151,7 @@ int launch_tc_thin_grads(const PathParams& p, const float* dout_tiled, const vis
 int launch_untile(const float* in, float* out, int64_t B, int64_t T, int F, cudaStream_t st);
 size_t fast_partials_floats(int NL, int H, int S);
 // biases, dW_ih_l0[:, :S], dW_out, db_out from the per-CTA partials written by path_bwd_fast
-int launch_fast_partials_reduce(const PathParams& p, const visde_weight_grads* gw, cudaStream_t st);
+int launch_fast_partials_reduce(const PathParams& p, const visde_weight_grads* gw, cudaStream_t st, int ncta = 0);
 
 // --- SIMT fp32 GEMMs with (b,t) row gathering -------------------------------------------
 // A "row source": row k = (b, t) with b = k / T, t = k % T lives at

@@ -718,10 +718,10 @@ int launch_path_bwd_fast(const PathParams& p, cudaStream_t st) { return dispatch
 
 size_t fast_partials_floats(int NL, int H, int S) { return (size_t)256 * fast_part_floats(NL, H, S); }
 
-int launch_fast_partials_reduce(const PathParams& p, const visde_weight_grads* gw, cudaStream_t st) {
+int launch_fast_partials_reduce(const PathParams& p, const visde_weight_grads* gw, cudaStream_t st, int ncta) {
   FastReduceArgs a{};
   a.part = p.cta_part;
-  a.ncta = fast_grid(p.B);
+  a.ncta = ncta > 0 ? ncta : fast_grid(p.B);
   a.NL = p.NL;
   a.H = p.H;
   a.S = p.S;
