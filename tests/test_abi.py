@@ -70,6 +70,83 @@ def test_sizes_and_validation(lib):
     assert lib.visde_path_fwd(C.byref(ok), 0.1, None, None, None, None, C.byref(w), None, None, None, None, None, 0, None) == 0
 
 
+def test_caller_entry_points_validate_without_a_gpu(lib):
+    """Argument validation of the SURVEY 8f entry points returns the documented codes before anything is launched."""
+    from viforsdes_b200 import _lib
+
+    # core/euler_maruyama.py:20-23 raises ValueError on dt <= 0; user SDEs have no device functor
+    assert lib.visde_em_fwd(4, 4, _lib.SDE_GENERIC, 0, 0.05, None, None, None, 0, None, None) == _lib.EINVAL
+    assert b"PyTorch" in lib.visde_last_error()
+    assert lib.visde_em_fwd(4, 4, _lib.SDE_OU, 0, 0.0, None, None, None, 0, None, None) == _lib.EINVAL
+    assert lib.visde_em_fwd(4, 4, _lib.SDE_LV, 3, 0.05, None, None, None, 0, None, None) == _lib.EINVAL  # NULL tensors
+    assert lib.visde_em_fwd(0, 4, _lib.SDE_LV, 3, 0.05, None, None, None, 0, None, None) == _lib.OK       # empty batch
+    assert lib.visde_em_bwd(0, 4, _lib.SDE_LV, 3, 0.05, None, None, 0, None, None, None, None, None) == _lib.OK
+    assert lib.visde_em_bwd(2, 4, _lib.SDE_LV, 3, 0.05, None, None, 0, None, None, None, None, None) == _lib.EINVAL
+    assert lib.visde_philox_normal(1, 2, 2, 5, None, None) == _lib.EINVAL  # one Philox block gives four normals
+    assert lib.visde_philox_normal(1, 0, 2, 2, None, None) == _lib.OK
+    # posterior summary
+    assert lib.visde_path_summary_workspace_bytes(1000, 801, 2) >= 3 * 801 * 2 * 4
+    assert lib.visde_path_summary(10, 5, 0, 0, None, None, None, None, None, 0, None) == _lib.EINVAL
+    assert lib.visde_path_summary(10, 0, 2, 0, None, None, None, None, None, 0, None) == _lib.OK  # no grid points
+    assert lib.visde_path_summary(10, 5, 2, 0, 1, None, 1, 1, None, 0, None) == _lib.EWORKSPACE
+    # optimiser tail
+    assert lib.visde_grad_sqnorm_workspace_bytes() >= 4 * 148
+    assert lib.visde_grad_sqnorm(16, 16, None, 0, None, None, 0, None) == _lib.EINVAL           # sqnorm NULL
+    assert lib.visde_grad_sqnorm(16, 16, None, 0, 16, None, 0, None) == _lib.EWORKSPACE
+    assert lib.visde_grad_sqnorm(16, 4, None, 0, 16, 16, 1 << 20, None) == _lib.EINVAL          # unaligned gradient pointer
+    args = (0.001, 0.9, 0.999, 1e-8, 0.01)
+    assert lib.visde_adamw_ema_step(0, None, None, None, None, None, *args, 1, 1.0, None, None, 0.999, None) == _lib.OK
+    assert lib.visde_adamw_ema_step(8, 16, 16, 16, 16, None, *args, 0, 1.0, None, None, 0.999, None) == _lib.EINVAL  # step from 1
+    assert lib.visde_adamw_ema_step(8, 16, 16, 16, 16, None, 0.001, 1.0, 0.999, 1e-8, 0.01, 1, 1.0, None, None, 0.999,
+                                    None) == _lib.EINVAL  # beta1 must be < 1
+    assert lib.visde_adamw_ema_step(8, None, 16, 16, 16, None, *args, 1, 1.0, None, None, 0.999, None) == _lib.EINVAL
+
+
+def test_host_mirrors_of_the_callers_validate_on_cpu():
+    """euler_maruyama keeps the reference's ValueErrors and its PyTorch loop for user SDEs (CPU tensors allowed there);
+    the fused ops refuse CPU tensors; FlatParameters aliases parameters and gradients into flat buffers."""
+    import torch
+    from torch import nn
+
+    from viforsdes_b200 import sde as vs
+    from viforsdes_b200.euler_maruyama import euler_maruyama, pretrain_mse
+    from viforsdes_b200.optim import FlatParameters, FusedAdamWEma
+    from viforsdes_b200.posterior import summarise_paths
+    from viforsdes_b200.state_space import StateSpace
+
+    ou = vs.OrnsteinUhlenbeck()
+    x0, th = torch.zeros(3, 1), torch.tensor([[1.0, 0.5, 0.2]]).repeat(3, 1)
+    with pytest.raises(ValueError, match="dt must be positive"):
+        euler_maruyama(ou, x0, th, 1.0, 0.0)
+    with pytest.raises(ValueError, match="time_horizon must be positive"):
+        euler_maruyama(ou, x0, th, 0.0, 0.1)
+    # CPU tensors: the reference loop (a device functor exists only on CUDA)
+    noise = torch.randn(3, 10, 1, generator=torch.Generator().manual_seed(0))
+    paths = euler_maruyama(ou, x0, th, 1.0, 0.1, noise=noise)
+    x = x0.clone()
+    for t in range(10):
+        x = x + th[:, 0:1] * (th[:, 1:2] - x) * 0.1 + th[:, 2:3] * noise[:, t] * 0.1**0.5
+    assert paths.shape == (3, 11, 1) and torch.allclose(paths[:, -1], x, atol=1e-6)
+    mse = pretrain_mse(ou, th, torch.tensor([0.0, 1.0]), torch.tensor([[0.0], [0.3]]), 1.0, 0.1, noise=noise)
+    assert torch.isfinite(mse)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        torch.ops.visde.em_fwd(x0, th, None, 0, 4, 0.1, ou.device_kind, 0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        summarise_paths(torch.zeros(4, 3, 2), StateSpace(2, [0]))
+    lin = nn.Linear(3, 2)
+    w0 = lin.weight.detach().clone()
+    flat = FlatParameters([[lin.weight], [lin.bias]])
+    assert flat.segments == [(0, 8), (8, 12)] and torch.equal(lin.weight, w0)
+    lin(torch.ones(1, 3)).sum().backward()
+    assert flat.grads[:6].abs().sum() > 0 and lin.weight.grad.data_ptr() == flat.grads.data_ptr()
+    flat.zero_grad()
+    assert lin.weight.grad.abs().sum() == 0
+    with pytest.raises(RuntimeError, match="CUDA"):
+        FusedAdamWEma(flat, lrs=[1e-3, 1e-3])
+    with pytest.raises(ValueError):
+        FusedAdamWEma(flat, lrs=[1e-3])
+
+
 def test_ops_reject_cpu_tensors():
     """No CPU fallback: the product path fails loudly off-GPU."""
     import torch

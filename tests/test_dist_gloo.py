@@ -61,6 +61,21 @@ def _worker(rank: int, world: int, port: int) -> None:
         assert torch.allclose(shadow[0], torch.full((4,), 0.5)) and torch.allclose(shadow[1], torch.full((2, 2), 5.0))
         t = torch.tensor([float(rank)])
         assert allreduce_mean_(t).item() == 0.5
+        # FlatParameters: the gradient views of a module ARE the bucket, one collective averages them in place
+        from viforsdes_b200.optim import FlatParameters
+
+        torch.manual_seed(1)
+        net = torch.nn.Linear(4, 3)
+        flat = FlatParameters([list(net.parameters())])
+        net(x[lo:hi]).pow(2).mean().backward()
+        allreduce_mean_(flat.grads)
+        ref2 = torch.nn.Linear(4, 3)
+        with torch.no_grad():
+            ref2.weight.copy_(net.weight)
+            ref2.bias.copy_(net.bias)
+        ref2(x).pow(2).mean().backward()
+        assert torch.allclose(net.weight.grad, ref2.weight.grad, atol=1e-6)
+        assert torch.allclose(net.bias.grad, ref2.bias.grad, atol=1e-6)
     finally:
         dist.destroy_process_group()
 
