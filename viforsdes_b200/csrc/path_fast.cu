@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
   constexpr int kTmaThread = NTHR - 32, kLoaderBase = NTHR - 64 - (SMALL > 32 ? 32 : 0), kDoutThread = NTHR / 2;
   constexpr int O_GP = 0, O_GM = S, O_EPS = 2 * S, O_Z = 3 * S, O_RAW = 4 * S, O_GL = 5 * S;
   __shared__ __align__(16) float sring[NSR][NL * kStashSlots * HP];
-  __shared__ __align__(16) float small[3][SMALLP];
+  __shared__ __align__(16) float small[4][SMALLP];  // 3 rows live at a time; 4 slots so that the slot index is a mask
   __shared__ __align__(8) uint64_t sbar[NSR];
   const uint32_t row_bytes = (uint32_t)srow * 4u;
   if (tid == 0) {
@@ -433,8 +433,8 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
     // prologue: rows T-1, T-2 of the small ring directly, row T-3 pending; stash rows T-1..T-3 in flight
     float pend = 0.f;
     if (lt >= 0 && lt < SMALL) {
-      if (T >= 1) small[(T - 1) % 3][lt] = src[(int64_t)(T - 1) * dec];
-      if (T >= 2) small[(T - 2) % 3][lt] = src[(int64_t)(T - 2) * dec];
+      if (T >= 1) small[(T - 1) & 3][lt] = src[(int64_t)(T - 1) * dec];
+      if (T >= 2) small[(T - 2) & 3][lt] = src[(int64_t)(T - 2) * dec];
       if (T >= 3) pend = src[(int64_t)(T - 3) * dec];
       src += (int64_t)(T - 4) * dec;  // next row to fetch (may point before the array; guarded by t)
     }
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
         bulk_load_1d(&sring[n % NSR][0], st_b + (int64_t)(t - 3) * srow, row_bytes, &sbar[n % NSR]);
       }
       if (lt >= 0 && lt < SMALL) {
-        if (t >= 2) small[(t - 2) % 3][lt] = pend;
+        if (t >= 2) small[(t - 2) & 3][lt] = pend;
         if (t >= 3) pend = *src;
         src -= dec;
       }
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
       float sm[SMALLP];
 #pragma unroll
       for (int q = 0; q < SMALLP / 4; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(&small[t % 3][4 * q]);
+        const float4 v = *reinterpret_cast<const float4*>(&small[t & 3][4 * q]);
         sm[4 * q] = v.x; sm[4 * q + 1] = v.y; sm[4 * q + 2] = v.z; sm[4 * q + 3] = v.w;
       }
       // this unit's stashed gates (row t) and previous hidden state (row t-1)
@@ -571,17 +571,10 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
 #pragma unroll
           for (int ps = 0; ps < NPZ; ++ps) {
             const int item = ps * RPP + grp;
-            const int gate = item / S;
-            float2 a = make_float2(0.f, 0.f), c = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int q = 0; q < SL / 2; q += 2) {
-              // pick the gate's slice without divergence
-              float2 x0 = gate == 0 ? d0[q] : gate == 1 ? d1[q] : d2[q];
-              float2 x1 = gate == 0 ? d0[q + 1] : gate == 1 ? d1[q + 1] : d2[q + 1];
-              fma2(a, wzg[ps][q], x0);
-              fma2(c, wzg[ps][q + 1], x1);
-            }
-            part[ps] = ks_allreduce<KS>((a.x + a.y) + (c.x + c.y));
+            const int gate = item < NZ ? item / S : 0;  // items beyond 3 S carry zero weights
+            float2 gs[SL / 2];
+            load_slice2<SL>(&dgb[par][0][gate][ks * (SL + 4)], gs);  // this lane group's gate: no register selects
+            part[ps] = ks_allreduce<KS>(dot2<SL>(wzg[ps], gs));
           }
 #pragma unroll
           for (int s = 0; s < S; ++s)
