@@ -404,6 +404,8 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
   }
   __syncthreads();
   uint32_t rows_issued = 0;  // total stash rows issued so far by this CTA (slot / phase bookkeeping)
+  constexpr uint32_t kRowBytesP = NL * kStashSlots * HP * 4;  // ring slot pitch
+  const uint32_t sbar_a = smem_u32(&sbar[0]), sring_a = smem_u32(&sring[0][0]);
 
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     float dz[S], dhc[NL], sdg_lane = 0.f;
@@ -446,28 +448,32 @@ __global__ void __launch_bounds__(HP* KS, 1) path_bwd_fast_kernel(PathParams p) 
         bulk_load_1d(&sring[n % NSR][0], st_b + (int64_t)r * srow, row_bytes, &sbar[n % NSR]);
       }
     }
+    const float* tma_src = st_b + (int64_t)(T - 4) * srow;  // next row the copy thread fetches (guarded by t >= 3)
     rows_issued += (uint32_t)T;
     __syncthreads();
     if (T > 0) mbar_wait(&sbar[row0 % NSR], (row0 / NSR) & 1);  // row T-1
+    uint32_t n_cur = row0;  // issue number of row t: advanced once per step
     float htop = (unit_ok && T > 0) ? sring[row0 % NSR][((NL - 1) * kStashSlots + kStashH) * H + i] : 0.f;
 
     for (int t = T - 1; t >= 0; --t) {
       const int par = t & 1;
-      const uint32_t n_cur = row0 + (uint32_t)(T - 1 - t);
-      const float* row_cur = &sring[n_cur % NSR][0];
-      const float* row_prev = &sring[(n_cur + 1) % NSR][0];
+      static_assert(NSR == 4, "slot arithmetic below uses masks");
+      const uint32_t s_cur = n_cur & 3u, s_prev = (n_cur + 1) & 3u, s_new = (n_cur + 3) & 3u;
+      const float* row_cur = &sring[0][0] + s_cur * (NL * kStashSlots * HP);
+      const float* row_prev = &sring[0][0] + s_prev * (NL * kStashSlots * HP);
       // keep the pipelines full: stash row t-3, small row t-3 (parked next step), park row t-2
       if (tid == kTmaThread && t >= 3) {
-        const uint32_t n = n_cur + 3;
-        mbar_expect_tx(&sbar[n % NSR], row_bytes);
-        bulk_load_1d(&sring[n % NSR][0], st_b + (int64_t)(t - 3) * srow, row_bytes, &sbar[n % NSR]);
+        mbar_expect_tx_addr(sbar_a + 8u * s_new, row_bytes);
+        bulk_load_1d_addr(sring_a + kRowBytesP * s_new, tma_src, row_bytes, sbar_a + 8u * s_new);
       }
+      tma_src -= srow;
       if (lt >= 0 && lt < SMALL) {
         if (t >= 2) small[(t - 2) & 3][lt] = pend;
         if (t >= 3) pend = *src;
         src -= dec;
       }
-      if (t >= 1) mbar_wait(&sbar[(n_cur + 1) % NSR], ((n_cur + 1) / NSR) & 1);  // row t-1 (h_prev)
+      if (t >= 1) mbar_wait_addr(sbar_a + 8u * s_prev, ((n_cur + 1) >> 2) & 1u);  // row t-1 (h_prev)
+      ++n_cur;
 
       // this step's uniform scalars from the shared ring
       float sm[SMALLP];
