@@ -331,7 +331,7 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
   if (use_fasts(d, p)) return launch_path_fwd_fasts(p, st);
   if (use_fast(d, p)) {
     const int fam = d->variant & 0xff;
-    const int nb = (fam == VISDE_VARIANT_FAST || fam == VISDE_VARIANT_TC) ? 0 : tiled_batch_tile(d->B, fam == VISDE_VARIANT_TILED);
+    const int nb = (fam == VISDE_VARIANT_FAST || fam == VISDE_VARIANT_TC) ? 0 : tiled_batch_tile(d->B, fam == VISDE_VARIANT_TILED, false);
     return nb > 0 ? launch_path_fwd_tiled(p, nb, st) : launch_path_fwd_fast(p, st);
   }
   return launch_path_fwd_generic(p, st);
@@ -409,7 +409,7 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
       // more trajectories than SMs: the batch-tiled kernel carries 4-8 trajectories through every barrier / shuffle round
       const int fam = d->variant & 0xff;
       const int nb = (fam == VISDE_VARIANT_FAST || fam == VISDE_VARIANT_TC || p.H > 64 || d->T == 0)
-                         ? 0 : tiled_batch_tile(d->B, fam == VISDE_VARIANT_TILED);
+                         ? 0 : tiled_batch_tile(d->B, fam == VISDE_VARIANT_TILED, true);
       rc = nb > 0 ? launch_path_bwd_tiled(p, nb, &part_ctas, st) : launch_path_bwd_fast(p, st);
     } else {
       rc = fastsk ? launch_path_bwd_fasts(p, gw, st) : launch_path_bwd_generic(p, st);

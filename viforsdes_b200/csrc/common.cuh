@@ -128,7 +128,7 @@ bool fast_supported(const PathParams& p);
 int launch_path_fwd_fast(const PathParams& p, cudaStream_t st);
 int launch_path_bwd_fast(const PathParams& p, cudaStream_t st);
 // batch-tiled family for B > #SM (path_tiled.cu): NB trajectories per CTA, weights in shared memory
-int tiled_batch_tile(int64_t B, bool force);
+int tiled_batch_tile(int64_t B, bool force, bool bwd);
 int launch_path_fwd_tiled(const PathParams& p, int NB, cudaStream_t st);
 int launch_path_bwd_tiled(const PathParams& p, int NB, int* ncta, cudaStream_t st);  // same outputs + partial records as the fast family
 // register-resident family for wide state spaces, 4 < S <= 16 (path_fast_s.cu); the backward also writes the bias

@@ -867,14 +867,19 @@ int dispatch_s(const PathParams& p, cudaStream_t st) {
 
 }  // namespace
 
-// trajectories per tile for a batch of B on this device (0 = use the one-trajectory-per-CTA family)
-int tiled_batch_tile(int64_t B, bool force) {
+// trajectories per tile for a batch of B on this device (0 = use the one-trajectory-per-CTA family).
+// Cost model in units of "one wave of one-trajectory CTAs", measured on B200 at H = 64, NL = 2, T = 100
+// (tools/crossover_fast_tiled.sh, profiles/r1_ou_batch_sweep.md): a wave of 4-trajectory tiles costs 2.9 (forward) /
+// 3.3 (backward) of them, a wave of 8-trajectory tiles 4.4 / 6.0; each family needs ceil(B / (tile * #SM)) waves.
+int tiled_batch_tile(int64_t B, bool force, bool bwd) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (B > (int64_t)4 * sms) return 8;
-  if (B > sms || force) return 4;
-  return 0;
+  auto waves = [&](int tile) { return (double)((B + (int64_t)tile * sms - 1) / ((int64_t)tile * sms)); };
+  const double c1 = waves(1), c4 = waves(4) * (bwd ? 3.32 : 2.9), c8 = waves(8) * (bwd ? 5.95 : 4.42);
+  const int tiled = c8 < c4 ? 8 : 4;
+  if (force) return tiled;
+  return (c1 <= c4 && c1 <= c8) ? 0 : tiled;
 }
 
 int launch_path_fwd_tiled(const PathParams& p, int NB, cudaStream_t st) {
