@@ -167,3 +167,32 @@ def test_checkpoint_keys_match_reference():
     for k in range(2):
         want |= {f"gru.weight_ih_l{k}", f"gru.weight_hh_l{k}", f"gru.bias_ih_l{k}", f"gru.bias_hh_l{k}"}
     assert keys == want
+
+
+def test_device_adam_matches_torch_adam_and_skips():
+    """The sync-free Adam of the pre-training loop == torch.optim.Adam + clip_grad_norm_(1.0), and a masked step leaves
+    parameter and state untouched (what the reference does with `if torch.isfinite(mse)`, inference/trainer.py:238-241)."""
+    import torch
+
+    from viforsdes_b200.euler_maruyama import PretrainConfig, _DeviceAdam
+
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(6, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=0.02)
+    mine = p0.clone().requires_grad_(True)
+    dev = _DeviceAdam(mine, 0.02)
+    for k in range(8):
+        grad = torch.randn(6, generator=g) * (5.0 if k % 2 else 0.1)
+        if k == 3:  # skipped step (non-finite objective)
+            before = mine.detach().clone()
+            dev.step(torch.full((6,), float("nan")), torch.tensor(False))
+            assert torch.equal(mine.detach(), before)
+            continue
+        ref.grad = grad.clone()
+        torch.nn.utils.clip_grad_norm_([ref], 1.0)
+        opt.step()
+        dev.step(grad, torch.tensor(True))
+    assert torch.allclose(mine.detach(), ref.detach(), rtol=1e-5, atol=1e-7)
+    with pytest.raises(ValueError):
+        PretrainConfig(n_iterations=0)

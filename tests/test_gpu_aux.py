@@ -324,3 +324,47 @@ def test_context_fold_matches_unfused(E, Cd, B, T):
     names = ["paths", "means", "chol", "g_tokens", "g_theta", "g_proj_w", "g_proj_b", "g_w_ih_l0", "g_b_ih_l0", "g_w_hh_l1", "g_out_w"]
     for a, b, nm in zip(outs[1], outs[0], names):
         assert_close(a, b, rtol=2e-4, atol_scale=5e-5, name=nm)
+
+
+def test_pretrain_loop_matches_reference_control_flow():
+    """pretrain_sde_parameters (sync-free: device Adam, device best-so-far) against the reference's loop structure
+    (inference/trainer.py:208-250: torch.optim.Adam, clip_grad_norm_, three .item() per step) on the same draws."""
+    from viforsdes_b200.euler_maruyama import PretrainConfig, pretrain_mse, pretrain_sde_parameters
+    from viforsdes_b200.sde import OrnsteinUhlenbeck
+
+    sde, dt, horizon = OrnsteinUhlenbeck(), 0.05, 5.0
+    true = torch.tensor([1.2, 0.8, 0.25])
+    obs_t = torch.arange(0.0, 5.5, 1.0).cuda()
+    obs_v = (true[1] + (0.2 - true[1]) * torch.exp(-true[0] * obs_t.cpu())).unsqueeze(1).cuda()
+    cfg = PretrainConfig(n_iterations=120, batch_size=512, learning_rate=0.05, init_scale=0.5)
+    pos = [0, 2]
+
+    torch.manual_seed(11)
+    best = pretrain_sde_parameters(sde, obs_t, obs_v, horizon, dt, pos, [], cfg, seed=100)
+
+    torch.manual_seed(11)
+    d = 3
+    mu = torch.zeros(d, device="cuda")
+    mu[[1]] = cfg.init_scale * torch.randn(1, device="cuda")
+    mu = torch.nn.Parameter(mu)
+    log_sigma = torch.nn.Parameter(torch.zeros(d, device="cuda"))
+    opt = torch.optim.Adam([mu, log_sigma], lr=cfg.learning_rate)
+    best_ref, best_mse, first_mse = mu.detach().clone(), float("inf"), None
+    for step in range(cfg.n_iterations):
+        opt.zero_grad()
+        eps = torch.randn(cfg.batch_size, d, device="cuda")
+        log_theta = mu + log_sigma.exp() * eps
+        theta = log_theta.clone()
+        theta[:, pos] = log_theta[:, pos].exp()
+        mse = pretrain_mse(sde, theta, obs_t, obs_v, horizon, dt, [], seed=100 + step)
+        first_mse = mse.item() if first_mse is None else first_mse
+        if torch.isfinite(mse) and mse.item() < best_mse:
+            best_ref, best_mse = mu.detach().clone(), mse.item()
+        if torch.isfinite(mse):
+            mse.backward()
+            torch.nn.utils.clip_grad_norm_([mu, log_sigma], 1.0)
+            opt.step()
+    assert_close(best, best_ref, rtol=1e-4, atol_scale=1e-4, name="best_mu")
+    assert best_mse < 0.5 * first_mse, (best_mse, first_mse)
+    # the fitted mean reverts towards the generating parameters (theta_1 is identified by the plateau of the observations)
+    assert abs(best[1].item() - true[1].item()) < 0.25
