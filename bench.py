@@ -269,6 +269,18 @@ def main() -> None:
         cnt = (C.c_int * len(_lib.STAGES))()
         _lib.check(lib.visde_profile_end(ms, cnt))
         eager_ms_per_step = sum(a.elapsed_time(b) for a, b in ev2) / K
+        # ---- informational: a complete data-parallel head iteration = the timed step + the fused unscale / clip / AdamW / EMA
+        # over the flat parameter and gradient buffers (lr = 0 keeps the weights: same kernels and traffic, same inputs later)
+        opt = it.make_optimizer(lr=0.0, max_norm=1.0, ema_decay=0.999)
+        ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for i in range(K):
+            flush.zero_()
+            ev3[i][0].record()
+            step(graph=use_graph)
+            opt.step()
+            ev3[i][1].record()
+        torch.cuda.synchronize()
+        train_ms_per_step = sum(a.elapsed_time(b) for a, b in ev3) / K
         tt = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -369,6 +381,7 @@ def main() -> None:
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                    "samples": clocks["samples"]},
         "wall_ms_per_step_incl_flush": t_wall / K * 1e3, "eager_ms_per_step": eager_ms_per_step,
+        "head_train_ms_per_step": train_ms_per_step,
     }
     print(json.dumps(line))
     if world > 1:

@@ -368,3 +368,95 @@ def test_pretrain_loop_matches_reference_control_flow():
     assert best_mse < 0.5 * first_mse, (best_mse, first_mse)
     # the fitted mean reverts towards the generating parameters (theta_1 is identified by the plateau of the observations)
     assert abs(best[1].item() - true[1].item()) < 0.25
+
+
+def _module_iteration(inp, head, theta_req=True):
+    """One ELBO iteration through the public modules on the tensors of a synthetic `Inputs` (what PathIteration fuses)."""
+    from viforsdes_b200 import sde as vs
+    from viforsdes_b200.elbo import path_elbo_terms
+    from viforsdes_b200.observations import GaussianObservationLikelihood, Observations
+    from viforsdes_b200.state_space import StateSpace
+    from viforsdes_b200.types import DiffusionPathSample
+
+    x0 = inp.x0.cuda().requires_grad_(True)
+    full = inp.context_full.cuda().requires_grad_(True)
+    theta = inp.theta.cuda().requires_grad_(theta_req)
+    paths, means, chol = head.sample_diffusion_paths(x0, full[:, :-1], theta, inp.eps.cuda(), inp.dt)
+    S = inp.x0.shape[1]
+    sample = DiffusionPathSample(paths, means, chol, StateSpace(S, list(inp.positive_dims)))
+    sde = vs.OrnsteinUhlenbeck() if inp.kind == "ou" else vs.LotkaVolterra()
+    terms = path_elbo_terms(sde, Observations(times=inp.obs_times, values=inp.obs_values),
+                            GaussianObservationLikelihood(variance=inp.obs_variance), theta, sample, inp.dt)
+    loss = -(terms[:, 0] + terms[:, 1] - terms[:, 2] + terms[:, 3]).mean()
+    loss.backward()
+    return paths, terms, x0.grad, full.grad, theta.grad, loss
+
+
+def _head_from_inputs(inp):
+    from viforsdes_b200.head import DiffusionTransitionHead, HeadConfig
+
+    S, H, NL = inp.x0.shape[1], inp.w_hh[0].shape[1], len(inp.w_hh)
+    head = DiffusionTransitionHead(S, inp.context_full.shape[2], inp.theta.shape[1], HeadConfig(hidden_dim=H, num_layers=NL))
+    with torch.no_grad():
+        for k in range(NL):
+            getattr(head.gru, f"weight_ih_l{k}").copy_(inp.w_ih[k])
+            getattr(head.gru, f"weight_hh_l{k}").copy_(inp.w_hh[k])
+            getattr(head.gru, f"bias_ih_l{k}").copy_(inp.b_ih[k])
+            getattr(head.gru, f"bias_hh_l{k}").copy_(inp.b_hh[k])
+        head.out_proj.weight.copy_(inp.out_w)
+        head.out_proj.bias.copy_(inp.out_b)
+    return head.cuda().train()
+
+
+@pytest.mark.parametrize("kind,B,T", [("lv", 16, 40), ("ou", 300, 12)])
+def test_path_iteration_matches_module_path_and_trains(kind, B, T):
+    """bench.py's device-resident iteration (runner.PathIteration: C ABI, static buffers, CUDA graph) against the
+    torch.library / nn.Module path on the same synthetic inputs; then three complete head training steps (graph replay +
+    fused clip + AdamW + EMA on the flat buffers) against torch.optim.AdamW + clip_grad_norm_ + EMA lerp on the module."""
+    from viforsdes_b200.runner import PathIteration
+    from viforsdes_b200.synthetic import make_inputs
+    from tests._util import head_grads
+
+    inp = make_inputs(kind, B, T, context_dim=128, hidden_dim=64, num_layers=2, seed=5)
+    it = PathIteration(inp, "cuda")
+    it.step()
+    head = _head_from_inputs(inp)
+    paths, terms, gx0, gctx, gth, _ = _module_iteration(inp, head)
+    r = it.results()
+    assert_close(r["paths"], paths, rtol=1e-6, name="paths")
+    assert_close(r["terms"], terms, rtol=1e-5, name="terms")
+    assert_close(r["grads"]["x0"], gx0, rtol=1e-5, name="g_x0")
+    assert_close(r["grads"]["context"], gctx[:, :T], rtol=1e-5, name="g_ctx")
+    assert_close(r["grads"]["theta"], gth, rtol=1e-5, name="g_theta")
+    for nm, g in head_grads(head).items():
+        assert_close(r["grads"][nm], g, rtol=1e-5, name=f"g_{nm}")
+    # --- three training steps of the head
+    lr, max_norm, decay = 2e-3, 1.0, 0.9
+    opt = it.make_optimizer(lr=lr, max_norm=max_norm, ema_decay=decay)
+    it.capture()
+    ref_opt = torch.optim.AdamW(head.parameters(), lr=lr)
+    shadow = [p.detach().clone() for p in head.parameters()]
+    losses = []
+    for _ in range(3):
+        it.replay()
+        opt.step()
+        ref_opt.zero_grad()
+        *_, loss = _module_iteration(inp, head)
+        losses.append(loss.item())
+        torch.nn.utils.clip_grad_norm_(head.parameters(), max_norm)
+        ref_opt.step()
+        with torch.no_grad():
+            for s_, p_ in zip(shadow, head.parameters()):
+                s_.lerp_(p_.detach(), 1 - decay)
+    torch.cuda.synchronize()
+    names = {f"w_ih_l{k}": it.w[0][k] for k in range(2)} | {f"w_hh_l{k}": it.w[1][k] for k in range(2)} | \
+            {f"b_ih_l{k}": it.w[2][k] for k in range(2)} | {f"b_hh_l{k}": it.w[3][k] for k in range(2)} | \
+            {"out_w": it.out_w, "out_b": it.out_b}
+    mod = {f"w_ih_l{k}": getattr(head.gru, f"weight_ih_l{k}") for k in range(2)} | \
+          {f"w_hh_l{k}": getattr(head.gru, f"weight_hh_l{k}") for k in range(2)} | \
+          {f"b_ih_l{k}": getattr(head.gru, f"bias_ih_l{k}") for k in range(2)} | \
+          {f"b_hh_l{k}": getattr(head.gru, f"bias_hh_l{k}") for k in range(2)} | \
+          {"out_w": head.out_proj.weight, "out_b": head.out_proj.bias}
+    for nm in names:
+        assert_close(names[nm], mod[nm], rtol=2e-4, atol_scale=2e-5, name=f"trained {nm}")
+    assert len(opt.ema_views()) == 10

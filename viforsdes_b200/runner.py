@@ -35,10 +35,17 @@ class PathIteration:
         # bf16 = what the reference's autocast encoder hands to the head (grad_context comes back in the same dtype)
         self.ctx = inp.context_full.to(dev).to(context_dtype).contiguous()
         cdt = _lib.BF16 if context_dtype == torch.bfloat16 else _lib.F32
-        self.w = [[to(t) for t in ws] for ws in (inp.w_ih, inp.w_hh, inp.b_ih, inp.b_hh)]
-        self.out_w, self.out_b = to(inp.out_w), to(inp.out_b)
-        # all 4*NL+2 weight gradients are views of ONE flat buffer: it is the all-reduce bucket
-        shapes = [tuple(t.shape) for ws in self.w for t in ws] + [tuple(self.out_w.shape), tuple(self.out_b.shape)]
+        # the 4*NL+2 parameter tensors are views of ONE flat buffer and so are their gradients (same offsets): the gradient
+        # buffer is the all-reduce bucket and the pair is what the fused clip + AdamW + EMA step walks (make_optimizer)
+        host_w = [list(ws) for ws in (inp.w_ih, inp.w_hh, inp.b_ih, inp.b_hh)]
+        shapes = [tuple(t.shape) for ws in host_w for t in ws] + [tuple(inp.out_w.shape), tuple(inp.out_b.shape)]
+        self.param_bucket = FlatBucket(shapes, dev)
+        with torch.no_grad():
+            for v, t in zip(self.param_bucket.views, [t for ws in host_w for t in ws] + [inp.out_w, inp.out_b]):
+                v.copy_(t)
+        pv = self.param_bucket.views
+        self.w = [pv[i * NL:(i + 1) * NL] for i in range(4)]
+        self.out_w, self.out_b = pv[4 * NL], pv[4 * NL + 1]
         self.bucket = FlatBucket(shapes, dev, extra=1)  # + the ELBO scalar: one all-reduce per iteration
         self.elbo_sign = torch.tensor([1.0, 1.0, -1.0, 1.0], **f) / B  # mean_b(obs + sde - gen + jac)
         v = self.bucket.views
@@ -125,6 +132,18 @@ class PathIteration:
 
     def replay(self) -> None:
         self.graph.replay()
+
+    def make_optimizer(self, lr: float = 1e-3, max_norm: float = 1.0, ema_decay: float | None = 0.999, **adamw):
+        """Fused unscale + clip + AdamW + EMA over the head's flat parameter / gradient pair (inference/trainer.py:199-203,
+        126): `opt.step()` after `replay()` (+ the all-reduce) is a complete data-parallel head iteration, no host sync."""
+        from types import SimpleNamespace
+
+        from viforsdes_b200.optim import FusedAdamWEma
+
+        n = self.param_bucket.flat.numel()
+        flat = SimpleNamespace(data=self.param_bucket.flat, grads=self.bucket.flat[:n], segments=[(0, n)],
+                               groups=[list(self.param_bucket.views)])
+        return FusedAdamWEma(flat, [lr], max_norm=max_norm, ema_decay=ema_decay, **adamw)
 
     def stage_elbo(self) -> None:
         """Write the batch-mean ELBO of this rank into the bucket's tail slot (two tiny kernels)."""
