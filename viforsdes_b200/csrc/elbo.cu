@@ -400,7 +400,10 @@ int dispatch(const ElboParams& p, cudaStream_t st, bool bwd) {
   if (p.S <= 1) return launch_both<1>(p, st, bwd);
   if (p.S <= 2) return launch_both<2>(p, st, bwd);
   if (p.S <= 4) return launch_both<4>(p, st, bwd);
+  if (p.S <= 6) return launch_both<6>(p, st, bwd);
   if (p.S <= 8) return launch_both<8>(p, st, bwd);
+  if (p.S <= 10) return launch_both<10>(p, st, bwd);  // BASELINE config 5 (10-D Lorenz-96): 100 instead of 256 matrix registers
+  if (p.S <= 12) return launch_both<12>(p, st, bwd);
   return launch_both<16>(p, st, bwd);
 }
 
