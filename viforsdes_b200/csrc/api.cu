@@ -121,6 +121,10 @@ BwdWs bwd_ws(const visde_dims* d) {
     size_t pt = tc_thin_partial_floats(d->B, d->NL, d->S);
     if (pt > pf) pf = pt;
   }
+  if (d->S > 4 && d->H <= 64) {  // wide-state family
+    size_t pt = fasts_thin_partial_floats(d->B, d->T, d->S, d->H);
+    if (pt > pf) pf = pt;
+  }
   w.partial_floats = pf;
   w.partials = off;
   off += align_up(sizeof(float) * pf);
@@ -487,15 +491,9 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
       if (rc) return rc;
     }
     if (fastsk && d->T > 0) {
-      // wide-state family: the S-sized reductions are time-parallel GEMMs over (b, t)
-      RowSrc bz[1] = {RowSrc{paths, (int64_t)(d->T + 1) * S, S, 0, S, VISDE_F32}};
-      TnOut oz{gw->w_ih[0], ld0, 0, S};
-      rc = launch_gemm_tn(dg_src(0), G, G, 0, bz, 1, d->B, d->T, &oz, 1, partials, ws.partial_floats, st);
-      if (rc) return rc;
-      RowSrc A{p.dout, d->T * (int64_t)p.n_out, p.n_out, 0, p.n_out, VISDE_F32};
-      RowSrc bo[2] = {h_src(NL - 1, 0), ones};
-      TnOut oo[2] = {{gw->out_w, H, 0, H}, {gw->out_b, 1, H, 1}};
-      rc = launch_gemm_tn(A, p.n_out, p.n_out, 0, bo, 2, d->B, d->T, oo, 2, partials, ws.partial_floats, st);
+      // wide-state family: the S-sized reductions (dW_ih_l0[:, :S], dW_out, db_out) are one time-parallel pass over (b, t)
+      p.paths = const_cast<float*>(paths);
+      rc = launch_fasts_thin_grads(p, gw, partials, ws.partial_floats, st);
       if (rc) return rc;
     }
     if (tcrec) return tc_wgrads_tiled(ctx, dg_tiled, p.stash, d->B, d->T, S, C, P, H, NL, gw, partials, ws.partial_floats, st);

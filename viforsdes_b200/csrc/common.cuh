@@ -137,6 +137,10 @@ bool fasts_supported(const PathParams& p);
 size_t fasts_partials_floats(int NL, int H);
 int launch_path_fwd_fasts(const PathParams& p, cudaStream_t st);
 int launch_path_bwd_fasts(const PathParams& p, const visde_weight_grads* gw, cudaStream_t st);
+// dW_ih_l0[:, :S], dW_out, db_out of the wide-state family in one time-parallel pass over d_pre / d_out / the stash (fasts_thin.cu)
+size_t fasts_thin_partial_floats(int64_t B, int64_t T, int S, int H);
+int launch_fasts_thin_grads(const PathParams& p, const visde_weight_grads* gw, float* partials, size_t partial_floats,
+                            cudaStream_t st);
 // tensor-core recurrence family for large batches (path_tc.cu): 128 trajectories per CTA, tcgen05 gate GEMMs
 bool tc_rec_supported(const PathParams& p);
 int launch_gth(const PathParams& p, float* gth, cudaStream_t st);  // per-trajectory constant part of the layer-0 gates
