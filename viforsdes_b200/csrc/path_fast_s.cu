@@ -221,23 +221,28 @@ __global__ void __launch_bounds__(kThr, 1) path_fwd_fasts_kernel(PathParams p) {
       __syncthreads();
       // ---- reparameterised Euler-Maruyama update: one state dimension per thread computes z_{t+1} (the only part on
       // the critical path); means / chol / raw leave after the barrier, one element per thread, straight from obuf
-      float zn_keep = 0.f;
-      if (tid < S) {
-        const int s = tid;
-        float acc = 0.f;
-        const float* ev = epsbuf + par * S;
-        const float* Lr = obuf + S + s * (s + 1) / 2;
-        for (int j = 0; j < s; ++j) acc = fmaf(Lr[j], ev[j], acc);
-        acc = fmaf(fmaxf(Lr[s], VISDE_DIAG_MIN), ev[s], acc);
-        zn_keep = zbuf[s] + obuf[s] * p.dt + acc * p.sqrt_dt;
-        zbuf[s] = zn_keep;
-        epsbuf[(par ^ 1) * S + s] = eps_next;
+      // (first version: S threads each walked their row of L serially while seven warps waited at the barrier below --
+      // 19 % of the kernel's stall samples.)  Now thread (s, j) = (tid / 16, tid % 16) forms L[s][j] eps[j] and the 16 lanes
+      // of a row reduce with four shuffles: the whole CTA takes part and the chain is 2 LDS + 4 SHFL.
+      {
+        const int s = tid >> 4, j = tid & 15;
+        float term = 0.f;
+        if (s < S && j <= s) {
+          const float raw = obuf[S + s * (s + 1) / 2 + j];
+          term = (j == s ? fmaxf(raw, VISDE_DIAG_MIN) : raw) * epsbuf[par * S + j];
+        }
+        term += __shfl_xor_sync(0xffffffffu, term, 8);
+        term += __shfl_xor_sync(0xffffffffu, term, 4);
+        term += __shfl_xor_sync(0xffffffffu, term, 2);
+        term += __shfl_xor_sync(0xffffffffu, term, 1);
+        if (j == 0 && s < S) zbuf[s] = zbuf[s] + obuf[s] * p.dt + term * p.sqrt_dt;
+        if (tid < S) epsbuf[(par ^ 1) * S + tid] = eps_next;
       }
       __syncthreads();
       {
         const int64_t row = b * p.T + t;
         if (tid < S) {
-          p.paths[(b * (p.T + 1) + t + 1) * S + tid] = zn_keep;
+          p.paths[(b * (p.T + 1) + t + 1) * S + tid] = zbuf[tid];
           p.means[row * S + tid] = obuf[tid];
         }
         if (tid < S * S) {  // S <= 16: one element of the S x S factor per thread
