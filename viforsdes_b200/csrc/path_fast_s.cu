@@ -373,6 +373,14 @@ __global__ void __launch_bounds__(kThr, 1) path_bwd_fasts_kernel(PathParams p) {
     __syncthreads();
     if (T > 0) mbar_wait(&sbar[row0 % NSR], (row0 / NSR) & 1);
 
+    // row / column of the Cholesky entry behind output row m = tid (constant per thread: not recomputed every step)
+    int out_r = tid, out_c = 0;
+    if (tid >= S && tid < NOUT) {
+      const int ti = tid - S;
+      out_r = 0;
+      while ((out_r + 1) * (out_r + 2) / 2 <= ti) ++out_r;
+      out_c = ti - out_r * (out_r + 1) / 2;
+    }
     for (int t = T - 1; t >= 0; --t) {
       const int par = t & 1;
       const uint32_t n_cur = row0 + (uint32_t)(T - 1 - t);
@@ -398,14 +406,7 @@ __global__ void __launch_bounds__(kThr, 1) path_bwd_fasts_kernel(PathParams p) {
       // ---- cotangent of the output projection, one row per thread (kernels/backward.py:300-334); the thread
       // folds the pending d z partial sums of step t+1 into the d z it needs (double-buffered by step parity)
       if (tid < NOUT) {
-        const int m = tid;
-        int r = m, c = 0;
-        if (m >= S) {
-          const int ti = m - S;
-          r = 0;
-          while ((r + 1) * (r + 2) / 2 <= ti) ++r;
-          c = ti - r * (r + 1) / 2;
-        }
+        const int m = tid, r = out_r, c = out_c;
         float dz = dzb[par * 16 + r] + sm[O_GP + r];
 #pragma unroll
         for (int w = 0; w < 8; ++w) dz += redz[w * 16 + r];
@@ -435,10 +436,16 @@ __global__ void __launch_bounds__(kThr, 1) path_bwd_fasts_kernel(PathParams p) {
       // dh of the top layer: W_out^T d_out, rows m = ks, ks + 4, ... per lane
       float dh;
       {
-        float a = 0.f;
+        float a0 = 0.f, a1 = 0.f;  // two chains, unrolled: the loop is on the step's critical path
         const float* wc = woT + (unit_ok ? i : 0);
-        for (int m = ks; m < NOUT; m += kKS) a = fmaf(wc[m * kWoPitch], doutb[m], a);
-        dh = dhc[NL - 1] + ks_allreduce4(a);
+        int m = ks;
+#pragma unroll 2
+        for (; m + kKS < NOUT; m += 2 * kKS) {
+          a0 = fmaf(wc[m * kWoPitch], doutb[m], a0);
+          a1 = fmaf(wc[(m + kKS) * kWoPitch], doutb[m + kKS], a1);
+        }
+        if (m < NOUT) a0 = fmaf(wc[m * kWoPitch], doutb[m], a0);
+        dh = dhc[NL - 1] + ks_allreduce4(a0 + a1);
       }
 #pragma unroll
       for (int k = NL - 1; k >= 0; --k) {
