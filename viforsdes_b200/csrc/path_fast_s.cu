@@ -166,12 +166,16 @@ __global__ void __launch_bounds__(kThr, 1) path_fwd_fasts_kernel(PathParams p) {
         if (k == 0) {
           // lane ks adds the state columns s = ks, ks + 4, ...; the shuffle reduction below sums them
           float er = lead * (gi_cur[0] + gth[0]), eu = lead * (gi_cur[1] + gth[1]), en = lead * (gi_cur[2] + gth[2]);
-          for (int s = ks; s < S; s += kKS) {
-            const float zs = zbuf[s];
-            const float* wz = wz_s + s * kWzPitch + i;
-            er = fmaf(wz[0], zs, er);
-            eu = fmaf(wz[kHP], zs, eu);
-            en = fmaf(wz[2 * kHP], zs, en);
+#pragma unroll
+          for (int q = 0; q < VISDE_MAX_STATE / kKS; ++q) {  // predicated and unrolled: the loads of all terms overlap
+            const int s = ks + kKS * q;
+            if (s < S) {
+              const float zs = zbuf[s];
+              const float* wz = wz_s + s * kWzPitch + i;
+              er = fmaf(wz[0], zs, er);
+              eu = fmaf(wz[kHP], zs, eu);
+              en = fmaf(wz[2 * kHP], zs, en);
+            }
           }
           pr = er + acc_hh[0][0];
           pu = eu + acc_hh[0][1];
@@ -211,12 +215,15 @@ __global__ void __launch_bounds__(kThr, 1) path_fwd_fasts_kernel(PathParams p) {
         for (int g = 0; g < 3; ++g) acc_hh[k][g] = dot16(whh[k][g], hs);
       }
       // ---- output projection: lane group i takes rows i, i + 64, ...
-      for (int ps = 0; ps < npass; ++ps) {
-        const int m = ps * kHP + i;
-        float2 ws[kSL / 2];
-        load_slice16(wout_s + (int64_t)m * kHB + ks * kSLP, ws);
-        const float v = ks_allreduce4(dot16(ws, hs));
-        if (ks == 0 && m < NOUT) obuf[m] = v + bout_s[m];
+#pragma unroll
+      for (int ps = 0; ps < 3; ++ps) {  // n_out <= 152 = 3 passes of 64 rows; unrolled so that the passes overlap
+        if (ps < npass) {
+          const int m = ps * kHP + i;
+          float2 ws[kSL / 2];
+          load_slice16(wout_s + m * kHB + ks * kSLP, ws);
+          const float v = ks_allreduce4(dot16(ws, hs));
+          if (ks == 0 && m < NOUT) obuf[m] = v + bout_s[m];
+        }
       }
       __syncthreads();
       // ---- reparameterised Euler-Maruyama update: one state dimension per thread computes z_{t+1} (the only part on
