@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(kThr, 1) path_bwd_fasts_kernel(PathParams p) {
   extern __shared__ __align__(16) float smem_bs[];
   float* dgb = smem_bs;                                   // [2][NL][4][kHB]
   float* sring = dgb + 2 * NL * kDgSlots * kHB;           // [4][NL * 5 * kHP]
-  float* small = sring + 4 * NL * kStashSlots * kHP;      // [3][SMALL]
-  float* woT = small + 3 * ((SMALL + 3) / 4 * 4);         // [NOUT][kWoPitch]  W_out[m][i]
+  float* small = sring + 4 * NL * kStashSlots * kHP;      // [4][SMALL]: 3 rows live; 4 slots so that the slot index is a mask
+  float* woT = small + 4 * ((SMALL + 3) / 4 * 4);         // [NOUT][kWoPitch]  W_out[m][i]
   float* wzr = woT + NOUT * kWoPitch;                     // [3 * kHP][16]     W_ih_l0[g*H+i][s] at [(g*64+i)*16 + s]
   float* doutb = wzr + 3 * kHP * 16;                      // [NOUT]
   float* dzb = doutb + ((NOUT + 3) / 4 * 4);              // [2][16]
@@ -348,23 +348,32 @@ __global__ void __launch_bounds__(kThr, 1) path_bwd_fasts_kernel(PathParams p) {
     float* dg_p = p.dg + (b * p.T + (T - 1)) * (int64_t)(NL * kDgSlots * H) + ks * H + (unit_ok ? i : 0);
 
     // loader threads: element j (and j + kThr) of the small row of step r
-    auto small_src = [&](int j, int r) -> float {
-      if (j < O_GM) return p.g_paths[(b * (p.T + 1) + r + 1) * S + j];
-      if (j < O_EPS) return p.g_means[(b * p.T + r) * S + (j - O_GM)];
-      if (j < O_RAW) return p.eps[(b * p.T + r) * S + (j - O_EPS)];
-      if (j < O_GL) { const int d = j - O_RAW; return p.raw[(b * p.T + r) * NTRIL + d * (d + 1) / 2 + d]; }
-      return p.g_chol[(b * p.T + r) * S * S + (j - O_GL)];
+    // loader threads: element j (and j + kThr) of the small row of step r sits at base[j] + r * stride[j]; the pointer
+    // and the stride are formed once per trajectory, the time loop only steps the pointer back by one row
+    auto small_ptr = [&](int j, int64_t* stride) -> const float* {
+      if (j < O_GM) { *stride = S; return p.g_paths + (b * (p.T + 1) + 1) * S + j; }
+      if (j < O_EPS) { *stride = S; return p.g_means + b * p.T * S + (j - O_GM); }
+      if (j < O_RAW) { *stride = S; return p.eps + b * p.T * S + (j - O_EPS); }
+      if (j < O_GL) { const int d = j - O_RAW; *stride = NTRIL; return p.raw + b * p.T * NTRIL + d * (d + 1) / 2 + d; }
+      *stride = S * S;
+      return p.g_chol + b * p.T * S * S + (j - O_GL);
     };
     float pend0 = 0.f, pend1 = 0.f;
+    const float *src0 = nullptr, *src1 = nullptr;
+    int64_t dec0 = 0, dec1 = 0;
     if (tid < SMALL) {
-      if (T >= 1) small[((T - 1) % 3) * SMALLP + tid] = small_src(tid, T - 1);
-      if (T >= 2) small[((T - 2) % 3) * SMALLP + tid] = small_src(tid, T - 2);
-      if (T >= 3) pend0 = small_src(tid, T - 3);
+      src0 = small_ptr(tid, &dec0);
+      if (T >= 1) small[((T - 1) & 3) * SMALLP + tid] = src0[(int64_t)(T - 1) * dec0];
+      if (T >= 2) small[((T - 2) & 3) * SMALLP + tid] = src0[(int64_t)(T - 2) * dec0];
+      if (T >= 3) pend0 = src0[(int64_t)(T - 3) * dec0];
+      src0 += (int64_t)(T - 4) * dec0;  // next row to fetch (guarded by t >= 3 below)
     }
     if (tid + kThr < SMALL) {
-      if (T >= 1) small[((T - 1) % 3) * SMALLP + tid + kThr] = small_src(tid + kThr, T - 1);
-      if (T >= 2) small[((T - 2) % 3) * SMALLP + tid + kThr] = small_src(tid + kThr, T - 2);
-      if (T >= 3) pend1 = small_src(tid + kThr, T - 3);
+      src1 = small_ptr(tid + kThr, &dec1);
+      if (T >= 1) small[((T - 1) & 3) * SMALLP + tid + kThr] = src1[(int64_t)(T - 1) * dec1];
+      if (T >= 2) small[((T - 2) & 3) * SMALLP + tid + kThr] = src1[(int64_t)(T - 2) * dec1];
+      if (T >= 3) pend1 = src1[(int64_t)(T - 3) * dec1];
+      src1 += (int64_t)(T - 4) * dec1;
     }
     if (tid < 32) dzb[tid] = 0.f;
     if (tid < 128) redz[tid] = 0.f;
@@ -399,15 +408,17 @@ __global__ void __launch_bounds__(kThr, 1) path_bwd_fasts_kernel(PathParams p) {
         bulk_load_1d(&sring[(n % NSR) * sring_pitch], st_b + (int64_t)(t - 3) * srow, row_bytes, &sbar[n % NSR]);
       }
       if (tid < SMALL) {
-        if (t >= 2) small[((t - 2) % 3) * SMALLP + tid] = pend0;
-        if (t >= 3) pend0 = small_src(tid, t - 3);
+        if (t >= 2) small[((t - 2) & 3) * SMALLP + tid] = pend0;
+        if (t >= 3) pend0 = *src0;
+        src0 -= dec0;
       }
       if (tid + kThr < SMALL) {
-        if (t >= 2) small[((t - 2) % 3) * SMALLP + tid + kThr] = pend1;
-        if (t >= 3) pend1 = small_src(tid + kThr, t - 3);
+        if (t >= 2) small[((t - 2) & 3) * SMALLP + tid + kThr] = pend1;
+        if (t >= 3) pend1 = *src1;
+        src1 -= dec1;
       }
       if (t >= 1) mbar_wait(&sbar[(n_cur + 1) % NSR], ((n_cur + 1) / NSR) & 1);
-      const float* sm = small + (t % 3) * SMALLP;
+      const float* sm = small + (t & 3) * SMALLP;
       __syncthreads();  // the d z partial sums of step t+1 (redz) are complete
 
       // ---- cotangent of the output projection, one row per thread (kernels/backward.py:300-334); the thread
@@ -556,7 +567,7 @@ size_t fasts_fwd_smem(const PathParams& p) {
 }
 size_t fasts_bwd_smem(const PathParams& p) {
   const int SMALL = 4 * p.S + p.S * p.S, SMALLP = (SMALL + 3) / 4 * 4;
-  return sizeof(float) * ((size_t)2 * p.NL * kDgSlots * kHB + (size_t)4 * p.NL * kStashSlots * kHP + 3 * (size_t)SMALLP +
+  return sizeof(float) * ((size_t)2 * p.NL * kDgSlots * kHB + (size_t)4 * p.NL * kStashSlots * kHP + 4 * (size_t)SMALLP +
                           (size_t)p.n_out * kWoPitch + 3 * kHP * 16 + ((size_t)p.n_out + 3) / 4 * 4 + 32 + 128 + 8);
 }
 
