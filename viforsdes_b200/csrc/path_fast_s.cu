@@ -145,6 +145,12 @@ __global__ void __launch_bounds__(kThr, 1) path_fwd_fasts_kernel(PathParams p) {
     }
     const bool st_on = p.stash != nullptr && unit_ok;
     float* st_lane = p.stash ? p.stash + b * p.T * (int64_t)(NL * kStashSlots * H) + ks * H + (unit_ok ? i : 0) : nullptr;
+    // output pointers of this thread (one element per array per step), advanced by one row per step
+    float* paths_o = p.paths + (b * (p.T + 1) + 1) * S + (tid < S ? tid : 0);
+    float* means_o = p.means + b * p.T * S + (tid < S ? tid : 0);
+    float* chol_o = p.chol + b * p.T * S * S + (tid < S * S ? tid : 0);
+    float* raw_o = p.raw ? p.raw + b * p.T * NTRIL + (tid < NTRIL ? tid : 0) : nullptr;
+    const int chol_r = tid / S, chol_c = tid % S;
     __syncthreads();  // zbuf / epsbuf of this trajectory visible
 
     for (int64_t t = 0; t < p.T; ++t) {
@@ -247,21 +253,23 @@ __global__ void __launch_bounds__(kThr, 1) path_fwd_fasts_kernel(PathParams p) {
       }
       __syncthreads();
       {
-        const int64_t row = b * p.T + t;
         if (tid < S) {
-          p.paths[(b * (p.T + 1) + t + 1) * S + tid] = zbuf[tid];
-          p.means[row * S + tid] = obuf[tid];
+          *paths_o = zbuf[tid];
+          *means_o = obuf[tid];
         }
         if (tid < S * S) {  // S <= 16: one element of the S x S factor per thread
-          const int r = tid / S, c = tid % S;
           float L = 0.f;
-          if (c <= r) {
-            const float raw = obuf[S + r * (r + 1) / 2 + c];
-            L = (c == r) ? fmaxf(raw, VISDE_DIAG_MIN) : raw;
+          if (chol_c <= chol_r) {
+            const float raw = obuf[S + chol_r * (chol_r + 1) / 2 + chol_c];
+            L = (chol_c == chol_r) ? fmaxf(raw, VISDE_DIAG_MIN) : raw;
           }
-          p.chol[row * S * S + tid] = L;
+          *chol_o = L;
         }
-        if (p.raw && tid < NTRIL) p.raw[row * NTRIL + tid] = obuf[S + tid];
+        if (raw_o && tid < NTRIL) *raw_o = obuf[S + tid];
+        paths_o += S;
+        means_o += S;
+        chol_o += S * S;
+        if (raw_o) raw_o += NTRIL;
       }
       if (st_lane) st_lane += NL * kStashSlots * H;
 #pragma unroll
