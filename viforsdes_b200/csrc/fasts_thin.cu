@@ -197,8 +197,13 @@ int launch_fasts_thin_grads(const PathParams& p, const visde_weight_grads* gw, f
     default: kern = fasts_thin_kernel<10>; break;
   }
   const size_t smem2 = sizeof(float) * 2 * kThinRows * a.pitch;
-  // per device and per instantiation: opting in to > 48 KB is idempotent and cheap next to the launch
-  VISDE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+  static DeviceOnce attr_once[11];  // per instantiation and per device (not repeated per launch: legal under stream capture)
+  int attr_dev = 0;
+  DeviceOnce& once = attr_once[rbq < 2 ? 2 : rbq > 10 ? 10 : rbq];
+  if (once.needed(&attr_dev)) {
+    VISDE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    once.done(attr_dev);
+  }
   kern<<<ncta, kThinThreads, smem2, st>>>(a);
   VISDE_CUDA_CHECK(cudaGetLastError());
   ThinReduceArgs r{partials, ncta, a.rec, p.S, p.H, a.G, p.n_out, a.ld0, gw->w_ih[0], gw->out_w, gw->out_b};
