@@ -6,7 +6,8 @@ buffer is at the same time the NCCL all-reduce bucket (``dist.allreduce_mean_(fl
 their own learning rate (training_context.py:97-102: ``learning_rate`` / ``sde_param_lr``) are contiguous segments."""
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Sequence
+from contextlib import contextmanager
+from typing import Dict, Iterable, Iterator, List, Optional, Sequence
 
 import torch
 from torch import Tensor, nn
@@ -87,6 +88,35 @@ class FusedAdamWEma:
                     _ptr(self.ema[sl]) if self.ema is not None else None, lr, self.betas[0], self.betas[1], self.eps,
                     self.wd, self.step_count, self.max_norm if clip else 0.0, _ptr(self.sqnorm) if clip else None,
                     _ptr(inv_scale), self.ema_decay if self.ema_decay is not None else 0.0, st))
+
+    @contextmanager
+    def ema_applied(self) -> Iterator[None]:
+        """``ExponentialMovingAverage.apply`` (exponential_moving_average.py:30-42): run the body with the shadow weights in
+        place of the parameters (posterior sampling), then restore them.  Two flat copies instead of 2 x #tensors."""
+        if self.ema is None:
+            raise RuntimeError("this optimiser keeps no EMA shadow (ema_decay=None)")
+        backup = self.flat.data.clone()
+        with torch.no_grad():
+            self.flat.data.copy_(self.ema)
+        try:
+            yield
+        finally:
+            with torch.no_grad():
+                self.flat.data.copy_(backup)
+
+    def state_dict(self) -> Dict[str, object]:
+        """Checkpoint / resume: moments, shadow and step count (parameters live in the module's own state_dict)."""
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "ema": None if self.ema is None else self.ema.clone(), "step": self.step_count}
+
+    def load_state_dict(self, state: Dict[str, object]) -> None:
+        if state["exp_avg"].numel() != self.exp_avg.numel():
+            raise ValueError("optimizer state does not match the flat parameter buffer")
+        self.exp_avg.copy_(state["exp_avg"])
+        self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        if self.ema is not None and state.get("ema") is not None:
+            self.ema.copy_(state["ema"])
+        self.step_count = int(state["step"])
 
     def ema_views(self) -> List[Tensor]:
         """EMA shadow tensors shaped like the parameters (``ExponentialMovingAverage.shadow`` values, in order)."""
