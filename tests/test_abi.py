@@ -196,3 +196,17 @@ def test_device_adam_matches_torch_adam_and_skips():
     assert torch.allclose(mine.detach(), ref.detach(), rtol=1e-5, atol=1e-7)
     with pytest.raises(ValueError):
         PretrainConfig(n_iterations=0)
+
+
+def test_prototype_arity_matches_header():
+    """Every ctypes prototype has exactly as many arguments as the C declaration in include/visde.h (ABI drift guard)."""
+    from viforsdes_b200 import _lib
+
+    text = (ROOT / "include" / "visde.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    decls = dict(re.findall(r"\b(visde_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text))
+    assert set(decls) == set(_lib.PROTOTYPES)
+    for name, params in decls.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib.PROTOTYPES[name][1]), f"{name}: header declares {n} parameters, ctypes binds {len(_lib.PROTOTYPES[name][1])}"
