@@ -139,6 +139,16 @@ typedef struct {
 int visde_version(void);
 const char* visde_last_error(void);
 
+/* Which kernel family visde_path_fwd (backward = 0) / visde_path_bwd (backward = 1) runs the recurrence with for these dims
+ * on the current device, assuming a tcgen05-eligible context (fp32, 16-byte aligned): introspection for logs and tests, no
+ * launch.  AUTO decides per direction: one trajectory per CTA below one wave of SMs, 4- / 8-trajectory tiles by a measured
+ * waves x cost model, the tensor-core recurrence from B >= 3 072, the wide-state variant for S > 4.  Negative on bad dims. */
+enum {
+  VISDE_FAMILY_GENERIC = 0, VISDE_FAMILY_FAST = 1, VISDE_FAMILY_TILED4 = 2, VISDE_FAMILY_TILED8 = 3, VISDE_FAMILY_TC = 4,
+  VISDE_FAMILY_FAST_S = 5
+};
+int visde_recurrence_family(const visde_dims* d, int backward);
+
 /* bytes of the activation stash written by visde_path_fwd (save != 0) and read by _bwd */
 size_t visde_stash_bytes(const visde_dims* d);
 /* scratch bytes for visde_path_fwd (backward=0) / visde_path_bwd (backward=1) */

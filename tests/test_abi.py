@@ -210,3 +210,27 @@ def test_prototype_arity_matches_header():
         params = params.strip()
         n = 0 if params in ("", "void") else params.count(",") + 1
         assert n == len(_lib.PROTOTYPES[name][1]), f"{name}: header declares {n} parameters, ctypes binds {len(_lib.PROTOTYPES[name][1])}"
+
+
+def test_auto_family_selection_table(lib):
+    """visde_recurrence_family pins what AUTO picks (148 SMs: the default when no device is present, and a B200's count):
+    the measured waves x cost model of tiled_batch_tile (profiles/r1_ou_batch_sweep.md) and the family boundaries."""
+    from viforsdes_b200 import _lib as L
+
+    def fam(B, back, S=1, H=64, NL=2, Cd=256, variant=L.VARIANT_AUTO, T=100):
+        d = L.Dims(B, T, S, Cd, 3, H, NL, variant)
+        return lib.visde_recurrence_family(C.byref(d), back)
+
+    F, T4, T8, TC, FS, G = L.FAMILY_FAST, L.FAMILY_TILED4, L.FAMILY_TILED8, L.FAMILY_TC, L.FAMILY_FAST_S, L.FAMILY_GENERIC
+    #            B: (forward, backward)
+    table = {128: (F, F), 148: (F, F), 200: (F, F), 296: (F, F), 444: (T4, F), 592: (T4, T4), 740: (T8, F),
+             1024: (T8, T8), 1184: (T8, T8), 2048: (T8, T8), 3071: (T8, T8), 3072: (TC, TC), 65536: (TC, TC)}
+    for B, (fw, bw) in table.items():
+        assert (fam(B, 0), fam(B, 1)) == (fw, bw), f"B={B}: {(fam(B, 0), fam(B, 1))}"
+    assert fam(8192, 0, S=10) == FS and fam(8192, 1, S=10) == FS        # wide state: BASELINE config 5
+    assert fam(8192, 0, H=128) == G and fam(128, 1, NL=3) == G          # outside the register-resident shapes
+    assert fam(8192, 0, Cd=64) == T8                                      # no tcgen05 K0 for this context width: no TC recurrence
+    assert fam(8192, 0, variant=L.VARIANT_FAST) == F and fam(37, 1, variant=L.VARIANT_TILED) == T4
+    assert fam(601, 0, variant=L.VARIANT_TILED) == T8 and fam(130, 0, variant=L.VARIANT_TC, Cd=128) == TC
+    assert fam(8192, 0, variant=L.VARIANT_AUTO | 0x100) == T8            # VISDE_FLAG_NO_TENSOR_CORES
+    assert fam(1, 0, NL=5) == L.EINVAL

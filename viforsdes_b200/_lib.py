@@ -15,6 +15,7 @@ F32, BF16 = 0, 1
 SDE_GENERIC, SDE_OU, SDE_LV = 0, 1, 2
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_FAST, VARIANT_TILED, VARIANT_TC = 0, 1, 2, 3, 4
 OK, EINVAL, ECUDA, EWORKSPACE = 0, -1, -2, -3
+FAMILY_GENERIC, FAMILY_FAST, FAMILY_TILED4, FAMILY_TILED8, FAMILY_TC, FAMILY_FAST_S = range(6)
 STAGES = ("K0_ctx_gemm", "K1_path_fwd", "K5_elbo_fwd", "K6_elbo_bwd", "K2_path_bwd", "K3_grad_ctx", "K4_wgrad")
 
 _fp = C.c_void_p
@@ -43,6 +44,7 @@ class Obs(C.Structure):
 PROTOTYPES = {
     "visde_version": (C.c_int, []),
     "visde_last_error": (C.c_char_p, []),
+    "visde_recurrence_family": (C.c_int, [C.POINTER(Dims), C.c_int]),
     "visde_stash_bytes": (C.c_size_t, [C.POINTER(Dims)]),
     "visde_workspace_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int]),
     "visde_path_fwd": (C.c_int, [C.POINTER(Dims), C.c_float, _fp, C.POINTER(CtxView), _fp, _fp, C.POINTER(Weights),

@@ -261,6 +261,26 @@ size_t visde_workspace_bytes(const visde_dims* d, int backward) {
   return bwd_ws(d).total + 256;
 }
 
+int visde_recurrence_family(const visde_dims* d, int backward) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  PathParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = d->B; p.T = d->T; p.S = d->S; p.C = d->C; p.P = d->P; p.H = d->H; p.NL = d->NL;
+  p.n_tril = d->S * (d->S + 1) / 2;
+  p.n_out = d->S + p.n_tril;
+  // the same predicates, in the same order, as visde_path_fwd / visde_path_bwd below
+  if (d->T > 0 && tc_rec_possible(d) && tc_rec_supported(p)) return VISDE_FAMILY_TC;
+  if (use_fasts(d, p)) return VISDE_FAMILY_FAST_S;
+  if (use_fast(d, p)) {
+    const int fam = d->variant & 0xff;
+    const bool pinned = fam == VISDE_VARIANT_FAST || fam == VISDE_VARIANT_TC || (backward && d->T == 0);
+    const int nb = pinned ? 0 : tiled_batch_tile(d->B, fam == VISDE_VARIANT_TILED, backward != 0);
+    return nb == 8 ? VISDE_FAMILY_TILED8 : nb == 4 ? VISDE_FAMILY_TILED4 : VISDE_FAMILY_FAST;
+  }
+  return VISDE_FAMILY_GENERIC;
+}
+
 int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_ctx_view* ctx,
                    const float* theta, const float* eps, const visde_weights* w, float* paths,
                    float* means, float* chol, void* stash, void* workspace, size_t workspace_bytes,
