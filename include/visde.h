@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define VISDE_VERSION 1
+#define VISDE_VERSION 2
 #define VISDE_MAX_LAYERS 4
 #define VISDE_MAX_STATE 16
 #define VISDE_MAX_HIDDEN 256
@@ -201,10 +201,25 @@ int visde_profile_end(double* ms_per_stage, int* launches_per_stage);
 /* ---- host-buffer session: one ELBO iteration of the path through HOST memory ------------- */
 typedef struct visde_session visde_session;
 
-/* Allocates device buffers, pinned staging and a stream for dims d (context is a dense
- * [B,T+1,C] fp32 host tensor of which rows 0..T-1 are used). */
+/* Hooks of a user-defined SDE (sde_kind GENERIC): the reference calls the user's Python drift / diffusion on the
+ * flattened state-space path (inference/evidence_lower_bound.py:37-40, core/sde.py:8-15) and differentiates them with
+ * autograd.  The session owns the DEVICE tensors; the caller evaluates on them, on the stream it is handed, and returns
+ * 0 (non-zero aborts the iteration with VISDE_EINVAL).
+ *   eval: x [B*T,S] (x_t = to_state(z_t), t < T), theta [B,P] -> drift [B*T,S], diffusion [B*T,S,S] (lower-triangular)
+ *   vjp : cotangents g_drift, g_diffusion -> g_x [B*T,S], g_theta [B,P] (both fully overwritten; sum over t for theta) */
+typedef struct {
+  int (*eval)(void* user, const float* x, const float* theta, float* drift, float* diffusion, void* stream);
+  int (*vjp)(void* user, const float* x, const float* theta, const float* g_drift, const float* g_diffusion, float* g_x,
+             float* g_theta, void* stream);
+  void* user;
+} visde_user_sde;
+
+/* Allocates device buffers and two streams for dims d.  The host context is a dense [B,T+1,C] tensor of ctx_dtype
+ * (VISDE_F32, or VISDE_BF16 = what the reference's autocast encoder emits, inference/trainer.py:171-175; halves the
+ * dominant H2D term) of which rows 0..T-1 are used; grad_context comes back in the same dtype.  user_sde: hooks for
+ * sde_kind GENERIC (copied), NULL otherwise. */
 int visde_session_create(const visde_dims* d, int sde_kind, uint32_t positive_mask, int32_t n_obs,
-                         int32_t obs_dim, visde_session** out);
+                         int32_t obs_dim, int32_t ctx_dtype, const visde_user_sde* user_sde, visde_session** out);
 void visde_session_destroy(visde_session* s);
 /* bytes copied host->device / device->host by one visde_session_step */
 size_t visde_session_h2d_bytes(const visde_session* s);
@@ -212,14 +227,14 @@ size_t visde_session_d2h_bytes(const visde_session* s);
 /* number of kernels one visde_session_step launches */
 int visde_session_launches(const visde_session* s);
 
-/* HOST in: x0, context [B,T+1,C], theta, eps, weights (host pointers in visde_weights),
+/* HOST in: x0, context [B,T+1,C] (the session's ctx_dtype), theta, eps, weights (host pointers in visde_weights),
  * obs (host pointers).  HOST out: terms [B,4], grad_x0 [B,S], grad_theta [B,P], weight grads
  * (host pointers), and grad_context [B,T+1,C] if non-NULL (row T zero).  The loss is
  * -(mean_b(obs + sde - gen + jac)); its cotangent 1/B is applied inside. Synchronous. */
-int visde_session_step(visde_session* s, float dt, const float* x0, const float* context,
+int visde_session_step(visde_session* s, float dt, const float* x0, const void* context,
                        const float* theta, const float* eps, const visde_weights* w_host,
                        const visde_obs* obs_host, float* terms, float* grad_x0, float* grad_theta,
-                       const visde_weight_grads* gw_host, float* grad_context);
+                       const visde_weight_grads* gw_host, void* grad_context);
 
 /* Pipelined form of visde_session_step (same arguments): enqueue the H2D copies on the session's
  * copy stream and the kernels + D2H on its compute stream, and return without waiting.  The session
@@ -229,10 +244,10 @@ int visde_session_step(visde_session* s, float dt, const float* x0, const float*
  * matching visde_session_wait, which blocks until the OLDEST in-flight iteration's outputs are in
  * host memory.  Pinned host memory is required for the overlap (pageable memory degrades to
  * synchronous copies).  visde_session_step == submit + wait. */
-int visde_session_submit(visde_session* s, float dt, const float* x0, const float* context,
+int visde_session_submit(visde_session* s, float dt, const float* x0, const void* context,
                          const float* theta, const float* eps, const visde_weights* w_host,
                          const visde_obs* obs_host, float* terms, float* grad_x0, float* grad_theta,
-                         const visde_weight_grads* gw_host, float* grad_context);
+                         const visde_weight_grads* gw_host, void* grad_context);
 int visde_session_wait(visde_session* s);
 
 /* ---- callers either side of the path ----------------------------------------- */

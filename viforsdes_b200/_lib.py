@@ -10,12 +10,14 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libvisde.so"
 MAX_LAYERS = 4
+VERSION = 2  # include/visde.h VISDE_VERSION
 
 F32, BF16 = 0, 1
 SDE_GENERIC, SDE_OU, SDE_LV = 0, 1, 2
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_FAST, VARIANT_TILED, VARIANT_TC = 0, 1, 2, 3, 4
 OK, EINVAL, ECUDA, EWORKSPACE = 0, -1, -2, -3
 FAMILY_GENERIC, FAMILY_FAST, FAMILY_TILED4, FAMILY_TILED8, FAMILY_TC, FAMILY_FAST_S = range(6)
+FAMILY_NAMES = ("generic", "fast", "tiled4", "tiled8", "tc", "fast_s")
 STAGES = ("K0_ctx_gemm", "K1_path_fwd", "K5_elbo_fwd", "K6_elbo_bwd", "K2_path_bwd", "K3_grad_ctx", "K4_wgrad")
 
 _fp = C.c_void_p
@@ -33,6 +35,14 @@ class Weights(C.Structure):
 
 class CtxView(C.Structure):
     _fields_ = [("ptr", _fp), ("batch_stride", C.c_int64), ("time_stride", C.c_int64), ("dtype", C.c_int32)]
+
+
+SDE_EVAL_FN = C.CFUNCTYPE(C.c_int, _fp, _fp, _fp, _fp, _fp, _fp)
+SDE_VJP_FN = C.CFUNCTYPE(C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp)
+
+
+class UserSde(C.Structure):
+    _fields_ = [("eval", SDE_EVAL_FN), ("vjp", SDE_VJP_FN), ("user", _fp)]
 
 
 class Obs(C.Structure):
@@ -58,7 +68,8 @@ PROTOTYPES = {
                                  C.POINTER(Obs), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
     "visde_profile_begin": (C.c_int, [C.c_int]),
     "visde_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
-    "visde_session_create": (C.c_int, [C.POINTER(Dims), C.c_int, C.c_uint32, C.c_int32, C.c_int32, C.POINTER(_fp)]),
+    "visde_session_create": (C.c_int, [C.POINTER(Dims), C.c_int, C.c_uint32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.POINTER(UserSde), C.POINTER(_fp)]),
     "visde_session_destroy": (None, [_fp]),
     "visde_session_h2d_bytes": (C.c_size_t, [_fp]),
     "visde_session_d2h_bytes": (C.c_size_t, [_fp]),
@@ -106,7 +117,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.visde_version() != 1:
+        if lib.visde_version() != VERSION:
             raise RuntimeError("libvisde.so version mismatch; rebuild")
         _lib = lib
     return _lib

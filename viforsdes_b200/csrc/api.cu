@@ -239,6 +239,28 @@ __global__ void add_inplace_kernel(float* dst, const float* src, int64_t n) {
   if (i < n) dst[i] += src[i];
 }
 
+// user-SDE sessions: x[b,t,:] = to_state(z[b,t,:]) for t < T (inference/state_space.py:20-25; softplus threshold 20)
+__global__ void state_rows_kernel(const float* __restrict__ z, int64_t B, int64_t T, int S, uint32_t mask, float* __restrict__ x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * T * S) return;
+  const int s = (int)(i % S);
+  const int64_t bt = i / S, b = bt / T, t = bt % T;
+  const float v = z[(b * (T + 1) + t) * S + s];
+  x[i] = ((mask >> s) & 1u) ? (v > 20.f ? v : log1pf(expf(v))) : v;
+}
+// g_z[b,t,:] += g_x[b,t,:] * d to_state / dz for t < T (the chain the reference's autograd walks from drift / diffusion)
+__global__ void chain_state_grad_kernel(const float* __restrict__ z, const float* __restrict__ g_x, int64_t B, int64_t T, int S,
+                                        uint32_t mask, float* __restrict__ g_z) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * T * S) return;
+  const int s = (int)(i % S);
+  const int64_t bt = i / S, b = bt / T, t = bt % T;
+  const int64_t zi = (b * (T + 1) + t) * S + s;
+  const float v = z[zi];
+  const float d = ((mask >> s) & 1u) ? (v > 20.f ? 1.f : 1.f / (1.f + expf(-v))) : 1.f;
+  g_z[zi] += g_x[i] * d;
+}
+
 }  // namespace
 }  // namespace visde
 
@@ -717,7 +739,8 @@ int visde_profile_end(double* ms_per_stage, int* launches_per_stage) {
 // iteration i (compute stream): visde_session_submit / visde_session_wait.  Everything downstream
 // of the inputs (paths, stash, workspaces, gradients) exists once: the compute stream serialises it.
 struct visde_session_inputs {
-  float *x0, *ctx, *theta, *eps;
+  float *x0, *theta, *eps;
+  void* ctx;  // [B,T+1,C] in the session's context dtype
   visde_weights w;
   int32_t* obs_idx;
   float *obs_values, *obs_matrix;
@@ -737,13 +760,17 @@ struct visde_session {
   int sde_kind;
   uint32_t pos_mask;
   int n_obs, obs_dim;
+  int ctx_dtype;          // VISDE_F32 | VISDE_BF16: host context and grad_context element type
+  visde_user_sde user;    // sde_kind GENERIC: caller-evaluated drift / diffusion hooks
   cudaStream_t st, copy_st;
   std::vector<void*> allocs;
   visde_session_inputs in[2];
   uint64_t n_submitted, n_waited;
   // device buffers
   float *paths, *means, *chol, *terms, *g_terms;
-  float *g_z, *g_means, *g_chol, *g_theta_elbo, *grad_x0, *grad_theta, *grad_ctx;
+  float *g_z, *g_means, *g_chol, *g_theta_elbo, *grad_x0, *grad_theta;
+  void* grad_ctx;  // [B,T+1,C] in the context dtype
+  float *x_state, *drift, *diffusion, *g_drift, *g_diffusion, *g_x, *g_theta_sde;  // user-SDE sessions only
   void *stash, *ws_f, *ws_b;
   size_t ws_f_bytes, ws_b_bytes;
   visde_weight_grads gw;
@@ -763,6 +790,7 @@ int dev_alloc(visde_session* s, Tp** p, size_t bytes) {
   return VISDE_OK;
 }
 size_t w_ih_floats(const visde_dims& d, int k) { return (size_t)3 * d.H * (k ? d.H : d.S + d.C + d.P); }
+size_t ctx_elem_bytes(const visde_session* s) { return s->ctx_dtype == VISDE_BF16 ? 2 : 4; }
 
 int session_alloc(visde_session* s) {
   const visde_dims* d = &s->d;
@@ -772,7 +800,8 @@ int session_alloc(visde_session* s) {
 #define A_(ptr, n) if ((rc = dev_alloc(s, &(ptr), sizeof(float) * (n)))) return rc;
   for (int q = 0; q < 2; ++q) {
     visde_session_inputs& in = s->in[q];
-    A_(in.x0, B * S) A_(in.ctx, B * (T + 1) * C) A_(in.theta, B * P) A_(in.eps, B * T * S)
+    A_(in.x0, B * S) A_(in.theta, B * P) A_(in.eps, B * T * S)
+    if ((rc = dev_alloc(s, &in.ctx, ctx_elem_bytes(s) * B * (T + 1) * C))) return rc;
     A_(in.obs_values, (size_t)s->n_obs * s->obs_dim) A_(in.obs_matrix, (size_t)s->obs_dim * S)
     if ((rc = dev_alloc(s, &in.obs_idx, sizeof(int32_t) * s->n_obs))) return rc;
     for (int k = 0; k < d->NL; ++k) {
@@ -789,7 +818,12 @@ int session_alloc(visde_session* s) {
   }
   A_(s->paths, B * (T + 1) * S) A_(s->means, B * T * S) A_(s->chol, B * T * S * S) A_(s->terms, B * 4) A_(s->g_terms, B * 4)
   A_(s->g_z, B * (T + 1) * S) A_(s->g_means, B * T * S) A_(s->g_chol, B * T * S * S) A_(s->g_theta_elbo, B * P)
-  A_(s->grad_x0, B * S) A_(s->grad_theta, B * P) A_(s->grad_ctx, B * (T + 1) * C)
+  A_(s->grad_x0, B * S) A_(s->grad_theta, B * P)
+  if ((rc = dev_alloc(s, &s->grad_ctx, ctx_elem_bytes(s) * B * (T + 1) * C))) return rc;
+  if (s->sde_kind == VISDE_SDE_GENERIC) {
+    A_(s->x_state, B * T * S) A_(s->drift, B * T * S) A_(s->diffusion, B * T * S * S) A_(s->g_drift, B * T * S)
+    A_(s->g_diffusion, B * T * S * S) A_(s->g_x, B * T * S) A_(s->g_theta_sde, B * P)
+  }
   if ((rc = dev_alloc(s, &s->stash, visde_stash_bytes(d)))) return rc;
   s->ws_f_bytes = visde_workspace_bytes(d, 0);
   s->ws_b_bytes = visde_workspace_bytes(d, 1);
@@ -811,12 +845,15 @@ int session_alloc(visde_session* s) {
 extern "C" {
 
 int visde_session_create(const visde_dims* d, int sde_kind, uint32_t positive_mask, int32_t n_obs,
-                         int32_t obs_dim, visde_session** out) {
+                         int32_t obs_dim, int32_t ctx_dtype, const visde_user_sde* user_sde, visde_session** out) {
   int rc = check_dims(d);
   if (rc) return rc;
   VISDE_REQUIRE(out != nullptr, "out is NULL");
-  VISDE_REQUIRE(sde_kind == VISDE_SDE_OU || sde_kind == VISDE_SDE_LV,
-                "the host session supports the built-in OU / LV functors only");
+  VISDE_REQUIRE(sde_kind == VISDE_SDE_OU || sde_kind == VISDE_SDE_LV || sde_kind == VISDE_SDE_GENERIC,
+                "unknown sde_kind %d", sde_kind);
+  VISDE_REQUIRE(sde_kind != VISDE_SDE_GENERIC || (user_sde && user_sde->eval && user_sde->vjp),
+                "a user-SDE session needs the eval and vjp hooks (visde_user_sde)");
+  VISDE_REQUIRE(ctx_dtype == VISDE_F32 || ctx_dtype == VISDE_BF16, "context dtype must be VISDE_F32 or VISDE_BF16");
   VISDE_REQUIRE(d->B > 0 && d->T > 0, "session needs B > 0 and T > 0");
   VISDE_REQUIRE(n_obs >= 0 && obs_dim >= 0, "bad observation sizes");
   visde_session* s = new visde_session();
@@ -825,6 +862,8 @@ int visde_session_create(const visde_dims* d, int sde_kind, uint32_t positive_ma
   s->pos_mask = positive_mask;
   s->n_obs = n_obs;
   s->obs_dim = obs_dim;
+  s->ctx_dtype = ctx_dtype;
+  if (user_sde) s->user = *user_sde;
   const size_t B = d->B, T = d->T, S = d->S, C = d->C, P = d->P, H = d->H, G = 3 * H;
   const size_t n_out = S + S * (S + 1) / 2;
   if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess ||
@@ -840,10 +879,10 @@ int visde_session_create(const visde_dims* d, int sde_kind, uint32_t positive_ma
   size_t wfloats = n_out * H + n_out;
   for (int k = 0; k < d->NL; ++k) wfloats += w_ih_floats(*d, k) + G * H + 2 * G;
   // grad_ctx row T is never written by the kernels: zero it once
-  cudaMemsetAsync(s->grad_ctx, 0, sizeof(float) * B * (T + 1) * C, s->st);
+  cudaMemsetAsync(s->grad_ctx, 0, ctx_elem_bytes(s) * B * (T + 1) * C, s->st);
   cudaStreamSynchronize(s->st);
-  s->h2d = sizeof(float) * (B * S + B * (T + 1) * C + B * P + B * T * S + wfloats + (size_t)n_obs * obs_dim) +
-           sizeof(int32_t) * n_obs;
+  s->h2d = sizeof(float) * (B * S + B * P + B * T * S + wfloats + (size_t)n_obs * obs_dim) +
+           ctx_elem_bytes(s) * B * (T + 1) * C + sizeof(int32_t) * n_obs;
   s->d2h = sizeof(float) * (B * 4 + B * S + B * P + wfloats);
   // K0, K1, elbo fwd, cotangent fill, elbo bwd, K2, K3, grad_theta gemm, (2 NL + 1) x (tn + reduce), add
   s->launches = 8 + 2 * (2 * d->NL + 1) + 1;
@@ -876,31 +915,54 @@ static int session_enqueue(visde_session* s, visde_session_inputs& in, float dt,
   const visde_dims& d = s->d;
   const size_t B = d.B, T = d.T, C = d.C, P = d.P;
   const visde_obs& od = *od_p;
-  visde_ctx_view cv{in.ctx, (int64_t)((T + 1) * C), (int64_t)C, VISDE_F32};
-  visde_ctx_grad_view gv{s->grad_ctx, (int64_t)((T + 1) * C), (int64_t)C, VISDE_F32};
+  visde_ctx_view cv{in.ctx, (int64_t)((T + 1) * C), (int64_t)C, s->ctx_dtype};
+  visde_ctx_grad_view gv{s->grad_ctx, (int64_t)((T + 1) * C), (int64_t)C, s->ctx_dtype};
+  const bool generic = s->sde_kind == VISDE_SDE_GENERIC;
+  const int64_t n_x = (int64_t)B * T * d.S;
   int rc = visde_path_fwd(&d, dt, in.x0, &cv, in.theta, in.eps, &in.w, s->paths, s->means, s->chol, s->stash, s->ws_f,
                           s->ws_f_bytes, st);
   if (rc) return rc;
-  rc = visde_elbo_fwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, in.theta, nullptr, nullptr, &od,
+  if (generic) {
+    // evidence_lower_bound.py:31-40: x_t = to_state(z_t), then the caller's drift / diffusion on the [B*T, S] rows
+    state_rows_kernel<<<(unsigned)((n_x + 255) / 256), 256, 0, st>>>(s->paths, d.B, d.T, d.S, s->pos_mask, s->x_state);
+    VISDE_CUDA_CHECK(cudaGetLastError());
+    if (s->user.eval(s->user.user, s->x_state, in.theta, s->drift, s->diffusion, st) != 0) {
+      set_error("session: the user SDE eval hook failed");
+      return VISDE_EINVAL;
+    }
+  }
+  rc = visde_elbo_fwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, in.theta, s->drift, s->diffusion, &od,
                       s->terms, st);
   if (rc) return rc;
   fill_loss_cotangent_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(s->g_terms, (int64_t)B);
   VISDE_CUDA_CHECK(cudaGetLastError());
-  rc = visde_elbo_bwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, in.theta, nullptr, nullptr, &od,
-                      s->g_terms, s->g_z, s->g_means, s->g_chol, s->g_theta_elbo, nullptr, nullptr, st);
+  rc = visde_elbo_bwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, in.theta, s->drift, s->diffusion, &od,
+                      s->g_terms, s->g_z, s->g_means, s->g_chol, s->g_theta_elbo, s->g_drift, s->g_diffusion, st);
   if (rc) return rc;
+  if (generic) {
+    if (s->user.vjp(s->user.user, s->x_state, in.theta, s->g_drift, s->g_diffusion, s->g_x, s->g_theta_sde, st) != 0) {
+      set_error("session: the user SDE vjp hook failed");
+      return VISDE_EINVAL;
+    }
+    chain_state_grad_kernel<<<(unsigned)((n_x + 255) / 256), 256, 0, st>>>(s->paths, s->g_x, d.B, d.T, d.S, s->pos_mask, s->g_z);
+    VISDE_CUDA_CHECK(cudaGetLastError());
+  }
   rc = visde_path_bwd(&d, dt, s->g_z, s->g_means, s->g_chol, &cv, in.theta, in.eps, &in.w, s->paths, s->stash,
                       s->grad_x0, &gv, s->grad_theta, &s->gw, s->ws_b, s->ws_b_bytes, st);
   if (rc) return rc;
   add_inplace_kernel<<<(unsigned)((B * P + 255) / 256), 256, 0, st>>>(s->grad_theta, s->g_theta_elbo, (int64_t)(B * P));
   VISDE_CUDA_CHECK(cudaGetLastError());
+  if (generic) {
+    add_inplace_kernel<<<(unsigned)((B * P + 255) / 256), 256, 0, st>>>(s->grad_theta, s->g_theta_sde, (int64_t)(B * P));
+    VISDE_CUDA_CHECK(cudaGetLastError());
+  }
   return VISDE_OK;
 }
 
-int visde_session_submit(visde_session* s, float dt, const float* x0, const float* context,
+int visde_session_submit(visde_session* s, float dt, const float* x0, const void* context,
                          const float* theta, const float* eps, const visde_weights* w_host,
                          const visde_obs* obs_host, float* terms, float* grad_x0, float* grad_theta,
-                         const visde_weight_grads* gw_host, float* grad_context) {
+                         const visde_weight_grads* gw_host, void* grad_context) {
   VISDE_REQUIRE(s && x0 && context && theta && eps && w_host && obs_host && terms && grad_x0 && grad_theta && gw_host,
                 "session_submit: NULL argument");
   VISDE_REQUIRE(obs_host->n_obs == s->n_obs && obs_host->obs_dim == s->obs_dim, "session_submit: observation shape changed");
@@ -915,7 +977,7 @@ int visde_session_submit(visde_session* s, float dt, const float* x0, const floa
 #define H2D(dst, src, n) VISDE_CUDA_CHECK(cudaMemcpyAsync((void*)(dst), (src), sizeof(float) * (n), cudaMemcpyHostToDevice, cs))
 #define D2H(dst, src, n) VISDE_CUDA_CHECK(cudaMemcpyAsync((dst), (src), sizeof(float) * (n), cudaMemcpyDeviceToHost, st))
   H2D(in.x0, x0, B * S);
-  H2D(in.ctx, context, B * (T + 1) * C);
+  VISDE_CUDA_CHECK(cudaMemcpyAsync(in.ctx, context, ctx_elem_bytes(s) * B * (T + 1) * C, cudaMemcpyHostToDevice, cs));
   H2D(in.theta, theta, B * P);
   H2D(in.eps, eps, B * T * S);
   for (int k = 0; k < d.NL; ++k) {
@@ -948,7 +1010,7 @@ int visde_session_submit(visde_session* s, float dt, const float* x0, const floa
   }
   if (in.graph) {
     VISDE_CUDA_CHECK(cudaGraphLaunch(in.graph, st));
-  } else if (in.uses >= 1 && !g_prof_on) {
+  } else if (in.uses >= 1 && !g_prof_on && s->sde_kind != VISDE_SDE_GENERIC) {  // user hooks launch outside any capture
     cudaGraph_t g = nullptr;
     VISDE_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     rc = session_enqueue(s, in, dt, &od, st);
@@ -989,7 +1051,8 @@ int visde_session_submit(visde_session* s, float dt, const float* x0, const floa
   }
   D2H(gw_host->out_w, s->gw.out_w, n_out * H);
   D2H(gw_host->out_b, s->gw.out_b, n_out);
-  if (grad_context) D2H(grad_context, s->grad_ctx, B * (T + 1) * C);
+  if (grad_context)
+    VISDE_CUDA_CHECK(cudaMemcpyAsync(grad_context, s->grad_ctx, ctx_elem_bytes(s) * B * (T + 1) * C, cudaMemcpyDeviceToHost, st));
 #undef H2D
 #undef D2H
   VISDE_CUDA_CHECK(cudaEventRecord(in.done, st));
@@ -1005,10 +1068,10 @@ int visde_session_wait(visde_session* s) {
   return VISDE_OK;
 }
 
-int visde_session_step(visde_session* s, float dt, const float* x0, const float* context,
+int visde_session_step(visde_session* s, float dt, const float* x0, const void* context,
                        const float* theta, const float* eps, const visde_weights* w_host,
                        const visde_obs* obs_host, float* terms, float* grad_x0, float* grad_theta,
-                       const visde_weight_grads* gw_host, float* grad_context) {
+                       const visde_weight_grads* gw_host, void* grad_context) {
   VISDE_REQUIRE(s != nullptr, "session_step: NULL session");
   VISDE_REQUIRE(s->n_submitted == s->n_waited, "session_step: iterations still in flight; call visde_session_wait first");
   int rc = visde_session_submit(s, dt, x0, context, theta, eps, w_host, obs_host, terms, grad_x0, grad_theta, gw_host,

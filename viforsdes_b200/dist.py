@@ -104,6 +104,9 @@ class EmaSync:
     def sync(self) -> None:
         if not self.shadow:
             return
+        if len(self.shadow) == 1 and self.shadow[0].dtype == torch.float32 and self.shadow[0].is_contiguous():
+            allreduce_mean_(self.shadow[0], self.group)  # flat shadow (optim.FusedAdamWEma.ema): averaged in place
+            return
         flat = torch.cat([s.reshape(-1).to(torch.float32) for s in self.shadow])
         allreduce_mean_(flat, self.group)
         off = 0

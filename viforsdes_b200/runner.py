@@ -17,9 +17,12 @@ from viforsdes_b200.synthetic import Inputs
 class PathIteration:
     def __init__(self, inp: Inputs, device: torch.device | str = "cuda", variant: int = _lib.VARIANT_AUTO,
                  context_dtype: torch.dtype = torch.float32) -> None:
-        if inp.sde_kind == _lib.SDE_GENERIC:
-            raise ValueError("PathIteration covers the built-in OU / LV functors; user SDEs go through "
-                             "viforsdes_b200.elbo.compute_evidence_lower_bound")
+        # user SDEs (sde_kind GENERIC): drift / diffusion and their vector-Jacobian products are evaluated in PyTorch on the
+        # flattened [B*T, S] path between the kernels, as inference/evidence_lower_bound.py:37-40 does
+        self.generic = inp.sde_kind == _lib.SDE_GENERIC
+        if self.generic and inp.sde is None:
+            raise ValueError("sde_kind GENERIC needs the user SDE object (Inputs.sde)")
+        self.sde = inp.sde
         self.lib = _lib.load()
         dev = torch.device(device)
         self.dev = dev
@@ -59,6 +62,9 @@ class PathIteration:
         self.g_terms = torch.tensor([s, s, -s, s], **f).repeat(B, 1).contiguous()
         self.g_z, self.g_means, self.g_chol = torch.empty_like(self.paths), torch.empty_like(self.means), torch.empty_like(self.chol)
         self.g_theta_elbo = torch.empty(B, P, **f)
+        self.g_drift = torch.empty(B, T, S, **f) if self.generic else None
+        self.g_diffusion = torch.empty(B, T, S, S, **f) if self.generic else None
+        self.pos_dims = [s for s in range(S) if (inp.positive_mask >> s) & 1]
         self.grad_x0, self.grad_theta = torch.empty(B, S, **f), torch.empty(B, P, **f)
         self.grad_ctx = torch.zeros(B, T + 1, Cd, device=dev, dtype=context_dtype)
         u8 = dict(device=dev, dtype=torch.uint8)
@@ -94,41 +100,93 @@ class PathIteration:
         _lib.check(lib.visde_path_fwd(C.byref(d), self.dt, p(self.x0), C.byref(self.cv), p(self.theta), p(self.eps),
                                       C.byref(self.ws_struct), p(self.paths), p(self.means), p(self.chol), p(self.stash),
                                       p(self.ws_f), self.ws_f.numel(), st))
+        dr = df = None
+        if self.generic:
+            self._eval_user_sde()
+            dr, df = p(self._drift_c), p(self._diffusion_c)
         _lib.check(lib.visde_elbo_fwd(C.byref(d), self.dt, self.sde_kind, self.mask, p(self.paths), p(self.means),
-                                      p(self.chol), p(self.theta), None, None, C.byref(self.obs), p(self.terms), st))
+                                      p(self.chol), p(self.theta), dr, df, C.byref(self.obs), p(self.terms), st))
+
+    def _eval_user_sde(self) -> None:
+        """x_t = to_state(z_t) -> drift [B,T,S], diffusion [B,T,S,S] through the user's PyTorch callbacks, recorded for
+        the vector-Jacobian product of the backward (evidence_lower_bound.py:31-40)."""
+        B, T, S, P = self.B, self.T, self.S, self.P
+        z_t = self.paths[:, :-1]
+        x = z_t
+        if self.pos_dims:
+            x = z_t.clone()
+            x[..., self.pos_dims] = torch.nn.functional.softplus(z_t[..., self.pos_dims])
+        with torch.enable_grad():
+            self._x_leaf = x.reshape(B * T, S).detach().requires_grad_(True)
+            self._th_leaf = self.theta.detach().requires_grad_(True)
+            th_flat = self._th_leaf[:, None, :].expand(B, T, P).reshape(B * T, P)
+            self._drift = self.sde.drift(self._x_leaf, th_flat)
+            self._diffusion = self.sde.diffusion(self._x_leaf, th_flat)
+        self._drift_c = self._drift.detach().to(torch.float32).reshape(B, T, S).contiguous()
+        self._diffusion_c = self._diffusion.detach().to(torch.float32).reshape(B, T, S, S).contiguous()
+
+    def _user_sde_vjp(self) -> None:
+        """g_drift / g_diffusion -> g_x (chained into g_z through the state transform) and g_theta."""
+        B, T, S = self.B, self.T, self.S
+        outs, gouts = [], []
+        for o, g in ((self._drift, self.g_drift), (self._diffusion, self.g_diffusion)):
+            if o.requires_grad:
+                outs.append(o)
+                gouts.append(g.reshape(o.shape).to(o.dtype))
+        gx = gth = None
+        if outs:
+            gx, gth = torch.autograd.grad(outs, [self._x_leaf, self._th_leaf], gouts, allow_unused=True)
+        if gx is not None:
+            gx = gx.reshape(B, T, S)
+            if self.pos_dims:
+                gx = gx.clone()
+                gx[..., self.pos_dims] *= torch.sigmoid(self.paths[:, :-1][..., self.pos_dims])
+            self.g_z[:, :T].add_(gx)
+        self._g_theta_sde = gth
 
     def backward(self) -> None:
         lib, d = self.lib, self.dims
         st = torch.cuda.current_stream(self.dev).cuda_stream
         p = lambda t: t.data_ptr()  # noqa: E731
+        dr, df, gdr, gdf = ((p(self._drift_c), p(self._diffusion_c), p(self.g_drift), p(self.g_diffusion))
+                            if self.generic else (None, None, None, None))
         _lib.check(lib.visde_elbo_bwd(C.byref(d), self.dt, self.sde_kind, self.mask, p(self.paths), p(self.means),
-                                      p(self.chol), p(self.theta), None, None, C.byref(self.obs), p(self.g_terms),
-                                      p(self.g_z), p(self.g_means), p(self.g_chol), p(self.g_theta_elbo), None, None, st))
+                                      p(self.chol), p(self.theta), dr, df, C.byref(self.obs), p(self.g_terms),
+                                      p(self.g_z), p(self.g_means), p(self.g_chol), p(self.g_theta_elbo), gdr, gdf, st))
+        if self.generic:
+            self._user_sde_vjp()
         _lib.check(lib.visde_path_bwd(C.byref(d), self.dt, p(self.g_z), p(self.g_means), p(self.g_chol),
                                       C.byref(self.cv), p(self.theta), p(self.eps), C.byref(self.ws_struct),
                                       p(self.paths), p(self.stash), p(self.grad_x0), C.byref(self.gv), p(self.grad_theta),
                                       C.byref(self.gw_struct), p(self.ws_b), self.ws_b.numel(), st))
         self.grad_theta.add_(self.g_theta_elbo)
+        if self.generic and self._g_theta_sde is not None:
+            self.grad_theta.add_(self._g_theta_sde)
 
     def step(self) -> None:
         with torch.cuda.device(self.dev):
             self.forward()
             self.backward()
 
-    def capture(self) -> None:
+    def capture(self, post=None) -> None:
         """Capture one iteration (every kernel of K0..K4 + the ELBO kernels, all buffers static) into a CUDA graph:
-        `replay()` then costs one launch instead of ~14 and leaves no gaps between the dependent kernels."""
+        `replay()` then costs one launch instead of ~14 and leaves no gaps between the dependent kernels.  `post` (e.g. the
+        NCCL all-reduce of the gradient bucket, which is capturable) is recorded behind the kernels in the same graph."""
         cur = torch.cuda.current_stream(self.dev)
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):  # warm-up on the capture side: per-kernel attributes, tensor-map encoders
             for _ in range(2):
                 self.step()
+                if post is not None:
+                    post()
         cur.wait_stream(side)
         torch.cuda.synchronize(self.dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.step()
+            if post is not None:
+                post()
 
     def replay(self) -> None:
         self.graph.replay()

@@ -12,23 +12,96 @@ from torch import Tensor
 from viforsdes_b200 import _lib
 
 
-def _pin(t: Tensor) -> Tensor:
-    t = t.detach().to(torch.float32).contiguous().cpu()
+def _pin(t: Tensor, dtype: torch.dtype = torch.float32) -> Tensor:
+    t = t.detach().to(dtype).contiguous().cpu()
     return t.pin_memory() if torch.cuda.is_available() else t
+
+
+class _DeviceArray:
+    """A raw device pointer handed to a hook, exposed through ``__cuda_array_interface__`` so that
+    ``torch.as_tensor`` aliases it (no copy)."""
+
+    def __init__(self, ptr: int, shape) -> None:
+        self.__cuda_array_interface__ = {"shape": tuple(int(n) for n in shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def _alias(ptr: int, shape, device) -> Tensor:
+    return torch.as_tensor(_DeviceArray(ptr, shape), device=device)
+
+
+class _UserSdeHooks:
+    """ctypes trampolines of ``visde_user_sde``: run the user's PyTorch ``drift`` / ``diffusion`` (SDE protocol,
+    src/variational_sde/core/sde.py:8-15) and their autograd vector-Jacobian product on the session's device
+    tensors and stream -- the reference's evidence_lower_bound.py:37-40 call, moved behind the C ABI."""
+
+    def __init__(self, sde, B: int, T: int, S: int, P: int) -> None:
+        self.sde, self.B, self.T, self.S, self.P = sde, B, T, S, P
+        self.error: BaseException | None = None
+        self._drift = self._diffusion = self._x = self._th = None
+        self.struct = _lib.UserSde(_lib.SDE_EVAL_FN(self._eval), _lib.SDE_VJP_FN(self._vjp), None)
+
+    def _eval(self, _user, x_ptr, th_ptr, drift_ptr, diff_ptr, stream) -> int:
+        try:
+            B, T, S, P = self.B, self.T, self.S, self.P
+            dev = torch.device("cuda", torch.cuda.current_device())
+            with torch.cuda.stream(torch.cuda.ExternalStream(stream or 0)):
+                with torch.enable_grad():
+                    self._x = _alias(x_ptr, (B * T, S), dev).requires_grad_(True)
+                    self._th = _alias(th_ptr, (B, P), dev).requires_grad_(True)
+                    th_flat = self._th[:, None, :].expand(B, T, P).reshape(B * T, P)
+                    self._drift = self.sde.drift(self._x, th_flat)
+                    self._diffusion = self.sde.diffusion(self._x, th_flat)
+                with torch.no_grad():
+                    _alias(drift_ptr, (B * T, S), dev).copy_(self._drift.reshape(B * T, S))
+                    _alias(diff_ptr, (B * T, S, S), dev).copy_(self._diffusion.reshape(B * T, S, S))
+            return 0
+        except BaseException as e:  # noqa: BLE001  (must not unwind through the C frame)
+            self.error = e
+            return -1
+
+    def _vjp(self, _user, x_ptr, th_ptr, g_drift_ptr, g_diff_ptr, g_x_ptr, g_th_ptr, stream) -> int:
+        try:
+            B, T, S, P = self.B, self.T, self.S, self.P
+            dev = torch.device("cuda", torch.cuda.current_device())
+            with torch.cuda.stream(torch.cuda.ExternalStream(stream or 0)):
+                outs, gouts = [], []
+                for o, ptr in ((self._drift, g_drift_ptr), (self._diffusion, g_diff_ptr)):
+                    if o.requires_grad:
+                        outs.append(o)
+                        gouts.append(_alias(ptr, tuple(o.shape), dev).to(o.dtype))
+                gx = gth = None
+                if outs:
+                    gx, gth = torch.autograd.grad(outs, [self._x, self._th], gouts, allow_unused=True)
+                gx_out, gth_out = _alias(g_x_ptr, (B * T, S), dev), _alias(g_th_ptr, (B, P), dev)
+                gx_out.zero_() if gx is None else gx_out.copy_(gx)
+                gth_out.zero_() if gth is None else gth_out.copy_(gth)
+                self._drift = self._diffusion = self._x = self._th = None
+            return 0
+        except BaseException as e:  # noqa: BLE001
+            self.error = e
+            return -1
 
 
 class HostSession:
     def __init__(self, *, x0: Tensor, context_full: Tensor, theta: Tensor, eps: Tensor, w_ih: List[Tensor],
                  w_hh: List[Tensor], b_ih: List[Tensor], b_hh: List[Tensor], out_w: Tensor, out_b: Tensor, dt: float,
                  sde_kind: int, positive_mask: int, obs_idx: Tensor, obs_values: Tensor, obs_variance: float,
-                 variant: int = _lib.VARIANT_AUTO, want_grad_context: bool = False) -> None:
+                 variant: int = _lib.VARIANT_AUTO, want_grad_context: bool = False, sde=None,
+                 context_dtype: torch.dtype = torch.float32) -> None:
+        """`context_dtype` bfloat16 = the reference's AMP mode (the encoder runs under bf16 autocast,
+        inference/trainer.py:171-175): the host context and grad_context are bf16, which halves the dominant H2D term.
+        `sde`: the user SDE object when `sde_kind` is GENERIC."""
         self.lib = _lib.load()
+        if context_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("context_dtype must be float32 or bfloat16")
         B, S = x0.shape
         T, Cd = context_full.shape[1] - 1, context_full.shape[2]
         P, NL, H = theta.shape[1], len(w_hh), w_hh[0].shape[1]
         self.dims = _lib.Dims(B, T, S, Cd, P, H, NL, variant)
         self.dt = float(dt)
-        self.x0, self.ctx, self.theta, self.eps = _pin(x0), _pin(context_full), _pin(theta), _pin(eps)
+        self.context_dtype = context_dtype
+        self.x0, self.ctx, self.theta, self.eps = _pin(x0), _pin(context_full, context_dtype), _pin(theta), _pin(eps)
         self.w = [[_pin(t) for t in ws] for ws in (w_ih, w_hh, b_ih, b_hh)]
         self.out_w, self.out_b = _pin(out_w), _pin(out_b)
         # two host output sets: iteration i+1 may be submitted before the outputs of i are consumed
@@ -39,8 +112,15 @@ class HostSession:
         self.obs = _lib.Obs(self.obs_idx.shape[0], self.obs_values.shape[1], self.obs_idx.data_ptr(),
                             self.obs_values.data_ptr(), None, float(obs_variance))
         self.handle = C.c_void_p()
-        _lib.check(self.lib.visde_session_create(C.byref(self.dims), sde_kind, positive_mask, self.obs.n_obs,
-                                                 self.obs.obs_dim, C.byref(self.handle)))
+        self._hooks = None
+        if sde_kind == _lib.SDE_GENERIC:
+            if sde is None:
+                raise ValueError("sde_kind GENERIC needs the user SDE object (sde=...)")
+            self._hooks = _UserSdeHooks(sde, B, T, S, P)
+        _lib.check(self.lib.visde_session_create(
+            C.byref(self.dims), sde_kind, positive_mask, self.obs.n_obs, self.obs.obs_dim,
+            _lib.BF16 if context_dtype == torch.bfloat16 else _lib.F32,
+            C.byref(self._hooks.struct) if self._hooks else None, C.byref(self.handle)))
 
     @classmethod
     def from_problem(cls, p, **kw) -> "HostSession":
@@ -49,7 +129,9 @@ class HostSession:
         full = torch.zeros(B, T + 1, Cd)
         full[:, :T] = p.context
         w = p.weights
-        kind = {"ou": _lib.SDE_OU, "lv": _lib.SDE_LV}[p.name]
+        kind = {"ou": _lib.SDE_OU, "lv": _lib.SDE_LV}.get(p.name, _lib.SDE_GENERIC)
+        if kind == _lib.SDE_GENERIC:
+            kw.setdefault("sde", p.sde)
         mask = 0
         for d in p.positive_dims:
             mask |= 1 << d
@@ -64,7 +146,7 @@ class HostSession:
         return cls(x0=inp.x0, context_full=inp.context_full, theta=inp.theta, eps=inp.eps, w_ih=inp.w_ih,
                    w_hh=inp.w_hh, b_ih=inp.b_ih, b_hh=inp.b_hh, out_w=inp.out_w, out_b=inp.out_b, dt=inp.dt,
                    sde_kind=inp.sde_kind, positive_mask=inp.positive_mask, obs_idx=inp.obs_idx,
-                   obs_values=inp.obs_values, obs_variance=inp.obs_variance, **kw)
+                   obs_values=inp.obs_values, obs_variance=inp.obs_variance, sde=inp.sde, **kw)
 
     def _wstruct(self, groups, ow, ob) -> _lib.Weights:
         s = _lib.Weights()
@@ -81,7 +163,7 @@ class HostSession:
     @property
     def d2h_bytes(self) -> int:
         g = self._out[0]["grad_ctx"]
-        extra = g.numel() * 4 if g is not None else 0
+        extra = g.numel() * g.element_size() if g is not None else 0
         return int(self.lib.visde_session_d2h_bytes(self.handle)) + extra
 
     @property
@@ -94,16 +176,20 @@ class HostSession:
             "gw": [[pin(torch.empty_like(t)) for t in ws] for ws in self.w],
             "g_out_w": pin(torch.empty_like(self.out_w)), "g_out_b": pin(torch.empty_like(self.out_b)),
             "terms": pin(torch.empty(B, 4)), "grad_x0": pin(torch.empty(B, S)), "grad_theta": pin(torch.empty(B, P)),
-            "grad_ctx": pin(torch.empty(B, T + 1, Cd)) if want_grad_context else None,
+            "grad_ctx": pin(torch.empty(B, T + 1, Cd, dtype=self.context_dtype)) if want_grad_context else None,
         }
 
     def _call(self, fn, o) -> None:
         w = self._wstruct(self.w, self.out_w, self.out_b)
         gw = self._wstruct(o["gw"], o["g_out_w"], o["g_out_b"])
-        _lib.check(fn(
+        rc = fn(
             self.handle, self.dt, self.x0.data_ptr(), self.ctx.data_ptr(), self.theta.data_ptr(), self.eps.data_ptr(),
             C.byref(w), C.byref(self.obs), o["terms"].data_ptr(), o["grad_x0"].data_ptr(), o["grad_theta"].data_ptr(),
-            C.byref(gw), None if o["grad_ctx"] is None else o["grad_ctx"].data_ptr()))
+            C.byref(gw), None if o["grad_ctx"] is None else o["grad_ctx"].data_ptr())
+        if rc and self._hooks is not None and self._hooks.error is not None:
+            err, self._hooks.error = self._hooks.error, None
+            raise err  # the user's drift / diffusion raised inside a hook
+        _lib.check(rc)
 
     def _results(self, o) -> Dict[str, object]:
         grads = {"x0": o["grad_x0"], "theta": o["grad_theta"], "out_w": o["g_out_w"], "out_b": o["g_out_b"]}

@@ -43,6 +43,26 @@ class _Workloads(dict):
 WORKLOADS = _Workloads(WORKLOADS)
 
 
+class Lorenz96:
+    """The user-defined SDE of BASELINE.json configs[4], written against the reference's ``SDE``
+    protocol (src/variational_sde/core/sde.py:8-15) and evaluated in PyTorch on the flattened path exactly as
+    inference/evidence_lower_bound.py:37-40 calls it: cyclic ``drift_i = (x_{i+1} - x_{i-2}) x_{i-1} - x_i + F``,
+    ``diffusion = sigma I``; sde_parameters = (F, sigma)."""
+
+    sde_param_dim = 2
+
+    def __init__(self, state_dim: int = 10) -> None:
+        self.state_dim = state_dim
+
+    def drift(self, x: Tensor, sde_parameters: Tensor) -> Tensor:
+        ahead, behind, behind2 = (torch.roll(x, k, dims=-1) for k in (-1, 1, 2))
+        return (ahead - behind2) * behind - x + sde_parameters[..., 0:1]
+
+    def diffusion(self, x: Tensor, sde_parameters: Tensor) -> Tensor:
+        eye = torch.eye(self.state_dim, dtype=x.dtype, device=x.device)
+        return sde_parameters[..., 1].reshape(-1, 1, 1) * eye
+
+
 @dataclass
 class Inputs:
     kind: str
@@ -62,6 +82,7 @@ class Inputs:
     obs_times: Tensor
     obs_values: Tensor
     obs_variance: float
+    sde: object = None  # user SDE object (sde_kind GENERIC): drift / diffusion evaluated in PyTorch
 
     @property
     def positive_mask(self) -> int:
@@ -135,4 +156,5 @@ def make_inputs(kind: str, batch: int, n_steps: int, *, dt: float = 0.05, contex
         x0[:, list(pos)] = _softplus_inverse(x0[:, list(pos)])
     eps = randn(batch, T, S).to(torch.float32)
     return Inputs(kind, sk, pos, x0.to(torch.float32), ctx_full, theta.to(torch.float32), eps, w_ih, w_hh, b_ih, b_hh,
-                  out_w, out_b, dt, times.to(torch.float32), values.to(torch.float32), var)
+                  out_w, out_b, dt, times.to(torch.float32), values.to(torch.float32), var,
+                  Lorenz96(S) if kind == "l96" else None)
