@@ -277,16 +277,20 @@ int visde_path_summary(int64_t n, int64_t T1, int32_t S, uint32_t positive_mask,
 
 /* Optimiser tail of inference/trainer.py:199-203,126 over flat fp32 buffers (the all-reduce bucket):
  * visde_grad_sqnorm: sqnorm (device scalar) = [accumulate ? sqnorm : 0] + inv_scale^2 * sum g^2   (inv_scale: device
- *   scalar of GradScaler.unscale_, or NULL); deterministic.
+ *   scalar of GradScaler.unscale_, or NULL); deterministic.  skipped_steps (device int64 counter, may be NULL) is
+ *   incremented when the result is non-finite, i.e. when some gradient is inf / NaN (GradScaler's found_inf).
  * visde_adamw_ema_step: g *= inv_scale * min(1, max_norm / (sqrt(sqnorm) + 1e-6)) (clip_grad_norm_; skipped when
  *   sqnorm == NULL or max_norm <= 0), torch.optim.AdamW update (decoupled weight decay, `step` counts from 1), then
- *   ema = lerp(ema, param, 1 - ema_decay) (exponential_moving_average.py:25-28; ema may be NULL).  No host sync. */
+ *   ema = lerp(ema, param, 1 - ema_decay) (exponential_moving_average.py:25-28; ema may be NULL).  When sqnorm is
+ *   given and non-finite the parameter / moment update is SKIPPED like GradScaler.step() (trainer.py:202) and only the
+ *   EMA moves (trainer.py:126); with skipped_steps the bias corrections use step - *skipped_steps.  No host sync. */
 size_t visde_grad_sqnorm_workspace_bytes(void);
 int visde_grad_sqnorm(int64_t n, const float* grads, const float* inv_scale, int accumulate, float* sqnorm,
-                      void* workspace, size_t workspace_bytes, void* stream);
+                      int64_t* skipped_steps, void* workspace, size_t workspace_bytes, void* stream);
 int visde_adamw_ema_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema,
                          float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
-                         float max_norm, const float* sqnorm, const float* inv_scale, float ema_decay, void* stream);
+                         float max_norm, const float* sqnorm, const float* inv_scale, float ema_decay,
+                         const int64_t* skipped_steps, void* stream);
 
 #ifdef __cplusplus
 }

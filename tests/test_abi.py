@@ -91,15 +91,15 @@ def test_caller_entry_points_validate_without_a_gpu(lib):
     assert lib.visde_path_summary(10, 5, 2, 0, 1, None, 1, 1, None, 0, None) == _lib.EWORKSPACE
     # optimiser tail
     assert lib.visde_grad_sqnorm_workspace_bytes() >= 4 * 148
-    assert lib.visde_grad_sqnorm(16, 16, None, 0, None, None, 0, None) == _lib.EINVAL           # sqnorm NULL
-    assert lib.visde_grad_sqnorm(16, 16, None, 0, 16, None, 0, None) == _lib.EWORKSPACE
-    assert lib.visde_grad_sqnorm(16, 4, None, 0, 16, 16, 1 << 20, None) == _lib.EINVAL          # unaligned gradient pointer
+    assert lib.visde_grad_sqnorm(16, 16, None, 0, None, None, None, 0, None) == _lib.EINVAL           # sqnorm NULL
+    assert lib.visde_grad_sqnorm(16, 16, None, 0, 16, None, None, 0, None) == _lib.EWORKSPACE
+    assert lib.visde_grad_sqnorm(16, 4, None, 0, 16, None, 16, 1 << 20, None) == _lib.EINVAL          # unaligned gradient pointer
     args = (0.001, 0.9, 0.999, 1e-8, 0.01)
-    assert lib.visde_adamw_ema_step(0, None, None, None, None, None, *args, 1, 1.0, None, None, 0.999, None) == _lib.OK
-    assert lib.visde_adamw_ema_step(8, 16, 16, 16, 16, None, *args, 0, 1.0, None, None, 0.999, None) == _lib.EINVAL  # step from 1
+    assert lib.visde_adamw_ema_step(0, None, None, None, None, None, *args, 1, 1.0, None, None, 0.999, None, None) == _lib.OK
+    assert lib.visde_adamw_ema_step(8, 16, 16, 16, 16, None, *args, 0, 1.0, None, None, 0.999, None, None) == _lib.EINVAL  # step from 1
     assert lib.visde_adamw_ema_step(8, 16, 16, 16, 16, None, 0.001, 1.0, 0.999, 1e-8, 0.01, 1, 1.0, None, None, 0.999,
-                                    None) == _lib.EINVAL  # beta1 must be < 1
-    assert lib.visde_adamw_ema_step(8, None, 16, 16, 16, None, *args, 1, 1.0, None, None, 0.999, None) == _lib.EINVAL
+                                    None, None) == _lib.EINVAL  # beta1 must be < 1
+    assert lib.visde_adamw_ema_step(8, None, 16, 16, 16, None, *args, 1, 1.0, None, None, 0.999, None, None) == _lib.EINVAL
 
 
 def test_host_mirrors_of_the_callers_validate_on_cpu():

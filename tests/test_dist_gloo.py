@@ -83,11 +83,19 @@ def _worker(rank: int, world: int, port: int) -> None:
 def test_shard_range_partitions_batch():
     for total in (1, 7, 8, 8192):
         for world in (1, 2, 3, 8):
-            spans = [shard_range(total, r, world) for r in range(world)]
+            spans = [shard_range(total, r, world, allow_uneven=True) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+            # equal-weight averaging of per-rank means is the global mean only with the shard weights applied
+            from viforsdes_b200.dist import shard_weight
+            assert abs(sum(shard_weight(total, r, world) for r in range(world)) - world) < 1e-12
+            if total % world:
+                with pytest.raises(ValueError):
+                    shard_range(total, 0, world)
+            else:
+                assert spans == [shard_range(total, r, world) for r in range(world)]
 
 
 @pytest.mark.timeout(120)

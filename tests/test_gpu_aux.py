@@ -462,6 +462,53 @@ def test_path_iteration_matches_module_path_and_trains(kind, B, T):
     assert len(opt.ema_views()) == 10
 
 
+def test_fused_optimizer_skips_non_finite_steps_like_gradscaler():
+    """trainer.py:199-203: scaler.unscale_ -> clip_grad_norm_ -> scaler.step(optimizer) skips optimizer.step() when any
+    gradient is inf / NaN; ema.update() (trainer.py:126) still runs.  Reference = torch.optim.AdamW + torch.amp.GradScaler
+    semantics restated with plain PyTorch on the same gradients."""
+    from viforsdes_b200.optim import FlatParameters, FusedAdamWEma
+
+    gen = torch.Generator().manual_seed(5)
+    n, lr, decay, scale = 1037, 3e-3, 0.9, 256.0
+    p0 = torch.randn(n, generator=gen)
+    grads = [scale * torch.randn(n, generator=gen) for _ in range(5)]
+    grads[1][17] = float("inf")
+    grads[3][n - 1] = float("nan")
+    # reference
+    ref = nn.Parameter(p0.clone().double())
+    ropt = torch.optim.AdamW([ref], lr=lr)
+    shadow = ref.detach().clone()
+    for g in grads:
+        ref.grad = g.double() / scale
+        if torch.isfinite(ref.grad).all():
+            torch.nn.utils.clip_grad_norm_([ref], 1.0)
+            ropt.step()
+        shadow.lerp_(ref.detach(), 1 - decay)
+    # fused
+    param = nn.Parameter(p0.clone().cuda())
+    flat = FlatParameters([[param]])
+    opt = FusedAdamWEma(flat, lrs=[lr], max_norm=1.0, ema_decay=decay)
+    inv = torch.tensor([1.0 / scale], device="cuda")
+    seen = []
+    for g in grads:
+        param.grad = None  # what optimizer.zero_grad(set_to_none=True) does: the step re-attaches the flat view
+        opt._check_views()
+        param.grad.copy_(g)
+        before = param.detach().clone()
+        opt.step(inv_scale=inv)
+        seen.append(bool(opt.found_inf.item()))
+        if seen[-1]:
+            assert torch.equal(param.detach(), before), "a skipped step must leave the parameters untouched"
+    assert seen == [False, True, False, True, False]
+    assert int(opt.skipped_steps.item()) == 2
+    assert torch.isfinite(param).all() and torch.isfinite(opt.exp_avg).all() and torch.isfinite(opt.ema).all()
+    assert_close(param, ref.detach(), rtol=2e-5, atol_scale=2e-6, name="param after skipped steps")
+    assert_close(opt.ema_views()[0], shadow, rtol=2e-5, atol_scale=2e-6, name="ema after skipped steps")
+    assert opt.state_dict()["step"] == 3
+    with pytest.raises(ValueError):
+        opt.load_state_dict({"exp_avg": opt.exp_avg, "exp_avg_sq": opt.exp_avg_sq, "ema": None, "step": 1})
+
+
 def test_fused_optimizer_ema_apply_and_resume():
     """EMA swap for sampling (exponential_moving_average.py:30-42) and checkpoint / resume of the fused optimiser."""
     from viforsdes_b200.optim import FlatParameters, FusedAdamWEma

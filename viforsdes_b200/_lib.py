@@ -87,9 +87,9 @@ PROTOTYPES = {
     "visde_path_summary": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_uint32, _fp, _fp, _fp, _fp, _fp, C.c_size_t,
                                      _fp]),
     "visde_grad_sqnorm_workspace_bytes": (C.c_size_t, []),
-    "visde_grad_sqnorm": (C.c_int, [C.c_int64, _fp, _fp, C.c_int, _fp, _fp, C.c_size_t, _fp]),
+    "visde_grad_sqnorm": (C.c_int, [C.c_int64, _fp, _fp, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
     "visde_adamw_ema_step": (C.c_int, [C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_float, C.c_float,
-                                       C.c_float, C.c_int64, C.c_float, _fp, _fp, C.c_float, _fp]),
+                                       C.c_float, C.c_int64, C.c_float, _fp, _fp, C.c_float, _fp, _fp]),
 }
 
 _lib: C.CDLL | None = None

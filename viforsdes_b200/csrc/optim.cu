@@ -40,14 +40,19 @@ __global__ void __launch_bounds__(kOptThreads) sqnorm_partial_kernel(const float
 }
 
 // one warp: sums the partials in a fixed order; sqnorm = (accumulate ? sqnorm : 0) + sum * inv_scale^2
-__global__ void sqnorm_final_kernel(const float* part, int nparts, const float* inv_scale, int accumulate, float* sqnorm) {
+__global__ void sqnorm_final_kernel(const float* part, int nparts, const float* inv_scale, int accumulate, float* sqnorm,
+                                    long long* skipped) {
   float acc = 0.f;
   for (int i = threadIdx.x; i < nparts; i += 32) acc += part[i];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (threadIdx.x == 0) {
     const float is = inv_scale ? *inv_scale : 1.f;
-    *sqnorm = (accumulate ? *sqnorm : 0.f) + acc * is * is;
+    const float r = (accumulate ? *sqnorm : 0.f) + acc * is * is;
+    *sqnorm = r;
+    // GradScaler.step (trainer.py:202): a non-finite gradient anywhere makes the squared norm non-finite; the optimiser
+    // step is then skipped and does not count towards the bias corrections
+    if (skipped && !isfinite(r)) *skipped += 1;
   }
 }
 
@@ -61,6 +66,8 @@ struct AdamParams {
   float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, max_norm, ema_w;
   const float* sqnorm;     // device scalar: squared global gradient norm (after unscale), or nullptr = no clipping
   const float* inv_scale;  // device scalar (GradScaler), or nullptr
+  const long long* skipped;  // device counter of skipped (non-finite) steps, or nullptr
+  long long step;
 };
 
 __device__ __forceinline__ void adam_elem(const AdamParams& a, float coef, float& p, float g, float& m, float& v, float& e) {
@@ -73,7 +80,20 @@ __device__ __forceinline__ void adam_elem(const AdamParams& a, float coef, float
   e = fmaf(a.ema_w, p - e, e);                  // shadow.lerp_(param, 1 - decay)
 }
 
+// the skipped step of GradScaler.step(): parameters and moments stay, the EMA shadow still moves (trainer.py:126)
 __global__ void __launch_bounds__(kOptThreads) adamw_ema_kernel(AdamParams a) {
+  if (a.sqnorm && !isfinite(*a.sqnorm)) {  // found_inf: scaler.step() skips optimizer.step()
+    if (!a.ema) return;
+    const int64_t stride = (int64_t)gridDim.x * kOptThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kOptThreads + threadIdx.x; i < a.n; i += stride)
+      a.ema[i] = fmaf(a.ema_w, a.p[i] - a.ema[i], a.ema[i]);
+    return;
+  }
+  if (a.skipped) {  // bias corrections from the number of steps actually taken
+    const double s = (double)(a.step - *a.skipped);
+    a.bc1 = (float)(1.0 - pow((double)a.beta1, s));
+    a.bc2_sqrt = (float)sqrt(1.0 - pow((double)a.beta2, s));
+  }
   float coef = a.inv_scale ? *a.inv_scale : 1.f;
   if (a.sqnorm && a.max_norm > 0.f) {
     const float c = a.max_norm / (sqrtf(*a.sqnorm) + 1e-6f);  // nn.utils.clip_grad_norm_
@@ -120,7 +140,7 @@ extern "C" {
 size_t visde_grad_sqnorm_workspace_bytes(void) { return kOptMaxBlocks * sizeof(float); }
 
 int visde_grad_sqnorm(int64_t n, const float* grads, const float* inv_scale, int accumulate, float* sqnorm,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+                      int64_t* skipped_steps, void* workspace, size_t workspace_bytes, void* stream) {
   VISDE_REQUIRE(n >= 0, "grad_sqnorm: negative size");
   VISDE_REQUIRE(sqnorm, "grad_sqnorm: sqnorm is NULL");
   VISDE_REQUIRE(n == 0 || (grads && aligned16(grads)), "grad_sqnorm: grads must be a 16-byte aligned device pointer");
@@ -132,14 +152,16 @@ int visde_grad_sqnorm(int64_t n, const float* grads, const float* inv_scale, int
   const int nb = opt_blocks(n);
   sqnorm_partial_kernel<<<nb, kOptThreads, 0, st>>>(grads, n, reinterpret_cast<float*>(workspace));
   VISDE_CUDA_CHECK(cudaGetLastError());
-  sqnorm_final_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const float*>(workspace), nb, inv_scale, accumulate, sqnorm);
+  sqnorm_final_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const float*>(workspace), nb, inv_scale, accumulate, sqnorm,
+                                        reinterpret_cast<long long*>(skipped_steps));
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
 
 int visde_adamw_ema_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema,
                          float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
-                         float max_norm, const float* sqnorm, const float* inv_scale, float ema_decay, void* stream) {
+                         float max_norm, const float* sqnorm, const float* inv_scale, float ema_decay,
+                         const int64_t* skipped_steps, void* stream) {
   VISDE_REQUIRE(n >= 0, "adamw_ema_step: negative size");
   VISDE_REQUIRE(step >= 1, "adamw_ema_step: step counts from 1, got %lld", (long long)step);
   VISDE_REQUIRE(lr >= 0.f && eps >= 0.f && weight_decay >= 0.f, "adamw_ema_step: invalid learning rate / eps / weight decay");
@@ -154,6 +176,7 @@ int visde_adamw_ema_step(int64_t n, float* params, const float* grads, float* ex
   a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   a.max_norm = max_norm; a.ema_w = 1.f - ema_decay; a.sqnorm = sqnorm; a.inv_scale = inv_scale;
+  a.skipped = reinterpret_cast<const long long*>(skipped_steps); a.step = step;
   adamw_ema_kernel<<<opt_blocks(n), kOptThreads, 0, (cudaStream_t)stream>>>(a);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;

@@ -34,11 +34,23 @@ def init_process_group(backend: str | None = None) -> Tuple[int, int, int]:
     return rank, local_rank, world
 
 
-def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
-    """Contiguous shard [lo, hi) of `total` trajectories for `rank` (sizes differ by at most 1)."""
+def shard_range(total: int, rank: int, world: int, allow_uneven: bool = False) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of `total` trajectories for `rank`.  The gradient exchange averages per-rank batch
+    MEANS with equal weight (`allreduce_mean_`), which is the global-batch mean only for equal shards: an uneven split
+    is refused unless the caller says it rescales (`shard_weight`) before the all-reduce."""
     base, rem = divmod(total, world)
+    if rem and not allow_uneven:
+        raise ValueError(f"{total} trajectories do not split evenly over {world} ranks; pass allow_uneven=True and "
+                         "scale each rank's gradients / ELBO by shard_weight() before the all-reduce")
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_weight(total: int, rank: int, world: int) -> float:
+    """local_B * world / total: the factor that turns an equal-weight average of per-rank batch means into the
+    global-batch mean when shards are uneven (1.0 for an even split)."""
+    lo, hi = shard_range(total, rank, world, allow_uneven=True)
+    return (hi - lo) * world / total
 
 
 class FlatBucket:

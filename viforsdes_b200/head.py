@@ -33,6 +33,23 @@ class HeadConfig:
             raise ValueError("value must be positive")
 
 
+class _FlooredDiagonal(torch.autograd.Function):
+    """``lower_bound`` of src/variational_sde/primitives/bounds.py:10-31: max(x, floor) whose cotangent passes where the
+    input is above the floor OR the cotangent is negative (pushing a clamped entry back up stays possible).  The kernels
+    bake the same rule in (csrc/path_*.cu); this PyTorch form serves the single-step ``forward``."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, floor: float) -> Tensor:  # type: ignore[override]
+        ctx.save_for_backward(x)
+        ctx.floor = floor
+        return x.clamp_min(floor)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):  # type: ignore[override]
+        (x,) = ctx.saved_tensors
+        return torch.where((x >= ctx.floor) | (g < 0), g, torch.zeros_like(g)), None
+
+
 class DiffusionTransitionHead(nn.Module):
     _tril_rows: Tensor
     _tril_cols: Tensor
@@ -69,6 +86,24 @@ class DiffusionTransitionHead(nn.Module):
 
     def init_hidden(self, batch: int, device: torch.device, dtype: torch.dtype = torch.float32) -> Tensor:
         return torch.zeros(self.num_layers, batch, self.hidden_dim, device=device, dtype=dtype)
+
+    def forward(self, x_t: Tensor, context_t: Tensor, sde_parameters: Tensor,
+                hidden: Tensor | None = None) -> tuple[Tensor, Tensor, Tensor]:
+        """The single-step spec of the transition (src/variational_sde/models/head.py:68-86), in plain PyTorch on any
+        device: one ``nn.GRU`` step on cat[x_t, context_t, theta] -> out_proj -> (mu [B,S], L [B,S,S], hidden [NL,B,H]).
+        Not the hot path -- ``sample_diffusion_paths`` runs all T steps inside the fused kernels -- but the API users step
+        manually, and the statement of the step math the kernels are tested against."""
+        step_in = torch.cat([x_t, context_t, sde_parameters], dim=-1).unsqueeze(1)
+        out, hidden = self.gru(step_in, hidden)
+        params = self.out_proj(out.squeeze(1))
+        return params[..., : self.state_dim], self._tril_from_params(params[..., self.state_dim:]), hidden
+
+    def _tril_from_params(self, params: Tensor) -> Tensor:
+        """Row-major lower-triangular fill, diagonal floored at DIAG_MIN (head.py:88-97)."""
+        vals = torch.where(self._diag_mask, _FlooredDiagonal.apply(params, DIAG_MIN), params)
+        L = params.new_zeros(params.shape[0], self.state_dim, self.state_dim)
+        L[:, self._tril_rows, self._tril_cols] = vals
+        return L
 
     def _weight_lists(self):
         nl = self.num_layers

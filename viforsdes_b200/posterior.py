@@ -64,23 +64,35 @@ def summarise_paths(z: Tensor, state_space: StateSpace, want_x: bool = True) -> 
     return x, mean, std
 
 
+class _EvalMode:
+    """``self.model.eval()`` of variational_posterior.py:96 for the modules this function is handed: the head AND the
+    encoder (dropout / other train-mode behaviour must be off while sampling); restores the previous modes on exit."""
+
+    def __init__(self, *modules) -> None:
+        self.modules = [m for m in modules if isinstance(m, torch.nn.Module)]
+
+    def __enter__(self):
+        self.was = [m.training for m in self.modules]
+        for m in self.modules:
+            m.eval()
+        return self
+
+    def __exit__(self, *exc) -> None:
+        for m, w in zip(self.modules, self.was):
+            m.train(w)
+
+
 @torch.no_grad()
 def sample_posterior(encoder: EncoderProtocol, head: HeadProtocol, sde_parameter_posterior, observations: Observations,
                      n: int, time_horizon: float, time_step: float, state_space: StateSpace,
                      noise: Optional[Tensor] = None) -> VariationalPosteriorSamples:
     """``VariationalPosterior.sample`` (variational_posterior.py:93-114) without the EMA swap (the caller owns it)."""
-    was_training = getattr(head, "training", False)
-    if hasattr(head, "eval"):
-        head.eval()
-    try:
+    with _EvalMode(encoder, head):
         sde_parameters = sde_parameter_posterior.rsample(n)
         x0 = observations.values[0].unsqueeze(0).expand(n, -1).contiguous()
         result = sample_diffusion_paths(encoder, head, observations, sde_parameters, x0, time_horizon, time_step,
                                         state_space, noise=noise)
         x, _, _ = summarise_paths(result.z, state_space) if result.z.is_cuda else (result.x, None, None)
-    finally:
-        if was_training and hasattr(head, "train"):
-            head.train()
     return VariationalPosteriorSamples(sde_parameters=sde_parameters, diffusion_paths=x)
 
 
@@ -91,15 +103,9 @@ def summarise_posterior(encoder: EncoderProtocol, head: HeadProtocol, sde_parame
     """``VariationalPosterior.summary`` (variational_posterior.py:116-135)."""
     sde_parameters = sde_parameter_posterior.rsample(n_samples)
     x0 = observations.values[0].unsqueeze(0).expand(n_samples, -1).contiguous()
-    was_training = getattr(head, "training", False)
-    if hasattr(head, "eval"):
-        head.eval()
-    try:
+    with _EvalMode(encoder, head):
         result = sample_diffusion_paths(encoder, head, observations, sde_parameters, x0, time_horizon, time_step,
                                         state_space, noise=noise)
-    finally:
-        if was_training and hasattr(head, "train"):
-            head.train()
     _, mean, std = summarise_paths(result.z, state_space, want_x=False)
     q = torch.quantile(sde_parameters, torch.tensor(QUANTILE_LEVELS, device=sde_parameters.device,
                                                     dtype=sde_parameters.dtype), dim=0)
