@@ -15,6 +15,12 @@ def test_head_forward_matches_oracle_step(kind, S, NL, H):
     # push some diagonal entries below DIAG_MIN so the floored branch and its gradient rule are exercised
     w.out_b[w.state_dim] = -0.5
     head = build_head(p, device="cpu").double()
+    with torch.no_grad():  # build_head copied through fp32 parameters: restore the exact float64 weights
+        for k in range(NL):
+            for nm, src in (("weight_ih", w.w_ih), ("weight_hh", w.w_hh), ("bias_ih", w.b_ih), ("bias_hh", w.b_hh)):
+                getattr(head.gru, f"{nm}_l{k}").copy_(src[k])
+        head.out_proj.weight.copy_(w.out_w)
+        head.out_proj.bias.copy_(w.out_b)
     hidden0 = [0.1 * torch.randn(4, H, dtype=torch.float64) for _ in range(NL)]
     z = p.x0.clone().requires_grad_(True)
     mu_r, L_r, hid_r = O.head_step(w.map(lambda t: t.clone().requires_grad_(True)), z, p.context[:, 0], p.theta, hidden0)
