@@ -25,13 +25,20 @@ def assert_close(a, ref, rtol=1e-4, atol_scale=1e-5, name=""):
                            f"{err.max().item():.3e} (scale {scale:.3e}, normwise {err.max().item() / (scale or 1):.3e})")
 
 
-def assert_parity(a, ref32, ref64, rtol=1e-4, atol_scale=1e-5, noise_mult=3.0, name=""):
+# achieved errors of every assert_parity call: tests/conftest.py writes them to gpurun_out/parity_log.jsonl at session end,
+# tools/parity_table.py turns that into profiles/parity_r2.md
+PARITY_LOG: list = []
+NOISE_CAP = 1e-3  # the fp32-noise widening never exceeds this fraction of the tensor's magnitude
+
+
+def assert_parity(a, ref32, ref64, rtol=1e-4, atol_scale=1e-5, noise_mult=3.0, name="", noise_cap=NOISE_CAP):
     """Parity against the fp64 oracle with the fp32 bar of BASELINE.json (rtol 1e-4 elementwise plus an
     absolute floor of atol_scale x max|ref|), widened by `noise_mult` x the rounding noise the
-    reference's own fp32 path shows on this tensor (max|ref32 - ref64|).  The widening matters for
-    Lotka-Volterra-like problems (|z| ~ 70-450, saturated gates, A_ii = L_ii sqrt(dt) ~ 1e-3): there the
-    ELBO cotangents are differences of O(1/A_ii^2) terms and any two fp32 implementations -- including
-    the reference's PyTorch path vs its own Triton kernels -- differ by more than 1e-4 relative."""
+    reference's own fp32 path shows on this tensor (max|ref32 - ref64|), the widening capped at
+    `noise_cap` x max|ref|.  The widening matters for Lotka-Volterra-like problems (|z| ~ 70-450, saturated
+    gates, A_ii = L_ii sqrt(dt) ~ 1e-3): there the ELBO cotangents are differences of O(1/A_ii^2) terms and
+    any two fp32 implementations -- including the reference's PyTorch path vs its own Triton kernels --
+    differ by more than 1e-4 relative.  The achieved normwise error is recorded in PARITY_LOG."""
     a, r32, r64 = (t.detach().double().cpu() for t in (a, ref32, ref64))
     assert a.shape == r64.shape, f"{name}: shape {tuple(a.shape)} vs {tuple(r64.shape)}"
     if a.numel() == 0:
@@ -39,7 +46,11 @@ def assert_parity(a, ref32, ref64, rtol=1e-4, atol_scale=1e-5, noise_mult=3.0, n
     scale = r64.abs().max().item()
     noise = (r32 - r64).abs().max().item()
     err = (a - r64).abs()
-    tol = rtol * r64.abs() + atol_scale * scale + noise_mult * noise
+    widen = min(noise_mult * noise, noise_cap * scale)
+    tol = rtol * r64.abs() + atol_scale * scale + widen
+    PARITY_LOG.append({"name": name, "numel": a.numel(), "scale": scale, "max_abs_err": err.max().item(),
+                       "normwise_err": err.max().item() / (scale or 1.0), "fp32_ref_noise_normwise": noise / (scale or 1.0),
+                       "widening_normwise": widen / (scale or 1.0)})
     bad = err > tol
     assert not bad.any(), (f"{name}: {int(bad.sum())}/{a.numel()} elements off; max abs err {err.max().item():.3e}, "
                            f"scale {scale:.3e}, fp32-reference noise {noise:.3e}")
@@ -129,12 +140,12 @@ def oracle_refs(p: O.Problem):
     return O.run_fwd_bwd(p), O.run_fwd_bwd(p, dtype=torch.float64)
 
 
-def check_iteration(cuda_out, r32, r64, tag=""):
+def check_iteration(cuda_out, r32, r64, tag="", noise_cap=NOISE_CAP):
     """paths / means / chol / 4 ELBO terms / every gradient against the oracle pair."""
     paths, means, chol, terms, grads = cuda_out
     for a, b32, b64, nm in zip((paths, means, chol), r32[:3], r64[:3], ("paths", "means", "chol")):
-        assert_parity(a, b32, b64, name=f"{tag}{nm}")
+        assert_parity(a, b32, b64, name=f"{tag}{nm}", noise_cap=noise_cap)
     for j, nm in enumerate(("obs", "sde", "gen", "jac")):
-        assert_parity(terms[:, j], getattr(r32[3], nm), getattr(r64[3], nm), name=f"{tag}term_{nm}")
+        assert_parity(terms[:, j], getattr(r32[3], nm), getattr(r64[3], nm), name=f"{tag}term_{nm}", noise_cap=noise_cap)
     for nm in r64[4]:
-        assert_parity(grads[nm], r32[4][nm], r64[4][nm], name=f"{tag}grad_{nm}")
+        assert_parity(grads[nm], r32[4][nm], r64[4][nm], name=f"{tag}grad_{nm}", noise_cap=noise_cap)

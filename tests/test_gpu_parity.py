@@ -219,7 +219,9 @@ def test_diag_floor_branch_and_gradient_rule():
     r32, r64 = oracle_refs(p)
     for v in (_lib.VARIANT_GENERIC, _lib.VARIANT_FAST):
         ops.set_variant(v)
-        check_iteration(run_cuda_fwd_bwd(p), r32, r64, tag=f"v{v}/")
+        # the floor's gradient rule is DISCONTINUOUS in raw (bias 0.02 puts L_11 within rounding distance of the floor), so
+        # the fp32 and fp64 oracles themselves take different branches on a few entries: wider noise cap for this test only
+        check_iteration(run_cuda_fwd_bwd(p), r32, r64, tag=f"diagfloor/v{v}/", noise_cap=2e-2)
 
 
 def test_bf16_and_contiguous_context():
