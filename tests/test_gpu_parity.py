@@ -43,7 +43,15 @@ CASES["lv_h64_c128_t1"] = ("lv", 4, 1, dict(context_dim=128, hidden_dim=64, num_
 CASES["ou_h64_c128_l1_t2"] = ("ou", 3, 2, dict(context_dim=128, hidden_dim=64, num_layers=1))
 TC_OK = {"lv_h64_c128_l2", "ou_h64_c256_l1", "lv_h64_c256_l2", "l96s6_h64_c128_l2", "lv_h64_c128_b150_two_tiles",
          "ou_h64_c128_l1_b130", "l96s4_h64_c128_l2", "lv_h64_c128_t1", "ou_h64_c128_l1_t2"}
-TC_REC_OK = TC_OK - {"l96s6_h64_c128_l2"}
+# wide-state tensor-core recurrence (4 < S <= 10, NL = 2; path_tcw.cu): ragged two-tile batch, odd S, single / two steps
+CASES["l96s10_h64_c128_b150_tcw"] = ("l96", 150, 12, dict(context_dim=128, hidden_dim=64, num_layers=2, state_dim=10))
+CASES["l96s5_h64_c128_tcw"] = ("l96", 5, 21, dict(context_dim=128, hidden_dim=64, num_layers=2, state_dim=5))
+CASES["l96s7_h64_c256_t1_tcw"] = ("l96", 3, 1, dict(context_dim=256, hidden_dim=64, num_layers=2, state_dim=7))
+CASES["l96s10_h64_c128_t2_tcw"] = ("l96", 130, 2, dict(context_dim=128, hidden_dim=64, num_layers=2, state_dim=10))
+CASES["l96s9_h64_c128_tcw"] = ("l96", 4, 33, dict(context_dim=128, hidden_dim=64, num_layers=2, state_dim=9))
+TCW = {"l96s10_h64_c128_b150_tcw", "l96s5_h64_c128_tcw", "l96s7_h64_c256_t1_tcw", "l96s10_h64_c128_t2_tcw", "l96s9_h64_c128_tcw"}
+TC_OK |= TCW
+TC_REC_OK = set(TC_OK)
 NO_TC = 0x100  # VISDE_FLAG_NO_TENSOR_CORES
 # batch sizes that do not divide the tile of the batch-tiled family
 CASES["lv_h64_b37_ragged_tile"] = ("lv", 37, 9, dict(context_dim=16, hidden_dim=64, num_layers=2))
@@ -62,7 +70,7 @@ FAST_OK |= {"lv_h64_b601_tile8", "ou_h32_l1_b610_tile8", "l96s4_h64_b597_tile8"}
 # wide-state register-resident family (4 < S <= 16, H <= 64, NL <= 2)
 CASES["l96s16_h32_l1"] = ("l96", 3, 9, dict(context_dim=8, hidden_dim=32, num_layers=1, state_dim=16))
 CASES["l96s5_h64_l2_b150"] = ("l96", 150, 5, dict(context_dim=16, hidden_dim=64, num_layers=2, state_dim=5))
-FASTS_OK = {"l96s10_h64_l2", "l96s6_h64_c128_l2", "l96s16_h32_l1", "l96s5_h64_l2_b150"}
+FASTS_OK = {"l96s10_h64_l2", "l96s6_h64_c128_l2", "l96s16_h32_l1", "l96s5_h64_l2_b150"} | TCW
 
 
 def _variants(name):
@@ -147,6 +155,20 @@ def test_elbo_iteration_matches_oracle(name):
     p = O.make_problem(kind, B, T, **kw)
     r32, r64 = oracle_refs(p)
     check_iteration(run_cuda_fwd_bwd(p), r32, r64, tag=f"{name}/")
+
+
+@pytest.mark.parametrize("name", ["lv_h64_c128_b150_two_tiles", "ou_h64_c128_l1_b130", "l96s4_h64_c128_l2",
+                                  "l96s10_h64_c128_b150_tcw", "l96s5_h64_c128_tcw", "l96s6_h64_c128_l2"])
+def test_elbo_iteration_tensor_core_recurrence(name):
+    """The same complete iteration with the recurrence FORCED onto the tcgen05 families (AUTO picks them only from
+    B >= 3072): narrow (S <= 4) and wide-state (4 < S <= 10) kernels, ragged two-tile batches."""
+    from viforsdes_b200 import _lib, ops
+
+    kind, B, T, kw = CASES[name]
+    p = O.make_problem(kind, B, T, **kw)
+    r32, r64 = oracle_refs(p)
+    ops.set_variant(_lib.VARIANT_TC)
+    check_iteration(run_cuda_fwd_bwd(p), r32, r64, tag=f"tc/{name}/")
 
 
 @pytest.mark.parametrize("name", ["stepwise_ou", "stepwise_lv", "stepwise_l96", "stepwise_ou_h64"])

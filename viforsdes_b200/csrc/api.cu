@@ -67,13 +67,16 @@ int check_dims(const visde_dims* d) {
 }
 
 struct StashLayout {
-  size_t h_floats, raw_floats;
+  size_t h_floats, raw_floats, otile_floats;
 };
 // B rounded up to the 128-trajectory tile of the tensor-core recurrence (its stash / gi_ctx layouts are tiled)
 size_t padded_B(const visde_dims* d) { return ((size_t)d->B + 127) / 128 * 128; }
 
+bool tcw_rec_possible(const visde_dims* d);
 StashLayout stash_layout(const visde_dims* d) {
-  return {padded_B(d) * d->T * d->NL * kStashSlots * d->H, (size_t)d->B * d->T * (size_t)(d->S * (d->S + 1) / 2)};
+  // the wide-state tensor-core family keeps its tiled step records (mu | raw Cholesky | z) for the backward
+  const size_t ot = tcw_rec_possible(d) ? padded_B(d) * d->T * (size_t)tcw_out_feats(d->S) : 0;
+  return {padded_B(d) * d->T * d->NL * kStashSlots * d->H, (size_t)d->B * d->T * (size_t)(d->S * (d->S + 1) / 2), ot};
 }
 
 // AUTO switches to the tensor-core recurrence family from this batch size on: below it the 128-trajectory tiles
@@ -88,8 +91,15 @@ bool tc_rec_possible(const visde_dims* d) {
          d->S <= 4 && (d->C == 128 || d->C == 256) && !(d->variant & VISDE_FLAG_NO_TENSOR_CORES);
 }
 
+// wide-state tensor-core recurrence (path_tcw.cu): 4 < S <= 10, two layers; same batch threshold as the narrow family
+bool tcw_rec_possible(const visde_dims* d) {
+  const int fam = d->variant & 0xff;
+  return (fam == VISDE_VARIANT_TC || (fam == VISDE_VARIANT_AUTO && d->B >= kTcRecMinBatch)) && d->H == 64 && d->NL == 2 &&
+         d->S > 4 && d->S <= kTcwMaxS && (d->C == 128 || d->C == 256) && !(d->variant & VISDE_FLAG_NO_TENSOR_CORES);
+}
+
 struct BwdWs {
-  size_t dg, dout, sdg, partials, wsplit, cta_part, dg_tiled, ctx_f32, total, partial_floats;
+  size_t dg, dout, sdg, partials, wsplit, cta_part, dg_tiled, ctx_f32, wimg, ctile, total, partial_floats;
 };
 BwdWs bwd_ws(const visde_dims* d) {
   BwdWs w{};
@@ -103,6 +113,7 @@ BwdWs bwd_ws(const visde_dims* d) {
   {
     size_t fl = bt * n_out;
     if (tc_rec_possible(d) && padded_B(d) * d->T * 16 > fl) fl = padded_B(d) * d->T * 16;  // tiled [tile][t][16][128]
+    if (tcw_rec_possible(d)) fl = padded_B(d) * d->T * n_out;                              // tiled [tile][t][n_out][128]
     off += align_up(sizeof(float) * fl);
   }
   w.sdg = off;
@@ -125,6 +136,10 @@ BwdWs bwd_ws(const visde_dims* d) {
     size_t pt = fasts_thin_partial_floats(d->B, d->T, d->S, d->H);
     if (pt > pf) pf = pt;
   }
+  if (tcw_rec_possible(d)) {
+    size_t pt = tcw_thin_partial_floats(d->B, d->NL, d->S);
+    if (pt > pf) pf = pt;
+  }
   w.partial_floats = pf;
   w.partials = off;
   off += align_up(sizeof(float) * pf);
@@ -133,9 +148,13 @@ BwdWs bwd_ws(const visde_dims* d) {
   w.cta_part = off;
   off += align_up(sizeof(float) * fast_partials_floats(d->NL, d->H, d->S));
   w.dg_tiled = off;   // d_pre of the tensor-core backward, row-fastest tiled
-  if (tc_rec_possible(d)) off += align_up(sizeof(float) * padded_B(d) * d->T * d->NL * kDgSlots * d->H);
+  if (tc_rec_possible(d) || tcw_rec_possible(d)) off += align_up(sizeof(float) * padded_B(d) * d->T * d->NL * kDgSlots * d->H);
   w.ctx_f32 = off;    // fp32 copy of a bf16 context for the tcgen05 GEMM stages
   off += ctx_f32_bytes(d);
+  w.wimg = off;       // wide-state tensor-core family: weight tile images, tiled cotangent records
+  if (tcw_rec_possible(d)) off += tcw_image_bytes();
+  w.ctile = off;
+  if (tcw_rec_possible(d)) off += align_up(sizeof(float) * padded_B(d) * d->T * (size_t)tcw_cot_feats(d->S));
   w.total = off;
   return w;
 }
@@ -181,10 +200,19 @@ bool use_tc(const visde_dims* d, const visde_ctx_view* ctx) {
 bool use_tc_rec(const visde_dims* d, const PathParams& p, const visde_ctx_view* ctx) {
   return tc_rec_possible(d) && tc_rec_supported(p) && use_tc(d, ctx);
 }
+bool use_tcw_rec(const visde_dims* d, const PathParams& p, const visde_ctx_view* ctx) {
+  return tcw_rec_possible(d) && tcw_rec_supported(p) && use_tc(d, ctx);
+}
 
 size_t fwd_gi_bytes(const visde_dims* d) { return align_up(sizeof(float) * padded_B(d) * d->T * 3 * d->H); }
 size_t fwd_wsplit_bytes(const visde_dims* d) { return align_up(sizeof(float) * tc_weight_scratch_floats(d->H, d->C)); }
 size_t fwd_gth_bytes(const visde_dims* d) { return align_up(sizeof(float) * padded_B(d) * 3 * d->H); }
+// weight images + tiled noise + (inference mode: no stash) the tiled step records of the wide-state tensor-core family
+size_t fwd_tcw_bytes(const visde_dims* d) {
+  if (!tcw_rec_possible(d)) return 0;
+  return tcw_image_bytes() + align_up(sizeof(float) * padded_B(d) * d->T * d->S) +
+         align_up(sizeof(float) * padded_B(d) * d->T * (size_t)tcw_out_feats(d->S));
+}
 
 bool use_fast(const visde_dims* d, const PathParams& p) {
   if ((d->variant & 0xff) == VISDE_VARIANT_GENERIC) return false;
@@ -274,12 +302,12 @@ const char* visde_last_error(void) { return g_err; }
 size_t visde_stash_bytes(const visde_dims* d) {
   if (check_dims(d) != VISDE_OK) return 0;
   StashLayout s = stash_layout(d);
-  return align_up(sizeof(float) * s.h_floats) + align_up(sizeof(float) * s.raw_floats) + 256;
+  return align_up(sizeof(float) * s.h_floats) + align_up(sizeof(float) * s.raw_floats) + align_up(sizeof(float) * s.otile_floats) + 256;
 }
 
 size_t visde_workspace_bytes(const visde_dims* d, int backward) {
   if (check_dims(d) != VISDE_OK) return 0;
-  if (!backward) return fwd_gi_bytes(d) + fwd_wsplit_bytes(d) + fwd_gth_bytes(d) + ctx_f32_bytes(d) + 256;
+  if (!backward) return fwd_gi_bytes(d) + fwd_wsplit_bytes(d) + fwd_gth_bytes(d) + ctx_f32_bytes(d) + fwd_tcw_bytes(d) + 256;
   return bwd_ws(d).total + 256;
 }
 
@@ -293,6 +321,7 @@ int visde_recurrence_family(const visde_dims* d, int backward) {
   p.n_out = d->S + p.n_tril;
   // the same predicates, in the same order, as visde_path_fwd / visde_path_bwd below
   if (d->T > 0 && tc_rec_possible(d) && tc_rec_supported(p)) return VISDE_FAMILY_TC;
+  if (d->T > 0 && tcw_rec_possible(d) && tcw_rec_supported(p)) return VISDE_FAMILY_TC;
   if (use_fasts(d, p)) return VISDE_FAMILY_FAST_S;
   if (use_fast(d, p)) {
     const int fam = d->variant & 0xff;
@@ -318,9 +347,11 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
   VISDE_REQUIRE(((d->variant & 0xff) != VISDE_VARIANT_FAST && (d->variant & 0xff) != VISDE_VARIANT_TILED) ||
                     (d->H <= 64 && d->H % 4 == 0 && d->NL <= 2 && d->S <= ((d->variant & 0xff) == VISDE_VARIANT_FAST ? 16 : 4)),
                 "fast variant requested for an unsupported shape (H=%d NL=%d S=%d)", d->H, d->NL, d->S);
-  VISDE_REQUIRE((d->variant & 0xff) != VISDE_VARIANT_TC || (d->H == 64 && d->NL <= 2 && d->S <= 4 && (use_tc(d, ctx) || ctx_convertible(d, ctx))),
-                "tensor-core recurrence requested for an unsupported shape (needs H=64, NL<=2, S<=4, fp32 16-byte "
-                "aligned context with C in {128, 256}; got H=%d NL=%d S=%d C=%d)", d->H, d->NL, d->S, d->C);
+  VISDE_REQUIRE((d->variant & 0xff) != VISDE_VARIANT_TC ||
+                    (d->H == 64 && ((d->NL <= 2 && d->S <= 4) || (d->NL == 2 && d->S <= kTcwMaxS)) &&
+                     (use_tc(d, ctx) || ctx_convertible(d, ctx))),
+                "tensor-core recurrence requested for an unsupported shape (needs H=64 and NL<=2, S<=4 or NL=2, S<=10; fp32 "
+                "16-byte aligned context with C in {128, 256}; got H=%d NL=%d S=%d C=%d)", d->H, d->NL, d->S, d->C);
   if (workspace_bytes < visde_workspace_bytes(d, 0) - 256 || (!workspace && d->T > 0)) {
     set_error("path_fwd: workspace too small (%zu < %zu)", workspace_bytes, visde_workspace_bytes(d, 0));
     return VISDE_EWORKSPACE;
@@ -346,8 +377,17 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
     StashLayout s = stash_layout(d);
     p.stash = reinterpret_cast<float*>(stash);
     p.raw = reinterpret_cast<float*>(reinterpret_cast<char*>(stash) + align_up(sizeof(float) * s.h_floats));
+    p.otile = reinterpret_cast<float*>(reinterpret_cast<char*>(p.raw) + align_up(sizeof(float) * s.raw_floats));
   }
-  const bool tcrec = d->T > 0 && use_tc_rec(d, p, ctx);
+  const bool tcwrec = d->T > 0 && use_tcw_rec(d, p, ctx);
+  if (tcwrec) {
+    char* tcw_ws = reinterpret_cast<char*>(workspace) + fwd_gi_bytes(d) + fwd_wsplit_bytes(d) + fwd_gth_bytes(d) + ctx_f32_bytes(d);
+    p.wimg = tcw_ws;
+    p.epst = reinterpret_cast<float*>(tcw_ws + tcw_image_bytes());
+    // inference mode keeps no stash: the step records then live in the workspace
+    if (!stash) p.otile = reinterpret_cast<float*>(tcw_ws + tcw_image_bytes() + align_up(sizeof(float) * padded_B(d) * d->T * d->S));
+  }
+  const bool tcrec = (d->T > 0 && use_tc_rec(d, p, ctx)) || tcwrec;
   if (d->T > 0) {
     // K0: context rows of W_ih_l0 as one time-parallel GEMM, b_ih_l0 folded in
     StageTimer tm(VISDE_STAGE_K0_CTX_GEMM, tcrec ? 3 : 1, st);
@@ -372,7 +412,11 @@ int visde_path_fwd(const visde_dims* d, float dt, const float* x0, const visde_c
     }
     if (rc) return rc;
   }
-  StageTimer tm(VISDE_STAGE_K1_PATH_FWD, 1, st);
+  StageTimer tm(VISDE_STAGE_K1_PATH_FWD, tcwrec ? 4 : 1, st);
+  if (tcwrec) {
+    if ((rc = launch_tcw_images(p, p.wimg, true, false, st))) return rc;
+    return launch_path_fwd_tcw(p, st);
+  }
   if (tcrec) return launch_path_fwd_tc(p, st);
   if (use_fasts(d, p)) return launch_path_fwd_fasts(p, st);
   if (use_fast(d, p)) {
@@ -430,7 +474,9 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
   p.dout = reinterpret_cast<float*>(wsb + ws.dout);
   p.sdg = reinterpret_cast<float*>(wsb + ws.sdg);
   p.paths = const_cast<float*>(paths);
-  const bool tcrec = d->T > 0 && use_tc_rec(d, p, ctx);
+  p.otile = reinterpret_cast<float*>(reinterpret_cast<char*>(p.raw) + align_up(sizeof(float) * sl.raw_floats));
+  const bool tcwrec = d->T > 0 && use_tcw_rec(d, p, ctx);
+  const bool tcrec = (d->T > 0 && use_tc_rec(d, p, ctx)) || tcwrec;
   const bool fastsk = !tcrec && use_fasts(d, p);
   const bool fastk = !tcrec && !fastsk && use_fast(d, p);
   p.cta_part = (fastk || fastsk) ? reinterpret_cast<float*>(wsb + ws.cta_part) : nullptr;
@@ -442,12 +488,21 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
   if (tcrec) {
     // tensor-core family: reads the tiled stash the forward wrote and emits d_pre / d_out row-fastest tiled; the
     // thin reductions over (b, t) run right behind it, K3 / K4 below read the tiled buffers directly
-    StageTimer tm(VISDE_STAGE_K2_PATH_BWD, 3, st);
+    StageTimer tm(VISDE_STAGE_K2_PATH_BWD, tcwrec ? 9 : 3, st);
     p.dg = reinterpret_cast<float*>(wsb + ws.dg_tiled);
     dg_tiled = p.dg;
-    rc = launch_path_bwd_tc(p, st);
-    if (rc) return rc;
-    rc = launch_tc_thin_grads(p, p.dout, gw, partials, ws.partial_floats, st);
+    if (tcwrec) {
+      // wide-state family: weight images + tiled cotangent records first, S-sized reductions as time-parallel passes behind
+      p.wimg = wsb + ws.wimg;
+      p.ctile = reinterpret_cast<float*>(wsb + ws.ctile);
+      if ((rc = launch_tcw_images(p, p.wimg, false, true, st))) return rc;
+      if ((rc = launch_path_bwd_tcw(p, st))) return rc;
+      rc = launch_tcw_thin_grads(p, gw, partials, ws.partial_floats, st);
+    } else {
+      rc = launch_path_bwd_tc(p, st);
+      if (rc) return rc;
+      rc = launch_tc_thin_grads(p, p.dout, gw, partials, ws.partial_floats, st);
+    }
     if (rc) return rc;
   } else {
     StageTimer tm(VISDE_STAGE_K2_PATH_BWD, fastsk ? 2 : 1, st);

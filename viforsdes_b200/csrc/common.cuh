@@ -84,6 +84,11 @@ struct PathParams {
   float* dout;     // [B*T,n_out]
   float* sdg;      // [B,3H]  sum_t d_gi of layer 0
   float* cta_part; // fast family: per-CTA partial sums of the thin weight-gradient pieces (or nullptr)
+  // wide-state tensor-core family (path_tcw.cu): weight tile images, tiled noise, tiled step records, tiled cotangents
+  void* wimg;
+  float* epst;   // [tile][t][S][128]
+  float* otile;  // [tile][t][2S + S(S+1)/2][128]: mu | raw Cholesky | z_{t+1}   (lives in the stash: the backward reads it)
+  float* ctile;  // [tile][t][3S + S*S][128]: gP[t+1] | gM | gL | eps
 };
 
 __host__ __device__ inline int64_t stash_row_floats(int NL, int H) { return (int64_t)NL * kStashSlots * H; }
@@ -151,6 +156,22 @@ int launch_path_bwd_tc(const PathParams& p, cudaStream_t st);
 size_t tc_thin_partial_floats(int64_t B, int NL, int S);
 int launch_tc_thin_grads(const PathParams& p, const float* dout_tiled, const visde_weight_grads* gw, float* partials,
                          size_t partial_floats, cudaStream_t st);
+// wide-state tensor-core family (4 < S <= 10, NL = 2): path_tcw.cu forward, path_tcw_bwd.cu backward
+constexpr int kTcwMaxS = 10;  // S (S + 1) / 2 <= 64: the Cholesky rows of W_out are one N = 64 MMA
+// row-fastest tiled per-step record written by the wide forward: mu (S) | raw Cholesky entries (S (S + 1) / 2) | z_{t+1} (S)
+__host__ __device__ constexpr int tcw_out_feats(int S) { return 2 * S + S * (S + 1) / 2; }
+// row-fastest tiled cotangent record read by the wide backward: gP[t+1] (S) | gM (S) | gL (S x S) | eps (S)
+__host__ __device__ constexpr int tcw_cot_feats(int S) { return 3 * S + S * S; }
+bool tcw_rec_supported(const PathParams& p);
+size_t tcw_image_bytes();
+int launch_tcw_images(const PathParams& p, void* img, bool fwd, bool bwd, cudaStream_t st);
+int launch_tcw_tile(const float* src, int64_t B, int64_t T, int F, int64_t bstride, int64_t tstride, float* dst, int FD, int f_off,
+                    cudaStream_t st);
+int launch_path_fwd_tcw(const PathParams& p, cudaStream_t st);  // needs p.wimg (forward images), p.epst, p.otile, tiled gi_ctx
+int launch_path_bwd_tcw(const PathParams& p, cudaStream_t st);  // needs p.wimg (backward images), p.ctile, p.otile, tiled stash
+size_t tcw_thin_partial_floats(int64_t B, int NL, int S);
+int launch_tcw_thin_grads(const PathParams& p, const visde_weight_grads* gw, float* partials, size_t partial_floats,
+                          cudaStream_t st);
 // [ceil(B/128)][T][F][128] row-fastest -> [B][T][F]
 int launch_untile(const float* in, float* out, int64_t B, int64_t T, int F, cudaStream_t st);
 size_t fast_partials_floats(int NL, int H, int S);

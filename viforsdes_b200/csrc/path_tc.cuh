@@ -50,3 +50,28 @@ __device__ __forceinline__ float exp2i(int a) { return __uint_as_float((uint32_t
 
 }  // namespace
 }  // namespace visde
+
+// ---- wide-state variant of the tensor-core recurrence (4 < S <= 10, NL = 2; path_tcw.cu, path_tcw_bwd.cu) -----------------
+// Shared memory cannot hold the three recurrent matrices (144 KB as fp16 hi/lo tiles) next to the 64 KB of operand tiles AND
+// the S-sized tables of a wide state space, so one 48 KB buffer is time-shared between two matrices: their swizzled hi/lo
+// tile images are prepared once per launch in the workspace and streamed in with cp.async.bulk (L2 -> shared memory, 96 KB
+// per step and SM) behind the MMAs that read the previous occupant.
+namespace visde {
+constexpr int kWImg = 2 * kWTileBytes;            // hi + lo tile image of one [192 x 64] matrix: 49 152 B
+constexpr int kOutRows = 80;                      // W_out tile rows: 0..63 Cholesky entries (row-major tril), 64..79 mu
+constexpr int kOutImg = 2 * kOutRows * 128;       // 20 480 B
+// image block in the workspace: header (ew, eo as int32) | forward images W_hh_l0, W_ih_l1, W_hh_l1 | W_out image |
+// backward (transposed, K-permuted) images of the same three matrices
+constexpr size_t kImgHdr = 256;
+constexpr size_t kImgFwd0 = kImgHdr;
+constexpr size_t kImgOut = kImgFwd0 + 3 * (size_t)kWImg;
+constexpr size_t kImgBwd0 = kImgOut + kOutImg;
+constexpr size_t kImgBytes = kImgBwd0 + 3 * (size_t)kWImg;
+// (row, column) of row-major lower-triangular entry ti
+__host__ __device__ constexpr int tril_row(int ti) {
+  int r = 0;
+  while ((r + 1) * (r + 2) / 2 <= ti) ++r;
+  return r;
+}
+__host__ __device__ constexpr int tril_col(int ti) { return ti - tril_row(ti) * (tril_row(ti) + 1) / 2; }
+}  // namespace visde
