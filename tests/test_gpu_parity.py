@@ -49,6 +49,8 @@ CASES["l96s5_h64_c128_tcw"] = ("l96", 5, 21, dict(context_dim=128, hidden_dim=64
 CASES["l96s7_h64_c256_t1_tcw"] = ("l96", 3, 1, dict(context_dim=256, hidden_dim=64, num_layers=2, state_dim=7))
 CASES["l96s10_h64_c128_t2_tcw"] = ("l96", 130, 2, dict(context_dim=128, hidden_dim=64, num_layers=2, state_dim=10))
 CASES["l96s9_h64_c128_tcw"] = ("l96", 4, 33, dict(context_dim=128, hidden_dim=64, num_layers=2, state_dim=9))
+# staged ELBO kernels (wide state, user SDE, B >= 64): several 128-point chunks with a halo (T = 300), ragged last chunk
+CASES["l96s6_h32_b70_t300_staged_elbo"] = ("l96", 70, 300, dict(context_dim=16, hidden_dim=32, num_layers=2, state_dim=6))
 TCW = {"l96s10_h64_c128_b150_tcw", "l96s5_h64_c128_tcw", "l96s7_h64_c256_t1_tcw", "l96s10_h64_c128_t2_tcw", "l96s9_h64_c128_tcw"}
 TC_OK |= TCW
 TC_REC_OK = set(TC_OK)
@@ -70,7 +72,7 @@ FAST_OK |= {"lv_h64_b601_tile8", "ou_h32_l1_b610_tile8", "l96s4_h64_b597_tile8"}
 # wide-state register-resident family (4 < S <= 16, H <= 64, NL <= 2)
 CASES["l96s16_h32_l1"] = ("l96", 3, 9, dict(context_dim=8, hidden_dim=32, num_layers=1, state_dim=16))
 CASES["l96s5_h64_l2_b150"] = ("l96", 150, 5, dict(context_dim=16, hidden_dim=64, num_layers=2, state_dim=5))
-FASTS_OK = {"l96s10_h64_l2", "l96s6_h64_c128_l2", "l96s16_h32_l1", "l96s5_h64_l2_b150"} | TCW
+FASTS_OK = {"l96s10_h64_l2", "l96s6_h64_c128_l2", "l96s16_h32_l1", "l96s5_h64_l2_b150", "l96s6_h32_b70_t300_staged_elbo"} | TCW
 
 
 def _variants(name):
@@ -148,7 +150,8 @@ def test_backward_matches_oracle_autograd(name):
 
 
 @pytest.mark.parametrize("name", ["ou_h64_l2", "lv_h64_l2", "lv_h16_l1", "l96s4_h24_l3", "l96s10_h64_l2",
-                                  "lv_h64_c128_l2", "ou_h64_c256_l1", "l96s6_h64_c128_l2"])
+                                  "lv_h64_c128_l2", "ou_h64_c256_l1", "l96s6_h64_c128_l2", "l96s6_h32_b70_t300_staged_elbo",
+                                  "l96s5_h64_l2_b150"])
 def test_elbo_iteration_matches_oracle(name):
     """paths, ELBO terms and every gradient of -mean(obs + sde - gen + jac): the full hot path."""
     kind, B, T, kw = CASES[name]

@@ -167,6 +167,8 @@ size_t tcw_image_bytes();
 int launch_tcw_images(const PathParams& p, void* img, bool fwd, bool bwd, cudaStream_t st);
 int launch_tcw_tile(const float* src, int64_t B, int64_t T, int F, int64_t bstride, int64_t tstride, float* dst, int FD, int f_off,
                     cudaStream_t st);
+int launch_tcw_tile_multi(const float* const* src, const int64_t* bstride, const int64_t* tstride, const int* F, const int* f_off,
+                          int nsrc, int64_t B, int64_t T, float* dst, int FD, cudaStream_t st);
 int launch_path_fwd_tcw(const PathParams& p, cudaStream_t st);  // needs p.wimg (forward images), p.epst, p.otile, tiled gi_ctx
 int launch_path_bwd_tcw(const PathParams& p, cudaStream_t st);  // needs p.wimg (backward images), p.ctile, p.otile, tiled stash
 size_t tcw_thin_partial_floats(int64_t B, int NL, int S);
@@ -255,6 +257,7 @@ struct ElboParams {
   float* g_theta;
   float* g_drift;
   float* g_diffusion;
+  int vec16;  // set by the launcher: the S x S factor blocks may be accessed with 16-byte loads / stores
 };
 int launch_elbo_fwd(const ElboParams& p, cudaStream_t st);
 int launch_elbo_bwd(const ElboParams& p, cudaStream_t st);

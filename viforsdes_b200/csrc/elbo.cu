@@ -64,12 +64,56 @@ __device__ __forceinline__ void load_vec(const float* p, int S, float (&v)[SMAX]
   for (int i = 0; i < SMAX; ++i) v[i] = i < S ? p[i] : 0.f;
 }
 
+// A thread's S x S factor block is S*S contiguous floats, the next thread's starts S*S floats later: scalar loads of the 55
+// lower-triangular entries cost 55 instructions that each touch 32 scattered sectors per warp (elbo_bwd_kernel<10> sat at
+// 1 TB/s on LSU issue).  When the block is a whole number of 16-byte words (S == SMAX, S*S % 4 == 0: S = 6, 8, 10, 12, 16)
+// it is read with S*S/4 LDG.128 instead -- every sector fetched is consumed by two consecutive instructions of the same thread.
 template <int SMAX>
-__device__ __forceinline__ void load_tril_scaled(const float* p, int S, float scale, float (&A)[SMAX][SMAX]) {
+__device__ __forceinline__ void load_tril_scaled(const float* p, int S, float scale, float (&A)[SMAX][SMAX], bool vec16 = false) {
+  if (SMAX >= 6 && (SMAX * SMAX) % 4 == 0 && S == SMAX && vec16) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int q = 0; q < SMAX * SMAX / 4; ++q) {
+      const float4 v = p4[q];
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = (4 * q + k) / SMAX, j = (4 * q + k) % SMAX;
+        A[i][j] = j <= i ? e[k] * scale : 0.f;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < SMAX; ++i)
 #pragma unroll
     for (int j = 0; j < SMAX; ++j) A[i][j] = (i < S && j <= i) ? p[i * S + j] * scale : 0.f;
+}
+
+// cotangent of a factor block: G[i][j] = coef * (w[i] y[j] - [i == j] / A[i][i]) for j <= i, 0 above the diagonal; same
+// 16-byte access rule as load_tril_scaled
+template <int SMAX>
+__device__ __forceinline__ void store_tril_grad(float* dst, int S, float coef, const float (&w)[SMAX], const float (&y)[SMAX],
+                                                const float (&A)[SMAX][SMAX], bool vec16) {
+  if (SMAX >= 6 && (SMAX * SMAX) % 4 == 0 && S == SMAX && vec16) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int q = 0; q < SMAX * SMAX / 4; ++q) {
+      float e[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = (4 * q + k) / SMAX, j = (4 * q + k) % SMAX;
+        e[k] = j <= i ? coef * (w[i] * y[j] - (i == j ? 1.f / A[i][i] : 0.f)) : 0.f;
+      }
+      d4[q] = make_float4(e[0], e[1], e[2], e[3]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < SMAX; ++i)
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j)
+      if (i < S && j < S) dst[i * S + j] = j <= i ? coef * (w[i] * y[j] - (i == j ? 1.f / A[i][i] : 0.f)) : 0.f;
 }
 
 template <int SMAX>
@@ -128,7 +172,7 @@ __device__ __forceinline__ void sde_transition(const ElboParams& p, int64_t b, i
     const float* D = p.diffusion + (b * p.T + t) * (int64_t)S * S;
 #pragma unroll
     for (int i = 0; i < SMAX; ++i) r[i] = i < S ? xn[i] - (xt[i] + f[i] * p.dt) : 0.f;
-    load_tril_scaled<SMAX>(D, S, sq, A);
+    load_tril_scaled<SMAX>(D, S, sq, A, p.vec16 != 0);
   }
 }
 
@@ -140,7 +184,7 @@ __device__ __forceinline__ void gen_transition(const ElboParams& p, int64_t b, i
   const float* mu = p.means + (b * p.T + t) * S;
 #pragma unroll
   for (int i = 0; i < SMAX; ++i) r[i] = i < S ? zn[i] - (zt[i] + mu[i] * p.dt) : 0.f;
-  load_tril_scaled<SMAX>(p.chol + (b * p.T + t) * (int64_t)S * S, S, sqrtf(p.dt), A);
+  load_tril_scaled<SMAX>(p.chol + (b * p.T + t) * (int64_t)S * S, S, sqrtf(p.dt), A, p.vec16 != 0);
 }
 
 // observation log-likelihood at grid index tau (all observations whose idx == tau)
@@ -291,15 +335,9 @@ __global__ void __launch_bounds__(SMAX <= 4 ? kElboMaxThreads : kElboThreads) el
           if (i < S) {
             gz[i] += g_gen * w[i];
             p.g_means[row * S + i] = g_gen * w[i] * p.dt;
-#pragma unroll
-            for (int j = 0; j < SMAX; ++j)
-              if (j < S) {
-                float g = 0.f;
-                if (j <= i) g = g_gen * sq * (w[i] * y[j] - (i == j ? 1.f / A[i][i] : 0.f));
-                p.g_chol[(row * S + i) * S + j] = g;
-              }
           }
         }
+        store_tril_grad<SMAX>(p.g_chol + row * (int64_t)S * S, S, g_gen * sq, w, y, A, p.vec16 != 0);
         // SDE transition: gradients w.r.t. x_t (direct + through f, D) and theta
         sde_transition<SMAX>(p, b, tau, th, xt, xn, r, A);
         gauss_solve<SMAX>(S, A, r, y, w, true);
@@ -343,18 +381,9 @@ __global__ void __launch_bounds__(SMAX <= 4 ? kElboMaxThreads : kElboThreads) el
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < SMAX; ++i) {
-            if (i < S) {
-              p.g_drift[row * S + i] = g_sde * w[i] * p.dt;
-#pragma unroll
-              for (int j = 0; j < SMAX; ++j)
-                if (j < S) {
-                  float g = 0.f;
-                  if (j <= i) g = g_sde * sq * (w[i] * y[j] - (i == j ? 1.f / A[i][i] : 0.f));
-                  p.g_diffusion[(row * S + i) * S + j] = g;
-                }
-            }
-          }
+          for (int i = 0; i < SMAX; ++i)
+            if (i < S) p.g_drift[row * S + i] = g_sde * w[i] * p.dt;
+          store_tril_grad<SMAX>(p.g_diffusion + row * (int64_t)S * S, S, g_sde * sq, w, y, A, p.vec16 != 0);
         }
       }
 #pragma unroll
@@ -385,6 +414,7 @@ int elbo_threads(int64_t B, int64_t T, int smax) {
   return (int)(t < kElboThreads ? kElboThreads : (t > kElboMaxThreads ? kElboMaxThreads : t));
 }
 
+
 template <int SMAX>
 int launch_both(const ElboParams& p, cudaStream_t st, bool bwd) {
   if (bwd)
@@ -395,8 +425,11 @@ int launch_both(const ElboParams& p, cudaStream_t st, bool bwd) {
   return VISDE_OK;
 }
 
-int dispatch(const ElboParams& p, cudaStream_t st, bool bwd) {
-  if (p.B == 0) return VISDE_OK;
+int dispatch(const ElboParams& p_in, cudaStream_t st, bool bwd) {
+  if (p_in.B == 0) return VISDE_OK;
+  ElboParams p = p_in;
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };  // NULL counts as aligned
+  p.vec16 = al(p.chol) && al(p.diffusion) && al(p.g_chol) && al(p.g_diffusion) && (p.S * p.S) % 4 == 0;
   if (p.S <= 1) return launch_both<1>(p, st, bwd);
   if (p.S <= 2) return launch_both<2>(p, st, bwd);
   if (p.S <= 4) return launch_both<4>(p, st, bwd);

@@ -112,27 +112,42 @@ __global__ void __launch_bounds__(1024) tcw_images_kernel(PathParams p, uint8_t*
 // ---------------------------------------------------------------------------------------------------------------------
 // [B, T, F] rows (strided) -> features [f_off, f_off + F) of the row-fastest tiled record [tile][t][FD][128]
 // ---------------------------------------------------------------------------------------------------------------------
-// `steps` grid steps per block (chosen so that a row's steps * F floats are a few hundred contiguous bytes)
-__global__ void __launch_bounds__(256) tcw_tile_kernel(const float* __restrict__ src, int64_t B, int64_t T, int F, int64_t bstride,
-                                                       int64_t tstride, float* __restrict__ dst, int FD, int f_off, int steps) {
-  extern __shared__ float tile_s[];  // [128 rows][steps * F + 1]
-  const int64_t tb = blockIdx.y, t0 = (int64_t)blockIdx.x * steps;
-  const int nt = (int)(T - t0 < steps ? T - t0 : steps);
-  const int pitch = steps * F + 1;
-  const bool dense = tstride == F;  // the nt * F floats of a row are contiguous
-  for (int r = threadIdx.x >> 5; r < kTileRows; r += 8) {
-    const int64_t b = tb * kTileRows + r;
-    for (int e = threadIdx.x & 31; e < nt * F; e += 32) {
-      float v = 0.f;  // pad rows carry exact zeros
-      if (b < B) v = dense ? src[b * bstride + t0 * tstride + e] : src[b * bstride + (t0 + e / F) * tstride + e % F];
-      tile_s[r * pitch + e] = v;
+// up to four sources per launch (the backward tiles gP | gM | gL | eps into one record); `steps` grid steps per block
+struct TileSrc {
+  const float* src;
+  int64_t bstride, tstride;
+  int F, f_off;
+};
+struct TileArgs {
+  TileSrc s[4];
+  int nsrc, FD, steps;
+  int64_t B, T;
+  float* dst;
+};
+__global__ void __launch_bounds__(256) tcw_tile_kernel(TileArgs a) {
+  extern __shared__ float tile_s[];  // [128 rows][steps * Fmax + 1]
+  const int64_t tb = blockIdx.y, t0 = (int64_t)blockIdx.x * a.steps;
+  const int nt = (int)(a.T - t0 < a.steps ? a.T - t0 : a.steps);
+  for (int q = 0; q < a.nsrc; ++q) {
+    const TileSrc& sc = a.s[q];
+    const int F = sc.F, pitch = a.steps * F + 1;
+    const bool dense = sc.tstride == F;  // the nt * F floats of a row are contiguous
+    if (q > 0) __syncthreads();
+    for (int r = threadIdx.x >> 5; r < kTileRows; r += 8) {
+      const int64_t b = tb * kTileRows + r;
+      for (int e = threadIdx.x & 31; e < nt * F; e += 32) {
+        float v = 0.f;  // pad rows carry exact zeros
+        if (b < a.B)
+          v = dense ? sc.src[b * sc.bstride + t0 * sc.tstride + e] : sc.src[b * sc.bstride + (t0 + e / F) * sc.tstride + e % F];
+        tile_s[r * pitch + e] = v;
+      }
     }
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < nt * F * kTileRows; idx += 256) {
-    const int r = idx & 127, e = idx >> 7;  // e = tt * F + f
-    const int tt = e / F, f = e - tt * F;
-    dst[((tb * T + t0 + tt) * FD + f_off + f) * (int64_t)kTileRows + r] = tile_s[r * pitch + e];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nt * F * kTileRows; idx += 256) {
+      const int r = idx & 127, e = idx >> 7;  // e = tt * F + f
+      const int tt = e / F, f = e - tt * F;
+      a.dst[((tb * a.T + t0 + tt) * a.FD + sc.f_off + f) * (int64_t)kTileRows + r] = tile_s[r * pitch + e];
+    }
   }
 }
 
@@ -610,25 +625,41 @@ int launch_tcw_images(const PathParams& p, void* img, bool fwd, bool bwd, cudaSt
   return VISDE_OK;
 }
 
-int launch_tcw_tile(const float* src, int64_t B, int64_t T, int F, int64_t bstride, int64_t tstride, float* dst, int FD, int f_off,
-                    cudaStream_t st) {
+// srcs: nsrc x (pointer, batch stride, time stride, F, feature offset in the record)
+int launch_tcw_tile_multi(const float* const* src, const int64_t* bstride, const int64_t* tstride, const int* F, const int* f_off,
+                          int nsrc, int64_t B, int64_t T, float* dst, int FD, cudaStream_t st) {
+  TileArgs a{};
+  int fmax = 1;
+  for (int q = 0; q < nsrc; ++q) {
+    a.s[q] = TileSrc{src[q], bstride[q], tstride[q], F[q], f_off[q]};
+    if (F[q] > fmax) fmax = F[q];
+  }
+  a.nsrc = nsrc;
+  a.FD = FD;
+  a.steps = fmax >= 96 ? 2 : (192 / fmax > 16 ? 16 : 192 / fmax);
+  a.B = B;
+  a.T = T;
+  a.dst = dst;
   const int64_t ntiles = (B + kTileRows - 1) / kTileRows;
-  const int steps = F >= 192 ? 1 : (192 / F > 16 ? 16 : 192 / F);
-  const size_t smem = sizeof(float) * kTileRows * (steps * F + 1);
+  const size_t smem = sizeof(float) * kTileRows * (a.steps * fmax + 1);
   static DeviceOnce attr_once;
   int attr_dev = 0;
   if (attr_once.needed(&attr_dev)) {
-    VISDE_CUDA_CHECK(cudaFuncSetAttribute(tcw_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    VISDE_CUDA_CHECK(cudaFuncSetAttribute(tcw_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_once.done(attr_dev);
   }
-  if (smem > 128 * 1024) {
-    set_error("tile: %d features per step do not fit the staging buffer", F);
+  if (smem > 200 * 1024) {
+    set_error("tile: %d features per step do not fit the staging buffer", fmax);
     return VISDE_EINVAL;
   }
-  tcw_tile_kernel<<<dim3((unsigned)((T + steps - 1) / steps), (unsigned)ntiles), 256, smem, st>>>(src, B, T, F, bstride, tstride, dst,
-                                                                                                   FD, f_off, steps);
+  tcw_tile_kernel<<<dim3((unsigned)((T + a.steps - 1) / a.steps), (unsigned)ntiles), 256, smem, st>>>(a);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
+}
+
+int launch_tcw_tile(const float* src, int64_t B, int64_t T, int F, int64_t bstride, int64_t tstride, float* dst, int FD, int f_off,
+                    cudaStream_t st) {
+  return launch_tcw_tile_multi(&src, &bstride, &tstride, &F, &f_off, 1, B, T, dst, FD, st);
 }
 
 int launch_path_fwd_tcw(const PathParams& p, cudaStream_t st) {

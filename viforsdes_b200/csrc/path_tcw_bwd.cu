@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
   using L = TcwBwdSmem<S>;
   constexpr int NL = 2;
   constexpr int NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL, CZ = L::CZ, OF = tcw_out_feats(S), CF = tcw_cot_feats(S);
-  static_assert(S > 4 && S <= kTcwMaxS && 3 * S <= CZ, "wide-state tensor-core recurrence: 4 < S <= 10");
+  constexpr int SP = (S + 1) / 2 * 2;
+  static_assert(S > 4 && S <= kTcwMaxS && 3 * SP <= CZ, "wide-state tensor-core recurrence: 4 < S <= 10");
   static_assert(L::bytes <= 227 * 1024, "shared memory budget");
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t IN0_COL = 256, DIR_COL = 320;
@@ -70,9 +71,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
   const int ew = reinterpret_cast<const int*>(img)[0];
 
   for (int idx = tid; idx < NOUT * 64; idx += kBwdThreads) woutm[idx] = p.out_w[idx];
-  for (int idx = tid; idx < 64 * CZ; idx += kBwdThreads) {
-    const int i = idx / CZ, q = idx % CZ;
-    wzc[idx] = q < 3 * S ? p.w_ih[0][(int64_t)((q / S) * 64 + i) * ld0 + (q % S)] : 0.f;
+  for (int idx = tid; idx < 64 * CZ; idx += kBwdThreads) {  // [i][g * SP + s], SP = S rounded up to even (float2 pairs)
+    const int i = idx / CZ, q = idx % CZ, g = q / SP, sidx = q % SP;
+    wzc[idx] = (g < 3 && sidx < S) ? p.w_ih[0][(int64_t)(g * 64 + i) * ld0 + sidx] : 0.f;
   }
   if (tid == 0) {
     mbar_init(&bars->full[0], kEpiThreads);
@@ -187,9 +188,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           dz[s] += ct[s * kTileRows];                 // gP[t + 1]
           ev[s] = ct[(2 * S + S * S + s) * kTileRows];  // eps_t
         }
-        float dzp[S];
+        float2 dzp2[SP / 2];  // this thread's share of d z_t through the state columns of W_ih_l0 (packed FFMA2 pairs)
 #pragma unroll
-        for (int s = 0; s < S; ++s) dzp[s] = 0.f;
+        for (int s = 0; s < SP / 2; ++s) dzp2[s] = make_float2(0.f, 0.f);
         float sc_in = 0.f;
 
 #pragma unroll
@@ -202,9 +203,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             if (tid == 0 && t >= 1) load_y(0);
           }
           // ---------- pass 1: dh of this thread's 32 units, row maximum ----------
-          float dh[kUPT];
+          float2 dh2[kUPT / 2];  // dh of unit c * 8 + q lives in dh2[c * 4 + q / 2].{x, y}
 #pragma unroll
-          for (int q = 0; q < kUPT; ++q) dh[q] = 0.f;
+          for (int q = 0; q < kUPT / 2; ++q) dh2[q] = make_float2(0.f, 0.f);
           if (k == NL - 1) {
             // cotangent of the output projection (kernels/backward.py:300-334), one entry at a time: d_out[m] is written
             // to the tiled buffer and contracted with W_out[m, this thread's 32 units]
@@ -213,18 +214,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             auto contract = [&](int m, float d) {
               if (cg == 0) dor[m * kTileRows] = d;
               const float* wr = woutm + m * 64 + cg * 8;
+              const float2 d2 = make_float2(d, d);
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 const float4 wa = *reinterpret_cast<const float4*>(wr + c * 16);
                 const float4 wb = *reinterpret_cast<const float4*>(wr + c * 16 + 4);
-                dh[c * 8 + 0] = fmaf(wa.x, d, dh[c * 8 + 0]);
-                dh[c * 8 + 1] = fmaf(wa.y, d, dh[c * 8 + 1]);
-                dh[c * 8 + 2] = fmaf(wa.z, d, dh[c * 8 + 2]);
-                dh[c * 8 + 3] = fmaf(wa.w, d, dh[c * 8 + 3]);
-                dh[c * 8 + 4] = fmaf(wb.x, d, dh[c * 8 + 4]);
-                dh[c * 8 + 5] = fmaf(wb.y, d, dh[c * 8 + 5]);
-                dh[c * 8 + 6] = fmaf(wb.z, d, dh[c * 8 + 6]);
-                dh[c * 8 + 7] = fmaf(wb.w, d, dh[c * 8 + 7]);
+                fma2(dh2[c * 4 + 0], make_float2(wa.x, wa.y), d2);
+                fma2(dh2[c * 4 + 1], make_float2(wa.z, wa.w), d2);
+                fma2(dh2[c * 4 + 2], make_float2(wb.x, wb.y), d2);
+                fma2(dh2[c * 4 + 3], make_float2(wb.z, wb.w), d2);
               }
             };
             float gl_cur[S], gl_nxt[S];  // lower-triangular row of gL, one row ahead
@@ -262,10 +260,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             tmem_ld_wait();
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              float v = dh[c * 8 + q];
+              float& dref = (q & 1) ? dh2[c * 4 + q / 2].y : dh2[c * 4 + q / 2].x;
+              float v = dref;
               if (!first) v += fmaf(sc_prev[k], __uint_as_float(va[q]), __uint_as_float(vd[q]));
               if (k == 0) v = fmaf(sc_in, __uint_as_float(vi[q]), v);
-              dh[c * 8 + q] = v;
+              dref = v;
               mx = fmaxf(mx, fabsf(v));
             }
           }
@@ -296,7 +295,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             for (int q = 0; q < 8; ++q) {
               const int i = j0 + q;
               const float r = cr[q], u = cu[q], n = cn[q], nhh = cnh[q], hp = chp[q];
-              const float dhv = dh[c * 8 + q];
+              const float dhv = (q & 1) ? dh2[c * 4 + q / 2].y : dh2[c * 4 + q / 2].x;
               const float dnp = dhv * (1.f - u) * (1.f - n * n);
               const float dup = dhv * (hp - n) * u * (1.f - u);
               const float drp = dnp * nhh * r * (1.f - r);
@@ -311,13 +310,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
                 const float* wz = wzc + i * CZ;
                 float cc[CZ];
 #pragma unroll
-                for (int v = 0; v < (3 * S + 3) / 4; ++v) {
+                for (int v = 0; v < (3 * SP + 3) / 4; ++v) {
                   const float4 w4 = *reinterpret_cast<const float4*>(wz + 4 * v);
                   cc[4 * v] = w4.x; cc[4 * v + 1] = w4.y; cc[4 * v + 2] = w4.z; cc[4 * v + 3] = w4.w;
                 }
+                const float2 r2 = make_float2(drp, drp), u2 = make_float2(dup, dup), n2 = make_float2(dnp, dnp);
 #pragma unroll
-                for (int s = 0; s < S; ++s)
-                  dzp[s] = fmaf(cc[s], drp, fmaf(cc[S + s], dup, fmaf(cc[2 * S + s], dnp, dzp[s])));
+                for (int s = 0; s < SP / 2; ++s) {
+                  fma2(dzp2[s], make_float2(cc[2 * s], cc[2 * s + 1]), r2);
+                  fma2(dzp2[s], make_float2(cc[SP + 2 * s], cc[SP + 2 * s + 1]), u2);
+                  fma2(dzp2[s], make_float2(cc[2 * SP + 2 * s], cc[2 * SP + 2 * s + 1]), n2);
+                }
               }
               dr_[q] = drp * rs; du_[q] = dup * rs; dn_[q] = dnp * rs; dnh_[q] = dnh * rs;
             }
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           if (k == 1) sc_in = sc_this;
         }
 #pragma unroll
-        for (int s = 0; s < S; ++s) dzx[(cg * 128 + row) * S + s] = dzp[s];
+        for (int s = 0; s < S; ++s) dzx[(cg * 128 + row) * S + s] = (s & 1) ? dzp2[s / 2].y : dzp2[s / 2].x;
       }
       // grad_x0 = d z_0 + g_paths[:, 0]
       named_bar_sync(1 + quad, 64);
@@ -419,8 +422,6 @@ __host__ __device__ inline int tcw_part_floats(int NL, int S) {
   return NL * kDgSlots * 64 + 192 * S + nout * 64 + nout;
 }
 constexpr int kTwFeat = 4;    // dg features per thread in part A
-constexpr int kTwUnits = 8;   // hidden units per thread in part B
-constexpr int kTwM = 16;      // d_out entries per thread in part B
 
 template <int S>
 __global__ void __launch_bounds__(256) tcw_thin_a_kernel(const float* __restrict__ dg, const float* __restrict__ otile,
@@ -492,63 +493,105 @@ __global__ void __launch_bounds__(256) tcw_thin_a_kernel(const float* __restrict
   }
 }
 
-// grid (tile, unit group of 16 [2 par x 8 units], entry group of kTwM): acc[8 units][16 entries] per thread
+// dW_out[m][i] = sum_{rows, t} d_out[m] h_top[i] and db_out[m] = sum d_out[m]: an [80 x 64] x K SGEMM with K = (tile, t, row).
+// Both operands are K-contiguous in the tiled buffers ([feature][128 rows] per (tile, t)), so a CTA streams whole
+// (tile, t) records through a cp.async double buffer (65 + 64 lines of 512 B each, read exactly once) and every thread keeps a
+// 5 x 4 block of the product in registers (80 FFMA per 9 LDS.128); per-CTA partials are summed in a fixed order afterwards.
+constexpr int kTbThreads = 256, kTbPitch = 132;  // pitch 132 floats: quarter-warp LDS.128 of 8 consecutive rows hit 32 distinct banks
+constexpr int kTbMaxCtas = 148;  // 152 KB of staging per CTA: one CTA per SM
+
+__device__ __forceinline__ void cp_async16_w(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
 template <int S>
-__global__ void __launch_bounds__(256) tcw_thin_b_kernel(const float* __restrict__ dout, const float* __restrict__ stash, int T,
-                                                         float* __restrict__ part) {
-  constexpr int NL = 2, F = NL * kDgSlots * 64, NOUT = S + S * (S + 1) / 2;
-  const int64_t tb = blockIdx.x;
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, rq = w & 3, par = w >> 2;
-  const int row = rq * 32 + lane;
-  const int i0 = (blockIdx.y * 2 + par) * kTwUnits, m0 = blockIdx.z * kTwM;
+__global__ void __launch_bounds__(kTbThreads) tcw_thin_b_kernel(const float* __restrict__ dout, const float* __restrict__ stash,
+                                                                int64_t nrec, float* __restrict__ cta_part) {
+  constexpr int NL = 2, NOUT = S + S * (S + 1) / 2, MP = 80;  // m padded to 16 groups of 5
+  extern __shared__ __align__(16) float tb_s[];  // [2 stages][MP + 64][kTbPitch]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int64_t sstride = (int64_t)NL * kStashSlots * 64 * kTileRows;
-  const float* hsrc = stash + tb * T * sstride + ((int64_t)((NL - 1) * kStashSlots + kStashH) * 64 + i0) * kTileRows + row;
-  const float* dsrc = dout + tb * T * (int64_t)(NOUT * kTileRows) + row;
-  float acc[kTwUnits][kTwM], accd[kTwM];
-#pragma unroll
-  for (int m = 0; m < kTwM; ++m) {
-    accd[m] = 0.f;
-#pragma unroll
-    for (int j = 0; j < kTwUnits; ++j) acc[j][m] = 0.f;
-  }
-  for (int t = 0; t < T; ++t) {
-    float dv[kTwM], h[kTwUnits];
-#pragma unroll
-    for (int m = 0; m < kTwM; ++m) dv[m] = m0 + m < NOUT ? dsrc[((int64_t)t * NOUT + m0 + m) * kTileRows] : 0.f;
-#pragma unroll
-    for (int j = 0; j < kTwUnits; ++j) h[j] = hsrc[t * sstride + j * kTileRows];
-#pragma unroll
-    for (int m = 0; m < kTwM; ++m) {
-      accd[m] += dv[m];
-#pragma unroll
-      for (int j = 0; j < kTwUnits; ++j) acc[j][m] = fmaf(dv[m], h[j], acc[j][m]);
-    }
-  }
-  float* pw = part + tb * tcw_part_floats(NL, S) + F + 192 * S;
-  __shared__ float red2[8][(kTwUnits + 1) * kTwM];
-#pragma unroll
-  for (int m = 0; m < kTwM; ++m) {
-#pragma unroll
-    for (int j = 0; j < kTwUnits; ++j) {
-      float a = acc[j][m];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0) red2[w][j * kTwM + m] = a;
-    }
-    float d = accd[m];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    if (lane == 0) red2[w][kTwUnits * kTwM + m] = d;
-  }
+  const int64_t hoff = (int64_t)((NL - 1) * kStashSlots + kStashH) * 64 * kTileRows;
+  constexpr int STAGE = (MP + 64) * kTbPitch;
+  // rows NOUT..MP-1 of the d_out stage are never copied: zero them once
+  for (int i = tid; i < 2 * STAGE; i += kTbThreads) tb_s[i] = 0.f;
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 2 * (kTwUnits + 1) * kTwM; idx += blockDim.x) {
-    const int pp = idx / ((kTwUnits + 1) * kTwM), q = idx % ((kTwUnits + 1) * kTwM);
-    const float a = (red2[pp * 4 + 0][q] + red2[pp * 4 + 1][q]) + (red2[pp * 4 + 2][q] + red2[pp * 4 + 3][q]);
-    const int j = q / kTwM, m = m0 + q % kTwM;
-    if (m >= NOUT) continue;
-    if (j < kTwUnits) pw[m * 64 + (blockIdx.y * 2 + pp) * kTwUnits + j] = a;
-    else if (blockIdx.y == 0 && pp == 0) pw[NOUT * 64 + m] = a;
+  const int64_t per = (nrec + gridDim.x - 1) / gridDim.x;
+  const int64_t r_beg = (int64_t)blockIdx.x * per, r_end = r_beg + per < nrec ? r_beg + per : nrec;
+  auto stage = [&](int buf, int64_t rec) {  // record = (tile, t): d_out [NOUT][128] and h_top [64][128], contiguous lines
+    float* dst = tb_s + buf * STAGE;
+    const float* d = dout + rec * (int64_t)(NOUT * kTileRows);
+    const float* h = stash + rec * sstride + hoff;
+    for (int c = tid; c < (NOUT + 64) * 32; c += kTbThreads) {
+      const int f = c >> 5, q = c & 31;
+      const float* src = f < NOUT ? d + f * kTileRows + 4 * q : h + (f - NOUT) * kTileRows + 4 * q;
+      cp_async16_w(dst + (f < NOUT ? f : MP + f - NOUT) * kTbPitch + 4 * q, src);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float acc[5][4], accd[5];
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    accd[a] = 0.f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
   }
+  if (r_beg < r_end) stage(0, r_beg);
+  int cur = 0;
+  for (int64_t rec = r_beg; rec < r_end; ++rec) {
+    if (rec + 1 < r_end) {
+      stage(cur ^ 1, rec + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* As = tb_s + cur * STAGE + (ty * 5) * kTbPitch;           // d_out rows ty*5 .. ty*5+4
+    const float* Bs = tb_s + cur * STAGE + (MP + tx) * kTbPitch;          // h_top units tx, tx+16, tx+32, tx+48
+#pragma unroll 4
+    for (int r = 0; r < kTileRows; r += 4) {
+      float4 av[5], bv[4];
+#pragma unroll
+      for (int a = 0; a < 5; ++a) av[a] = *reinterpret_cast<const float4*>(As + a * kTbPitch + r);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = *reinterpret_cast<const float4*>(Bs + b * 16 * kTbPitch + r);
+#pragma unroll
+      for (int a = 0; a < 5; ++a) {
+        if (tx == 0) accd[a] += (av[a].x + av[a].y) + (av[a].z + av[a].w);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          acc[a][b] = fmaf(av[a].x, bv[b].x, acc[a][b]);
+          acc[a][b] = fmaf(av[a].y, bv[b].y, acc[a][b]);
+          acc[a][b] = fmaf(av[a].z, bv[b].z, acc[a][b]);
+          acc[a][b] = fmaf(av[a].w, bv[b].w, acc[a][b]);
+        }
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  // per-CTA record: [NOUT][64] dW_out | [NOUT] db_out
+  float* out = cta_part + (int64_t)blockIdx.x * (NOUT * 64 + NOUT);
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    const int m = ty * 5 + a;
+    if (m < NOUT) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) out[m * 64 + tx + 16 * b] = acc[a][b];
+      if (tx == 0) out[NOUT * 64 + m] = accd[a];
+    }
+  }
+}
+
+// fixed-order sum of the per-CTA records of tcw_thin_b_kernel
+__global__ void tcw_thin_b_reduce_kernel(const float* __restrict__ cta_part, int nctas, int n, float* __restrict__ out_w,
+                                         float* __restrict__ out_b, int n_w) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  float acc = 0.f;
+  for (int c = 0; c < nctas; ++c) acc += cta_part[(int64_t)c * n + idx];
+  if (idx < n_w) out_w[idx] = acc;
+  else out_b[idx - n_w] = acc;
 }
 
 struct TcwReduceArgs {
@@ -585,22 +628,30 @@ __global__ void tcw_thin_reduce_kernel(TcwReduceArgs a) {
     a.w_ih0[(int64_t)(off / a.S) * a.ld0 + off % a.S] = acc;
     return;
   }
-  off -= 192 * a.S;
-  if (off < a.n_out * 64) {
-    a.out_w[off] = acc;
-    return;
-  }
-  a.out_b[off - a.n_out * 64] = acc;
+  // dW_out / db_out come from tcw_thin_b_reduce_kernel (the per-tile records keep their slots unused)
 }
 
 template <int S>
-int launch_thin_tcw(const PathParams& p, float* partials, cudaStream_t st) {
+int launch_thin_tcw(const PathParams& p, const visde_weight_grads* gw, float* partials, cudaStream_t st) {
   const int64_t ntile = (p.B + kTileRows - 1) / kTileRows;
   constexpr int F = 2 * kDgSlots * 64, NOUT = S + S * (S + 1) / 2;
   tcw_thin_a_kernel<S><<<dim3((unsigned)ntile, F / (2 * kTwFeat)), 256, 0, st>>>(p.dg, p.otile, p.paths, p.B, (int)p.T, p.sdg, partials);
   VISDE_CUDA_CHECK(cudaGetLastError());
-  tcw_thin_b_kernel<S><<<dim3((unsigned)ntile, 64 / (2 * kTwUnits), (NOUT + kTwM - 1) / kTwM), 256, 0, st>>>(p.dout, p.stash, (int)p.T,
-                                                                                                         partials);
+  // dW_out / db_out: per-CTA records behind the per-tile records of part A
+  float* cta_part = partials + (size_t)ntile * tcw_part_floats(2, S);
+  const int64_t nrec = ntile * p.T;
+  const int nctas = (int)(nrec < kTbMaxCtas ? nrec : kTbMaxCtas);
+  const size_t smem = sizeof(float) * 2 * (80 + 64) * kTbPitch;
+  static DeviceOnce attr_once;
+  int attr_dev = 0;
+  if (attr_once.needed(&attr_dev)) {
+    VISDE_CUDA_CHECK(cudaFuncSetAttribute(tcw_thin_b_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_once.done(attr_dev);
+  }
+  tcw_thin_b_kernel<S><<<nctas, kTbThreads, smem, st>>>(p.dout, p.stash, nrec, cta_part);
+  VISDE_CUDA_CHECK(cudaGetLastError());
+  const int n = NOUT * 64 + NOUT;
+  tcw_thin_b_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(cta_part, nctas, n, gw->out_w, gw->out_b, NOUT * 64);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
@@ -610,18 +661,20 @@ int launch_thin_tcw(const PathParams& p, float* partials, cudaStream_t st) {
 size_t tcw_image_bytes() { return (kImgBytes + 255) / 256 * 256; }
 
 size_t tcw_thin_partial_floats(int64_t B, int NL, int S) {
-  return (size_t)((B + kTileRows - 1) / kTileRows) * tcw_part_floats(NL, S);
+  const int nout = S + S * (S + 1) / 2;
+  return (size_t)((B + kTileRows - 1) / kTileRows) * tcw_part_floats(NL, S) + (size_t)kTbMaxCtas * (nout * 64 + nout);
 }
 
 // p.stash / p.dg / p.dout / p.otile / p.ctile are tiled buffers; p.wimg holds the backward images
 int launch_path_bwd_tcw(const PathParams& p, cudaStream_t st) {
   // cotangent record [tile][t][3S + S*S][128]: gP[t+1] | gM | gL | eps
   const int S = p.S, CF = tcw_cot_feats(S);
-  int rc = launch_tcw_tile(p.g_paths + S, p.B, p.T, S, (p.T + 1) * (int64_t)S, S, p.ctile, CF, 0, st);
+  const float* src[4] = {p.g_paths + S, p.g_means, p.g_chol, p.eps};
+  const int64_t bs[4] = {(p.T + 1) * (int64_t)S, p.T * (int64_t)S, p.T * (int64_t)S * S, p.T * (int64_t)S};
+  const int64_t ts[4] = {S, S, (int64_t)S * S, S};
+  const int F[4] = {S, S, S * S, S}, fo[4] = {0, S, 2 * S, 2 * S + S * S};
+  int rc = launch_tcw_tile_multi(src, bs, ts, F, fo, 4, p.B, p.T, p.ctile, CF, st);
   if (rc) return rc;
-  if ((rc = launch_tcw_tile(p.g_means, p.B, p.T, S, p.T * (int64_t)S, S, p.ctile, CF, S, st))) return rc;
-  if ((rc = launch_tcw_tile(p.g_chol, p.B, p.T, S * S, p.T * (int64_t)S * S, S * S, p.ctile, CF, 2 * S, st))) return rc;
-  if ((rc = launch_tcw_tile(p.eps, p.B, p.T, S, p.T * (int64_t)S, S, p.ctile, CF, 2 * S + S * S, st))) return rc;
   switch (S) {
     case 5: return launch_bwd_tcw<5>(p, st);
     case 6: return launch_bwd_tcw<6>(p, st);
@@ -642,12 +695,12 @@ int launch_tcw_thin_grads(const PathParams& p, const visde_weight_grads* gw, flo
   }
   int rc;
   switch (p.S) {
-    case 5: rc = launch_thin_tcw<5>(p, partials, st); break;
-    case 6: rc = launch_thin_tcw<6>(p, partials, st); break;
-    case 7: rc = launch_thin_tcw<7>(p, partials, st); break;
-    case 8: rc = launch_thin_tcw<8>(p, partials, st); break;
-    case 9: rc = launch_thin_tcw<9>(p, partials, st); break;
-    case 10: rc = launch_thin_tcw<10>(p, partials, st); break;
+    case 5: rc = launch_thin_tcw<5>(p, gw, partials, st); break;
+    case 6: rc = launch_thin_tcw<6>(p, gw, partials, st); break;
+    case 7: rc = launch_thin_tcw<7>(p, gw, partials, st); break;
+    case 8: rc = launch_thin_tcw<8>(p, gw, partials, st); break;
+    case 9: rc = launch_thin_tcw<9>(p, gw, partials, st); break;
+    case 10: rc = launch_thin_tcw<10>(p, gw, partials, st); break;
     default: set_error("tcw thin gradients: unsupported state dim %d", p.S); return VISDE_EINVAL;
   }
   if (rc) return rc;
