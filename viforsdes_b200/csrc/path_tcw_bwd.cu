@@ -225,26 +225,34 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
                 fma2(dh2[c * 4 + 3], make_float2(wb.z, wb.w), d2);
               }
             };
-            float gl_cur[S], gl_nxt[S];  // lower-triangular row of gL, one row ahead
-#pragma unroll
-            for (int j = 0; j < 1; ++j) gl_cur[j] = ct[(2 * S + 0 * S + j) * kTileRows];
+            // every per-row value of this step in flight at once (one coalesced line each): gM, the raw diagonal and
+            // the lower triangle of gL, the latter in two halves so that the second half lands behind the first half's FFMAs
+            constexpr int SPLIT = (S * 7) / 10;  // rows [0, SPLIT) first
+            float gMv[S], rdv[S], glA[SPLIT * (SPLIT + 1) / 2], glB[NTRIL - SPLIT * (SPLIT + 1) / 2];
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-              if (s + 1 < S) {
+              gMv[s] = ct[(S + s) * kTileRows];
+              rdv[s] = otr[(S + s * (s + 1) / 2 + s) * kTileRows];  // raw (unfloored) diagonal entry
+            }
 #pragma unroll
-                for (int j = 0; j <= s + 1; ++j) gl_nxt[j] = ct[(2 * S + (s + 1) * S + j) * kTileRows];
-              }
-              const float gM = ct[(S + s) * kTileRows];
-              const float rd = otr[(S + s * (s + 1) / 2 + s) * kTileRows];  // raw (unfloored) diagonal entry
-              contract(s, fmaf(dz[s], p.dt, gM));
+            for (int s = 0; s < SPLIT; ++s)
+#pragma unroll
+              for (int j = 0; j <= s; ++j) glA[s * (s + 1) / 2 + j] = ct[(2 * S + s * S + j) * kTileRows];
+#pragma unroll
+            for (int s = SPLIT; s < S; ++s)
+#pragma unroll
+              for (int j = 0; j <= s; ++j) glB[s * (s + 1) / 2 + j - SPLIT * (SPLIT + 1) / 2] = ct[(2 * S + s * S + j) * kTileRows];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              contract(s, fmaf(dz[s], p.dt, gMv[s]));
 #pragma unroll
               for (int j = 0; j <= s; ++j) {
-                float d = fmaf(dz[s] * ev[j], p.sqrt_dt, gl_cur[j]);
-                if (j == s) d = (rd >= VISDE_DIAG_MIN || d < 0.f) ? d : 0.f;  // primitives/bounds.py:20
+                const float gl = s < SPLIT ? glA[s < SPLIT ? s * (s + 1) / 2 + j : 0]
+                                           : glB[s >= SPLIT ? s * (s + 1) / 2 + j - SPLIT * (SPLIT + 1) / 2 : 0];
+                float d = fmaf(dz[s] * ev[j], p.sqrt_dt, gl);
+                if (j == s) d = (rdv[s] >= VISDE_DIAG_MIN || d < 0.f) ? d : 0.f;  // primitives/bounds.py:20
                 contract(S + s * (s + 1) / 2 + j, d);
               }
-#pragma unroll
-              for (int j = 0; j < S; ++j) gl_cur[j] = gl_nxt[j];
             }
           }
           float mx = 0.f;
@@ -449,7 +457,8 @@ __global__ void __launch_bounds__(256) tcw_thin_a_kernel(const float* __restrict
 #pragma unroll
     for (int s = 0; s < S; ++s) accz[j][s] = 0.f;
   }
-  for (int t = 0; t < T; ++t) {
+#pragma unroll 4
+  for (int t = 0; t < T; ++t) {  // unrolled: the loads of four steps are in flight together (the pass is HBM-latency bound)
     float z[S];
 #pragma unroll
     for (int s = 0; s < S; ++s)

@@ -29,12 +29,12 @@ WORKLOADS = {
 
 
 class _Workloads(dict):
-    """Named configurations plus the pattern `<ou|lv>_b<B>_t<T>` (dt = 0.05) for the batch sweep of config 3."""
+    """Named configurations plus the pattern `<ou|lv|l96>_b<B>_t<T>` (dt = 0.05) for batch sweeps."""
 
     def __missing__(self, name: str):
         import re
 
-        m = re.fullmatch(r"(ou|lv)_b(\d+)_t(\d+)", name)
+        m = re.fullmatch(r"(ou|lv|l96)_b(\d+)_t(\d+)", name)
         if not m:
             raise KeyError(name)
         return (m.group(1), int(m.group(2)), int(m.group(3)), 0.05)
