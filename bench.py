@@ -424,9 +424,9 @@ def main() -> None:
         except Exception as e:  # informational leg: never fail the headline
             extra["roofline_point"] = {"error": f"{type(e).__name__}: {e}"}
 
+    if world > 1:
+        shutdown_ranks(rank, locals().get("it"))
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
     # ---- roofline --------------------------------------------------------------------------------
@@ -486,9 +486,37 @@ def main() -> None:
         "wall_ms_per_step_incl_flush": t_wall / K * 1e3, "eager_ms_per_step": eager_ms_per_step,
         "head_train_ms_per_step": train_ms_per_step, "extra": extra,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        os._exit(0)  # the process group was already torn down in shutdown_ranks
+
+
+def shutdown_ranks(rank: int, it) -> None:
+    """Orderly end of a multi-rank run.  The captured iteration holds NCCL kernels: the graph is released and the device
+    drained BEFORE the communicator goes away (destroying a process group under a live graph can block forever), and a
+    watchdog ends the process if the teardown still does not return.  Non-zero ranks exit here; rank 0 goes on to print."""
+    import threading
+
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.synchronize()
+    dist.barrier()
+    if it is not None and hasattr(it, "graph"):
+        del it.graph
+    torch.cuda.synchronize()
+    def teardown() -> None:
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
+
+    th = threading.Thread(target=teardown, daemon=True)
+    th.start()
+    th.join(20.0)  # a teardown that does not return must not keep the ranks (and the driver's clock) alive
+    if rank != 0:
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def inp_P(kind: str) -> int:
