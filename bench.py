@@ -453,6 +453,7 @@ def main() -> None:
     family = _lib.FAMILY_NAMES[lib.visde_recurrence_family(C.byref(it_dims(B, T, S, Cd, inp_P(kind), H, NL, variant)), 1)]
     roofline = {"kernel": dom, "achieved": d["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": (d["achieved_gbs"] / hbm_peak) if d["achieved_gbs"] else None, "traffic": traffic,
+                "bound": "hbm",
                 "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback 6.65 TB/s",
                 "kernel_ms": d["ms_per_step"] / max(1.0, d["launches_per_step"]),
                 "share_of_step": d["ms_per_step"] / eager_ms_per_step,
@@ -460,7 +461,26 @@ def main() -> None:
                           "kernel right after the timed region (the timed region itself is one graph replay per iteration)",
                 "algorithmic_bytes": "operator-contract tensors this kernel touches (SURVEY.md §8d; stash / gi_ctx / d_pre "
                                      "streams excluded: they are in `traffic`)"}
-    roofline.update(contract_roofline(S, Cd, H, NL, units_local, ms_per_step, family, hbm_peak, peaks, traffic_path))
+    if dom in ("K1_path_fwd", "K2_path_bwd"):
+        # the recurrence stages are not HBM-bound: their roof is the unit that executes the gate products.
+        # Algorithmic FLOPs of the stage = 2 x the recurrent MACs (K1: products with W; K2: the transposed products)
+        G, nt = 3 * H, S * (S + 1) // 2
+        rec_flops = 2 * (S * G + H * G + (NL - 1) * 2 * H * G + H * (S + nt) + nt)
+        tfl = rec_flops * units_local / (d["ms_per_step"] * 1e-3) / 1e12
+        if family == "tc":
+            unit_peak = (peaks.get("bf16_tflops_sustained") or 1360.5) / 3.0
+            bound, unit_name = "tensor", "tcgen05 kind::f16, fp16 hi/lo 3-pass split: a third of the measured dense 16-bit rate"
+        else:
+            unit_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+            bound, unit_name = "fp32_simt", "FFMA2 on 148 SMs x 128 lanes x 1.965 GHz"
+        roofline.update({"bound": bound, "achieved": tfl, "peak": unit_peak, "unit": "TFLOP/s", "frac": tfl / unit_peak,
+                         "peak_source": unit_name, "algorithmic_flops_per_unit": rec_flops,
+                         "hbm_achieved_gbs": d["achieved_gbs"], "hbm_frac": (d["achieved_gbs"] / hbm_peak) if d["achieved_gbs"] else None,
+                         "note": "latency-bound by construction: T serial steps per trajectory tile, "
+                                 f"{(B + 127) // 128 if family == 'tc' else min(B, 148)} of 148 SMs busy (DESIGN.md)"})
+    cr = contract_roofline(S, Cd, H, NL, units_local, ms_per_step, family, hbm_peak, peaks, traffic_path)
+    cr["path_bound"] = cr.pop("bound")
+    roofline.update(cr)
 
     cb = None
     if world == 1 and not args.no_cpu_baseline:
@@ -479,7 +499,7 @@ def main() -> None:
                 "l2": "512 MB flush write between timed steps; per-step working set > 126 MB L2"},
         "e2e": e2e, "gpu_launches": int(sum(cnt)),
         "roofline": roofline, "stages": stages, "stage_sum_ms": stage_sum,
-        "user_sde_ms_per_step": (eager_ms_per_step - stage_sum) if kind == "l96" else None,
+        "outside_stage_ms_per_step": eager_ms_per_step - stage_sum,  # PyTorch user SDE + VJP, gradient adds, (NCCL)
         "cpu_baseline": cb,
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                    "samples": clocks["samples"]},
