@@ -265,7 +265,9 @@ int visde_em_fwd(int64_t B, int64_t T, int sde_kind, uint32_t positive_mask, flo
 int visde_em_bwd(int64_t B, int64_t T, int sde_kind, uint32_t positive_mask, float dt, const float* theta,
                  const float* noise, uint64_t seed, const float* paths, const float* g_paths, float* grad_x0,
                  float* grad_theta, void* stream);
-/* out [B,T,S] (S <= 4): the standard normals visde_em_fwd / _bwd draw for (seed, b, t) */
+/* out [B,T,S]: counter-based standard normals -- Philox4x32-10, key = seed, counter = (t, group << 28, b), group = s / 4, Box-Muller.
+ * S <= 4 is the stream visde_em_fwd / _bwd draw in-kernel; S <= 16 serves the path op as a reproducible, rank-independent replacement
+ * of the reference's torch.randn(B, T, S) (inference/diffusion_path_sampler.py:57). */
 int visde_philox_normal(uint64_t seed, int64_t B, int64_t T, int32_t S, float* out, void* stream);
 
 /* posterior/variational_posterior.py:93-135 (sample / summary): z [n,T1,S] latent paths of the stash-less forward

@@ -521,15 +521,17 @@ def pretrain_mse(sde, theta: Tensor, obs_times: Tensor, obs_values: Tensor, n_st
     return ((paths[:, obs_idx] - obs_values.to(theta.dtype)) ** 2).mean()
 
 
-def philox_normal(seed: int, B: int, T: int, S: int):
+def philox_normal(seed: int, B: int, T: int, S: int, group: int = 0):
     """Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011: multipliers 0xD2511F53 / 0xCD9E8D57, Weyl key increments
     0x9E3779B9 / 0xBB67AE85) with counter (t_lo, t_hi, b_lo, b_hi) and key = seed, then Box-Muller on
     u = (top 24 bits + 0.5) 2^-24: the in-kernel noise of csrc/em.cu, restated in numpy (float64 transcendental part)."""
     import numpy as np
 
+    if S > 4:  # wide state spaces: one Philox block per four state dims, the group index in bits 28.. of the second counter word
+        return torch.cat([philox_normal(seed, B, T, min(4, S - 4 * g), group=g) for g in range((S + 3) // 4)], dim=-1)
     b, t = np.meshgrid(np.arange(B, dtype=np.uint64), np.arange(T, dtype=np.uint64), indexing="ij")
     m32 = np.uint64(0xFFFFFFFF)
-    c = [t & m32, t >> np.uint64(32), b & m32, b >> np.uint64(32)]
+    c = [t & m32, (t >> np.uint64(32)) | np.uint64(group << 28), b & m32, b >> np.uint64(32)]
     k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
     M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
     for _ in range(10):

@@ -82,7 +82,7 @@ def test_caller_entry_points_validate_without_a_gpu(lib):
     assert lib.visde_em_fwd(0, 4, _lib.SDE_LV, 3, 0.05, None, None, None, 0, None, None) == _lib.OK       # empty batch
     assert lib.visde_em_bwd(0, 4, _lib.SDE_LV, 3, 0.05, None, None, 0, None, None, None, None, None) == _lib.OK
     assert lib.visde_em_bwd(2, 4, _lib.SDE_LV, 3, 0.05, None, None, 0, None, None, None, None, None) == _lib.EINVAL
-    assert lib.visde_philox_normal(1, 2, 2, 5, None, None) == _lib.EINVAL  # one Philox block gives four normals
+    assert lib.visde_philox_normal(1, 2, 2, 17, None, None) == _lib.EINVAL  # S <= VISDE_MAX_STATE
     assert lib.visde_philox_normal(1, 0, 2, 2, None, None) == _lib.OK
     # posterior summary
     assert lib.visde_path_summary_workspace_bytes(1000, 801, 2) >= 3 * 801 * 2 * 4
@@ -227,7 +227,11 @@ def test_auto_family_selection_table(lib):
              1024: (T8, T8), 1184: (T8, T8), 2048: (T8, T8), 3071: (T8, T8), 3072: (TC, TC), 65536: (TC, TC)}
     for B, (fw, bw) in table.items():
         assert (fam(B, 0), fam(B, 1)) == (fw, bw), f"B={B}: {(fam(B, 0), fam(B, 1))}"
-    assert fam(8192, 0, S=10) == FS and fam(8192, 1, S=10) == FS        # wide state: BASELINE config 5
+    # wide state (BASELINE config 5, S = 10): the wide tensor-core family from 3 072 trajectories per GPU (N = 1, 2 of the
+    # strong-scaled run), the register-resident wide family below (N = 4, 8: measured crossover B ~ 2 100, profiles/r2_config5.md)
+    assert fam(8192, 0, S=10) == TC and fam(8192, 1, S=10) == TC and fam(4096, 1, S=10) == TC
+    assert fam(2048, 0, S=10) == FS and fam(1024, 1, S=10) == FS
+    assert fam(8192, 0, S=10, NL=1) == FS and fam(8192, 0, S=12) == FS    # outside the wide tensor-core shapes (NL = 2, S <= 10)
     assert fam(8192, 0, H=128) == G and fam(128, 1, NL=3) == G          # outside the register-resident shapes
     assert fam(8192, 0, Cd=64) == T8                                      # no tcgen05 K0 for this context width: no TC recurrence
     assert fam(8192, 0, variant=L.VARIANT_FAST) == F and fam(37, 1, variant=L.VARIANT_TILED) == T4

@@ -112,6 +112,35 @@ def test_em_philox_noise():
     assert torch.equal(philox_normal(seed, B, T, 1)[..., 0], n[..., 0])
 
 
+def test_philox_noise_for_the_path_op_wide_state():
+    """Counter-based noise for sample_diffusion_paths (opt-in replacement of torch.randn, diffusion_path_sampler.py:57): S = 10
+    draws against the numpy restatement, shard-layout independence via batch_offset, and the sampler wiring."""
+    from viforsdes_b200.euler_maruyama import philox_normal
+    from viforsdes_b200.observations import Observations
+    from viforsdes_b200.sampler import sample_diffusion_paths
+    from viforsdes_b200.state_space import StateSpace
+
+    seed, B, T, S = 0x1234ABCD5678, 37, 19, 10
+    n = philox_normal(seed, B, T, S)
+    ref = O.philox_normal(seed, B, T, S)
+    assert (n.cpu().double() - ref).abs().max().item() < 2e-5
+    assert torch.equal(n[..., :4], philox_normal(seed, B, T, 4)), "dims 0..3 must be the original four-normal stream"
+    assert abs(n.mean().item()) < 0.05 and abs(n.std().item() - 1.0) < 0.05
+    p = O.make_problem("l96", 8, 12, context_dim=16, hidden_dim=32, num_layers=1, state_dim=S)
+    head = build_head(p).eval()
+    ctx_full = torch.zeros(8, 13, 16, device="cuda")
+    ctx_full[:, :12] = p.context.cuda()
+    enc = lambda *a: ctx_full  # noqa: E731
+    obs = Observations(times=p.obs_times, values=p.obs_values)
+    full = sample_diffusion_paths(enc, head, obs, p.theta.cuda(), p.x0.cuda(), 0.6, p.dt, StateSpace(S), seed=seed)
+    again = sample_diffusion_paths(enc, head, obs, p.theta.cuda(), p.x0.cuda(), 0.6, p.dt, StateSpace(S), seed=seed)
+    assert torch.equal(full.z, again.z), "seeded sampling must be reproducible"
+    enc_hi = lambda *a: ctx_full[4:]  # noqa: E731
+    shard = sample_diffusion_paths(enc_hi, head, obs, p.theta.cuda()[4:], p.x0.cuda()[4:], 0.6, p.dt, StateSpace(S), seed=seed,
+                                   batch_offset=4)
+    assert torch.equal(shard.z, full.z[4:]), "a shard with batch_offset must reproduce its rows of the full batch"
+
+
 def test_em_pretraining_size_properties():
     """inference/trainer.py:208-259 sizes (4096 simulations, LV horizon 40 at dt 0.05 = 800 steps): bit-determinism, finite
     values, linearity of the reverse mode in the cotangent, fp64 oracle on a slice, and the fused objective."""

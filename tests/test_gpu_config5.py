@@ -96,6 +96,16 @@ def test_host_session_user_sde_matches_oracle(ctx_dtype):
         for k, v in ref.items():
             assert torch.equal(out["grads"][k], v), k
     assert sess.h2d_bytes > 0 and sess.launches > 0
+    # from the 4th call on the user-SDE hooks replay as CUDA graphs: same numbers
+    for _ in range(3):
+        out = sess.step()
+    assert sess._hooks.g_eval is not None and sess._hooks.g_vjp is not None, "hooks should have been captured"
+    for k, v in ref.items():
+        assert torch.equal(out["grads"][k], v), f"graph-replayed hooks changed {k}"
+    # changed inputs flow through the captured hooks
+    sess.theta.mul_(1.01)
+    moved = sess.step()
+    assert not torch.equal(moved["grads"]["theta"], ref["theta"])
     sess.close()
 
 

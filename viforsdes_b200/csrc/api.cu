@@ -826,6 +826,7 @@ struct visde_session {
   float *g_z, *g_means, *g_chol, *g_theta_elbo, *grad_x0, *grad_theta;
   void* grad_ctx;  // [B,T+1,C] in the context dtype
   float *x_state, *drift, *diffusion, *g_drift, *g_diffusion, *g_x, *g_theta_sde;  // user-SDE sessions only
+  float* ctx_f32;  // bf16 sessions: the context widened ONCE per iteration (forward and backward both read it)
   void *stash, *ws_f, *ws_b;
   size_t ws_f_bytes, ws_b_bytes;
   visde_weight_grads gw;
@@ -875,6 +876,10 @@ int session_alloc(visde_session* s) {
   A_(s->g_z, B * (T + 1) * S) A_(s->g_means, B * T * S) A_(s->g_chol, B * T * S * S) A_(s->g_theta_elbo, B * P)
   A_(s->grad_x0, B * S) A_(s->grad_theta, B * P)
   if ((rc = dev_alloc(s, &s->grad_ctx, ctx_elem_bytes(s) * B * (T + 1) * C))) return rc;
+  {
+    const visde_ctx_view host_layout{s->in[0].ctx, (int64_t)((T + 1) * C), (int64_t)C, VISDE_BF16};
+    if (s->ctx_dtype == VISDE_BF16 && ctx_convertible(d, &host_layout)) A_(s->ctx_f32, B * T * C)
+  }
   if (s->sde_kind == VISDE_SDE_GENERIC) {
     A_(s->x_state, B * T * S) A_(s->drift, B * T * S) A_(s->diffusion, B * T * S * S) A_(s->g_drift, B * T * S)
     A_(s->g_diffusion, B * T * S * S) A_(s->g_x, B * T * S) A_(s->g_theta_sde, B * P)
@@ -974,7 +979,13 @@ static int session_enqueue(visde_session* s, visde_session_inputs& in, float dt,
   visde_ctx_grad_view gv{s->grad_ctx, (int64_t)((T + 1) * C), (int64_t)C, s->ctx_dtype};
   const bool generic = s->sde_kind == VISDE_SDE_GENERIC;
   const int64_t n_x = (int64_t)B * T * d.S;
-  int rc = visde_path_fwd(&d, dt, in.x0, &cv, in.theta, in.eps, &in.w, s->paths, s->means, s->chol, s->stash, s->ws_f,
+  int rc;
+  if (s->ctx_f32) {  // bf16 host context: widen once, both directions consume the fp32 copy (grad_context stays bf16)
+    visde_ctx_view wide;
+    if ((rc = convert_ctx(&d, &cv, s->ctx_f32, &wide, st))) return rc;
+    cv = wide;
+  }
+  rc = visde_path_fwd(&d, dt, in.x0, &cv, in.theta, in.eps, &in.w, s->paths, s->means, s->chol, s->stash, s->ws_f,
                           s->ws_f_bytes, st);
   if (rc) return rc;
   if (generic) {

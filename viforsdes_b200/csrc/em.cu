@@ -35,8 +35,9 @@ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
   return c;
 }
 // four standard normals for (trajectory b, step t): u = (top 24 bits + 0.5) 2^-24 in (0, 1); Box-Muller pairs
-__device__ __forceinline__ void philox_normal4(uint64_t seed, int64_t b, int64_t t, float (&n)[4]) {
-  const U4 r = philox4x32_10(U4{(uint32_t)t, (uint32_t)((uint64_t)t >> 32), (uint32_t)b, (uint32_t)((uint64_t)b >> 32)},
+// `group` selects the block of four for state dims 4 * group .. 4 * group + 3 (wide state spaces; group 0 = the original stream)
+__device__ __forceinline__ void philox_normal4(uint64_t seed, int64_t b, int64_t t, float (&n)[4], uint32_t group = 0) {
+  const U4 r = philox4x32_10(U4{(uint32_t)t, (uint32_t)((uint64_t)t >> 32) | (group << 28), (uint32_t)b, (uint32_t)((uint64_t)b >> 32)},
                              (uint32_t)seed, (uint32_t)(seed >> 32));
   const float s = 5.9604644775390625e-8f;  // 2^-24
   const float u0 = ((float)(r.x >> 8) + 0.5f) * s, u1 = ((float)(r.y >> 8) + 0.5f) * s;
@@ -308,9 +309,11 @@ __global__ void __launch_bounds__(kEmThreads) em_bwd_kernel(EmParams p) {
 __global__ void philox_normal_kernel(uint64_t seed, int64_t B, int64_t T, int S, float* out) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= B * T) return;
-  float n4[4];
-  philox_normal4(seed, k / T, k % T, n4);
-  for (int s = 0; s < S; ++s) out[k * S + s] = n4[s];
+  for (int g = 0; 4 * g < S; ++g) {
+    float n4[4];
+    philox_normal4(seed, k / T, k % T, n4, (uint32_t)g);
+    for (int s = 4 * g; s < S && s < 4 * g + 4; ++s) out[k * S + s] = n4[s - 4 * g];
+  }
 }
 
 int em_model_dims(int sde_kind, int* S, int* P) {
@@ -370,7 +373,8 @@ int visde_em_bwd(int64_t B, int64_t T, int sde_kind, uint32_t positive_mask, flo
 }
 
 int visde_philox_normal(uint64_t seed, int64_t B, int64_t T, int32_t S, float* out, void* stream) {
-  VISDE_REQUIRE(S >= 1 && S <= 4, "philox_normal: 1 <= S <= 4 (one Philox block per (b, t)), got %d", S);
+  VISDE_REQUIRE(S >= 1 && S <= VISDE_MAX_STATE, "philox_normal: 1 <= S <= %d (one Philox block per four state dims), got %d",
+                VISDE_MAX_STATE, S);
   VISDE_REQUIRE(B >= 0 && T >= 0, "philox_normal: negative size");
   if (B * T == 0) return VISDE_OK;
   VISDE_REQUIRE(out, "philox_normal: out is NULL");
