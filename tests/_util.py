@@ -31,7 +31,7 @@ PARITY_LOG: list = []
 NOISE_CAP = 1e-3  # the fp32-noise widening never exceeds this fraction of the tensor's magnitude
 
 
-def assert_parity(a, ref32, ref64, rtol=1e-4, atol_scale=1e-5, noise_mult=3.0, name="", noise_cap=NOISE_CAP):
+def assert_parity(a, ref32, ref64, rtol=1e-4, atol_scale=1e-5, noise_mult=3.0, name="", noise_cap=NOISE_CAP, atol_abs=0.0):
     """Parity against the fp64 oracle with the fp32 bar of BASELINE.json (rtol 1e-4 elementwise plus an
     absolute floor of atol_scale x max|ref|), widened by `noise_mult` x the rounding noise the
     reference's own fp32 path shows on this tensor (max|ref32 - ref64|), the widening capped at
@@ -47,7 +47,7 @@ def assert_parity(a, ref32, ref64, rtol=1e-4, atol_scale=1e-5, noise_mult=3.0, n
     noise = (r32 - r64).abs().max().item()
     err = (a - r64).abs()
     widen = min(noise_mult * noise, noise_cap * scale)
-    tol = rtol * r64.abs() + atol_scale * scale + widen
+    tol = rtol * r64.abs() + atol_scale * scale + widen + atol_abs  # atol_abs: floor for terms that are physically zero
     PARITY_LOG.append({"name": name, "numel": a.numel(), "scale": scale, "max_abs_err": err.max().item(),
                        "normwise_err": err.max().item() / (scale or 1.0), "fp32_ref_noise_normwise": noise / (scale or 1.0),
                        "widening_normwise": widen / (scale or 1.0)})
@@ -145,7 +145,11 @@ def check_iteration(cuda_out, r32, r64, tag="", noise_cap=NOISE_CAP):
     paths, means, chol, terms, grads = cuda_out
     for a, b32, b64, nm in zip((paths, means, chol), r32[:3], r64[:3], ("paths", "means", "chol")):
         assert_parity(a, b32, b64, name=f"{tag}{nm}", noise_cap=noise_cap)
+    tscale = max(getattr(r64[3], nm).abs().max().item() for nm in ("obs", "sde", "gen", "jac"))
     for j, nm in enumerate(("obs", "sde", "gen", "jac")):
-        assert_parity(terms[:, j], getattr(r32[3], nm), getattr(r64[3], nm), name=f"{tag}term_{nm}", noise_cap=noise_cap)
+        # the four terms are summed into one ELBO: a term that is physically zero (log-Jacobian of a saturated softplus,
+        # ~1e-24) is held to the magnitude of the sum, not to its own
+        assert_parity(terms[:, j], getattr(r32[3], nm), getattr(r64[3], nm), name=f"{tag}term_{nm}", noise_cap=noise_cap,
+                      atol_abs=1e-7 * tscale)
     for nm in r64[4]:
         assert_parity(grads[nm], r32[4][nm], r64[4][nm], name=f"{tag}grad_{nm}", noise_cap=noise_cap)
