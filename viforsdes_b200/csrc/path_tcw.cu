@@ -21,6 +21,19 @@ namespace {
 
 constexpr int kFwdThreads = 256;
 
+// Phase timestamps of one CTA (tools/tcw_trace.py; build with NVCCFLAGS+=-DVISDE_TCW_TRACE): thread 0 and thread 224 (warp 7) of
+// CTA 0 write clock64() at the phase boundaries of steps 40..55 into a device array read back by visde_debug_tcw_trace
+#ifdef VISDE_TCW_TRACE
+__device__ long long g_tcw_trace_fwd[2 * 16 * 16];
+#define TCW_TRACE(slot)                                                                             \
+  do {                                                                                              \
+    if (blockIdx.x == 0 && (tid == 0 || tid == 224) && t >= 40 && t < 56)                           \
+      g_tcw_trace_fwd[((tid ? 1 : 0) * 16 + (int)(t - 40)) * 16 + (slot)] = clock64();              \
+  } while (0)
+#else
+#define TCW_TRACE(slot) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------------
 // weight images: one CTA per image
 // ---------------------------------------------------------------------------------------------------------------------
@@ -352,6 +365,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
 
       for (int64_t t = 0; t < T; ++t) {
         const bool has_next = t + 1 < T;
+        TCW_TRACE(0);
         // ---------------- layer 0 ----------------
 #pragma unroll
         for (int g = 0; g < 3; ++g)
@@ -360,6 +374,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
         mbar_wait(&bars->d0, ph_d0);
         ph_d0 ^= 1;
         tc_fence_after();
+        TCW_TRACE(1);
 #pragma unroll
         for (int c = 0; c < kUPT / 8; ++c) {
           const int j0 = u0 + c * 8;
@@ -418,6 +433,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
         }
         fence_proxy_async();
         tc_fence_before();
+        TCW_TRACE(2);
         mbar_arrive(&bars->a0);
         gi_p += 192 * kTileRows;
         if (warp == 0) {
@@ -444,9 +460,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
         eps_p += S * kTileRows;
 
         // ---------------- layer 1 ----------------
+        TCW_TRACE(3);
         mbar_wait(&bars->d1, ph_d1);
         ph_d1 ^= 1;
         tc_fence_after();
+        TCW_TRACE(4);
         if (tid == 0 && has_next) load_x(2);  // the layer-1 input product has finished reading X: stream W_hh_l1 in
 #pragma unroll
         for (int c = 0; c < kUPT / 8; ++c) {
@@ -489,6 +507,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
         }
         fence_proxy_async();
         tc_fence_before();
+        TCW_TRACE(5);
         mbar_arrive(&bars->a1);
         if (warp == 0) {
           mbar_wait(&bars->a1, ph_a1);
@@ -506,9 +525,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
         if (st_p) st_p += 2 * kStashSlots * 64 * kTileRows;
 
         // ---------------- output projection + reparameterised Euler-Maruyama update ----------------
+        TCW_TRACE(6);
         mbar_wait(&bars->out, ph_out);
         ph_out ^= 1;
         tc_fence_after();
+        TCW_TRACE(7);
         float mu[S], acc[S];
         {
           uint32_t mv[16];
@@ -546,6 +567,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
           if (writer) ot_p[(S + NTRIL + s) * kTileRows] = z[s];
         }
         ot_p += OF * kTileRows;
+        TCW_TRACE(8);
         if (tid == 0 && has_next) {
           // the recurrent product of layer 1 has finished reading X: stream W_ih_l1 back in for the next step
           mbar_wait(&bars->xr, ph_xr);
@@ -613,6 +635,12 @@ int launch_fwd_tcw(const PathParams& p, cudaStream_t st) {
 }
 
 }  // namespace
+
+#ifdef VISDE_TCW_TRACE
+extern "C" int visde_debug_tcw_trace_fwd(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_tcw_trace_fwd, sizeof(g_tcw_trace_fwd)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 bool tcw_rec_supported(const PathParams& p) {
   return p.H == 64 && p.NL == 2 && p.S > 4 && p.S <= kTcwMaxS && p.T >= 1 && p.T <= 65535 && p.B >= 1 &&

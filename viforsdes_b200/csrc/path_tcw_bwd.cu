@@ -17,6 +17,16 @@ namespace visde {
 namespace {
 
 constexpr int kBwdThreads = 256;
+#ifdef VISDE_TCW_TRACE
+__device__ long long g_tcw_trace_bwd[2 * 16 * 16];
+#define TCWB_TRACE(slot)                                                                            \
+  do {                                                                                              \
+    if (blockIdx.x == 0 && (tid == 0 || tid == 224) && t >= 40 && t < 56)                           \
+      g_tcw_trace_bwd[((tid ? 1 : 0) * 16 + (t - 40)) * 16 + (slot)] = clock64();                   \
+  } while (0)
+#else
+#define TCWB_TRACE(slot) do { } while (0)
+#endif
 constexpr int kRowExp = 9;  // rows are scaled so that max|dh| 2^e is in [2^9, 2^10)
 
 template <int S>
@@ -170,6 +180,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
         const bool first = t == T - 1;
         const uint32_t rpar = (uint32_t)(t & 1);
         const float* ct = ct_tile + (int64_t)t * (CF * kTileRows);
+        TCWB_TRACE(0);
         // ---- Y <- W_hh_l1^T for this step's layer-1 phase (its carried products are issued for t >= 1 only): every MMA
         // issued so far has completed once the last chunk's commit has (in-order tensor pipe)
         if (tid == 0 && t >= 1) {
@@ -196,9 +207,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
 #pragma unroll
         for (int k = NL - 1; k >= 0; --k) {
           if (k == 0) {
+            TCWB_TRACE(5);
             mbar_wait(&bars->in0, ph_in0);
             ph_in0 ^= 1;
             tc_fence_after();
+            TCWB_TRACE(6);
             // every MMA of the layer-1 phase has completed (the in0 commit follows its last chunk): Y <- W_hh_l0^T
             if (tid == 0 && t >= 1) load_y(0);
           }
@@ -255,6 +268,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
               }
             }
           }
+          if (k == 1) TCWB_TRACE(2); else TCWB_TRACE(7);
           float mx = 0.f;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -281,6 +295,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           named_bar_sync(1 + quad, 64);
           mx = fmaxf(mx, maxb[(xb * 2 + (cg ^ 1)) * 128 + row]);
           xb ^= 1;
+          if (k == 1) TCWB_TRACE(3); else TCWB_TRACE(8);
           const int er = row_exp_w(mx);
           const float rs = exp2i(er);
           const float sc_this = exp2i(-(er + ew));
@@ -377,6 +392,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             }
           }
           tmem_st_wait();
+          if (k == 1) TCWB_TRACE(4); else TCWB_TRACE(9);
           sc_prev[k] = sc_this;
           if (k == 1) sc_in = sc_this;
         }
@@ -666,6 +682,12 @@ int launch_thin_tcw(const PathParams& p, const visde_weight_grads* gw, float* pa
 }
 
 }  // namespace
+
+#ifdef VISDE_TCW_TRACE
+extern "C" int visde_debug_tcw_trace_bwd(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_tcw_trace_bwd, sizeof(g_tcw_trace_bwd)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 size_t tcw_image_bytes() { return (kImgBytes + 255) / 256 * 256; }
 
