@@ -488,7 +488,7 @@ int visde_path_bwd(const visde_dims* d, float dt, const float* g_paths, const fl
   if (tcrec) {
     // tensor-core family: reads the tiled stash the forward wrote and emits d_pre / d_out row-fastest tiled; the
     // thin reductions over (b, t) run right behind it, K3 / K4 below read the tiled buffers directly
-    StageTimer tm(VISDE_STAGE_K2_PATH_BWD, tcwrec ? 7 : 3, st);
+    StageTimer tm(VISDE_STAGE_K2_PATH_BWD, tcwrec ? 8 : 3, st);
     p.dg = reinterpret_cast<float*>(wsb + ws.dg_tiled);
     dg_tiled = p.dg;
     if (tcwrec) {

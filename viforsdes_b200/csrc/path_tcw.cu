@@ -146,13 +146,25 @@ __global__ void __launch_bounds__(256) tcw_tile_kernel(TileArgs a) {
     const int F = sc.F, pitch = a.steps * F + 1;
     const bool dense = sc.tstride == F;  // the nt * F floats of a row are contiguous
     if (q > 0) __syncthreads();
+    // a dense row segment that starts on a 16-byte boundary and is a whole number of float4 is read with LDG.128
+    const bool vec = dense && ((nt * F) & 3) == 0 && (sc.bstride & 3) == 0 && ((t0 * sc.tstride) & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(sc.src) & 15u) == 0;
     for (int r = threadIdx.x >> 5; r < kTileRows; r += 8) {
       const int64_t b = tb * kTileRows + r;
-      for (int e = threadIdx.x & 31; e < nt * F; e += 32) {
-        float v = 0.f;  // pad rows carry exact zeros
-        if (b < a.B)
-          v = dense ? sc.src[b * sc.bstride + t0 * sc.tstride + e] : sc.src[b * sc.bstride + (t0 + e / F) * sc.tstride + e % F];
-        tile_s[r * pitch + e] = v;
+      if (vec) {
+        const float4* row4 = reinterpret_cast<const float4*>(sc.src + b * sc.bstride + t0 * sc.tstride);
+        for (int e4 = threadIdx.x & 31; e4 < nt * F / 4; e4 += 32) {
+          const float4 v = b < a.B ? row4[e4] : make_float4(0.f, 0.f, 0.f, 0.f);
+          float* d = tile_s + r * pitch + 4 * e4;
+          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+      } else {
+        for (int e = threadIdx.x & 31; e < nt * F; e += 32) {
+          float v = 0.f;  // pad rows carry exact zeros
+          if (b < a.B)
+            v = dense ? sc.src[b * sc.bstride + t0 * sc.tstride + e] : sc.src[b * sc.bstride + (t0 + e / F) * sc.tstride + e % F];
+          tile_s[r * pitch + e] = v;
+        }
       }
     }
     __syncthreads();
@@ -218,10 +230,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
   const int ew = reinterpret_cast<const int*>(img)[0], eo = reinterpret_cast<const int*>(img)[1];
   const float sc = exp2i(-(ew + kHExp)), sco = exp2i(-(eo + kHExp));
 
-  for (int idx = tid; idx < 64 * CS; idx += kFwdThreads) {
+  for (int idx = tid; idx < 64 * CS; idx += kFwdThreads) {  // per unit: (r_s, u_s) pairs, then n_s, then b_hn
     const int j = idx / CS, q = idx % CS;
     float v = 0.f;
-    if (q < 3 * S) v = p.w_ih[0][(int64_t)((q / S) * 64 + j) * ld0 + (q % S)];
+    if (q < 2 * S) v = p.w_ih[0][(int64_t)((q & 1) * 64 + j) * ld0 + (q >> 1)];
+    else if (q < 3 * S) v = p.w_ih[0][(int64_t)(128 + j) * ld0 + (q - 2 * S)];
     else if (q == 3 * S) v = p.b_hh[0][128 + j];
     c0[idx] = v;
   }
@@ -393,10 +406,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
           for (int jj = 0; jj < 8; ++jj) {
             const int j = j0 + jj;
             const float* cw = c0 + j * CS;
-            float pr = fmaf(sc, __uint_as_float(dr[jj]), gcur[0][jj]);
-            float pu = fmaf(sc, __uint_as_float(du[jj]), gcur[1][jj]);
+            float2 pru = make_float2(fmaf(sc, __uint_as_float(dr[jj]), gcur[0][jj]), fmaf(sc, __uint_as_float(du[jj]), gcur[1][jj]));
             float pni = gcur[2][jj];
-            // state columns of W_ih_l0: 3 S weights per unit, broadcast reads (every lane of the warp has the same unit)
+            // state columns of W_ih_l0: 3 S weights per unit, broadcast reads (every lane of the warp has the same unit);
+            // the r and u rows are interleaved so that one packed FFMA2 serves both gates
             float cc[CS];
 #pragma unroll
             for (int v = 0; v < CS / 4; ++v) {
@@ -406,10 +419,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
             const float pnh = fmaf(sc, __uint_as_float(dn[jj]), cc[3 * S]);
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-              pr = fmaf(cc[s], z[s], pr);
-              pu = fmaf(cc[S + s], z[s], pu);
+              fma2(pru, make_float2(cc[2 * s], cc[2 * s + 1]), make_float2(z[s], z[s]));
               pni = fmaf(cc[2 * S + s], z[s], pni);
             }
+            const float pr = pru.x, pu = pru.y;
             const float r = sigmoid_f(pr);
             const float n = tanh_f(fmaf(r, pnh, pni));
             const float u = sigmoid_f(pu);

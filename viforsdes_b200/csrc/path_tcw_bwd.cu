@@ -700,12 +700,14 @@ size_t tcw_thin_partial_floats(int64_t B, int NL, int S) {
 int launch_path_bwd_tcw(const PathParams& p, cudaStream_t st) {
   // cotangent record [tile][t][3S + S*S][128]: gP[t+1] | gM | gL | eps
   const int S = p.S, CF = tcw_cot_feats(S);
-  const float* src[4] = {p.g_paths + S, p.g_means, p.g_chol, p.eps};
-  const int64_t bs[4] = {(p.T + 1) * (int64_t)S, p.T * (int64_t)S, p.T * (int64_t)S * S, p.T * (int64_t)S};
-  const int64_t ts[4] = {S, S, (int64_t)S * S, S};
-  const int F[4] = {S, S, S * S, S}, fo[4] = {0, S, 2 * S, 2 * S + S * S};
-  int rc = launch_tcw_tile_multi(src, bs, ts, F, fo, 4, p.B, p.T, p.ctile, CF, st);
+  // two launches: the three S-wide sources share one (16 grid steps per block: 640-byte row segments), gL has its own (S*S wide)
+  const float* src[3] = {p.g_paths + S, p.g_means, p.eps};
+  const int64_t bs[3] = {(p.T + 1) * (int64_t)S, p.T * (int64_t)S, p.T * (int64_t)S};
+  const int64_t ts[3] = {S, S, S};
+  const int F[3] = {S, S, S}, fo[3] = {0, S, 2 * S + S * S};
+  int rc = launch_tcw_tile_multi(src, bs, ts, F, fo, 3, p.B, p.T, p.ctile, CF, st);
   if (rc) return rc;
+  if ((rc = launch_tcw_tile(p.g_chol, p.B, p.T, S * S, p.T * (int64_t)S * S, S * S, p.ctile, CF, 2 * S, st))) return rc;
   switch (S) {
     case 5: return launch_bwd_tcw<5>(p, st);
     case 6: return launch_bwd_tcw<6>(p, st);
