@@ -66,7 +66,11 @@ constexpr size_t kImgHdr = 256;
 constexpr size_t kImgFwd0 = kImgHdr;
 constexpr size_t kImgOut = kImgFwd0 + 3 * (size_t)kWImg;
 constexpr size_t kImgBwd0 = kImgOut + kOutImg;
-constexpr size_t kImgBytes = kImgBwd0 + 3 * (size_t)kWImg;
+// backward image of W_out: B operand [64 hidden units][64 K] (fp16 hi | lo, 8 KB each); K order: Cholesky entry k for k < n_tril,
+// mu component k - n_tril for the next 64 - n_tril (the remaining mu components stay on the FP32 path)
+constexpr int kOutBwdImg = 2 * 64 * 128;
+constexpr size_t kImgOutBwd = kImgBwd0 + 3 * (size_t)kWImg;
+constexpr size_t kImgBytes = kImgOutBwd + kOutBwdImg;
 // (row, column) of row-major lower-triangular entry ti
 __host__ __device__ constexpr int tril_row(int ti) {
   int r = 0;

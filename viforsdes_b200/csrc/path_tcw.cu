@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(1024) tcw_images_kernel(PathParams p, uint8_t*
   __syncthreads();
   const int ew = scale_exp(amax[0]), eo = scale_exp(amax[1]);
   const float w_scale = exp2i(ew), o_scale = exp2i(eo);
-  const int job = blockIdx.x;  // 0..2 forward images, 3 W_out image, 4..6 backward images
+  const int job = blockIdx.x;  // 0..2 forward images, 3 W_out image, 4..6 backward images, 7 backward W_out image
   if (job == 0 && tid == 0) {
     reinterpret_cast<int*>(img)[0] = ew;
     reinterpret_cast<int*>(img)[1] = eo;
@@ -98,6 +98,26 @@ __global__ void __launch_bounds__(1024) tcw_images_kernel(PathParams p, uint8_t*
       split8(x, hi, lo);
       *reinterpret_cast<uint4*>(thi + sw128(n, c)) = hi;
       *reinterpret_cast<uint4*>(tlo + sw128(n, c)) = lo;
+    }
+  } else if (job == 7) {
+    if (!want_bwd) return;
+    // W_out as the B operand of dh_top (+)= d_out . W_out: rows = hidden unit i, K = output entries in the order of
+    // kImgOutBwd (path_tc.cuh)
+    uint8_t* thi = img + kImgOutBwd;
+    uint8_t* tlo = thi + 64 * 128;
+    for (int idx = tid; idx < 64 * 8; idx += blockDim.x) {
+      const int i = idx >> 3, c = idx & 7;
+      float x[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int k = c * 8 + q;
+        const int srow = k < NTRIL ? S + k : (k - NTRIL < S ? k - NTRIL : -1);
+        x[q] = srow >= 0 ? p.out_w[srow * 64 + i] * o_scale : 0.f;
+      }
+      uint4 hi, lo;
+      split8(x, hi, lo);
+      *reinterpret_cast<uint4*>(thi + sw128(i, c)) = hi;
+      *reinterpret_cast<uint4*>(tlo + sw128(i, c)) = lo;
     }
   } else {
     if (!want_bwd) return;
@@ -661,7 +681,7 @@ bool tcw_rec_supported(const PathParams& p) {
 }
 
 int launch_tcw_images(const PathParams& p, void* img, bool fwd, bool bwd, cudaStream_t st) {
-  tcw_images_kernel<<<7, 1024, 0, st>>>(p, reinterpret_cast<uint8_t*>(img), fwd ? 1 : 0, bwd ? 1 : 0);
+  tcw_images_kernel<<<8, 1024, 0, st>>>(p, reinterpret_cast<uint8_t*>(img), fwd ? 1 : 0, bwd ? 1 : 0);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }

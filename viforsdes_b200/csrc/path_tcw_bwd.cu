@@ -11,6 +11,8 @@
 //    broadcast shared-memory reads).
 //  * the S-sized reductions over (b, t) (dW_ih_l0[:, :S], dW_out, db_out, biases, sum_t d_gi) are time-parallel passes over
 //    the tiled d_pre / d_out / stash / step records (tcw_thin_* below), fixed-order sums: bit-deterministic.
+#include <type_traits>
+
 #include "path_tc.cuh"
 
 namespace visde {
@@ -36,13 +38,17 @@ struct TcwBwdSmem {
   static constexpr int OFF_W1 = 0;                                // W_ih_l1^T hi, lo (resident)
   static constexpr int OFF_Y = kWImg;                             // time-shared: W_hh_l1^T / W_hh_l0^T
   static constexpr int OFF_A = 2 * kWImg;                         // ring [2][hi, lo][128][128 B]
-  static constexpr int OFF_WOUT = OFF_A + 4 * kATileBytes;        // float [NOUT][64]: W_out[m][i]
-  static constexpr int OFF_WZ = OFF_WOUT + NOUT * 64 * 4;         // float [64][CZ]: W_ih_l0[g*64+i][s] at [i][g*S+s]
+  static constexpr int NTRIL = S * (S + 1) / 2;
+  static constexpr int KMU = 64 - NTRIL < S ? 64 - NTRIL : S;     // mu components that ride in the K = 64 MMA operand
+  static constexpr int NREST = S - KMU;                            // mu components contracted on the FP32 path
+  static constexpr int OFF_WOUT = OFF_A + 4 * kATileBytes;        // W_out B tile [hi, lo][64 units][128 B]
+  static constexpr int OFF_WREST = OFF_WOUT + kOutBwdImg;         // float [NREST][64]: W_out rows of the remaining mu components
+  static constexpr int OFF_WZ = OFF_WREST + (NREST > 0 ? NREST : 1) * 64 * 4;  // float [64][CZ]
   static constexpr int OFF_MAX = OFF_WZ + 64 * CZ * 4;            // float [2 buffers][2 cg][128]
   static constexpr int OFF_DZX = OFF_MAX + 2 * 2 * 128 * 4;       // float [2 cg][128][S]
   static constexpr int OFF_BAR = (OFF_DZX + 2 * 128 * S * 4 + 15) / 16 * 16;
   struct Bars {
-    uint64_t full[2], empty[2], in0, wy, pro;
+    uint64_t full[2], empty[2], in0, wy, pro, outd;
     uint32_t tmem_base;
   };
   static constexpr size_t bytes = OFF_BAR + sizeof(Bars) + 1024;
@@ -70,7 +76,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
   extern __shared__ __align__(1024) uint8_t smem_raw_tcwb[];
   uint8_t* smem = smem_raw_tcwb + ((1024u - (smem_u32(smem_raw_tcwb) & 1023u)) & 1023u);
   typename L::Bars* bars = reinterpret_cast<typename L::Bars*>(smem + L::OFF_BAR);
-  float* woutm = reinterpret_cast<float*>(smem + L::OFF_WOUT);
+  float* wrest = reinterpret_cast<float*>(smem + L::OFF_WREST);
   float* wzc = reinterpret_cast<float*>(smem + L::OFF_WZ);
   float* maxb = reinterpret_cast<float*>(smem + L::OFF_MAX);
   float* dzx = reinterpret_cast<float*>(smem + L::OFF_DZX);
@@ -78,9 +84,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
   const int ld0 = S + p.C + p.P;
   const int T = (int)p.T;
   const uint8_t* img = reinterpret_cast<const uint8_t*>(p.wimg);
-  const int ew = reinterpret_cast<const int*>(img)[0];
+  const int ew = reinterpret_cast<const int*>(img)[0], eo = reinterpret_cast<const int*>(img)[1];
+  constexpr int KMU = L::KMU, NREST = L::NREST;
 
-  for (int idx = tid; idx < NOUT * 64; idx += kBwdThreads) woutm[idx] = p.out_w[idx];
+  for (int idx = tid; idx < NREST * 64; idx += kBwdThreads) wrest[idx] = p.out_w[(KMU + idx / 64) * 64 + idx % 64];
   for (int idx = tid; idx < 64 * CZ; idx += kBwdThreads) {  // [i][g * SP + s], SP = S rounded up to even (float2 pairs)
     const int i = idx / CZ, q = idx % CZ, g = q / SP, sidx = q % SP;
     wzc[idx] = (g < 3 && sidx < S) ? p.w_ih[0][(int64_t)(g * 64 + i) * ld0 + sidx] : 0.f;
@@ -93,6 +100,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
     mbar_init(&bars->in0, 1);
     mbar_init(&bars->wy, 1);
     mbar_init(&bars->pro, 1);
+    mbar_init(&bars->outd, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&bars->tmem_base, TMEM_COLS);
@@ -102,8 +110,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
   const uint32_t tmem = bars->tmem_base;
   const int64_t ntiles = (p.B + kTileRows - 1) / kTileRows;
   if (tid == 0) {
-    mbar_expect_tx(&bars->pro, kWImg);
+    mbar_expect_tx(&bars->pro, kWImg + kOutBwdImg);
     bulk_load_1d(smem + L::OFF_W1, img + kImgBwd0 + kWImg, kWImg, &bars->pro);
+    bulk_load_1d(smem + L::OFF_WOUT, img + kImgOutBwd, kOutBwdImg, &bars->pro);
   }
   auto load_y = [&](int m) {  // thread 0: Y <- image of W_hh_l0^T (m = 0) / W_hh_l1^T (m = 2); the MMAs reading Y have completed
     mbar_expect_tx(&bars->wy, kWImg);
@@ -129,14 +138,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
       umma_f16(acc, dah, dbh, ID64, 1u);
     }
   };
+  const uint32_t wob = smem_u32(smem + L::OFF_WOUT);
   uint32_t gc = 0;  // chunks produced so far (ring position / phases); uniform over the CTA
+  bool pro_ok = false;  // this lane has seen the prologue copies (W_ih_l1^T, W_out tiles) land
 
   {
     const int quad = warp & 3, cg = warp >> 2;
     const int row = quad * 32 + lane;
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     uint8_t* a_ring = smem + L::OFF_A;
-    uint32_t ph_in0 = 0, xb = 0;
+    uint32_t ph_in0 = 0, ph_outd = 0, xb = 0;
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t b_raw = tile * kTileRows + row;
@@ -199,6 +210,111 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           dz[s] += ct[s * kTileRows];                 // gP[t + 1]
           ev[s] = ct[(2 * S + S * S + s) * kTileRows];  // eps_t
         }
+        // ---------- cotangent of the output projection (kernels/backward.py:300-334) as an MMA operand ----------
+        // d_out has n_out = S + S(S+1)/2 entries per row.  64 of them -- every Cholesky entry and the first KMU mu components --
+        // form one K = 64 A operand: this thread computes the 32 entries k = 32 cg + e of its row, the two threads of the row
+        // agree on a power-of-two row scale (like the d_pre chunks), the entries go into a ring slot as fp16 hi / lo and
+        // dh_top (+)= d_out . W_out is 12 MMAs into the dh_in0 columns (dead until the layer-1 chunks of this step write
+        // them).  The remaining mu components (one at S = 10) are contracted in FP32 in pass 1.
+        float sc_out = 0.f, rest_d[NREST > 0 ? NREST : 1];
+        {
+          const float* otr = ot_tile + (int64_t)t * (OF * kTileRows);
+          float* dor = do_tile + (int64_t)t * (NOUT * kTileRows);
+          float dv[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) dv[e] = 0.f;
+          auto half = [&](auto cgh_tag) {
+            constexpr int K0 = decltype(cgh_tag)::value * 32;
+            // loads first (one coalesced line each), then the arithmetic
+            float rdv[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+#pragma unroll
+              for (int j = 0; j <= s; ++j) {
+                const int k = s * (s + 1) / 2 + j;
+                if (k >= K0 && k < K0 + 32) {
+                  dv[k - K0] = ct[(2 * S + s * S + j) * kTileRows];
+                  if (j == s) rdv[s] = otr[(S + k) * kTileRows];  // raw (unfloored) diagonal entry
+                }
+              }
+              if (NTRIL + s >= K0 && NTRIL + s < K0 + 32 && s < KMU) dv[NTRIL + s - K0] = ct[(S + s) * kTileRows];  // gM
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+#pragma unroll
+              for (int j = 0; j <= s; ++j) {
+                const int k = s * (s + 1) / 2 + j;
+                if (k >= K0 && k < K0 + 32) {
+                  float d = fmaf(dz[s] * ev[j], p.sqrt_dt, dv[k - K0]);
+                  if (j == s) d = (rdv[s] >= VISDE_DIAG_MIN || d < 0.f) ? d : 0.f;  // primitives/bounds.py:20
+                  dv[k - K0] = d;
+                  dor[(S + k) * kTileRows] = d;
+                }
+              }
+              if (NTRIL + s >= K0 && NTRIL + s < K0 + 32 && s < KMU) {
+                const float d = fmaf(dz[s], p.dt, dv[NTRIL + s - K0]);
+                dv[NTRIL + s - K0] = d;
+                dor[s * kTileRows] = d;
+              }
+            }
+          };
+          if (cg == 0) half(std::integral_constant<int, 0>{}); else half(std::integral_constant<int, 1>{});
+#pragma unroll
+          for (int r = 0; r < NREST; ++r) {
+            rest_d[r] = fmaf(dz[KMU + r], p.dt, ct[(S + KMU + r) * kTileRows]);
+            if (cg == 0) dor[(KMU + r) * kTileRows] = rest_d[r];
+          }
+          float mxd = 0.f;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mxd = fmaxf(mxd, fabsf(dv[e]));
+          maxb[(xb * 2 + cg) * 128 + row] = mxd;
+          named_bar_sync(1 + quad, 64);
+          mxd = fmaxf(mxd, maxb[(xb * 2 + (cg ^ 1)) * 128 + row]);
+          xb ^= 1;
+          const int ed = row_exp_w(mxd);
+          const float rsd = exp2i(ed);
+          sc_out = exp2i(-(ed + eo));
+          const uint32_t slot = gc & 1;
+          if (gc >= 2) mbar_wait(&bars->empty[slot], ((gc >> 1) - 1) & 1);
+          uint8_t* ahi = a_ring + slot * SLOT_BYTES;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float x[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[q] = dv[c * 8 + q] * rsd;
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            *reinterpret_cast<uint4*>(ahi + sw128(row, 4 * cg + c)) = hi;
+            *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 4 * cg + c)) = lo;
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(&bars->full[slot]);
+          if (warp == (int)(gc & 7)) {
+            mbar_wait(&bars->full[slot], (gc >> 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+              if (!pro_ok) {  // first use of a prologue-copied tile by this lane
+                mbar_wait(&bars->pro, 0);
+                tc_fence_after();
+                pro_ok = true;
+              }
+              const uint32_t sb = a0 + slot * SLOT_BYTES;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint64_t dah = umma_desc(sb + j * 32, 16, 1024, 2), dal = umma_desc(sb + kATileBytes + j * 32, 16, 1024, 2);
+                const uint64_t dbh = umma_desc(wob + j * 32, 16, 1024, 2), dbl = umma_desc(wob + 64 * 128 + j * 32, 16, 1024, 2);
+                umma_f16(tmem + IN0_COL, dal, dbh, ID64, j > 0 ? 1u : 0u);
+                umma_f16(tmem + IN0_COL, dah, dbl, ID64, 1u);
+                umma_f16(tmem + IN0_COL, dah, dbh, ID64, 1u);
+              }
+              umma_commit(&bars->empty[slot]);
+              umma_commit(&bars->outd);
+            }
+            __syncwarp();
+          }
+          ++gc;
+        }
         float2 dzp2[SP / 2];  // this thread's share of d z_t through the state columns of W_ih_l0 (packed FFMA2 pairs)
 #pragma unroll
         for (int s = 0; s < SP / 2; ++s) dzp2[s] = make_float2(0.f, 0.f);
@@ -219,15 +335,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           float2 dh2[kUPT / 2];  // dh of unit c * 8 + q lives in dh2[c * 4 + q / 2].{x, y}
 #pragma unroll
           for (int q = 0; q < kUPT / 2; ++q) dh2[q] = make_float2(0.f, 0.f);
-          if (k == NL - 1) {
-            // cotangent of the output projection (kernels/backward.py:300-334), one entry at a time: d_out[m] is written
-            // to the tiled buffer and contracted with W_out[m, this thread's 32 units]
-            const float* otr = ot_tile + (int64_t)t * (OF * kTileRows);
-            float* dor = do_tile + (int64_t)t * (NOUT * kTileRows);
-            auto contract = [&](int m, float d) {
-              if (cg == 0) dor[m * kTileRows] = d;
-              const float* wr = woutm + m * 64 + cg * 8;
-              const float2 d2 = make_float2(d, d);
+          if (k == 1) {
+            // d_out . W_out has landed in the dh_in0 columns; the mu components outside the MMA operand are contracted here
+            mbar_wait(&bars->outd, ph_outd);
+            ph_outd ^= 1;
+            tc_fence_after();
+#pragma unroll
+            for (int r = 0; r < NREST; ++r) {
+              const float* wr = wrest + r * 64 + cg * 8;
+              const float2 d2 = make_float2(rest_d[r], rest_d[r]);
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 const float4 wa = *reinterpret_cast<const float4*>(wr + c * 16);
@@ -236,35 +352,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
                 fma2(dh2[c * 4 + 1], make_float2(wa.z, wa.w), d2);
                 fma2(dh2[c * 4 + 2], make_float2(wb.x, wb.y), d2);
                 fma2(dh2[c * 4 + 3], make_float2(wb.z, wb.w), d2);
-              }
-            };
-            // every per-row value of this step in flight at once (one coalesced line each): gM, the raw diagonal and
-            // the lower triangle of gL, the latter in two halves so that the second half lands behind the first half's FFMAs
-            constexpr int SPLIT = (S * 7) / 10;  // rows [0, SPLIT) first
-            float gMv[S], rdv[S], glA[SPLIT * (SPLIT + 1) / 2], glB[NTRIL - SPLIT * (SPLIT + 1) / 2];
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              gMv[s] = ct[(S + s) * kTileRows];
-              rdv[s] = otr[(S + s * (s + 1) / 2 + s) * kTileRows];  // raw (unfloored) diagonal entry
-            }
-#pragma unroll
-            for (int s = 0; s < SPLIT; ++s)
-#pragma unroll
-              for (int j = 0; j <= s; ++j) glA[s * (s + 1) / 2 + j] = ct[(2 * S + s * S + j) * kTileRows];
-#pragma unroll
-            for (int s = SPLIT; s < S; ++s)
-#pragma unroll
-              for (int j = 0; j <= s; ++j) glB[s * (s + 1) / 2 + j - SPLIT * (SPLIT + 1) / 2] = ct[(2 * S + s * S + j) * kTileRows];
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              contract(s, fmaf(dz[s], p.dt, gMv[s]));
-#pragma unroll
-              for (int j = 0; j <= s; ++j) {
-                const float gl = s < SPLIT ? glA[s < SPLIT ? s * (s + 1) / 2 + j : 0]
-                                           : glB[s >= SPLIT ? s * (s + 1) / 2 + j - SPLIT * (SPLIT + 1) / 2 : 0];
-                float d = fmaf(dz[s] * ev[j], p.sqrt_dt, gl);
-                if (j == s) d = (rdv[s] >= VISDE_DIAG_MIN || d < 0.f) ? d : 0.f;  // primitives/bounds.py:20
-                contract(S + s * (s + 1) / 2 + j, d);
               }
             }
           }
@@ -278,14 +365,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
               tmem_ld8_nowait(tl + (uint32_t)(k * 2 + rpar) * 64 + j0, va);
               tmem_ld8_nowait(tl + DIR_COL + (uint32_t)k * 64 + j0, vd);
             }
-            if (k == 0) tmem_ld8_nowait(tl + IN0_COL + j0, vi);
+            // k = 0: dh_in0 of this step; k = 1: d_out . W_out of this step (same columns, see the d_out phase)
+            tmem_ld8_nowait(tl + IN0_COL + j0, vi);
             tmem_ld_wait();
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               float& dref = (q & 1) ? dh2[c * 4 + q / 2].y : dh2[c * 4 + q / 2].x;
               float v = dref;
               if (!first) v += fmaf(sc_prev[k], __uint_as_float(va[q]), __uint_as_float(vd[q]));
-              if (k == 0) v = fmaf(sc_in, __uint_as_float(vi[q]), v);
+              v = fmaf(k == 0 ? sc_in : sc_out, __uint_as_float(vi[q]), v);
               dref = v;
               mx = fmaxf(mx, fabsf(v));
             }
@@ -379,9 +467,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
                   issue(tmem + (uint32_t)(k * 2 + ((t & 1) ^ 1)) * 64, sb, wy, c, true, c == 0);
                 }
                 if (k == 1) {
-                  if (gc < 8) {  // the first uses of the resident W_ih_l1^T tile: its prologue copy must have landed
+                  if (!pro_ok) {  // first use of a prologue-copied tile by this lane
                     mbar_wait(&bars->pro, 0);
                     tc_fence_after();
+                    pro_ok = true;
                   }
                   issue(tmem + IN0_COL, sb, w1, c, false, c == 0);
                 }
