@@ -70,7 +70,11 @@ constexpr size_t kImgBwd0 = kImgOut + kOutImg;
 // mu component k - n_tril for the next 64 - n_tril (the remaining mu components stay on the FP32 path)
 constexpr int kOutBwdImg = 2 * 64 * 128;
 constexpr size_t kImgOutBwd = kImgBwd0 + 3 * (size_t)kWImg;
-constexpr size_t kImgBytes = kImgOutBwd + kOutBwdImg;
+// backward image of the state columns of W_ih_l0: B operand [16 rows: state dim s][K = 192 in the K permutation of the
+// transposed recurrent matrices], three K-blocks of [16][128 B], fp16 hi | lo; scaled by 2^ez (header word 2)
+constexpr int kWzBwdImg = 2 * 3 * 16 * 128;
+constexpr size_t kImgWzBwd = kImgOutBwd + kOutBwdImg;
+constexpr size_t kImgBytes = kImgWzBwd + kWzBwdImg;
 // (row, column) of row-major lower-triangular entry ti
 __host__ __device__ constexpr int tril_row(int ti) {
   int r = 0;

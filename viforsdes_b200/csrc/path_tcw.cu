@@ -38,13 +38,14 @@ __device__ long long g_tcw_trace_fwd[2 * 16 * 16];
 // weight images: one CTA per image
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) tcw_images_kernel(PathParams p, uint8_t* __restrict__ img, int want_fwd, int want_bwd) {
-  __shared__ uint32_t amax[2];
+  __shared__ uint32_t amax[3];
   const int tid = threadIdx.x, lane = tid & 31;
-  const int S = p.S, NTRIL = p.n_tril;
-  if (tid == 0) amax[0] = amax[1] = 0u;
+  const int S = p.S, NTRIL = p.n_tril, ld0 = p.S + p.C + p.P;
+  if (tid == 0) amax[0] = amax[1] = amax[2] = 0u;
   __syncthreads();
   {
-    float mx = 0.f, mo = 0.f;
+    float mx = 0.f, mo = 0.f, mz = 0.f;
+    for (int idx = tid; idx < 192 * S; idx += blockDim.x) mz = fmaxf(mz, fabsf(p.w_ih[0][(int64_t)(idx / S) * ld0 + idx % S]));
     for (int m = 0; m < 3; ++m) {
       const float* src = m == 0 ? p.w_hh[0] : (m == 1 ? p.w_ih[1] : p.w_hh[1]);
       for (int idx = tid; idx < 192 * 64; idx += blockDim.x) mx = fmaxf(mx, fabsf(src[idx]));
@@ -54,19 +55,22 @@ __global__ void __launch_bounds__(1024) tcw_images_kernel(PathParams p, uint8_t*
     for (int o = 16; o > 0; o >>= 1) {
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       mo = fmaxf(mo, __shfl_xor_sync(0xffffffffu, mo, o));
+      mz = fmaxf(mz, __shfl_xor_sync(0xffffffffu, mz, o));
     }
     if (lane == 0) {
       atomicMax(&amax[0], __float_as_uint(mx));
       atomicMax(&amax[1], __float_as_uint(mo));
+      atomicMax(&amax[2], __float_as_uint(mz));
     }
   }
   __syncthreads();
-  const int ew = scale_exp(amax[0]), eo = scale_exp(amax[1]);
-  const float w_scale = exp2i(ew), o_scale = exp2i(eo);
-  const int job = blockIdx.x;  // 0..2 forward images, 3 W_out image, 4..6 backward images, 7 backward W_out image
+  const int ew = scale_exp(amax[0]), eo = scale_exp(amax[1]), ez = scale_exp(amax[2]);
+  const float w_scale = exp2i(ew), o_scale = exp2i(eo), z_scale = exp2i(ez);
+  const int job = blockIdx.x;  // 0..2 forward images, 3 W_out image, 4..6 backward images, 7 backward W_out, 8 backward W_z
   if (job == 0 && tid == 0) {
     reinterpret_cast<int*>(img)[0] = ew;
     reinterpret_cast<int*>(img)[1] = eo;
+    reinterpret_cast<int*>(img)[2] = ez;
   }
   if (job < 3) {
     if (!want_fwd) return;
@@ -98,6 +102,25 @@ __global__ void __launch_bounds__(1024) tcw_images_kernel(PathParams p, uint8_t*
       split8(x, hi, lo);
       *reinterpret_cast<uint4*>(thi + sw128(n, c)) = hi;
       *reinterpret_cast<uint4*>(tlo + sw128(n, c)) = lo;
+    }
+  } else if (job == 8) {
+    if (!want_bwd) return;
+    // state columns of W_ih_l0 as the B operand of d z_t (+)= d_gi_l0 . W_z: rows = state dim s (16, zero beyond S), K in the
+    // (chunk, gate, unit) permutation of the transposed recurrent matrices
+    uint8_t* thi = img + kImgWzBwd;
+    uint8_t* tlo = thi + 3 * 16 * 128;
+    for (int idx = tid; idx < 16 * 24; idx += blockDim.x) {
+      const int sdim = idx & 15, hg = idx >> 4;
+      const int gB = hg >> 1, half = hg & 1, c = gB / 3, g = gB % 3;
+      float x[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        x[q] = sdim < S ? p.w_ih[0][(int64_t)(g * 64 + c * 16 + half * 8 + q) * ld0 + sdim] * z_scale : 0.f;
+      uint4 hi, lo;
+      split8(x, hi, lo);
+      const uint32_t off = (uint32_t)(gB >> 2) * 2048u + sw128(sdim, (gB & 3) * 2 + half);
+      *reinterpret_cast<uint4*>(thi + off) = hi;
+      *reinterpret_cast<uint4*>(tlo + off) = lo;
     }
   } else if (job == 7) {
     if (!want_bwd) return;
@@ -681,7 +704,7 @@ bool tcw_rec_supported(const PathParams& p) {
 }
 
 int launch_tcw_images(const PathParams& p, void* img, bool fwd, bool bwd, cudaStream_t st) {
-  tcw_images_kernel<<<8, 1024, 0, st>>>(p, reinterpret_cast<uint8_t*>(img), fwd ? 1 : 0, bwd ? 1 : 0);
+  tcw_images_kernel<<<9, 1024, 0, st>>>(p, reinterpret_cast<uint8_t*>(img), fwd ? 1 : 0, bwd ? 1 : 0);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }

@@ -42,11 +42,10 @@ struct TcwBwdSmem {
   static constexpr int KMU = 64 - NTRIL < S ? 64 - NTRIL : S;     // mu components that ride in the K = 64 MMA operand
   static constexpr int NREST = S - KMU;                            // mu components contracted on the FP32 path
   static constexpr int OFF_WOUT = OFF_A + 4 * kATileBytes;        // W_out B tile [hi, lo][64 units][128 B]
-  static constexpr int OFF_WREST = OFF_WOUT + kOutBwdImg;         // float [NREST][64]: W_out rows of the remaining mu components
-  static constexpr int OFF_WZ = OFF_WREST + (NREST > 0 ? NREST : 1) * 64 * 4;  // float [64][CZ]
-  static constexpr int OFF_MAX = OFF_WZ + 64 * CZ * 4;            // float [2 buffers][2 cg][128]
-  static constexpr int OFF_DZX = OFF_MAX + 2 * 2 * 128 * 4;       // float [2 cg][128][S]
-  static constexpr int OFF_BAR = (OFF_DZX + 2 * 128 * S * 4 + 15) / 16 * 16;
+  static constexpr int OFF_WZ = OFF_WOUT + kOutBwdImg;            // W_z B tile [hi, lo][3 K-blocks][16 state dims][128 B]
+  static constexpr int OFF_WREST = OFF_WZ + kWzBwdImg;            // float [NREST][64]: W_out rows of the remaining mu components
+  static constexpr int OFF_MAX = OFF_WREST + (NREST > 0 ? NREST : 1) * 64 * 4;  // float [2 buffers][2 cg][128]
+  static constexpr int OFF_BAR = (OFF_MAX + 2 * 2 * 128 * 4 + 15) / 16 * 16;
   struct Bars {
     uint64_t full[2], empty[2], in0, wy, pro, outd;
     uint32_t tmem_base;
@@ -66,32 +65,24 @@ template <int S>
 __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams p) {
   using L = TcwBwdSmem<S>;
   constexpr int NL = 2;
-  constexpr int NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL, CZ = L::CZ, OF = tcw_out_feats(S), CF = tcw_cot_feats(S);
-  constexpr int SP = (S + 1) / 2 * 2;
-  static_assert(S > 4 && S <= kTcwMaxS && 3 * SP <= CZ, "wide-state tensor-core recurrence: 4 < S <= 10");
+  constexpr int NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL, OF = tcw_out_feats(S), CF = tcw_cot_feats(S);
+  static_assert(S > 4 && S <= kTcwMaxS, "wide-state tensor-core recurrence: 4 < S <= 10");
   static_assert(L::bytes <= 227 * 1024, "shared memory budget");
   constexpr uint32_t TMEM_COLS = 512;
-  constexpr uint32_t IN0_COL = 256, DIR_COL = 320;
+  constexpr uint32_t IN0_COL = 256, DIR_COL = 320, DZ_COL = 448;
   constexpr int SLOT_BYTES = 2 * kATileBytes;
   extern __shared__ __align__(1024) uint8_t smem_raw_tcwb[];
   uint8_t* smem = smem_raw_tcwb + ((1024u - (smem_u32(smem_raw_tcwb) & 1023u)) & 1023u);
   typename L::Bars* bars = reinterpret_cast<typename L::Bars*>(smem + L::OFF_BAR);
   float* wrest = reinterpret_cast<float*>(smem + L::OFF_WREST);
-  float* wzc = reinterpret_cast<float*>(smem + L::OFF_WZ);
   float* maxb = reinterpret_cast<float*>(smem + L::OFF_MAX);
-  float* dzx = reinterpret_cast<float*>(smem + L::OFF_DZX);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ld0 = S + p.C + p.P;
   const int T = (int)p.T;
   const uint8_t* img = reinterpret_cast<const uint8_t*>(p.wimg);
-  const int ew = reinterpret_cast<const int*>(img)[0], eo = reinterpret_cast<const int*>(img)[1];
+  const int ew = reinterpret_cast<const int*>(img)[0], eo = reinterpret_cast<const int*>(img)[1], ez = reinterpret_cast<const int*>(img)[2];
   constexpr int KMU = L::KMU, NREST = L::NREST;
 
   for (int idx = tid; idx < NREST * 64; idx += kBwdThreads) wrest[idx] = p.out_w[(KMU + idx / 64) * 64 + idx % 64];
-  for (int idx = tid; idx < 64 * CZ; idx += kBwdThreads) {  // [i][g * SP + s], SP = S rounded up to even (float2 pairs)
-    const int i = idx / CZ, q = idx % CZ, g = q / SP, sidx = q % SP;
-    wzc[idx] = (g < 3 && sidx < S) ? p.w_ih[0][(int64_t)(g * 64 + i) * ld0 + sidx] : 0.f;
-  }
   if (tid == 0) {
     mbar_init(&bars->full[0], kEpiThreads);
     mbar_init(&bars->full[1], kEpiThreads);
@@ -110,9 +101,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
   const uint32_t tmem = bars->tmem_base;
   const int64_t ntiles = (p.B + kTileRows - 1) / kTileRows;
   if (tid == 0) {
-    mbar_expect_tx(&bars->pro, kWImg + kOutBwdImg);
+    mbar_expect_tx(&bars->pro, kWImg + kOutBwdImg + kWzBwdImg);
     bulk_load_1d(smem + L::OFF_W1, img + kImgBwd0 + kWImg, kWImg, &bars->pro);
     bulk_load_1d(smem + L::OFF_WOUT, img + kImgOutBwd, kOutBwdImg, &bars->pro);
+    bulk_load_1d(smem + L::OFF_WZ, img + kImgWzBwd, kWzBwdImg, &bars->pro);
   }
   auto load_y = [&](int m) {  // thread 0: Y <- image of W_hh_l0^T (m = 0) / W_hh_l1^T (m = 2); the MMAs reading Y have completed
     mbar_expect_tx(&bars->wy, kWImg);
@@ -138,7 +130,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
       umma_f16(acc, dah, dbh, ID64, 1u);
     }
   };
-  const uint32_t wob = smem_u32(smem + L::OFF_WOUT);
+  const uint32_t wob = smem_u32(smem + L::OFF_WOUT), wzb = smem_u32(smem + L::OFF_WZ);
+  constexpr uint32_t ID16 = idesc_f16(16);
+  // 9 MMAs: d z_t [128,16] (+)= d_gi_l0 chunk (slots r, u, n) . W_z^T[K-groups of chunk c]
+  auto issue_dz = [&](uint32_t slot_base, int c) {
+    const uint32_t a_hi = slot_base, a_lo = slot_base + kATileBytes;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      const int gB = c * 3 + g;
+      const uint32_t boff = (uint32_t)(gB >> 2) * 2048u + (uint32_t)(gB & 3) * 32u;
+      const uint64_t dah = umma_desc(a_hi + g * 32, 16, 1024, 2), dal = umma_desc(a_lo + g * 32, 16, 1024, 2);
+      const uint64_t dbh = umma_desc(wzb + boff, 16, 1024, 2), dbl = umma_desc(wzb + 3 * 2048 + boff, 16, 1024, 2);
+      umma_f16(tmem + DZ_COL, dal, dbh, ID16, (c == 0 && g == 0) ? 0u : 1u);
+      umma_f16(tmem + DZ_COL, dah, dbl, ID16, 1u);
+      umma_f16(tmem + DZ_COL, dah, dbh, ID16, 1u);
+    }
+  };
   uint32_t gc = 0;  // chunks produced so far (ring position / phases); uniform over the CTA
   bool pro_ok = false;  // this lane has seen the prologue copies (W_ih_l1^T, W_out tiles) land
 
@@ -183,7 +190,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
       float dz[S];
 #pragma unroll
       for (int s = 0; s < S; ++s) dz[s] = 0.f;
-      float sc_prev[NL];
+      float sc_prev[NL], scz_prev = 0.f;  // 2^-(row exponent + weight exponent) of the products issued by the previous step
 #pragma unroll
       for (int k = 0; k < NL; ++k) sc_prev[k] = 0.f;
 
@@ -198,11 +205,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           if (gc >= 1) mbar_wait(&bars->empty[(gc - 1) & 1], ((gc - 1) >> 1) & 1);
           load_y(2);
         }
-        // ---- cotangent of z_{t+1}: both threads of a row add the two partial sums in the same order
+        // ---- cotangent of z_{t+1}: d z through the state columns of W_ih_l0 was accumulated on the tensor pipe by the layer-0
+        // chunks of step t + 1 (16 TMEM columns): all of them have completed once the last chunk's commit has
         if (!first) {
-          named_bar_sync(1 + quad, 64);
+          mbar_wait(&bars->empty[(gc - 1) & 1], ((gc - 1) >> 1) & 1);
+          tc_fence_after();
+          uint32_t zv[16];
+          tmem_ld16_nowait(tl + DZ_COL, zv);
+          tmem_ld_wait();
 #pragma unroll
-          for (int s = 0; s < S; ++s) dz[s] += dzx[(0 * 128 + row) * S + s] + dzx[(1 * 128 + row) * S + s];
+          for (int s = 0; s < S; ++s) dz[s] = fmaf(scz_prev, __uint_as_float(zv[s]), dz[s]);
         }
         float ev[S];
 #pragma unroll
@@ -315,9 +327,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           }
           ++gc;
         }
-        float2 dzp2[SP / 2];  // this thread's share of d z_t through the state columns of W_ih_l0 (packed FFMA2 pairs)
-#pragma unroll
-        for (int s = 0; s < SP / 2; ++s) dzp2[s] = make_float2(0.f, 0.f);
         float sc_in = 0.f;
 
 #pragma unroll
@@ -416,23 +425,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
               dg_k[(1 * 64 + i) * kTileRows] = dup;
               dg_k[(2 * 64 + i) * kTileRows] = dnp;
               dg_k[(3 * 64 + i) * kTileRows] = dnh;
-              if (k == 0) {
-                // state columns of W_ih_l0: 3 S weights per unit, broadcast float4 reads
-                const float* wz = wzc + i * CZ;
-                float cc[CZ];
-#pragma unroll
-                for (int v = 0; v < (3 * SP + 3) / 4; ++v) {
-                  const float4 w4 = *reinterpret_cast<const float4*>(wz + 4 * v);
-                  cc[4 * v] = w4.x; cc[4 * v + 1] = w4.y; cc[4 * v + 2] = w4.z; cc[4 * v + 3] = w4.w;
-                }
-                const float2 r2 = make_float2(drp, drp), u2 = make_float2(dup, dup), n2 = make_float2(dnp, dnp);
-#pragma unroll
-                for (int s = 0; s < SP / 2; ++s) {
-                  fma2(dzp2[s], make_float2(cc[2 * s], cc[2 * s + 1]), r2);
-                  fma2(dzp2[s], make_float2(cc[SP + 2 * s], cc[SP + 2 * s + 1]), u2);
-                  fma2(dzp2[s], make_float2(cc[2 * SP + 2 * s], cc[2 * SP + 2 * s + 1]), n2);
-                }
-              }
               dr_[q] = drp * rs; du_[q] = dup * rs; dn_[q] = dnp * rs; dnh_[q] = dnh * rs;
             }
             tmem_st8(tl + DIR_COL + (uint32_t)k * 64 + j0, dirv);
@@ -466,14 +458,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
                   tc_fence_after();
                   issue(tmem + (uint32_t)(k * 2 + ((t & 1) ^ 1)) * 64, sb, wy, c, true, c == 0);
                 }
-                if (k == 1) {
-                  if (!pro_ok) {  // first use of a prologue-copied tile by this lane
-                    mbar_wait(&bars->pro, 0);
-                    tc_fence_after();
-                    pro_ok = true;
-                  }
-                  issue(tmem + IN0_COL, sb, w1, c, false, c == 0);
+                if (!pro_ok) {  // first use of a prologue-copied tile (W_ih_l1^T, W_z) by this lane
+                  mbar_wait(&bars->pro, 0);
+                  tc_fence_after();
+                  pro_ok = true;
                 }
+                if (k == 1) issue(tmem + IN0_COL, sb, w1, c, false, c == 0);
+                else issue_dz(sb, c);
                 umma_commit(&bars->empty[slot]);
                 if (k == 1 && c == 3) umma_commit(&bars->in0);
               }
@@ -484,18 +475,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           if (k == 1) TCWB_TRACE(4); else TCWB_TRACE(9);
           sc_prev[k] = sc_this;
           if (k == 1) sc_in = sc_this;
+          else scz_prev = exp2i(-(er + ez));
         }
-#pragma unroll
-        for (int s = 0; s < S; ++s) dzx[(cg * 128 + row) * S + s] = (s & 1) ? dzp2[s / 2].y : dzp2[s / 2].x;
       }
-      // grad_x0 = d z_0 + g_paths[:, 0]
-      named_bar_sync(1 + quad, 64);
-      if (ok && cg == 0) {
+      // grad_x0 = d z_0 + g_paths[:, 0]; the state-column part of d z_0 sits in TMEM behind the last chunk's MMAs
+      {
+        mbar_wait(&bars->empty[(gc - 1) & 1], ((gc - 1) >> 1) & 1);
+        tc_fence_after();
+        uint32_t zv[16];
+        tmem_ld16_nowait(tl + DZ_COL, zv);
+        tmem_ld_wait();
+        tc_fence_before();
+        if (ok && cg == 0) {
 #pragma unroll
-        for (int s = 0; s < S; ++s)
-          p.grad_x0[b * S + s] = dz[s] + dzx[(0 * 128 + row) * S + s] + dzx[(1 * 128 + row) * S + s] + p.g_paths[b * (T + 1) * S + s];
+          for (int s = 0; s < S; ++s)
+            p.grad_x0[b * S + s] = fmaf(scz_prev, __uint_as_float(zv[s]), dz[s]) + p.g_paths[b * (T + 1) * S + s];
+        }
       }
-      named_bar_sync(1 + quad, 64);  // dzx is rewritten by the next tile
     }
     if (gc >= 2) mbar_wait(&bars->empty[(gc - 2) & 1], ((gc - 2) >> 1) & 1);
     if (gc >= 1) mbar_wait(&bars->empty[(gc - 1) & 1], ((gc - 1) >> 1) & 1);
