@@ -198,7 +198,38 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
         const bool first = t == T - 1;
         const uint32_t rpar = (uint32_t)(t & 1);
         const float* ct = ct_tile + (int64_t)t * (CF * kTileRows);
+        const float* otr = ot_tile + (int64_t)t * (OF * kTileRows);
         TCWB_TRACE(0);
+        // every global value this step's d_out phase needs is requested FIRST (one coalesced line each), ahead of the waits
+        // for the previous step's MMAs: gP[t+1], eps_t, and this thread's half of the K = 64 operand (gL / gM entries, raw
+        // diagonal entries for the floor rule)
+        float gpv[S], ev[S], dv[32], rdv[S], rest_gm[NREST > 0 ? NREST : 1];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          gpv[s] = ct[s * kTileRows];
+          ev[s] = ct[(2 * S + S * S + s) * kTileRows];
+          rdv[s] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) dv[e] = 0.f;
+        auto load_half = [&](auto cgh_tag) {
+          constexpr int K0 = decltype(cgh_tag)::value * 32;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+#pragma unroll
+            for (int j = 0; j <= s; ++j) {
+              const int k = s * (s + 1) / 2 + j;
+              if (k >= K0 && k < K0 + 32) {
+                dv[k - K0] = ct[(2 * S + s * S + j) * kTileRows];
+                if (j == s) rdv[s] = otr[(S + k) * kTileRows];  // raw (unfloored) diagonal entry
+              }
+            }
+            if (NTRIL + s >= K0 && NTRIL + s < K0 + 32 && s < KMU) dv[NTRIL + s - K0] = ct[(S + s) * kTileRows];  // gM
+          }
+        };
+        if (cg == 0) load_half(std::integral_constant<int, 0>{}); else load_half(std::integral_constant<int, 1>{});
+#pragma unroll
+        for (int r = 0; r < NREST; ++r) rest_gm[r] = ct[(S + KMU + r) * kTileRows];
         // ---- Y <- W_hh_l1^T for this step's layer-1 phase (its carried products are issued for t >= 1 only): every MMA
         // issued so far has completed once the last chunk's commit has (in-order tensor pipe)
         if (tid == 0 && t >= 1) {
@@ -216,12 +247,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
 #pragma unroll
           for (int s = 0; s < S; ++s) dz[s] = fmaf(scz_prev, __uint_as_float(zv[s]), dz[s]);
         }
-        float ev[S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-          dz[s] += ct[s * kTileRows];                 // gP[t + 1]
-          ev[s] = ct[(2 * S + S * S + s) * kTileRows];  // eps_t
-        }
+        for (int s = 0; s < S; ++s) dz[s] += gpv[s];
         // ---------- cotangent of the output projection (kernels/backward.py:300-334) as an MMA operand ----------
         // d_out has n_out = S + S(S+1)/2 entries per row.  64 of them -- every Cholesky entry and the first KMU mu components --
         // form one K = 64 A operand: this thread computes the 32 entries k = 32 cg + e of its row, the two threads of the row
@@ -230,27 +257,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
         // them).  The remaining mu components (one at S = 10) are contracted in FP32 in pass 1.
         float sc_out = 0.f, rest_d[NREST > 0 ? NREST : 1];
         {
-          const float* otr = ot_tile + (int64_t)t * (OF * kTileRows);
           float* dor = do_tile + (int64_t)t * (NOUT * kTileRows);
-          float dv[32];
-#pragma unroll
-          for (int e = 0; e < 32; ++e) dv[e] = 0.f;
           auto half = [&](auto cgh_tag) {
             constexpr int K0 = decltype(cgh_tag)::value * 32;
-            // loads first (one coalesced line each), then the arithmetic
-            float rdv[S];
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-#pragma unroll
-              for (int j = 0; j <= s; ++j) {
-                const int k = s * (s + 1) / 2 + j;
-                if (k >= K0 && k < K0 + 32) {
-                  dv[k - K0] = ct[(2 * S + s * S + j) * kTileRows];
-                  if (j == s) rdv[s] = otr[(S + k) * kTileRows];  // raw (unfloored) diagonal entry
-                }
-              }
-              if (NTRIL + s >= K0 && NTRIL + s < K0 + 32 && s < KMU) dv[NTRIL + s - K0] = ct[(S + s) * kTileRows];  // gM
-            }
 #pragma unroll
             for (int s = 0; s < S; ++s) {
 #pragma unroll
@@ -273,7 +282,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           if (cg == 0) half(std::integral_constant<int, 0>{}); else half(std::integral_constant<int, 1>{});
 #pragma unroll
           for (int r = 0; r < NREST; ++r) {
-            rest_d[r] = fmaf(dz[KMU + r], p.dt, ct[(S + KMU + r) * kTileRows]);
+            rest_d[r] = fmaf(dz[KMU + r], p.dt, rest_gm[r]);
             if (cg == 0) dor[(KMU + r) * kTileRows] = rest_d[r];
           }
           float mxd = 0.f;
