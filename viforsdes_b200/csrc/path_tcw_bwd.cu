@@ -541,6 +541,13 @@ __host__ __device__ inline int tcw_part_floats(int NL, int S) {
 }
 constexpr int kTwFeat = 4;    // dg features per thread in part A
 
+// volatile: the compiler must not sink these loads behind the FMAs of an earlier step (it re-serialises an unrolled batch otherwise)
+__device__ __forceinline__ float ldg_batch(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 template <int S>
 __global__ void __launch_bounds__(256) tcw_thin_a_kernel(const float* __restrict__ dg, const float* __restrict__ otile,
                                                          const float* __restrict__ paths, int64_t B, int T, float* __restrict__ sdg,
@@ -567,22 +574,46 @@ __global__ void __launch_bounds__(256) tcw_thin_a_kernel(const float* __restrict
 #pragma unroll
     for (int s = 0; s < S; ++s) accz[j][s] = 0.f;
   }
-#pragma unroll 4
-  for (int t = 0; t < T; ++t) {  // unrolled: the loads of four steps are in flight together (the pass is HBM-latency bound)
-    float z[S];
+  // four grid steps per trip, all their loads requested before the first use (the pass is HBM-latency bound: 74 % long_scoreboard
+  // stalls with one step in flight)
+  constexpr int TB = 4;
+  for (int t0 = 0; t0 < T; t0 += TB) {
+    float v[TB][kTwFeat], z[TB][S];
 #pragma unroll
-    for (int s = 0; s < S; ++s)
-      z[s] = !wz ? 0.f : (t == 0 ? (ok ? paths[b * (int64_t)(T + 1) * S + s] : 0.f) : zrec[(int64_t)(t - 1) * (OF * kTileRows) + s * kTileRows]);
-    const float* st = src + t * tstride;
-    float v[kTwFeat];
+    for (int u = 0; u < TB; ++u) {
+      const int t = t0 + u;
+      const bool in = t < T;
+      const float* st = src + (in ? t : 0) * tstride;
 #pragma unroll
-    for (int j = 0; j < kTwFeat; ++j) v[j] = st[j * kTileRows];
+      for (int j = 0; j < kTwFeat; ++j) v[u][j] = ldg_batch(st + j * kTileRows);
+      if (wz) {  // block-uniform
+        const float* zp = (t >= 1 && in) ? zrec + (int64_t)(t - 1) * (OF * kTileRows) : paths + b * (int64_t)(T + 1) * S;
+        const int zs = (t >= 1 && in) ? kTileRows : 1;
 #pragma unroll
-    for (int j = 0; j < kTwFeat; ++j) {
-      acc[j] += v[j];
+        for (int s = 0; s < S; ++s) z[u][s] = ldg_batch(zp + s * zs);
+      } else {
 #pragma unroll
-      for (int s = 0; s < S; ++s) accz[j][s] = fmaf(v[j], z[s], accz[j][s]);
+        for (int s = 0; s < S; ++s) z[u][s] = 0.f;
+      }
     }
+#pragma unroll
+    for (int u = 0; u < TB; ++u) {
+      const bool in = t0 + u < T;
+#pragma unroll
+      for (int j = 0; j < kTwFeat; ++j) v[u][j] = in ? v[u][j] : 0.f;
+      if (t0 + u == 0 && !ok) {  // pad rows have no z_0 (the clamped row's was read): their d_pre is exactly zero anyway
+#pragma unroll
+        for (int s = 0; s < S; ++s) z[u][s] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < TB; ++u)
+#pragma unroll
+      for (int j = 0; j < kTwFeat; ++j) {
+        acc[j] += v[u][j];
+#pragma unroll
+        for (int s = 0; s < S; ++s) accz[j][s] = fmaf(v[u][j], z[u][s], accz[j][s]);
+      }
   }
   if (wz && ok) {
 #pragma unroll
