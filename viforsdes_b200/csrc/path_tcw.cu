@@ -190,18 +190,44 @@ __global__ void __launch_bounds__(256) tcw_tile_kernel(TileArgs a) {
     const bool dense = sc.tstride == F;  // the nt * F floats of a row are contiguous
     if (q > 0) __syncthreads();
     // a dense row segment that starts on a 16-byte boundary and is a whole number of float4 is read with LDG.128
-    const bool vec = dense && ((nt * F) & 3) == 0 && (sc.bstride & 3) == 0 && ((t0 * sc.tstride) & 3) == 0 &&
+    const bool vec = dense && ((nt * F) & 3) == 0 && nt * F <= 256 && (sc.bstride & 3) == 0 && ((t0 * sc.tstride) & 3) == 0 &&
                      (reinterpret_cast<uintptr_t>(sc.src) & 15u) == 0;
-    for (int r = threadIdx.x >> 5; r < kTileRows; r += 8) {
-      const int64_t b = tb * kTileRows + r;
-      if (vec) {
-        const float4* row4 = reinterpret_cast<const float4*>(sc.src + b * sc.bstride + t0 * sc.tstride);
-        for (int e4 = threadIdx.x & 31; e4 < nt * F / 4; e4 += 32) {
-          const float4 v = b < a.B ? row4[e4] : make_float4(0.f, 0.f, 0.f, 0.f);
-          float* d = tile_s + r * pitch + 4 * e4;
-          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    if (vec) {
+      // four rows per trip, their LDG.128 requested as one batch (volatile: not re-serialised behind the shared-memory stores)
+      const int n4 = nt * F / 4, lane = threadIdx.x & 31;
+      for (int r0 = threadIdx.x >> 5; r0 < kTileRows; r0 += 32) {
+        float4 v[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t b = tb * kTileRows + r0 + 8 * u;
+          const float4* row4 = reinterpret_cast<const float4*>(sc.src + (b < a.B ? b : a.B - 1) * sc.bstride + t0 * sc.tstride);
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            const int e4 = lane + 32 * w;
+            v[u][w] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e4 < n4)
+              asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(v[u][w].x), "=f"(v[u][w].y), "=f"(v[u][w].z), "=f"(v[u][w].w)
+                           : "l"(row4 + e4));
+          }
         }
-      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + 8 * u;
+          const bool live = tb * kTileRows + r < a.B;  // pad rows carry exact zeros
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            const int e4 = lane + 32 * w;
+            if (e4 < n4) {
+              float* d = tile_s + r * pitch + 4 * e4;
+              d[0] = live ? v[u][w].x : 0.f; d[1] = live ? v[u][w].y : 0.f; d[2] = live ? v[u][w].z : 0.f; d[3] = live ? v[u][w].w : 0.f;
+            }
+          }
+        }
+      }
+    } else {
+      for (int r = threadIdx.x >> 5; r < kTileRows; r += 8) {
+        const int64_t b = tb * kTileRows + r;
         for (int e = threadIdx.x & 31; e < nt * F; e += 32) {
           float v = 0.f;  // pad rows carry exact zeros
           if (b < a.B)
