@@ -282,10 +282,16 @@ __global__ void __launch_bounds__(SMAX <= 4 ? kElboMaxThreads : kElboThreads) el
   }
 }
 
+// Backward.  A thread owns grid point tau and solves ITS transition (tau -> tau + 1) once; the cotangents that transition sends
+// to its end point (d lp / d z_{tau+1} = -w, d lp / d x_{tau+1} = -w) are handed to the thread of tau + 1 through shared
+// memory (slot tau + 1 of the chunk; the last slot carries over to the next chunk of the trajectory).  The first version
+// re-solved transition tau - 1 in thread tau: twice the triangular solves and twice the factor-block reads.
 template <int SMAX>
 __global__ void __launch_bounds__(SMAX <= 4 ? kElboMaxThreads : kElboThreads) elbo_bwd_kernel(ElboParams p) {
+  constexpr int NTMAX = SMAX <= 4 ? kElboMaxThreads : kElboThreads;
   __shared__ float red[kElboMaxThreads / 32];
-  const int S = p.S;
+  __shared__ float nxt[2][NTMAX + 1][SMAX];  // [0]: cotangent of z_next (generative term), [1]: of x_next (SDE term)
+  const int S = p.S, NT = blockDim.x;
   const float sq = sqrtf(p.dt);
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     float th[4] = {0.f, 0.f, 0.f, 0.f};
@@ -294,55 +300,51 @@ __global__ void __launch_bounds__(SMAX <= 4 ? kElboMaxThreads : kElboThreads) el
     const float g_obs = p.g_terms[b * 4 + 0], g_sde = p.g_terms[b * 4 + 1];
     const float g_gen = p.g_terms[b * 4 + 2], g_jac = p.g_terms[b * 4 + 3];
     float gth[3] = {0.f, 0.f, 0.f};
-    for (int64_t tau = threadIdx.x; tau <= p.T; tau += blockDim.x) {
-      float zt[SMAX], xt[SMAX], spg[SMAX], gz[SMAX], gx[SMAX];
-      load_vec<SMAX>(p.z + (b * (p.T + 1) + tau) * S, S, zt);
-      to_state_vec<SMAX>(S, p.pos_mask, zt, xt);
+    __syncthreads();  // the previous trajectory's readers are done with the hand-over slots
+    if (threadIdx.x < SMAX) nxt[0][0][threadIdx.x] = nxt[1][0][threadIdx.x] = 0.f;  // nothing arrives at tau = 0
+    for (int64_t c0 = 0; c0 <= p.T; c0 += NT) {
+      const int64_t tau = c0 + threadIdx.x;
+      const bool live = tau <= p.T;
+      float zt[SMAX], xt[SMAX], spg[SMAX], gz[SMAX], gx[SMAX], nz[SMAX], nx[SMAX];
 #pragma unroll
-      for (int i = 0; i < SMAX; ++i) {
-        bool pos = i < S && ((p.pos_mask >> i) & 1u);
-        spg[i] = pos ? softplus_grad_f(zt[i]) : 1.f;
-        gz[i] = 0.f;
-        gx[i] = 0.f;
-        if (pos && tau >= 1) gz[i] += g_jac * (1.f - 1.f / (1.f + expf(-zt[i])));
+      for (int i = 0; i < SMAX; ++i) gz[i] = gx[i] = nz[i] = nx[i] = 0.f, spg[i] = 1.f;
+      if (live) {
+        load_vec<SMAX>(p.z + (b * (p.T + 1) + tau) * S, S, zt);
+        to_state_vec<SMAX>(S, p.pos_mask, zt, xt);
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i) {
+          const bool pos = i < S && ((p.pos_mask >> i) & 1u);
+          spg[i] = pos ? softplus_grad_f(zt[i]) : 1.f;
+          if (pos && tau >= 1) gz[i] += g_jac * (1.f - 1.f / (1.f + expf(-zt[i])));
+        }
+        obs_term<SMAX>(p, tau, xt, g_obs, gx, true);
       }
-      obs_term<SMAX>(p, tau, xt, g_obs, gx, true);
-      float r[SMAX], y[SMAX], w[SMAX], A[SMAX][SMAX];
-      if (tau >= 1) {
-        // this point is x_next / z_next of transition tau-1: d lp / d next = -w
-        float zp[SMAX], xp[SMAX];
-        load_vec<SMAX>(p.z + (b * (p.T + 1) + tau - 1) * S, S, zp);
-        to_state_vec<SMAX>(S, p.pos_mask, zp, xp);
-        gen_transition<SMAX>(p, b, tau - 1, zp, zt, r, A);
-        gauss_solve<SMAX>(S, A, r, y, w, true);
-#pragma unroll
-        for (int i = 0; i < SMAX; ++i) gz[i] -= g_gen * w[i];
-        sde_transition<SMAX>(p, b, tau - 1, th, xp, xt, r, A);
-        gauss_solve<SMAX>(S, A, r, y, w, true);
-#pragma unroll
-        for (int i = 0; i < SMAX; ++i) gx[i] -= g_sde * w[i];
-      }
-      if (tau < p.T) {
+      if (live && tau < p.T) {
+        float r[SMAX], y[SMAX], w[SMAX], A[SMAX][SMAX];
         const int64_t row = b * p.T + tau;
         float zn[SMAX], xn[SMAX];
         load_vec<SMAX>(p.z + (b * (p.T + 1) + tau + 1) * S, S, zn);
         to_state_vec<SMAX>(S, p.pos_mask, zn, xn);
-        // generative (variational) transition: gradients w.r.t. z_t, mu_t, L_t
+        // generative (variational) transition: gradients w.r.t. z_t, z_{t+1}, mu_t, L_t
         gen_transition<SMAX>(p, b, tau, zt, zn, r, A);
         gauss_solve<SMAX>(S, A, r, y, w, true);
 #pragma unroll
         for (int i = 0; i < SMAX; ++i) {
           if (i < S) {
             gz[i] += g_gen * w[i];
+            nz[i] = -g_gen * w[i];
             p.g_means[row * S + i] = g_gen * w[i] * p.dt;
           }
         }
         store_tril_grad<SMAX>(p.g_chol + row * (int64_t)S * S, S, g_gen * sq, w, y, A, p.vec16 != 0);
-        // SDE transition: gradients w.r.t. x_t (direct + through f, D) and theta
+        // SDE transition: gradients w.r.t. x_t (direct + through f, D), x_{t+1} and theta
         sde_transition<SMAX>(p, b, tau, th, xt, xn, r, A);
         gauss_solve<SMAX>(S, A, r, y, w, true);
 #pragma unroll
-        for (int i = 0; i < SMAX; ++i) gx[i] += g_sde * w[i];  // through the mean's x_t term
+        for (int i = 0; i < SMAX; ++i) {
+          gx[i] += g_sde * w[i];  // through the mean's x_t term
+          nx[i] = -g_sde * w[i];
+        }
         if (p.sde_kind == VISDE_SDE_OU) {
           float gf = g_sde * w[0] * p.dt;
           float gD = g_sde * sq * (w[0] * y[0] - 1.f / A[0][0]);
@@ -386,9 +388,26 @@ __global__ void __launch_bounds__(SMAX <= 4 ? kElboMaxThreads : kElboThreads) el
           store_tril_grad<SMAX>(p.g_diffusion + row * (int64_t)S * S, S, g_sde * sq, w, y, A, p.vec16 != 0);
         }
       }
+      // hand the end-point cotangents to the thread of tau + 1
 #pragma unroll
-      for (int i = 0; i < SMAX; ++i)
-        if (i < S) p.g_z[(b * (p.T + 1) + tau) * S + i] = gz[i] + gx[i] * spg[i];
+      for (int i = 0; i < SMAX; ++i) {
+        nxt[0][threadIdx.x + 1][i] = nz[i];
+        nxt[1][threadIdx.x + 1][i] = nx[i];
+      }
+      __syncthreads();
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i)
+          if (i < S) p.g_z[(b * (p.T + 1) + tau) * S + i] = (gz[i] + nxt[0][threadIdx.x][i]) + (gx[i] + nxt[1][threadIdx.x][i]) * spg[i];
+      }
+      if (threadIdx.x == 0) {  // carry: the last thread's hand-over belongs to the first grid point of the next chunk
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i) {
+          nxt[0][0][i] = nxt[0][NT][i];
+          nxt[1][0][i] = nxt[1][NT][i];
+        }
+      }
+      __syncthreads();
     }
     float t0 = block_sum(gth[0], red), t1 = block_sum(gth[1], red), t2 = block_sum(gth[2], red);
     if (threadIdx.x == 0) {
