@@ -22,9 +22,10 @@ GHZ = 1.965
 for name, fn, labels in (
     ("forward", "visde_debug_tcw_trace_fwd", ["step start", "d0 ready", "L0 epilogue done", "a0 arrived+issue (warp0) / prefetch", "d1 ready",
                                                 "L1 epilogue done", "a1 arrived+issue", "out ready", "out epilogue done"]),
-    ("backward", "visde_debug_tcw_trace_bwd", ["step start", None, "dz + contract done (k=1 pass-1 start)", "k=1 pass 1 done (row scale agreed)",
-                                                 "k=1 pass 2 done (4 chunks issued)", "before in0 wait", "in0 ready", "k=0 pass-1 start",
-                                                 "k=0 pass 1 done", "k=0 pass 2 done"])):
+    ("backward", "visde_debug_tcw_trace_bwd", ["step start (loads requested)", "previous step's MMAs done, d z_t read from TMEM", "d_out . W_out landed (k=1 pass-1 start)",
+                                                 "k=1 pass 1 done (row scale agreed)", "k=1 pass 2 done (4 chunks issued)", "before in0 wait",
+                                                 "in0 ready", "k=0 pass-1 start", "k=0 pass 1 done", "k=0 pass 2 done",
+                                                 "   (d_out entries computed, row scale agreed)", "   (d_out operand written to the ring)"])):
     buf = (C.c_longlong * (2 * 16 * 16))()
     assert getattr(lib, fn)(buf) == 0
     for th, who in ((0, "thread 0 (warp 0, issuer)"), (1, "thread 224 (warp 7)")):

@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) dz[s] += gpv[s];
+        TCWB_TRACE(1);
         // ---------- cotangent of the output projection (kernels/backward.py:300-334) as an MMA operand ----------
         // d_out has n_out = S + S(S+1)/2 entries per row.  64 of them -- every Cholesky entry and the first KMU mu components --
         // form one K = 64 A operand: this thread computes the 32 entries k = 32 cg + e of its row, the two threads of the row
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           named_bar_sync(1 + quad, 64);
           mxd = fmaxf(mxd, maxb[(xb * 2 + (cg ^ 1)) * 128 + row]);
           xb ^= 1;
+          TCWB_TRACE(10);
           const int ed = row_exp_w(mxd);
           const float rsd = exp2i(ed);
           sc_out = exp2i(-(ed + eo));
@@ -310,6 +312,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           }
           fence_proxy_async();
           tc_fence_before();
+          TCWB_TRACE(11);
           mbar_arrive(&bars->full[slot]);
           if (warp == (int)(gc & 7)) {
             mbar_wait(&bars->full[slot], (gc >> 1) & 1);
