@@ -1,5 +1,6 @@
 // Helpers shared by the tensor-core recurrence kernels (path_tc.cu forward, path_tc_bwd.cu backward).
 #pragma once
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -18,8 +19,8 @@ constexpr int kUPT = 32;    // hidden units per epilogue thread
 constexpr int kHExp = 14;   // hidden states are scaled by 2^14 before the fp16 split
 
 // instruction descriptor: D fp32, A/B fp16 K-major, M = 128
-__host__ __device__ constexpr uint32_t idesc_f16(int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_f16(int N, int M = 128) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // byte offset of 16-byte chunk c (8 fp16) of row r in a K-major SWIZZLE_128B tile with 128-byte rows
 __device__ __forceinline__ uint32_t sw128(int r, int c) {
@@ -82,4 +83,9 @@ __host__ __device__ constexpr int tril_row(int ti) {
   return r;
 }
 __host__ __device__ constexpr int tril_col(int ti) { return ti - tril_row(ti) * (tril_row(ti) + 1) / 2; }
+// wide family: two 64-row CTAs per 128-row tile (MMA M = 64) while that still fits one CTA per SM; VISDE_TCW_M128=1 keeps M = 128
+inline bool tcw_half_tiles(int64_t ntiles, int sms) {
+  static const bool force128 = [] { const char* e = getenv("VISDE_TCW_M128"); return e && e[0] == '1'; }();
+  return !force128 && 2 * ntiles <= sms;
+}
 }  // namespace visde

@@ -279,9 +279,15 @@ __device__ __forceinline__ void issue_gemm_w(uint32_t dcol, uint32_t a_hi, uint3
   }
 }
 
-template <int S>
+// MT = trajectories per CTA = MMA M.  128: one CTA per tile, every TMEM lane a trajectory.  64: TWO CTAs per 128-row tile of the
+// global layouts (sub-tile = work item & 1), rows on lanes 0..15 of each 32-lane TMEM quadrant (the M = 64 accumulator layout),
+// lanes 16..31 of every warp idle -- the step is latency-bound, so when the batch has at most SMs / 2 tiles the second half of
+// the machine halves the tiles' serial time.
+template <int S, int MT>
 __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams p) {
   using L = TcwFwdSmem;
+  static_assert(MT == 128 || MT == 64, "MMA M");
+  constexpr int LPQ = MT / 4, SUBS = kTileRows / MT;
   constexpr int NTRIL = S * (S + 1) / 2, CS = L::CS, OF = tcw_out_feats(S);
   static_assert(S > 4 && S <= kTcwMaxS && NTRIL <= 64 && 3 * S + 1 <= CS, "wide-state tensor-core recurrence: 4 < S <= 10");
   constexpr uint32_t TMEM_COLS = 512;
@@ -332,7 +338,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  const int64_t ntiles = (p.B + kTileRows - 1) / kTileRows;
+  const int64_t nitems = (p.B + kTileRows - 1) / kTileRows * SUBS;
   if (tid == 0) {
     // resident tiles on `pro`, the first occupant of X (W_ih_l1) on `wx`
     mbar_expect_tx(&bars->pro, kWImg + kOutImg);
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
   const uint32_t a0h = smem_u32(smem + L::OFF_A), a0l = a0h + kATileBytes;
   const uint32_t a1h = a0h + 2 * kATileBytes, a1l = a1h + kATileBytes;
   const uint32_t woh = smem_u32(smem + L::OFF_WOUT), wol = woh + kOutRows * 128;
-  constexpr uint32_t ID192 = idesc_f16(192), ID128 = idesc_f16(128), ID64 = idesc_f16(64), ID16 = idesc_f16(16);
+  constexpr uint32_t ID192 = idesc_f16(192, MT), ID128 = idesc_f16(128, MT), ID64 = idesc_f16(64, MT), ID16 = idesc_f16(16, MT);
   constexpr uint32_t NROWS = 128 * 128;  // byte offset of gate rows 128.. (the n block) in a weight tile
   uint32_t ph_init = 0, ph_a0 = 0, ph_a1 = 0, ph_wx = 0, ph_xr = 0;  // issuer-side phases (thread 0)
   auto issue_recurrent_l0 = [&]() {  // D0 = h0 . W_hh_l0^T (for the next step)
@@ -383,30 +389,35 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
 
   {
     const int quad = warp & 3, cg = warp >> 2;
-    const int row = quad * 32 + lane;
+    const bool act = lane < LPQ;                     // lanes past the quadrant's rows only take part in the collectives
+    const int row = quad * LPQ + (lane & (LPQ - 1));  // row of the CTA's A tile / accumulator (idle lanes alias a live row for loads)
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     const int u0 = cg * kUPT;
     uint8_t* a_tiles = smem + L::OFF_A;
     const float hs = exp2i(kHExp);
     uint32_t ph_d0 = 0, ph_d1 = 0, ph_out = 0;
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t b_raw = tile * kTileRows + row;
-      const bool ok = b_raw < p.B;
-      const int64_t b = ok ? b_raw : p.B - 1;
-      const bool writer = cg == 0;  // pad rows write too: the tiled records of pad rows are never read as data
+    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int64_t tile = item / SUBS;
+      const int grow = (int)(item % SUBS) * MT + row;  // row of the 128-row tile of the global layouts
+      const int64_t b_raw = tile * kTileRows + grow;
+      const bool ok = act && b_raw < p.B;
+      const int64_t b = b_raw < p.B ? b_raw : p.B - 1;
+      const bool writer = cg == 0 && act;  // pad rows write too: the tiled records of pad rows are never read as data
       // X holds W_ih_l1 at every tile start.  The first tile's copy was issued in the prologue; a later tile re-issues it so
       // that every tile consumes exactly one completion of `wx` at its step 0 (the last reader of X, the layer-1 input
       // product of the previous tile's final step, completed before this thread passed that step's d1 wait)
-      if (tid == 0 && tile != (int64_t)blockIdx.x) load_x(1);
+      if (tid == 0 && item != (int64_t)blockIdx.x) load_x(1);
       // h(-1) = 0
 #pragma unroll
       for (int k = 0; k < 2; ++k)
 #pragma unroll
         for (int c = 0; c < kUPT / 8; ++c) {
           const uint32_t off = sw128(row, (u0 >> 3) + c);
-          *reinterpret_cast<uint4*>(a_tiles + (2 * k) * kATileBytes + off) = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(a_tiles + (2 * k + 1) * kATileBytes + off) = make_uint4(0, 0, 0, 0);
+          if (act) {
+            *reinterpret_cast<uint4*>(a_tiles + (2 * k) * kATileBytes + off) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(a_tiles + (2 * k + 1) * kATileBytes + off) = make_uint4(0, 0, 0, 0);
+          }
         }
       fence_proxy_async();
       mbar_arrive(&bars->init);
@@ -433,11 +444,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
       for (int k = 0; k < 2; ++k)
 #pragma unroll
         for (int j = 0; j < kUPT; ++j) hprev[k][j] = 0.f;
-      const float* gi_p = p.gi_ctx + tile * T * (int64_t)(192 * kTileRows) + (int64_t)u0 * kTileRows + row;
-      float* st_p = p.stash ? p.stash + tile * T * (int64_t)(2 * kStashSlots * 64 * kTileRows) + (int64_t)u0 * kTileRows + row
-                            : nullptr;
-      const float* eps_p = p.epst + tile * T * (int64_t)(S * kTileRows) + row;
-      float* ot_p = p.otile + tile * T * (int64_t)(OF * kTileRows) + row;
+      const float* gi_p = p.gi_ctx + tile * T * (int64_t)(192 * kTileRows) + (int64_t)u0 * kTileRows + grow;
+      float* st_p = p.stash && act ? p.stash + tile * T * (int64_t)(2 * kStashSlots * 64 * kTileRows) + (int64_t)u0 * kTileRows + grow
+                                   : nullptr;
+      const float* eps_p = p.epst + tile * T * (int64_t)(S * kTileRows) + grow;
+      float* ot_p = p.otile + tile * T * (int64_t)(OF * kTileRows) + grow;
 
       float g01[3][16], g23[3][16];
 #pragma unroll
@@ -510,8 +521,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
           uint4 hi, lo;
           split8(hx, hi, lo);
           const uint32_t off = sw128(row, j0 >> 3);
-          *reinterpret_cast<uint4*>(a_tiles + off) = hi;
-          *reinterpret_cast<uint4*>(a_tiles + kATileBytes + off) = lo;
+          if (act) {
+            *reinterpret_cast<uint4*>(a_tiles + off) = hi;
+            *reinterpret_cast<uint4*>(a_tiles + kATileBytes + off) = lo;
+          }
         }
         fence_proxy_async();
         tc_fence_before();
@@ -584,8 +597,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
           uint4 hi, lo;
           split8(hx, hi, lo);
           const uint32_t off = sw128(row, j0 >> 3);
-          *reinterpret_cast<uint4*>(a_tiles + 2 * kATileBytes + off) = hi;
-          *reinterpret_cast<uint4*>(a_tiles + 3 * kATileBytes + off) = lo;
+          if (act) {
+            *reinterpret_cast<uint4*>(a_tiles + 2 * kATileBytes + off) = hi;
+            *reinterpret_cast<uint4*>(a_tiles + 3 * kATileBytes + off) = lo;
+          }
         }
         fence_proxy_async();
         tc_fence_before();
@@ -702,14 +717,18 @@ int launch_fwd_tcw(const PathParams& p, cudaStream_t st) {
   static DeviceOnce attr_once;
   int attr_dev = 0;
   if (attr_once.needed(&attr_dev)) {
-    VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_fwd_tcw_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_fwd_tcw_kernel<S, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_fwd_tcw_kernel<S, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_once.done(attr_dev);
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ntiles = (p.B + kTileRows - 1) / kTileRows;
-  path_fwd_tcw_kernel<S><<<(unsigned)(ntiles < sms ? ntiles : sms), kFwdThreads, smem, st>>>(p);
+  if (tcw_half_tiles(ntiles, sms))
+    path_fwd_tcw_kernel<S, 64><<<(unsigned)(2 * ntiles), kFwdThreads, smem, st>>>(p);
+  else
+    path_fwd_tcw_kernel<S, 128><<<(unsigned)(ntiles < sms ? ntiles : sms), kFwdThreads, smem, st>>>(p);
   VISDE_CUDA_CHECK(cudaGetLastError());
   tcw_expand_kernel<S><<<dim3((unsigned)p.T, (unsigned)ntiles), 256, 0, st>>>(p.otile, p.x0, p.B, p.T, p.paths, p.means, p.chol);
   VISDE_CUDA_CHECK(cudaGetLastError());

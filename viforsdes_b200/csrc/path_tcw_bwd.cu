@@ -61,9 +61,12 @@ __device__ __forceinline__ int row_exp_w(float mx) {
   return e < -100 ? -100 : e;
 }
 
-template <int S>
+// MT: trajectories per CTA = MMA M (128, or 64 with two CTAs per tile of the global layouts: see path_fwd_tcw_kernel)
+template <int S, int MT>
 __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams p) {
   using L = TcwBwdSmem<S>;
+  static_assert(MT == 128 || MT == 64, "MMA M");
+  constexpr int LPQ = MT / 4, SUBS = kTileRows / MT;
   constexpr int NL = 2;
   constexpr int NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL, OF = tcw_out_feats(S), CF = tcw_cot_feats(S);
   static_assert(S > 4 && S <= kTcwMaxS, "wide-state tensor-core recurrence: 4 < S <= 10");
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  const int64_t ntiles = (p.B + kTileRows - 1) / kTileRows;
+  const int64_t nitems = (p.B + kTileRows - 1) / kTileRows * SUBS;
   if (tid == 0) {
     mbar_expect_tx(&bars->pro, kWImg + kOutBwdImg + kWzBwdImg);
     bulk_load_1d(smem + L::OFF_W1, img + kImgBwd0 + kWImg, kWImg, &bars->pro);
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
 
   // ---- MMA issue: chunk gc is issued by lane 0 of warp gc % 8 once all 256 threads have written it
   const uint32_t w1 = smem_u32(smem + L::OFF_W1), wy = smem_u32(smem + L::OFF_Y), a0 = smem_u32(smem + L::OFF_A);
-  constexpr uint32_t ID64 = idesc_f16(64);
+  constexpr uint32_t ID64 = idesc_f16(64, MT);
   // 9 MMAs: acc[128,64] (+)= A_chunk[slots] . W^T[K-groups of chunk c]; wbase = hi tile of the transposed matrix
   auto issue = [&](uint32_t acc, uint32_t slot_base, uint32_t wbase, int c, bool n_is_nh, bool fresh) {
     const uint32_t a_hi = slot_base, a_lo = slot_base + kATileBytes;
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
     }
   };
   const uint32_t wob = smem_u32(smem + L::OFF_WOUT), wzb = smem_u32(smem + L::OFF_WZ);
-  constexpr uint32_t ID16 = idesc_f16(16);
+  constexpr uint32_t ID16 = idesc_f16(16, MT);
   // 9 MMAs: d z_t [128,16] (+)= d_gi_l0 chunk (slots r, u, n) . W_z^T[K-groups of chunk c]
   auto issue_dz = [&](uint32_t slot_base, int c) {
     const uint32_t a_hi = slot_base, a_lo = slot_base + kATileBytes;
@@ -151,20 +154,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
 
   {
     const int quad = warp & 3, cg = warp >> 2;
-    const int row = quad * 32 + lane;
+    const bool act = lane < LPQ;                     // lanes past the quadrant's rows only take part in the collectives
+    const int row = quad * LPQ + (lane & (LPQ - 1));  // row of the CTA's operand tiles / accumulators
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     uint8_t* a_ring = smem + L::OFF_A;
     uint32_t ph_in0 = 0, ph_outd = 0, xb = 0;
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t b_raw = tile * kTileRows + row;
-      const bool ok = b_raw < p.B;
-      const int64_t b = ok ? b_raw : p.B - 1;
-      const float* st_tile = p.stash + tile * T * (int64_t)(NL * kStashSlots * 64 * kTileRows) + row;
-      float* dg_tile = p.dg + tile * T * (int64_t)(NL * kDgSlots * 64 * kTileRows) + row;
-      const float* ct_tile = p.ctile + tile * T * (int64_t)(CF * kTileRows) + row;  // pad rows hold zeros
-      const float* ot_tile = p.otile + tile * T * (int64_t)(OF * kTileRows) + row;
-      float* do_tile = p.dout + tile * T * (int64_t)(NOUT * kTileRows) + row;
+    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int64_t tile = item / SUBS;
+      const int grow = (int)(item % SUBS) * MT + row;  // row of the 128-row tile of the global layouts
+      const int64_t b_raw = tile * kTileRows + grow;
+      const bool ok = act && b_raw < p.B;
+      const int64_t b = b_raw < p.B ? b_raw : p.B - 1;
+      const float* st_tile = p.stash + tile * T * (int64_t)(NL * kStashSlots * 64 * kTileRows) + grow;
+      float* dg_tile = p.dg + tile * T * (int64_t)(NL * kDgSlots * 64 * kTileRows) + grow;
+      const float* ct_tile = p.ctile + tile * T * (int64_t)(CF * kTileRows) + grow;  // pad rows hold zeros
+      const float* ot_tile = p.otile + tile * T * (int64_t)(OF * kTileRows) + grow;
+      float* do_tile = p.dout + tile * T * (int64_t)(NOUT * kTileRows) + grow;
 
       float pv[2][5][8];
       auto load_chunk = [&](float (&dst)[5][8], int tt, int kk, int cc) {
@@ -270,13 +276,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
                   float d = fmaf(dz[s] * ev[j], p.sqrt_dt, dv[k - K0]);
                   if (j == s) d = (rdv[s] >= VISDE_DIAG_MIN || d < 0.f) ? d : 0.f;  // primitives/bounds.py:20
                   dv[k - K0] = d;
-                  dor[(S + k) * kTileRows] = d;
+                  if (act) dor[(S + k) * kTileRows] = d;
                 }
               }
               if (NTRIL + s >= K0 && NTRIL + s < K0 + 32 && s < KMU) {
                 const float d = fmaf(dz[s], p.dt, dv[NTRIL + s - K0]);
                 dv[NTRIL + s - K0] = d;
-                dor[s * kTileRows] = d;
+                if (act) dor[s * kTileRows] = d;
               }
             }
           };
@@ -284,12 +290,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
 #pragma unroll
           for (int r = 0; r < NREST; ++r) {
             rest_d[r] = fmaf(dz[KMU + r], p.dt, rest_gm[r]);
-            if (cg == 0) dor[(KMU + r) * kTileRows] = rest_d[r];
+            if (cg == 0 && act) dor[(KMU + r) * kTileRows] = rest_d[r];
           }
           float mxd = 0.f;
 #pragma unroll
           for (int e = 0; e < 32; ++e) mxd = fmaxf(mxd, fabsf(dv[e]));
-          maxb[(xb * 2 + cg) * 128 + row] = mxd;
+          if (act) maxb[(xb * 2 + cg) * 128 + row] = mxd;
           named_bar_sync(1 + quad, 64);
           mxd = fmaxf(mxd, maxb[(xb * 2 + (cg ^ 1)) * 128 + row]);
           xb ^= 1;
@@ -307,8 +313,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             for (int q = 0; q < 8; ++q) x[q] = dv[c * 8 + q] * rsd;
             uint4 hi, lo;
             split8(x, hi, lo);
-            *reinterpret_cast<uint4*>(ahi + sw128(row, 4 * cg + c)) = hi;
-            *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 4 * cg + c)) = lo;
+            if (act) {
+              *reinterpret_cast<uint4*>(ahi + sw128(row, 4 * cg + c)) = hi;
+              *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 4 * cg + c)) = lo;
+            }
           }
           fence_proxy_async();
           tc_fence_before();
@@ -400,7 +408,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             }
           }
           // ---------- the two threads of the row agree on the power-of-two scale ----------
-          maxb[(xb * 2 + cg) * 128 + row] = mx;
+          if (act) maxb[(xb * 2 + cg) * 128 + row] = mx;
           named_bar_sync(1 + quad, 64);
           mx = fmaxf(mx, maxb[(xb * 2 + (cg ^ 1)) * 128 + row]);
           xb ^= 1;
@@ -433,29 +441,33 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
               const float drp = dnp * nhh * r * (1.f - r);
               const float dnh = dnp * r;
               dirv[q] = __float_as_uint(dhv * u);
-              dg_k[(0 * 64 + i) * kTileRows] = drp;
-              dg_k[(1 * 64 + i) * kTileRows] = dup;
-              dg_k[(2 * 64 + i) * kTileRows] = dnp;
-              dg_k[(3 * 64 + i) * kTileRows] = dnh;
+              if (act) {
+                dg_k[(0 * 64 + i) * kTileRows] = drp;
+                dg_k[(1 * 64 + i) * kTileRows] = dup;
+                dg_k[(2 * 64 + i) * kTileRows] = dnp;
+                dg_k[(3 * 64 + i) * kTileRows] = dnh;
+              }
               dr_[q] = drp * rs; du_[q] = dup * rs; dn_[q] = dnp * rs; dnh_[q] = dnh * rs;
             }
             tmem_st8(tl + DIR_COL + (uint32_t)k * 64 + j0, dirv);
             const uint32_t slot = gc & 1;
             if (gc >= 2) mbar_wait(&bars->empty[slot], ((gc >> 1) - 1) & 1);
             uint8_t* ahi = a_ring + slot * SLOT_BYTES;
-            uint4 hi, lo;
-            split8(dr_, hi, lo);
-            *reinterpret_cast<uint4*>(ahi + sw128(row, 0 + cg)) = hi;
-            *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 0 + cg)) = lo;
-            split8(du_, hi, lo);
-            *reinterpret_cast<uint4*>(ahi + sw128(row, 2 + cg)) = hi;
-            *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 2 + cg)) = lo;
-            split8(dn_, hi, lo);
-            *reinterpret_cast<uint4*>(ahi + sw128(row, 4 + cg)) = hi;
-            *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 4 + cg)) = lo;
-            split8(dnh_, hi, lo);
-            *reinterpret_cast<uint4*>(ahi + sw128(row, 6 + cg)) = hi;
-            *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 6 + cg)) = lo;
+            if (act) {
+              uint4 hi, lo;
+              split8(dr_, hi, lo);
+              *reinterpret_cast<uint4*>(ahi + sw128(row, 0 + cg)) = hi;
+              *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 0 + cg)) = lo;
+              split8(du_, hi, lo);
+              *reinterpret_cast<uint4*>(ahi + sw128(row, 2 + cg)) = hi;
+              *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 2 + cg)) = lo;
+              split8(dn_, hi, lo);
+              *reinterpret_cast<uint4*>(ahi + sw128(row, 4 + cg)) = hi;
+              *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 4 + cg)) = lo;
+              split8(dnh_, hi, lo);
+              *reinterpret_cast<uint4*>(ahi + sw128(row, 6 + cg)) = hi;
+              *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 6 + cg)) = lo;
+            }
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(&bars->full[slot]);
@@ -519,14 +531,18 @@ int launch_bwd_tcw(const PathParams& p, cudaStream_t st) {
   static DeviceOnce attr_once;
   int attr_dev = 0;
   if (attr_once.needed(&attr_dev)) {
-    VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_bwd_tcw_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_bwd_tcw_kernel<S, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VISDE_CUDA_CHECK(cudaFuncSetAttribute(path_bwd_tcw_kernel<S, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_once.done(attr_dev);
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ntiles = (p.B + kTileRows - 1) / kTileRows;
-  path_bwd_tcw_kernel<S><<<(unsigned)(ntiles < sms ? ntiles : sms), kBwdThreads, smem, st>>>(p);
+  if (tcw_half_tiles(ntiles, sms))
+    path_bwd_tcw_kernel<S, 64><<<(unsigned)(2 * ntiles), kBwdThreads, smem, st>>>(p);
+  else
+    path_bwd_tcw_kernel<S, 128><<<(unsigned)(ntiles < sms ? ntiles : sms), kBwdThreads, smem, st>>>(p);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }
