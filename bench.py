@@ -208,6 +208,8 @@ def main() -> None:
                     help="dtype of context / grad_context in the device-resident leg (bf16 = the reference's AMP mode)")
     ap.add_argument("--e2e-context-dtype", default="bf16", choices=["f32", "bf16"],
                     help="dtype of the HOST context of the e2e leg (bf16 = the reference's autocast encoder output)")
+    ap.add_argument("--e2e-noise", default="device", choices=["device", "host"],
+                    help="e2e leg: eps drawn on the device per iteration (what the reference's sampler does) or copied from host")
     ap.add_argument("--no-graph", action="store_true", help="launch the iteration kernel by kernel in the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -377,7 +379,8 @@ def main() -> None:
         e2e = None
         if not args.no_e2e:
             e2e_dt = torch.bfloat16 if args.e2e_context_dtype == "bf16" else torch.float32
-            sess = HostSession.from_inputs(inp, context_dtype=e2e_dt)
+            sess = HostSession.from_inputs(inp, context_dtype=e2e_dt,
+                                           device_noise_seed=(1234 + rank) if args.e2e_noise == "device" else None)
             for _ in range(max(6, W // 2)):  # past the session's eager warm-up: user-SDE hooks are CUDA graphs from the 4th call
                 sess.step()
             # (a) synchronous call per step: latency of one iteration through host buffers
@@ -406,6 +409,9 @@ def main() -> None:
                    "d2h_bytes_per_step": sess.d2h_bytes, "ms_per_step": t_pipe / K * 1e3,
                    "sync_ms_per_step": t_sync / K * 1e3, "sync_value": units * K / t_sync,
                    "host_context_dtype": args.e2e_context_dtype,
+                   "noise": ("drawn on the device inside the timed region, a fresh Philox stream per iteration (the reference's "
+                             "sampler draws torch.randn on the device, inference/diffusion_path_sampler.py:57)"
+                             if args.e2e_noise == "device" else "copied from pinned host memory every step"),
                    "api": "visde_session_submit/_wait (C ABI, pinned host buffers, 2 iterations in flight: H2D of step "
                           "i+1 overlaps the kernels of step i); the user SDE's drift / diffusion + VJP run in PyTorch "
                           "through the session's visde_user_sde hooks; sync_* = visde_session_step, one blocking call "

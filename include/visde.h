@@ -226,8 +226,14 @@ size_t visde_session_h2d_bytes(const visde_session* s);
 size_t visde_session_d2h_bytes(const visde_session* s);
 /* number of kernels one visde_session_step launches */
 int visde_session_launches(const visde_session* s);
+/* eps == NULL in visde_session_step / _submit: the iteration draws its noise ON THE DEVICE, as the reference's sampler
+ * does (inference/diffusion_path_sampler.py:57, torch.randn on the model's device) -- iteration i (0-based count of
+ * submitted iterations) uses visde_philox_normal(seed + i, B, T, S); nothing of eps crosses the bus and
+ * visde_session_h2d_bytes drops by 4 B T S.  Default seed 0. */
+int visde_session_set_noise_seed(visde_session* s, uint64_t seed);
 
-/* HOST in: x0, context [B,T+1,C] (the session's ctx_dtype), theta, eps, weights (host pointers in visde_weights),
+/* HOST in: x0, context [B,T+1,C] (the session's ctx_dtype), theta, eps (NULL: drawn on the device, see
+ * visde_session_set_noise_seed), weights (host pointers in visde_weights),
  * obs (host pointers).  HOST out: terms [B,4], grad_x0 [B,S], grad_theta [B,P], weight grads
  * (host pointers), and grad_context [B,T+1,C] if non-NULL (row T zero).  The loss is
  * -(mean_b(obs + sde - gen + jac)); its cotangent 1/B is applied inside. Synchronous. */

@@ -124,3 +124,35 @@ def test_host_session_user_sde_hook_errors_propagate():
     sess.close()
     with pytest.raises(ValueError):  # GENERIC without hooks is refused by the C ABI wrapper
         HostSession.from_problem(O.make_problem("l96", 2, 5, context_dim=8, hidden_dim=64, num_layers=1, state_dim=5), sde=None)
+
+
+@pytest.mark.parametrize("name,S", [("l96", 10), ("ou", 1)])
+def test_host_session_device_noise_matches_host_fed_philox(name, S):
+    """eps == NULL: iteration i draws visde_philox_normal(seed + i) on the device (diffusion_path_sampler.py:57 draws on the
+    device too); the same draws fed from the host give bit-identical outputs, and eps leaves the H2D byte count."""
+    from viforsdes_b200.euler_maruyama import philox_normal
+    from viforsdes_b200.session import HostSession
+
+    B, T, seed = 6, 17, 1234
+    kw = dict(context_dim=32, hidden_dim=64, num_layers=2)
+    p = O.make_problem(name, B, T, state_dim=S, **kw) if name == "l96" else O.make_problem(name, B, T, **kw)
+    dev = HostSession.from_problem(p, device_noise_seed=seed)
+    outs = []
+    for _ in range(3):  # ou: the third step replays the captured graph behind a fresh draw
+        o = dev.step()  # views of the session's two host output sets: copy before they are reused
+        outs.append({k: v.clone() for k, v in o["grads"].items()} | {"terms": o["terms"].clone()})
+    fed = HostSession.from_problem(p)
+    assert fed.h2d_bytes - dev.h2d_bytes == 4 * B * T * S
+    for i, o in enumerate(outs):
+        fed.eps.copy_(philox_normal(seed + i, B, T, S).cpu())
+        r = fed.step()
+        assert torch.equal(r["terms"], o["terms"]), f"iteration {i}: terms differ"
+        for k, v in r["grads"].items():
+            assert torch.equal(v, o[k]), f"iteration {i}: {k} differs"
+    assert not torch.equal(outs[0]["terms"], outs[1]["terms"]), "every iteration must draw fresh noise"
+    # and the host-fed run agrees with the oracle on those draws
+    p.eps = philox_normal(seed + 2, B, T, S).cpu()
+    r32, r64 = oracle_refs(p)
+    _check(r, r32, r64, "device-noise/")
+    dev.close()
+    fed.close()

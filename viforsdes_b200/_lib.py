@@ -74,6 +74,7 @@ PROTOTYPES = {
     "visde_session_h2d_bytes": (C.c_size_t, [_fp]),
     "visde_session_d2h_bytes": (C.c_size_t, [_fp]),
     "visde_session_launches": (C.c_int, [_fp]),
+    "visde_session_set_noise_seed": (C.c_int, [_fp, C.c_uint64]),
     "visde_session_step": (C.c_int, [_fp, C.c_float, _fp, _fp, _fp, _fp, C.POINTER(Weights), C.POINTER(Obs), _fp, _fp,
                                      _fp, C.POINTER(Weights), _fp]),
     "visde_session_submit": (C.c_int, [_fp, C.c_float, _fp, _fp, _fp, _fp, C.POINTER(Weights), C.POINTER(Obs), _fp, _fp,

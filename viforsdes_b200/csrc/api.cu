@@ -239,6 +239,25 @@ __global__ void ctx_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, in
   const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + b * bstride + t * tstride + 2 * c2);
   *reinterpret_cast<float2*>(dst + bt * C + 2 * c2) = __bfloat1622float2(v);
 }
+// the same widening, eight values per thread (one 16-byte load, two 16-byte stores): rows whose start and strides are 16-byte aligned
+__global__ void ctx_bf16_to_f32_vec8_kernel(const __nv_bfloat16* __restrict__ src, int64_t bstride, int64_t tstride, int64_t B,
+                                            int64_t T, int C, float* __restrict__ dst) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*T*C/8 octets
+  const int64_t oct_c = C / 8;
+  if (idx >= B * T * oct_c) return;
+  const int64_t c8 = idx % oct_c, bt = idx / oct_c, t = bt % T, b = bt / T;
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + b * bstride + t * tstride + 8 * c8));
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  float f[8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {  // a bf16 is the upper half of the fp32 with the same value
+    f[2 * q] = __uint_as_float(w[q] << 16);
+    f[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+  }
+  float4* o = reinterpret_cast<float4*>(dst + bt * C + 8 * c8);
+  o[0] = make_float4(f[0], f[1], f[2], f[3]);
+  o[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
 bool ctx_convertible(const visde_dims* d, const visde_ctx_view* ctx) {
   if (!ctx || ctx->dtype != VISDE_BF16 || (d->variant & VISDE_FLAG_NO_TENSOR_CORES)) return false;
   if ((reinterpret_cast<uintptr_t>(ctx->ptr) & 3) || (ctx->batch_stride & 1) || (ctx->time_stride & 1)) return false;
@@ -246,6 +265,15 @@ bool ctx_convertible(const visde_dims* d, const visde_ctx_view* ctx) {
   return tc_supported(d->H, d->NL, d->C, &probe);
 }
 int convert_ctx(const visde_dims* d, const visde_ctx_view* ctx, float* buf, visde_ctx_view* out, cudaStream_t st) {
+  if (d->C % 8 == 0 && (reinterpret_cast<uintptr_t>(ctx->ptr) & 15) == 0 && ctx->batch_stride % 8 == 0 && ctx->time_stride % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(buf) & 15) == 0) {
+    const int64_t n8 = d->B * d->T * (d->C / 8);
+    ctx_bf16_to_f32_vec8_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(ctx->ptr),
+                                                                              ctx->batch_stride, ctx->time_stride, d->B, d->T, d->C, buf);
+    VISDE_CUDA_CHECK(cudaGetLastError());
+    *out = visde_ctx_view{buf, d->T * (int64_t)d->C, d->C, VISDE_F32};
+    return VISDE_OK;
+  }
   const int64_t n = d->B * d->T * (d->C / 2);
   ctx_bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(ctx->ptr),
                                                                        ctx->batch_stride, ctx->time_stride, d->B, d->T, d->C, buf);
@@ -807,9 +835,9 @@ struct visde_session_inputs {
   cudaEvent_t done;      // compute stream: kernels + D2H of the iteration that used this set
   // the kernel sequence of one iteration on this input set, captured once as a CUDA graph (one launch per iteration,
   // no gaps between the dependent kernels); re-captured when a scalar baked into the kernel parameters changes
-  cudaGraphExec_t graph;
+  cudaGraphExec_t graph[3];  // [0]: the whole iteration, or (user-SDE sessions) one graph per segment
   float graph_dt, graph_var;
-  bool graph_obsmat;
+  bool graph_obsmat, graph_failed;
   uint32_t uses;
 };
 
@@ -824,6 +852,9 @@ struct visde_session {
   std::vector<void*> allocs;
   visde_session_inputs in[2];
   uint64_t n_submitted, n_waited;
+  uint64_t noise_seed;    // eps == NULL: iteration i draws Philox standard normals with key noise_seed + i on the device
+  size_t eps_bytes;       // H2D bytes of eps (not copied by iterations that draw on the device)
+  bool device_noise;      // the last submitted iteration drew its noise on the device
   // device buffers
   float *paths, *means, *chol, *terms, *g_terms;
   float *g_z, *g_means, *g_chol, *g_theta_elbo, *grad_x0, *grad_theta;
@@ -946,6 +977,9 @@ int visde_session_create(const visde_dims* d, int sde_kind, uint32_t positive_ma
   cudaStreamSynchronize(s->st);
   s->h2d = sizeof(float) * (B * S + B * P + B * T * S + wfloats + (size_t)n_obs * obs_dim) +
            ctx_elem_bytes(s) * B * (T + 1) * C + sizeof(int32_t) * n_obs;
+  s->eps_bytes = sizeof(float) * B * T * S;
+  s->noise_seed = 0;
+  s->device_noise = false;
   s->d2h = sizeof(float) * (B * 4 + B * S + B * P + wfloats);
   // K0, K1, elbo fwd, cotangent fill, elbo bwd, K2, K3, grad_theta gemm, (2 NL + 1) x (tn + reduce), add
   s->launches = 8 + 2 * (2 * d->NL + 1) + 1;
@@ -962,19 +996,29 @@ void visde_session_destroy(visde_session* s) {
     if (s->in[q].loaded) cudaEventDestroy(s->in[q].loaded);
     if (s->in[q].consumed) cudaEventDestroy(s->in[q].consumed);
     if (s->in[q].done) cudaEventDestroy(s->in[q].done);
-    if (s->in[q].graph) cudaGraphExecDestroy(s->in[q].graph);
+    for (int g = 0; g < 3; ++g)
+      if (s->in[q].graph[g]) cudaGraphExecDestroy(s->in[q].graph[g]);
   }
   if (s->st) cudaStreamDestroy(s->st);
   if (s->copy_st) cudaStreamDestroy(s->copy_st);
   delete s;
 }
 
-size_t visde_session_h2d_bytes(const visde_session* s) { return s ? s->h2d : 0; }
+size_t visde_session_h2d_bytes(const visde_session* s) { return s ? s->h2d - (s->device_noise ? s->eps_bytes : 0) : 0; }
+int visde_session_set_noise_seed(visde_session* s, uint64_t seed) {
+  VISDE_REQUIRE(s != nullptr, "session_set_noise_seed: NULL session");
+  s->noise_seed = seed;
+  return VISDE_OK;
+}
 size_t visde_session_d2h_bytes(const visde_session* s) { return s ? s->d2h : 0; }
 int visde_session_launches(const visde_session* s) { return s ? s->launches : 0; }
 
-// kernel sequence of one iteration on input set `in` (everything between the H2D and the D2H copies)
-static int session_enqueue(visde_session* s, visde_session_inputs& in, float dt, const visde_obs* od_p, cudaStream_t st) {
+// kernel sequence of one iteration on input set `in` (everything between the H2D and the D2H copies), in three segments
+// around the two places where a user-SDE session hands control to the caller's hooks:
+//   segment 0: context widening, path forward, x_t = to_state(z_t)      -> [hook: drift / diffusion]
+//   segment 1: ELBO forward, loss cotangent, ELBO backward              -> [hook: their vector-Jacobian product]
+//   segment 2: chain into g_z, path backward, grad_theta sums
+static int session_segment(visde_session* s, visde_session_inputs& in, float dt, const visde_obs* od_p, cudaStream_t st, int seg) {
   const visde_dims& d = s->d;
   const size_t B = d.B, T = d.T, C = d.C, P = d.P;
   const visde_obs& od = *od_p;
@@ -984,35 +1028,31 @@ static int session_enqueue(visde_session* s, visde_session_inputs& in, float dt,
   const int64_t n_x = (int64_t)B * T * d.S;
   int rc;
   if (s->ctx_f32) {  // bf16 host context: widen once, both directions consume the fp32 copy (grad_context stays bf16)
-    visde_ctx_view wide;
-    if ((rc = convert_ctx(&d, &cv, s->ctx_f32, &wide, st))) return rc;
+    visde_ctx_view wide{s->ctx_f32, (int64_t)(T * C), (int64_t)C, VISDE_F32};
+    if (seg == 0 && (rc = convert_ctx(&d, &cv, s->ctx_f32, &wide, st))) return rc;
     cv = wide;
   }
-  rc = visde_path_fwd(&d, dt, in.x0, &cv, in.theta, in.eps, &in.w, s->paths, s->means, s->chol, s->stash, s->ws_f,
-                          s->ws_f_bytes, st);
-  if (rc) return rc;
-  if (generic) {
-    // evidence_lower_bound.py:31-40: x_t = to_state(z_t), then the caller's drift / diffusion on the [B*T, S] rows
-    state_rows_kernel<<<(unsigned)((n_x + 255) / 256), 256, 0, st>>>(s->paths, d.B, d.T, d.S, s->pos_mask, s->x_state);
-    VISDE_CUDA_CHECK(cudaGetLastError());
-    if (s->user.eval(s->user.user, s->x_state, in.theta, s->drift, s->diffusion, st) != 0) {
-      set_error("session: the user SDE eval hook failed");
-      return VISDE_EINVAL;
+  if (seg == 0) {
+    rc = visde_path_fwd(&d, dt, in.x0, &cv, in.theta, in.eps, &in.w, s->paths, s->means, s->chol, s->stash, s->ws_f,
+                        s->ws_f_bytes, st);
+    if (rc) return rc;
+    if (generic) {
+      // evidence_lower_bound.py:31-40: x_t = to_state(z_t), then the caller's drift / diffusion on the [B*T, S] rows
+      state_rows_kernel<<<(unsigned)((n_x + 255) / 256), 256, 0, st>>>(s->paths, d.B, d.T, d.S, s->pos_mask, s->x_state);
+      VISDE_CUDA_CHECK(cudaGetLastError());
     }
+    return VISDE_OK;
   }
-  rc = visde_elbo_fwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, in.theta, s->drift, s->diffusion, &od,
-                      s->terms, st);
-  if (rc) return rc;
-  fill_loss_cotangent_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(s->g_terms, (int64_t)B);
-  VISDE_CUDA_CHECK(cudaGetLastError());
-  rc = visde_elbo_bwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, in.theta, s->drift, s->diffusion, &od,
-                      s->g_terms, s->g_z, s->g_means, s->g_chol, s->g_theta_elbo, s->g_drift, s->g_diffusion, st);
-  if (rc) return rc;
+  if (seg == 1) {
+    rc = visde_elbo_fwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, in.theta, s->drift, s->diffusion, &od,
+                        s->terms, st);
+    if (rc) return rc;
+    fill_loss_cotangent_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(s->g_terms, (int64_t)B);
+    VISDE_CUDA_CHECK(cudaGetLastError());
+    return visde_elbo_bwd(&d, dt, s->sde_kind, s->pos_mask, s->paths, s->means, s->chol, in.theta, s->drift, s->diffusion, &od,
+                          s->g_terms, s->g_z, s->g_means, s->g_chol, s->g_theta_elbo, s->g_drift, s->g_diffusion, st);
+  }
   if (generic) {
-    if (s->user.vjp(s->user.user, s->x_state, in.theta, s->g_drift, s->g_diffusion, s->g_x, s->g_theta_sde, st) != 0) {
-      set_error("session: the user SDE vjp hook failed");
-      return VISDE_EINVAL;
-    }
     chain_state_grad_kernel<<<(unsigned)((n_x + 255) / 256), 256, 0, st>>>(s->paths, s->g_x, d.B, d.T, d.S, s->pos_mask, s->g_z);
     VISDE_CUDA_CHECK(cudaGetLastError());
   }
@@ -1028,11 +1068,62 @@ static int session_enqueue(visde_session* s, visde_session_inputs& in, float dt,
   return VISDE_OK;
 }
 
+// the caller's hook after segment `seg` of a user-SDE session (launched on the compute stream, outside any capture)
+static int session_hook(visde_session* s, visde_session_inputs& in, cudaStream_t st, int seg) {
+  if (s->sde_kind != VISDE_SDE_GENERIC) return VISDE_OK;
+  if (seg == 0 && s->user.eval(s->user.user, s->x_state, in.theta, s->drift, s->diffusion, st) != 0) {
+    set_error("session: the user SDE eval hook failed");
+    return VISDE_EINVAL;
+  }
+  if (seg == 1 && s->user.vjp(s->user.user, s->x_state, in.theta, s->g_drift, s->g_diffusion, s->g_x, s->g_theta_sde, st) != 0) {
+    set_error("session: the user SDE vjp hook failed");
+    return VISDE_EINVAL;
+  }
+  return VISDE_OK;
+}
+
+// segments [seg0, seg1) launched kernel by kernel, the hooks between / behind them included
+static int session_enqueue(visde_session* s, visde_session_inputs& in, float dt, const visde_obs* od_p, cudaStream_t st,
+                           int seg0 = 0, int seg1 = 3) {
+  for (int seg = seg0; seg < seg1; ++seg) {
+    int rc = session_segment(s, in, dt, od_p, st, seg);
+    if (!rc) rc = session_hook(s, in, st, seg);
+    if (rc) return rc;
+  }
+  return VISDE_OK;
+}
+
+// capture segments [seg0, seg1) (no hook inside) into an executable graph; nullptr when capture is unavailable
+static cudaGraphExec_t session_capture(visde_session* s, visde_session_inputs& in, float dt, const visde_obs* od_p, cudaStream_t st,
+                                       int seg0, int seg1, int* rc_out) {
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t ge = nullptr;
+  *rc_out = VISDE_OK;
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  int rc = VISDE_OK;
+  for (int seg = seg0; seg < seg1 && !rc; ++seg) rc = session_segment(s, in, dt, od_p, st, seg);
+  const cudaError_t ce = cudaStreamEndCapture(st, &g);
+  if (rc || ce != cudaSuccess || !g) {
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    return nullptr;  // the caller launches the segment plainly (and reports its error, if it has one)
+  }
+  if (cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) {
+    ge = nullptr;
+    cudaGetLastError();
+  }
+  cudaGraphDestroy(g);
+  return ge;
+}
+
 int visde_session_submit(visde_session* s, float dt, const float* x0, const void* context,
                          const float* theta, const float* eps, const visde_weights* w_host,
                          const visde_obs* obs_host, float* terms, float* grad_x0, float* grad_theta,
                          const visde_weight_grads* gw_host, void* grad_context) {
-  VISDE_REQUIRE(s && x0 && context && theta && eps && w_host && obs_host && terms && grad_x0 && grad_theta && gw_host,
+  VISDE_REQUIRE(s && x0 && context && theta && w_host && obs_host && terms && grad_x0 && grad_theta && gw_host,
                 "session_submit: NULL argument");
   VISDE_REQUIRE(obs_host->n_obs == s->n_obs && obs_host->obs_dim == s->obs_dim, "session_submit: observation shape changed");
   VISDE_REQUIRE(s->n_submitted - s->n_waited < 2, "session_submit: two iterations already in flight; call visde_session_wait");
@@ -1048,7 +1139,8 @@ int visde_session_submit(visde_session* s, float dt, const float* x0, const void
   H2D(in.x0, x0, B * S);
   VISDE_CUDA_CHECK(cudaMemcpyAsync(in.ctx, context, ctx_elem_bytes(s) * B * (T + 1) * C, cudaMemcpyHostToDevice, cs));
   H2D(in.theta, theta, B * P);
-  H2D(in.eps, eps, B * T * S);
+  if (eps) H2D(in.eps, eps, B * T * S);
+  s->device_noise = eps == nullptr;
   for (int k = 0; k < d.NL; ++k) {
     H2D(in.w.w_ih[k], w_host->w_ih[k], w_ih_floats(d, k));
     H2D(in.w.w_hh[k], w_host->w_hh[k], G * H);
@@ -1068,43 +1160,44 @@ int visde_session_submit(visde_session* s, float dt, const float* x0, const void
   od.obs_matrix = obs_host->obs_matrix ? in.obs_matrix : nullptr;
   VISDE_CUDA_CHECK(cudaEventRecord(in.loaded, cs));
   VISDE_CUDA_CHECK(cudaStreamWaitEvent(st, in.loaded, 0));
+  if (!eps) {
+    // diffusion_path_sampler.py:57 draws the noise on the device: here the counter-based stream of visde_philox_normal, a
+    // fresh key per iteration (ahead of the graph replay: the key is a kernel argument)
+    int prc = visde_philox_normal(s->noise_seed + s->n_submitted, d.B, d.T, d.S, in.eps, st);
+    if (prc) return prc;
+  }
 
   // first use of an input set runs kernel by kernel (per-kernel attributes, tensor-map encoders); from the second use
-  // on the same sequence is replayed as one CUDA graph
+  // on the same sequence is replayed from CUDA graphs: ONE graph per iteration, or -- user-SDE sessions, whose hooks run
+  // between the segments on the same stream -- one graph per segment
   int rc;
   const bool obs_mat = obs_host->obs_matrix != nullptr;
-  if (in.graph && (in.graph_dt != dt || in.graph_var != od.variance || in.graph_obsmat != obs_mat)) {
-    cudaGraphExecDestroy(in.graph);
-    in.graph = nullptr;
-  }
-  if (in.graph) {
-    VISDE_CUDA_CHECK(cudaGraphLaunch(in.graph, st));
-  } else if (in.uses >= 1 && !g_prof_on && s->sde_kind != VISDE_SDE_GENERIC) {  // user hooks launch outside any capture
-    cudaGraph_t g = nullptr;
-    VISDE_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = session_enqueue(s, in, dt, &od, st);
-    const cudaError_t ce = cudaStreamEndCapture(st, &g);
-    if (rc || ce != cudaSuccess || !g) {
-      if (g) cudaGraphDestroy(g);
-      cudaGetLastError();
-      if (!rc) rc = session_enqueue(s, in, dt, &od, st);  // capture unavailable: plain launches
-      if (rc) return rc;
-    } else {
-      const cudaError_t ie = cudaGraphInstantiate(&in.graph, g, 0);
-      cudaGraphDestroy(g);
-      if (ie != cudaSuccess) {
-        in.graph = nullptr;
-        cudaGetLastError();
-        if ((rc = session_enqueue(s, in, dt, &od, st))) return rc;
-      } else {
-        in.graph_dt = dt;
-        in.graph_var = od.variance;
-        in.graph_obsmat = obs_mat;
-        VISDE_CUDA_CHECK(cudaGraphLaunch(in.graph, st));
-      }
+  const bool generic = s->sde_kind == VISDE_SDE_GENERIC;
+  const int nseg = generic ? 3 : 1;
+  if (in.graph[0] && (in.graph_dt != dt || in.graph_var != od.variance || in.graph_obsmat != obs_mat)) {
+    for (int g = 0; g < 3; ++g) {
+      if (in.graph[g]) cudaGraphExecDestroy(in.graph[g]);
+      in.graph[g] = nullptr;
     }
-  } else {
-    if ((rc = session_enqueue(s, in, dt, &od, st))) return rc;
+  }
+  const bool use_graphs = in.uses >= 1 && !g_prof_on;
+  if (use_graphs && !in.graph[0] && !in.graph_failed) {
+    in.graph_dt = dt;
+    in.graph_var = od.variance;
+    in.graph_obsmat = obs_mat;
+  }
+  for (int g = 0; g < nseg; ++g) {
+    const int seg0 = generic ? g : 0, seg1 = generic ? g + 1 : 3;
+    if (use_graphs && !in.graph[g] && !in.graph_failed) {
+      in.graph[g] = session_capture(s, in, dt, &od, st, seg0, seg1, &rc);
+      if (!in.graph[g]) in.graph_failed = true;  // capture unavailable: plain launches from here on
+    }
+    if (use_graphs && in.graph[g]) {
+      VISDE_CUDA_CHECK(cudaGraphLaunch(in.graph[g], st));
+      if ((rc = session_hook(s, in, st, seg1 - 1))) return rc;
+    } else if ((rc = session_enqueue(s, in, dt, &od, st, seg0, seg1))) {
+      return rc;
+    }
   }
   ++in.uses;
   VISDE_CUDA_CHECK(cudaEventRecord(in.consumed, st));

@@ -4,7 +4,7 @@ one ELBO iteration of the path: pinned host tensors in, ELBO terms and gradients
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List
+from typing import Dict, List, Optional
 
 import torch
 from torch import Tensor
@@ -148,10 +148,13 @@ class HostSession:
                  w_hh: List[Tensor], b_ih: List[Tensor], b_hh: List[Tensor], out_w: Tensor, out_b: Tensor, dt: float,
                  sde_kind: int, positive_mask: int, obs_idx: Tensor, obs_values: Tensor, obs_variance: float,
                  variant: int = _lib.VARIANT_AUTO, want_grad_context: bool = False, sde=None,
-                 context_dtype: torch.dtype = torch.float32, graph_hooks: bool = True) -> None:
+                 context_dtype: torch.dtype = torch.float32, graph_hooks: bool = True,
+                 device_noise_seed: Optional[int] = None) -> None:
         """`context_dtype` bfloat16 = the reference's AMP mode (the encoder runs under bf16 autocast,
         inference/trainer.py:171-175): the host context and grad_context are bf16, which halves the dominant H2D term.
-        `sde`: the user SDE object when `sde_kind` is GENERIC."""
+        `sde`: the user SDE object when `sde_kind` is GENERIC.  `device_noise_seed`: draw the noise on the device as the
+        reference's sampler does (inference/diffusion_path_sampler.py:57) -- iteration i uses the Philox stream of
+        ``visde_philox_normal(seed + i)`` and `eps` never crosses the bus (it is then only a shape)."""
         self.lib = _lib.load()
         if context_dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("context_dtype must be float32 or bfloat16")
@@ -167,6 +170,7 @@ class HostSession:
         # two host output sets: iteration i+1 may be submitted before the outputs of i are consumed
         self._out = [self._make_outputs(B, S, P, T, Cd, want_grad_context) for _ in range(2)]
         self._submitted = self._waited = 0
+        self.device_noise_seed = device_noise_seed
         self.obs_idx = obs_idx.detach().to(torch.int32).contiguous().cpu()
         self.obs_values = obs_values.detach().to(torch.float32).contiguous().cpu()
         self.obs = _lib.Obs(self.obs_idx.shape[0], self.obs_values.shape[1], self.obs_idx.data_ptr(),
@@ -181,6 +185,8 @@ class HostSession:
             C.byref(self.dims), sde_kind, positive_mask, self.obs.n_obs, self.obs.obs_dim,
             _lib.BF16 if context_dtype == torch.bfloat16 else _lib.F32,
             C.byref(self._hooks.struct) if self._hooks else None, C.byref(self.handle)))
+        if device_noise_seed is not None:
+            _lib.check(self.lib.visde_session_set_noise_seed(self.handle, int(device_noise_seed)))
 
     @classmethod
     def from_problem(cls, p, **kw) -> "HostSession":
@@ -243,7 +249,8 @@ class HostSession:
         w = self._wstruct(self.w, self.out_w, self.out_b)
         gw = self._wstruct(o["gw"], o["g_out_w"], o["g_out_b"])
         rc = fn(
-            self.handle, self.dt, self.x0.data_ptr(), self.ctx.data_ptr(), self.theta.data_ptr(), self.eps.data_ptr(),
+            self.handle, self.dt, self.x0.data_ptr(), self.ctx.data_ptr(), self.theta.data_ptr(),
+            None if self.device_noise_seed is not None else self.eps.data_ptr(),
             C.byref(w), C.byref(self.obs), o["terms"].data_ptr(), o["grad_x0"].data_ptr(), o["grad_theta"].data_ptr(),
             C.byref(gw), None if o["grad_ctx"] is None else o["grad_ctx"].data_ptr())
         if rc and self._hooks is not None and self._hooks.error is not None:
