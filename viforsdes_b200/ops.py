@@ -46,7 +46,37 @@ def _require_cuda(*ts: Tensor) -> None:
 
 
 def _f32c(t: Tensor) -> Tensor:
+    if t.dtype == torch.float32 and not t.requires_grad and t.is_contiguous():
+        return t  # the common case (fp32 parameters / buffers handed over by autograd): no dispatcher round trips
     return t.detach().to(torch.float32).contiguous()
+
+
+_SIZES: dict = {}      # (dims..., variant, backward) -> bytes: the size queries are pure functions of the dims
+_WORKSPACE: dict = {}  # (device index, stream) -> uint8 scratch, grown on demand, reused by every call on that stream
+
+
+def _stash_bytes(lib, d: _lib.Dims) -> int:
+    key = (d.B, d.T, d.S, d.C, d.P, d.H, d.NL, d.variant, "stash")
+    if key not in _SIZES:
+        _SIZES[key] = int(lib.visde_stash_bytes(C.byref(d)))
+    return _SIZES[key]
+
+
+def _workspace(lib, d: _lib.Dims, backward: int, dev: torch.device) -> Tuple[Tensor, int]:
+    """Scratch for one launch.  Kernels on one stream run in order and the scratch holds nothing across calls, so one
+    buffer per (device, stream) serves every call (the reference allocates ~15 tensors per launch, kernels/forward.py:
+    398-497); under CUDA-graph capture the allocation goes to the graph's private pool instead."""
+    key = (d.B, d.T, d.S, d.C, d.P, d.H, d.NL, d.variant, backward)
+    if key not in _SIZES:
+        _SIZES[key] = int(lib.visde_workspace_bytes(C.byref(d), backward))
+    need = _SIZES[key]
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(need, device=dev, dtype=torch.uint8), need
+    slot = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream())
+    buf = _WORKSPACE.get(slot)
+    if buf is None or buf.numel() < need:
+        buf = _WORKSPACE[slot] = torch.empty(need, device=dev, dtype=torch.uint8)
+    return buf, need
 
 
 def _dims(B: int, T: int, S: int, Cdim: int, P: int, H: int, NL: int) -> _lib.Dims:
@@ -116,10 +146,9 @@ def path_fwd(x0: Tensor, context: Tensor, theta: Tensor, eps: Tensor, w_ih: List
     paths = torch.empty(B, T + 1, S, device=dev, dtype=torch.float32)
     means = torch.empty(B, T, S, device=dev, dtype=torch.float32)
     chol = torch.empty(B, T, S, S, device=dev, dtype=torch.float32)
-    stash = torch.empty(lib.visde_stash_bytes(C.byref(d)) if save else 0, device=dev, dtype=torch.uint8)
-    ws_bytes = lib.visde_workspace_bytes(C.byref(d), 0)
-    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    stash = torch.empty(_stash_bytes(lib, d) if save else 0, device=dev, dtype=torch.uint8)
     with torch.cuda.device(dev):
+        ws, ws_bytes = _workspace(lib, d, 0, dev)
         _lib.check(lib.visde_path_fwd(C.byref(d), dt, _ptr(x0f), C.byref(cv), _ptr(thf), _ptr(epf), C.byref(w),
                                       _ptr(paths), _ptr(means), _ptr(chol), _ptr(stash) if save else None,
                                       _ptr(ws), ws_bytes, _stream()))
@@ -164,9 +193,8 @@ def path_bwd(g_paths: Tensor, g_means: Tensor, g_chol: Tensor, context: Tensor, 
     g_ow, g_ob = torch.empty_like(ow), torch.empty_like(ob)
     gw = _weights_struct(gw_ih, gw_hh, gb_ih, gb_hh, g_ow, g_ob)
     gv = _lib.CtxView(_ptr(grad_ctx), grad_ctx.stride(0), grad_ctx.stride(1), cv.dtype)
-    ws_bytes = lib.visde_workspace_bytes(C.byref(d), 1)
-    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
     with torch.cuda.device(dev):
+        ws, ws_bytes = _workspace(lib, d, 1, dev)
         _lib.check(lib.visde_path_bwd(C.byref(d), dt, _ptr(_f32c(g_paths)), _ptr(_f32c(g_means)), _ptr(_f32c(g_chol)),
                                       C.byref(cv), _ptr(thf), _ptr(epf), C.byref(w), _ptr(_f32c(paths)), _ptr(stash),
                                       _ptr(grad_x0), C.byref(gv), _ptr(grad_theta), C.byref(gw), _ptr(ws), ws_bytes,
