@@ -37,7 +37,10 @@ __device__ long long g_tcw_trace_fwd[2 * 16 * 16];
 // ---------------------------------------------------------------------------------------------------------------------
 // weight images: one CTA per image
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) tcw_images_kernel(PathParams p, uint8_t* __restrict__ img, int want_fwd, int want_bwd) {
+// half_tiles: the images serve the 64-row kernels (path_*_tcw_kernel<S, 64>), whose two lane-half accumulators each hold 32 hidden
+// units: forward tile rows are ordered [unit half][gate][32 units] so that the B rows of one half are contiguous
+__global__ void __launch_bounds__(1024) tcw_images_kernel(PathParams p, uint8_t* __restrict__ img, int want_fwd, int want_bwd,
+                                                          int half_tiles) {
   __shared__ uint32_t amax[3];
   const int tid = threadIdx.x, lane = tid & 31;
   const int S = p.S, NTRIL = p.n_tril, ld0 = p.S + p.C + p.P;
@@ -79,9 +82,10 @@ __global__ void __launch_bounds__(1024) tcw_images_kernel(PathParams p, uint8_t*
     uint8_t* tlo = thi + kWTileBytes;
     for (int idx = tid; idx < 192 * 8; idx += blockDim.x) {
       const int n = idx >> 3, c = idx & 7;
+      const int srow = half_tiles ? ((n % 96) / 32) * 64 + (n / 96) * 32 + n % 32 : n;  // gate row of the nn.GRU matrix
       float x[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) x[q] = src[n * 64 + c * 8 + q] * w_scale;
+      for (int q = 0; q < 8; ++q) x[q] = src[srow * 64 + c * 8 + q] * w_scale;
       uint4 hi, lo;
       split8(x, hi, lo);
       *reinterpret_cast<uint4*>(thi + sw128(n, c)) = hi;
@@ -273,25 +277,37 @@ __device__ __forceinline__ void issue_gemm_w(uint32_t dcol, uint32_t a_hi, uint3
   for (int j = 0; j < 4; ++j) {
     const uint64_t dah = umma_desc(a_hi + j * 32, 16, 1024, 2), dal = umma_desc(a_lo + j * 32, 16, 1024, 2);
     const uint64_t dbh = umma_desc(b_hi + j * 32, 16, 1024, 2), dbl = umma_desc(b_lo + j * 32, 16, 1024, 2);
+#ifdef VISDE_TCW_EXP1  // timing experiment only (wrong numerics): one pass instead of three
+    umma_f16(dcol, dah, dbh, idesc, (accumulate || j > 0) ? 1u : 0u);
+#else
     umma_f16(dcol, dal, dbh, idesc, (accumulate || j > 0) ? 1u : 0u);
     umma_f16(dcol, dah, dbl, idesc, 1u);
     umma_f16(dcol, dah, dbh, idesc, 1u);
+#endif
   }
 }
 
-// MT = trajectories per CTA = MMA M.  128: one CTA per tile, every TMEM lane a trajectory.  64: TWO CTAs per 128-row tile of the
-// global layouts (sub-tile = work item & 1), rows on lanes 0..15 of each 32-lane TMEM quadrant (the M = 64 accumulator layout),
-// lanes 16..31 of every warp idle -- the step is latency-bound, so when the batch has at most SMs / 2 tiles the second half of
-// the machine halves the tiles' serial time.
+// MT = trajectories per CTA = MMA M.  128: one CTA per tile, every TMEM lane a trajectory, two threads per row (32 hidden units each).
+// 64: TWO CTAs per 128-row tile of the global layouts (sub-tile = work item & 1).  An M = 64 accumulator occupies lanes 0..15 of each
+// 32-lane TMEM quadrant; every product is issued TWICE with N halved -- hidden units 0..31 into lanes 0..15, units 32..63 into the
+// same columns of lanes 16..31 (D address + 16 lanes) -- so lane l of a warp owns row (l & 15) and unit half (l >> 4): four threads
+// per row, 16 hidden units each, every lane busy.  The epilogues are issue-bound, so halving the rows per SM halves their time;
+// used while the batch has at most SMs / 2 tiles.
 template <int S, int MT>
 __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams p) {
   using L = TcwFwdSmem;
   static_assert(MT == 128 || MT == 64, "MMA M");
   constexpr int LPQ = MT / 4, SUBS = kTileRows / MT;
+  constexpr bool HALF = MT == 64;
+  constexpr int UPT = HALF ? 16 : 32;  // hidden units per thread
+  constexpr int HU = HALF ? 32 : 64;   // hidden units per accumulator block (one lane half)
+  constexpr int NCH = UPT / 8, GA = UPT / 2;
   constexpr int NTRIL = S * (S + 1) / 2, CS = L::CS, OF = tcw_out_feats(S);
   static_assert(S > 4 && S <= kTcwMaxS && NTRIL <= 64 && 3 * S + 1 <= CS, "wide-state tensor-core recurrence: 4 < S <= 10");
   constexpr uint32_t TMEM_COLS = 512;
-  constexpr uint32_t D0_COL = 0, D1_COL = 192, TRIL_COL = D1_COL + 128, MU_COL = 448;
+  // M = 128: D0 0..191 | D1 192..447 (r, u, n_i, n_h) | Cholesky rows alias D1's n_i block | mu 448..463
+  // M = 64 : D0 0..95  | D1 96..223                    | Cholesky rows 224..287            | mu 288..303 (both lane halves)
+  constexpr uint32_t D0_COL = 0, D1_COL = 3 * HU, TRIL_COL = HALF ? 7 * HU : D1_COL + 2 * HU, MU_COL = HALF ? 7 * HU + 64 : 448;
   extern __shared__ __align__(1024) uint8_t smem_raw_tcw[];
   uint8_t* smem = smem_raw_tcw + ((1024u - (smem_u32(smem_raw_tcw) & 1023u)) & 1023u);
   typename L::Bars* bars = reinterpret_cast<typename L::Bars*>(smem + L::OFF_BAR);
@@ -323,13 +339,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
 
   if (tid == 0) {
     mbar_init(&bars->init, kEpiThreads);
-    mbar_init(&bars->d0, 1);
+    mbar_init(&bars->d0, MT == 64 ? 2 : 1);  // one commit per thread that issues into the barrier
     mbar_init(&bars->a0, kEpiThreads);
-    mbar_init(&bars->d1, 1);
+    mbar_init(&bars->d1, MT == 64 ? 4 : 1);
     mbar_init(&bars->a1, kEpiThreads);
-    mbar_init(&bars->out, 1);
+    mbar_init(&bars->out, MT == 64 ? 4 : 1);
     mbar_init(&bars->wx, 1);
-    mbar_init(&bars->xr, 1);
+    mbar_init(&bars->xr, MT == 64 ? 2 : 1);
     mbar_init(&bars->pro, 1);
     fence_barrier_init();
   }
@@ -355,25 +371,53 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
   const uint32_t a1h = a0h + 2 * kATileBytes, a1l = a1h + kATileBytes;
   const uint32_t woh = smem_u32(smem + L::OFF_WOUT), wol = woh + kOutRows * 128;
   constexpr uint32_t ID192 = idesc_f16(192, MT), ID128 = idesc_f16(128, MT), ID64 = idesc_f16(64, MT), ID16 = idesc_f16(16, MT);
-  constexpr uint32_t NROWS = 128 * 128;  // byte offset of gate rows 128.. (the n block) in a weight tile
+  constexpr uint32_t ID96 = idesc_f16(96, MT), ID32 = idesc_f16(32, MT);
+  constexpr uint32_t NROWS = 128 * 128;  // byte offset of gate rows 128.. (the n block) in a weight tile (M = 128 row order)
+  constexpr uint32_t HROWS = 96 * 128;   // M = 64 row order [half][gate][32]: byte offset of the second unit half
+  constexpr uint32_t LHALF = 16u << 16;  // TMEM address of the second lane half
   uint32_t ph_init = 0, ph_a0 = 0, ph_a1 = 0, ph_wx = 0, ph_xr = 0;  // issuer-side phases (thread 0)
+  // M = 64: FOUR issuing threads side by side (lane 0 of warps 0..3): warp w issues unit half h = w & 1, and of the two products
+  // on the critical path of a hand-off (layer-1 input: r, u | n_i; output: Cholesky rows | mu) block w >> 1; the two products that
+  // have a whole phase to complete (h0 . W_hh_l0, h1 . W_hh_l1) ride with block 0.  A hand-off then costs the issue time of 12 MMAs.
+  // Every completion barrier of the tensor pipe counts one commit per thread that issued into it.
+  constexpr int NISS = HALF ? 4 : 1;
+  constexpr uint32_t NI_OFF = HALF ? 3 * HU : 2 * HU, NH_OFF = HALF ? 2 * HU : 3 * HU;  // n_i / n_h blocks of D1
+  const uint32_t hh = HALF ? (uint32_t)(warp & 1) : 0u;
+  const bool blk0 = !HALF || (warp >> 1) == 0, blk1 = !HALF || (warp >> 1) == 1;
+  const uint32_t tm_h = tmem + hh * LHALF, wro = hh * HROWS;
   auto issue_recurrent_l0 = [&]() {  // D0 = h0 . W_hh_l0^T (for the next step)
-    issue_gemm_w(tmem + D0_COL, a0h, a0l, w0h, w0l, ID192, false);
+    if (!blk0) return;
+    if (HALF) issue_gemm_w(tm_h + D0_COL, a0h, a0l, w0h + wro, w0l + wro, ID96, false);
+    else issue_gemm_w(tmem + D0_COL, a0h, a0l, w0h, w0l, ID192, false);
     umma_commit(&bars->d0);
   };
-  auto issue_x_recurrent_l1 = [&]() {  // X holds W_hh_l1: D1[r, u] = h1 . W_hh_l1[r, u]^T, D1[n_h] = h1 . W_hh_l1[n]^T
-    issue_gemm_w(tmem + D1_COL, a1h, a1l, xh, xl, ID128, false);
-    issue_gemm_w(tmem + D1_COL + 192, a1h, a1l, xh + NROWS, xl + NROWS, ID64, false);
-    umma_commit(&bars->xr);
+  auto mma_x_recurrent_l1 = [&]() {  // X holds W_hh_l1: D1[r, u] = h1 . W_hh_l1[r, u]^T, D1[n_h] = h1 . W_hh_l1[n]^T
+    if (!blk0) return;
+    if (HALF) {  // r, u, n_h are adjacent: one N = 96 product
+      issue_gemm_w(tm_h + D1_COL, a1h, a1l, xh + wro, xl + wro, ID96, false);
+    } else {
+      issue_gemm_w(tmem + D1_COL, a1h, a1l, xh, xl, ID128, false);
+      issue_gemm_w(tmem + D1_COL + NH_OFF, a1h, a1l, xh + NROWS, xl + NROWS, ID64, false);
+    }
+  };
+  auto issue_x_recurrent_l1 = [&]() {
+    mma_x_recurrent_l1();
+    if (blk0) umma_commit(&bars->xr);
   };
   auto issue_x_input_l1 = [&]() {  // X holds W_ih_l1: r, u accumulate onto the recurrent part, n_i has its own columns
-    issue_gemm_w(tmem + D1_COL, a0h, a0l, xh, xl, ID128, true);
-    issue_gemm_w(tmem + D1_COL + 128, a0h, a0l, xh + NROWS, xl + NROWS, ID64, false);
+    if (HALF) {
+      if (blk0) issue_gemm_w(tm_h + D1_COL, a0h, a0l, xh + wro, xl + wro, ID64, true);
+      else issue_gemm_w(tm_h + D1_COL + NI_OFF, a0h, a0l, xh + wro + 64 * 128, xl + wro + 64 * 128, ID32, false);
+    } else {
+      issue_gemm_w(tmem + D1_COL, a0h, a0l, xh, xl, ID128, true);
+      issue_gemm_w(tmem + D1_COL + NI_OFF, a0h, a0l, xh + NROWS, xl + NROWS, ID64, false);
+    }
     umma_commit(&bars->d1);
   };
-  auto issue_out = [&]() {  // Cholesky rows into the (dead) n_i columns of D1, mu into the free columns
-    issue_gemm_w(tmem + TRIL_COL, a1h, a1l, woh, wol, ID64, false);
-    issue_gemm_w(tmem + MU_COL, a1h, a1l, woh + 64 * 128, wol + 64 * 128, ID16, false);
+  auto issue_out = [&]() {  // M = 128: Cholesky rows into the (dead) n_i columns of D1, mu into the free columns;
+                            // M = 64: every lane half gets the whole output row in its own columns
+    if (blk0) issue_gemm_w(tm_h + TRIL_COL, a1h, a1l, woh, wol, ID64, false);
+    if (blk1) issue_gemm_w(tm_h + MU_COL, a1h, a1l, woh + 64 * 128, wol + 64 * 128, ID16, false);
     umma_commit(&bars->out);
   };
   auto load_x = [&](int m) {  // thread 0: X <- image of W_ih_l1 (m = 1) / W_hh_l1 (m = 2); the MMAs reading X have completed
@@ -385,14 +429,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
     ph_wx ^= 1;
     tc_fence_after();
   };
-  if (tid == 0) mbar_wait(&bars->pro, 0);
+  if (warp < NISS) mbar_wait(&bars->pro, 0);
 
   {
     const int quad = warp & 3, cg = warp >> 2;
-    const bool act = lane < LPQ;                     // lanes past the quadrant's rows only take part in the collectives
-    const int row = quad * LPQ + (lane & (LPQ - 1));  // row of the CTA's A tile / accumulator (idle lanes alias a live row for loads)
+    constexpr bool act = true;
+    const int lh = HALF ? lane >> 4 : 0;              // M = 64: unit half = TMEM lane half of this thread
+    const int row = quad * LPQ + (lane & (LPQ - 1));  // row of the CTA's A tile / accumulators
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
-    const int u0 = cg * kUPT;
+    const int jc0 = cg * UPT;        // first of this thread's units inside its accumulator block (column offset)
+    const int u0 = lh * HU + jc0;    // ... as a hidden-unit index
     uint8_t* a_tiles = smem + L::OFF_A;
     const float hs = exp2i(kHExp);
     uint32_t ph_d0 = 0, ph_d1 = 0, ph_out = 0;
@@ -403,7 +449,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
       const int64_t b_raw = tile * kTileRows + grow;
       const bool ok = act && b_raw < p.B;
       const int64_t b = b_raw < p.B ? b_raw : p.B - 1;
-      const bool writer = cg == 0 && act;  // pad rows write too: the tiled records of pad rows are never read as data
+      const bool writer = cg == 0 && lh == 0;  // pad rows write too: the tiled records of pad rows are never read as data
       // X holds W_ih_l1 at every tile start.  The first tile's copy was issued in the prologue; a later tile re-issues it so
       // that every tile consumes exactly one completion of `wx` at its step 0 (the last reader of X, the layer-1 input
       // product of the previous tile's final step, completed before this thread passed that step's d1 wait)
@@ -412,7 +458,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
 #pragma unroll
       for (int k = 0; k < 2; ++k)
 #pragma unroll
-        for (int c = 0; c < kUPT / 8; ++c) {
+        for (int c = 0; c < NCH; ++c) {
           const uint32_t off = sw128(row, (u0 >> 3) + c);
           if (act) {
             *reinterpret_cast<uint4*>(a_tiles + (2 * k) * kATileBytes + off) = make_uint4(0, 0, 0, 0);
@@ -421,40 +467,39 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
         }
       fence_proxy_async();
       mbar_arrive(&bars->init);
-      if (warp == 0) {
+      if (warp < NISS) {
         mbar_wait(&bars->init, ph_init);
         ph_init ^= 1;
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one_sync()) {
           // h(-1) = 0: the A tiles are zero, so these just clear the accumulators (X holds the finite W_ih_l1 image: the
           // recurrent product of layer 1 is issued with whatever finite tile is there, 0 . w = 0)
           issue_recurrent_l0();
           mbar_wait(&bars->wx, ph_wx);  // no phase flip: issue_x_input_l1 of step 0 waits for the same completion
           tc_fence_after();
-          issue_gemm_w(tmem + D1_COL, a1h, a1l, xh, xl, ID128, false);
-          issue_gemm_w(tmem + D1_COL + 192, a1h, a1l, xh + NROWS, xl + NROWS, ID64, false);
+          mma_x_recurrent_l1();
         }
         __syncwarp();
       }
 
-      float z[S], hprev[2][kUPT];
+      float z[S], hprev[2][UPT];
 #pragma unroll
       for (int s = 0; s < S; ++s) z[s] = ok ? p.x0[b * S + s] : 0.f;
 #pragma unroll
       for (int k = 0; k < 2; ++k)
 #pragma unroll
-        for (int j = 0; j < kUPT; ++j) hprev[k][j] = 0.f;
+        for (int j = 0; j < UPT; ++j) hprev[k][j] = 0.f;
       const float* gi_p = p.gi_ctx + tile * T * (int64_t)(192 * kTileRows) + (int64_t)u0 * kTileRows + grow;
       float* st_p = p.stash && act ? p.stash + tile * T * (int64_t)(2 * kStashSlots * 64 * kTileRows) + (int64_t)u0 * kTileRows + grow
                                    : nullptr;
       const float* eps_p = p.epst + tile * T * (int64_t)(S * kTileRows) + grow;
       float* ot_p = p.otile + tile * T * (int64_t)(OF * kTileRows) + grow;
 
-      float g01[3][16], g23[3][16];
+      float g01[3][GA], g23[3][GA];  // context part of the layer-0 gates: first / second half of this thread's units
 #pragma unroll
       for (int g = 0; g < 3; ++g)
 #pragma unroll
-        for (int q = 0; q < 16; ++q) g01[g][q] = gi_p[(g * 64 + q) * kTileRows];
+        for (int q = 0; q < GA; ++q) g01[g][q] = gi_p[(g * 64 + q) * kTileRows];
 
       for (int64_t t = 0; t < T; ++t) {
         const bool has_next = t + 1 < T;
@@ -463,23 +508,24 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
 #pragma unroll
         for (int g = 0; g < 3; ++g)
 #pragma unroll
-          for (int q = 0; q < 16; ++q) g23[g][q] = gi_p[(g * 64 + 16 + q) * kTileRows];
+          for (int q = 0; q < GA; ++q) g23[g][q] = gi_p[(g * 64 + GA + q) * kTileRows];
         mbar_wait(&bars->d0, ph_d0);
         ph_d0 ^= 1;
         tc_fence_after();
         TCW_TRACE(1);
 #pragma unroll
-        for (int c = 0; c < kUPT / 8; ++c) {
-          const int j0 = u0 + c * 8;
+        for (int c = 0; c < NCH; ++c) {
+          const int j0 = u0 + c * 8, jc = jc0 + c * 8;
           uint32_t dr[8], du[8], dn[8];
-          tmem_ld8_nowait(tl + D0_COL + j0, dr);
-          tmem_ld8_nowait(tl + D0_COL + 64 + j0, du);
-          tmem_ld8_nowait(tl + D0_COL + 128 + j0, dn);
+          tmem_ld8_nowait(tl + D0_COL + jc, dr);
+          tmem_ld8_nowait(tl + D0_COL + HU + jc, du);
+          tmem_ld8_nowait(tl + D0_COL + 2 * HU + jc, dn);
           float gcur[3][8];
 #pragma unroll
           for (int g = 0; g < 3; ++g)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) gcur[g][q] = c < 2 ? g01[g][(c & 1) * 8 + q] : g23[g][(c & 1) * 8 + q];
+            for (int q = 0; q < 8; ++q)
+              gcur[g][q] = c < NCH / 2 ? g01[g][(c % (NCH / 2)) * 8 + q] : g23[g][(c % (NCH / 2)) * 8 + q];
           tmem_ld_wait();
           float hx[8];
 #pragma unroll
@@ -531,11 +577,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
         TCW_TRACE(2);
         mbar_arrive(&bars->a0);
         gi_p += 192 * kTileRows;
-        if (warp == 0) {
+        if (warp < NISS) {
           mbar_wait(&bars->a0, ph_a0);
           ph_a0 ^= 1;
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one_sync()) {
             wait_x();  // X = W_ih_l1
             issue_x_input_l1();
             if (has_next) issue_recurrent_l0();
@@ -546,7 +592,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
 #pragma unroll
           for (int g = 0; g < 3; ++g)
 #pragma unroll
-            for (int q = 0; q < 16; ++q) g01[g][q] = gi_p[(g * 64 + q) * kTileRows];
+            for (int q = 0; q < GA; ++q) g01[g][q] = gi_p[(g * 64 + q) * kTileRows];
         }
         // this step's noise (tiled: one coalesced line per component), in flight during layer 1
         float eps[S];
@@ -562,13 +608,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
         TCW_TRACE(4);
         if (tid == 0 && has_next) load_x(2);  // the layer-1 input product has finished reading X: stream W_hh_l1 in
 #pragma unroll
-        for (int c = 0; c < kUPT / 8; ++c) {
-          const int j0 = u0 + c * 8;
+        for (int c = 0; c < NCH; ++c) {
+          const int j0 = u0 + c * 8, jc = jc0 + c * 8;
           uint32_t dr[8], du[8], di[8], dn[8];
-          tmem_ld8_nowait(tl + D1_COL + j0, dr);
-          tmem_ld8_nowait(tl + D1_COL + 64 + j0, du);
-          tmem_ld8_nowait(tl + D1_COL + 128 + j0, di);
-          tmem_ld8_nowait(tl + D1_COL + 192 + j0, dn);
+          tmem_ld8_nowait(tl + D1_COL + jc, dr);
+          tmem_ld8_nowait(tl + D1_COL + HU + jc, du);
+          tmem_ld8_nowait(tl + D1_COL + NI_OFF + jc, di);
+          tmem_ld8_nowait(tl + D1_COL + NH_OFF + jc, dn);
           tmem_ld_wait();
           float hx[8];
 #pragma unroll
@@ -606,11 +652,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
         tc_fence_before();
         TCW_TRACE(5);
         mbar_arrive(&bars->a1);
-        if (warp == 0) {
+        if (warp < NISS) {
           mbar_wait(&bars->a1, ph_a1);
           ph_a1 ^= 1;
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one_sync()) {
             issue_out();
             if (has_next) {
               wait_x();  // X = W_hh_l1
@@ -749,7 +795,11 @@ bool tcw_rec_supported(const PathParams& p) {
 }
 
 int launch_tcw_images(const PathParams& p, void* img, bool fwd, bool bwd, cudaStream_t st) {
-  tcw_images_kernel<<<9, 1024, 0, st>>>(p, reinterpret_cast<uint8_t*>(img), fwd ? 1 : 0, bwd ? 1 : 0);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int half_tiles = tcw_half_tiles((p.B + kTileRows - 1) / kTileRows, sms) ? 1 : 0;
+  tcw_images_kernel<<<9, 1024, 0, st>>>(p, reinterpret_cast<uint8_t*>(img), fwd ? 1 : 0, bwd ? 1 : 0, half_tiles);
   VISDE_CUDA_CHECK(cudaGetLastError());
   return VISDE_OK;
 }

@@ -65,6 +65,18 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int j) { return u
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int j) { return umma_desc(tile + j * 1024, 4096, 512, 1); }
 
 
+// true on exactly one lane of a converged warp (always the same one).  A region guarded by it is known to the compiler to run on a
+// single lane, so warp-uniform operands of tcgen05.mma are moved to uniform registers directly; under `if (lane == 0)` every MMA gets
+// an ELECT / R2UR.BROADCAST / BRA.U.ANY loop around it (~13 instructions, ~100 cycles of issue per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 / bf16 operands, fp32 accumulate), ONE thread
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
