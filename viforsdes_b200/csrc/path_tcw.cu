@@ -115,11 +115,13 @@ __global__ void __launch_bounds__(1024) tcw_images_kernel(PathParams p, uint8_t*
     uint8_t* tlo = thi + 3 * 16 * 128;
     for (int idx = tid; idx < 16 * 24; idx += blockDim.x) {
       const int sdim = idx & 15, hg = idx >> 4;
-      const int gB = hg >> 1, half = hg & 1, c = gB / 3, g = gB % 3;
+      const int gB = hg >> 1, half = hg & 1;
+      // K-group gB: (chunk of 16 units, gate), or in the 64-row form (chunk of 32 units, gate, 16-unit half of the chunk)
+      const int g = half_tiles ? (gB % 6) / 2 : gB % 3;
+      const int u8 = half_tiles ? (gB / 6) * 32 + (gB % 2) * 16 + half * 8 : (gB / 3) * 16 + half * 8;
       float x[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        x[q] = sdim < S ? p.w_ih[0][(int64_t)(g * 64 + c * 16 + half * 8 + q) * ld0 + sdim] * z_scale : 0.f;
+      for (int q = 0; q < 8; ++q) x[q] = sdim < S ? p.w_ih[0][(int64_t)(g * 64 + u8 + q) * ld0 + sdim] * z_scale : 0.f;
       uint4 hi, lo;
       split8(x, hi, lo);
       const uint32_t off = (uint32_t)(gB >> 2) * 2048u + sw128(sdim, (gB & 3) * 2 + half);
@@ -134,12 +136,13 @@ __global__ void __launch_bounds__(1024) tcw_images_kernel(PathParams p, uint8_t*
     uint8_t* tlo = thi + 64 * 128;
     for (int idx = tid; idx < 64 * 8; idx += blockDim.x) {
       const int i = idx >> 3, c = idx & 7;
+      const int unit = half_tiles ? ((i & 31) >> 4) * 32 + (i >> 5) * 16 + (i & 15) : i;  // 64-row form: rows [unit half][chunk][16]
       float x[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int k = c * 8 + q;
         const int srow = k < NTRIL ? S + k : (k - NTRIL < S ? k - NTRIL : -1);
-        x[q] = srow >= 0 ? p.out_w[srow * 64 + i] * o_scale : 0.f;
+        x[q] = srow >= 0 ? p.out_w[srow * 64 + unit] * o_scale : 0.f;
       }
       uint4 hi, lo;
       split8(x, hi, lo);
@@ -156,10 +159,14 @@ __global__ void __launch_bounds__(1024) tcw_images_kernel(PathParams p, uint8_t*
     uint8_t* tlo = thi + kWTileBytes;
     for (int idx = tid; idx < 64 * 24; idx += blockDim.x) {
       const int i = idx & 63, hg = idx >> 6;
-      const int gB = hg >> 1, half = hg & 1, c = gB / 3, g = gB % 3;
+      const int gB = hg >> 1, half = hg & 1;
+      // 64-row form: K-group gB = (chunk of 32 units, gate, 16-unit half of the chunk); B row i = output unit in [unit half][chunk][16]
+      const int g = half_tiles ? (gB % 6) / 2 : gB % 3;
+      const int u8 = half_tiles ? (gB / 6) * 32 + (gB % 2) * 16 + half * 8 : (gB / 3) * 16 + half * 8;
+      const int unit = half_tiles ? ((i & 31) >> 4) * 32 + (i >> 5) * 16 + (i & 15) : i;
       float x[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) x[q] = src[(g * 64 + c * 16 + half * 8 + q) * 64 + i] * w_scale;
+      for (int q = 0; q < 8; ++q) x[q] = src[(g * 64 + u8 + q) * 64 + unit] * w_scale;
       uint4 hi, lo;
       split8(x, hi, lo);
       const uint32_t off = (uint32_t)(gB >> 2) * 8192u + sw128(i, (gB & 3) * 2 + half);

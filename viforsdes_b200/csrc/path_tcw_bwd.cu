@@ -61,18 +61,29 @@ __device__ __forceinline__ int row_exp_w(float mx) {
   return e < -100 ? -100 : e;
 }
 
-// MT: trajectories per CTA = MMA M (128, or 64 with two CTAs per tile of the global layouts: see path_fwd_tcw_kernel)
+// MT: trajectories per CTA = MMA M.  128: two threads per row, 4 chunks of 16 hidden units per layer phase (8 units per thread and
+// chunk), accumulators 64 columns wide.  64 (two CTAs per tile of the global layouts, see path_fwd_tcw_kernel): FOUR threads per row
+// -- lane l of a warp owns row l & 15 and, as lane half l >> 4, the output units whose accumulators sit on TMEM lanes 16 (l >> 4) ..
+// of its quadrant: every product is issued twice with N = 32 (unit half h into D + 16 h lanes).  A layer phase has 2 chunks of 32
+// hidden units; a chunk's A operand is two K = 64 tiles (gates r | u and n | n_hh) of 64 rows; lane half h owns units
+// {32 c + 16 h + w}: B rows (output units) are ordered [h][c][16] and K runs (chunk, gate, 32 units) in the images of this form.
 template <int S, int MT>
 __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams p) {
   using L = TcwBwdSmem<S>;
   static_assert(MT == 128 || MT == 64, "MMA M");
   constexpr int LPQ = MT / 4, SUBS = kTileRows / MT;
+  constexpr bool HALF = MT == 64;
+  constexpr int NCHK = HALF ? 2 : 4;      // chunks per layer phase
+  constexpr int CU = 64 / NCHK;           // hidden units per chunk
+  constexpr int BW = HALF ? 32 : 64;      // accumulator block width (output units per lane half)
+  constexpr uint32_t LHALF = 16u << 16;   // TMEM address of the second lane half
   constexpr int NL = 2;
   constexpr int NTRIL = S * (S + 1) / 2, NOUT = S + NTRIL, OF = tcw_out_feats(S), CF = tcw_cot_feats(S);
   static_assert(S > 4 && S <= kTcwMaxS, "wide-state tensor-core recurrence: 4 < S <= 10");
   static_assert(L::bytes <= 227 * 1024, "shared memory budget");
   constexpr uint32_t TMEM_COLS = 512;
-  constexpr uint32_t IN0_COL = 256, DIR_COL = 320, DZ_COL = 448;
+  // dh_carry ping-pong [layer][parity] | dh_in0 (also d_out . W_out) | direct term [layer] | d z_t
+  constexpr uint32_t IN0_COL = 4 * BW, DIR_COL = 5 * BW, DZ_COL = 7 * BW;
   constexpr int SLOT_BYTES = 2 * kATileBytes;
   extern __shared__ __align__(1024) uint8_t smem_raw_tcwb[];
   uint8_t* smem = smem_raw_tcwb + ((1024u - (smem_u32(smem_raw_tcwb) & 1023u)) & 1023u);
@@ -116,11 +127,33 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
 
   // ---- MMA issue: chunk gc is issued by lane 0 of warp gc % 8 once all 256 threads have written it
   const uint32_t w1 = smem_u32(smem + L::OFF_W1), wy = smem_u32(smem + L::OFF_Y), a0 = smem_u32(smem + L::OFF_A);
-  constexpr uint32_t ID64 = idesc_f16(64, MT);
-  // 9 MMAs: acc[128,64] (+)= A_chunk[slots] . W^T[K-groups of chunk c]; wbase = hi tile of the transposed matrix
+  constexpr uint32_t ID64 = idesc_f16(64, MT), ID32 = idesc_f16(32, MT);
+  // M = 128, 9 MMAs: acc[128,64] (+)= A_chunk[slots] . W^T[K-groups of chunk c]; wbase = hi tile of the transposed matrix.
+  // M = 64, 2 x 18 MMAs: acc_h[64,32] (+)= A_chunk[gate tiles] . W^T[K-groups of chunk c, rows of unit half h]
   auto issue = [&](uint32_t acc, uint32_t slot_base, uint32_t wbase, int c, bool n_is_nh, bool fresh) {
     const uint32_t a_hi = slot_base, a_lo = slot_base + kATileBytes;
     const uint32_t b_hi = wbase, b_lo = wbase + kWTileBytes;
+    if (HALF) {
+#pragma unroll
+      for (uint32_t h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const int ga = g < 2 ? g : (n_is_nh ? 3 : 2);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t aoff = (uint32_t)(ga >> 1) * 8192u + (uint32_t)(ga & 1) * 64u + (uint32_t)ks * 32u;
+            const int gB = c * 6 + g * 2 + ks;
+            const uint32_t boff = (uint32_t)(gB >> 2) * 8192u + (uint32_t)(gB & 3) * 32u + h * 4096u;
+            const uint64_t dah = umma_desc(a_hi + aoff, 16, 1024, 2), dal = umma_desc(a_lo + aoff, 16, 1024, 2);
+            const uint64_t dbh = umma_desc(b_hi + boff, 16, 1024, 2), dbl = umma_desc(b_lo + boff, 16, 1024, 2);
+            umma_f16(acc + h * LHALF, dal, dbh, ID32, (fresh && g == 0 && ks == 0) ? 0u : 1u);
+            umma_f16(acc + h * LHALF, dah, dbl, ID32, 1u);
+            umma_f16(acc + h * LHALF, dah, dbh, ID32, 1u);
+          }
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
       const int aslot = g < 2 ? g : (n_is_nh ? 3 : 2);
@@ -135,9 +168,30 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
   };
   const uint32_t wob = smem_u32(smem + L::OFF_WOUT), wzb = smem_u32(smem + L::OFF_WZ);
   constexpr uint32_t ID16 = idesc_f16(16, MT);
-  // 9 MMAs: d z_t [128,16] (+)= d_gi_l0 chunk (slots r, u, n) . W_z^T[K-groups of chunk c]
+  // d z_t [rows,16] (+)= d_gi_l0 chunk (gates r, u, n) . W_z^T[K-groups of chunk c]; M = 64: into both lane halves (every thread of a
+  // row carries d z)
   auto issue_dz = [&](uint32_t slot_base, int c) {
     const uint32_t a_hi = slot_base, a_lo = slot_base + kATileBytes;
+    if (HALF) {
+#pragma unroll
+      for (uint32_t h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t aoff = (uint32_t)(g >> 1) * 8192u + (uint32_t)(g & 1) * 64u + (uint32_t)ks * 32u;
+            const int gB = c * 6 + g * 2 + ks;
+            const uint32_t boff = (uint32_t)(gB >> 2) * 2048u + (uint32_t)(gB & 3) * 32u;
+            const uint64_t dah = umma_desc(a_hi + aoff, 16, 1024, 2), dal = umma_desc(a_lo + aoff, 16, 1024, 2);
+            const uint64_t dbh = umma_desc(wzb + boff, 16, 1024, 2), dbl = umma_desc(wzb + 3 * 2048 + boff, 16, 1024, 2);
+            umma_f16(tmem + h * LHALF + DZ_COL, dal, dbh, ID16, (c == 0 && g == 0 && ks == 0) ? 0u : 1u);
+            umma_f16(tmem + h * LHALF + DZ_COL, dah, dbl, ID16, 1u);
+            umma_f16(tmem + h * LHALF + DZ_COL, dah, dbh, ID16, 1u);
+          }
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
       const int gB = c * 3 + g;
@@ -154,8 +208,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
 
   {
     const int quad = warp & 3, cg = warp >> 2;
-    const bool act = lane < LPQ;                     // lanes past the quadrant's rows only take part in the collectives
+    const int lh = HALF ? lane >> 4 : 0;              // M = 64: unit half = TMEM lane half of this thread
     const int row = quad * LPQ + (lane & (LPQ - 1));  // row of the CTA's operand tiles / accumulators
+    const int t4 = lh * 2 + cg;                       // this thread among the threads of its row
+    const bool wr0 = lh == 0;                         // per-row values are computed by every lane half, stored by the first
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     uint8_t* a_ring = smem + L::OFF_A;
     uint32_t ph_in0 = 0, ph_outd = 0, xb = 0;
@@ -164,7 +220,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
       const int64_t tile = item / SUBS;
       const int grow = (int)(item % SUBS) * MT + row;  // row of the 128-row tile of the global layouts
       const int64_t b_raw = tile * kTileRows + grow;
-      const bool ok = act && b_raw < p.B;
+      const bool ok = wr0 && b_raw < p.B;
       const int64_t b = b_raw < p.B ? b_raw : p.B - 1;
       const float* st_tile = p.stash + tile * T * (int64_t)(NL * kStashSlots * 64 * kTileRows) + grow;
       float* dg_tile = p.dg + tile * T * (int64_t)(NL * kDgSlots * 64 * kTileRows) + grow;
@@ -174,7 +230,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
 
       float pv[2][5][8];
       auto load_chunk = [&](float (&dst)[5][8], int tt, int kk, int cc) {
-        const float* sk = st_tile + ((int64_t)tt * NL + kk) * (kStashSlots * 64 * kTileRows) + (cc * 16 + cg * 8) * kTileRows;
+        const float* sk = st_tile + ((int64_t)tt * NL + kk) * (kStashSlots * 64 * kTileRows) +
+                          (HALF ? cc * 32 + lh * 16 + cg * 8 : cc * 16 + cg * 8) * kTileRows;
         const float* hk = sk - (int64_t)NL * (kStashSlots * 64 * kTileRows) + kStashH * 64 * kTileRows;  // step tt - 1
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -186,8 +243,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
         }
       };
       auto load_ahead = [&](float (&dst)[5][8], int tt, int kk, int cc, int ahead) {
-        int lin = ((T - 1 - tt) * NL + (NL - 1 - kk)) * 4 + cc + ahead;
-        const int t2 = T - 1 - lin / (4 * NL), k2 = NL - 1 - (lin / 4) % NL, c2 = lin % 4;
+        int lin = ((T - 1 - tt) * NL + (NL - 1 - kk)) * NCHK + cc + ahead;
+        const int t2 = T - 1 - lin / (NCHK * NL), k2 = NL - 1 - (lin / NCHK) % NL, c2 = lin % NCHK;
         if (t2 >= 0) load_chunk(dst, t2, k2, c2);
       };
       load_ahead(pv[0], T - 1, NL - 1, 0, 0);
@@ -276,13 +333,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
                   float d = fmaf(dz[s] * ev[j], p.sqrt_dt, dv[k - K0]);
                   if (j == s) d = (rdv[s] >= VISDE_DIAG_MIN || d < 0.f) ? d : 0.f;  // primitives/bounds.py:20
                   dv[k - K0] = d;
-                  if (act) dor[(S + k) * kTileRows] = d;
+                  if (wr0) dor[(S + k) * kTileRows] = d;
                 }
               }
               if (NTRIL + s >= K0 && NTRIL + s < K0 + 32 && s < KMU) {
                 const float d = fmaf(dz[s], p.dt, dv[NTRIL + s - K0]);
                 dv[NTRIL + s - K0] = d;
-                if (act) dor[s * kTileRows] = d;
+                if (wr0) dor[s * kTileRows] = d;
               }
             }
           };
@@ -290,12 +347,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
 #pragma unroll
           for (int r = 0; r < NREST; ++r) {
             rest_d[r] = fmaf(dz[KMU + r], p.dt, rest_gm[r]);
-            if (cg == 0 && act) dor[(KMU + r) * kTileRows] = rest_d[r];
+            if (cg == 0 && wr0) dor[(KMU + r) * kTileRows] = rest_d[r];
           }
           float mxd = 0.f;
 #pragma unroll
           for (int e = 0; e < 32; ++e) mxd = fmaxf(mxd, fabsf(dv[e]));
-          if (act) maxb[(xb * 2 + cg) * 128 + row] = mxd;
+          if (wr0) maxb[(xb * 2 + cg) * 128 + row] = mxd;  // the other lane half computed the same value
           named_bar_sync(1 + quad, 64);
           mxd = fmaxf(mxd, maxb[(xb * 2 + (cg ^ 1)) * 128 + row]);
           xb ^= 1;
@@ -313,7 +370,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             for (int q = 0; q < 8; ++q) x[q] = dv[c * 8 + q] * rsd;
             uint4 hi, lo;
             split8(x, hi, lo);
-            if (act) {
+            if (wr0) {
               *reinterpret_cast<uint4*>(ahi + sw128(row, 4 * cg + c)) = hi;
               *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 4 * cg + c)) = lo;
             }
@@ -325,20 +382,24 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           if (warp == (int)(gc & 7)) {
             mbar_wait(&bars->full[slot], (gc >> 1) & 1);
             tc_fence_after();
-            if (lane == 0) {
-              if (!pro_ok) {  // first use of a prologue-copied tile by this lane
-                mbar_wait(&bars->pro, 0);
-                tc_fence_after();
-                pro_ok = true;
-              }
+            if (!pro_ok) {  // first use of a prologue-copied tile by this warp
+              mbar_wait(&bars->pro, 0);
+              tc_fence_after();
+              pro_ok = true;
+            }
+            if (elect_one_sync()) {
               const uint32_t sb = a0 + slot * SLOT_BYTES;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint64_t dah = umma_desc(sb + j * 32, 16, 1024, 2), dal = umma_desc(sb + kATileBytes + j * 32, 16, 1024, 2);
-                const uint64_t dbh = umma_desc(wob + j * 32, 16, 1024, 2), dbl = umma_desc(wob + 64 * 128 + j * 32, 16, 1024, 2);
-                umma_f16(tmem + IN0_COL, dal, dbh, ID64, j > 0 ? 1u : 0u);
-                umma_f16(tmem + IN0_COL, dah, dbl, ID64, 1u);
-                umma_f16(tmem + IN0_COL, dah, dbh, ID64, 1u);
+              for (uint32_t h = 0; h < (HALF ? 2u : 1u); ++h) {  // M = 64: W_out rows (hidden units) of half h, N = 32
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint64_t dah = umma_desc(sb + j * 32, 16, 1024, 2), dal = umma_desc(sb + kATileBytes + j * 32, 16, 1024, 2);
+                  const uint64_t dbh = umma_desc(wob + h * 4096u + j * 32, 16, 1024, 2);
+                  const uint64_t dbl = umma_desc(wob + 64 * 128 + h * 4096u + j * 32, 16, 1024, 2);
+                  umma_f16(tmem + h * LHALF + IN0_COL, dal, dbh, HALF ? ID32 : ID64, j > 0 ? 1u : 0u);
+                  umma_f16(tmem + h * LHALF + IN0_COL, dah, dbl, HALF ? ID32 : ID64, 1u);
+                  umma_f16(tmem + h * LHALF + IN0_COL, dah, dbh, HALF ? ID32 : ID64, 1u);
+                }
               }
               umma_commit(&bars->empty[slot]);
               umma_commit(&bars->outd);
@@ -360,10 +421,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             // every MMA of the layer-1 phase has completed (the in0 commit follows its last chunk): Y <- W_hh_l0^T
             if (tid == 0 && t >= 1) load_y(0);
           }
-          // ---------- pass 1: dh of this thread's 32 units, row maximum ----------
-          float2 dh2[kUPT / 2];  // dh of unit c * 8 + q lives in dh2[c * 4 + q / 2].{x, y}
+          // ---------- pass 1: dh of this thread's 8 NCHK units, row maximum ----------
+          float2 dh2[NCHK * 4];  // dh of the q-th unit of chunk c lives in dh2[c * 4 + q / 2].{x, y}
 #pragma unroll
-          for (int q = 0; q < kUPT / 2; ++q) dh2[q] = make_float2(0.f, 0.f);
+          for (int q = 0; q < NCHK * 4; ++q) dh2[q] = make_float2(0.f, 0.f);
           if (k == 1) {
             // d_out . W_out has landed in the dh_in0 columns; the mu components outside the MMA operand are contracted here
             mbar_wait(&bars->outd, ph_outd);
@@ -371,12 +432,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             tc_fence_after();
 #pragma unroll
             for (int r = 0; r < NREST; ++r) {
-              const float* wr = wrest + r * 64 + cg * 8;
+              const float* wr = wrest + r * 64 + (HALF ? lh * 16 + cg * 8 : cg * 8);
               const float2 d2 = make_float2(rest_d[r], rest_d[r]);
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const float4 wa = *reinterpret_cast<const float4*>(wr + c * 16);
-                const float4 wb = *reinterpret_cast<const float4*>(wr + c * 16 + 4);
+              for (int c = 0; c < NCHK; ++c) {
+                const float4 wa = *reinterpret_cast<const float4*>(wr + c * CU);
+                const float4 wb = *reinterpret_cast<const float4*>(wr + c * CU + 4);
                 fma2(dh2[c * 4 + 0], make_float2(wa.x, wa.y), d2);
                 fma2(dh2[c * 4 + 1], make_float2(wa.z, wa.w), d2);
                 fma2(dh2[c * 4 + 2], make_float2(wb.x, wb.y), d2);
@@ -387,12 +448,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           if (k == 1) TCWB_TRACE(2); else TCWB_TRACE(7);
           float mx = 0.f;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int j0 = c * 16 + cg * 8;
+          for (int c = 0; c < NCHK; ++c) {
+            const int j0 = c * 16 + cg * 8;  // column of this thread's units of chunk c inside an accumulator block
             uint32_t va[8], vd[8], vi[8];
             if (!first) {
-              tmem_ld8_nowait(tl + (uint32_t)(k * 2 + rpar) * 64 + j0, va);
-              tmem_ld8_nowait(tl + DIR_COL + (uint32_t)k * 64 + j0, vd);
+              tmem_ld8_nowait(tl + (uint32_t)(k * 2 + rpar) * BW + j0, va);
+              tmem_ld8_nowait(tl + DIR_COL + (uint32_t)k * BW + j0, vd);
             }
             // k = 0: dh_in0 of this step; k = 1: d_out . W_out of this step (same columns, see the d_out phase)
             tmem_ld8_nowait(tl + IN0_COL + j0, vi);
@@ -407,10 +468,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
               mx = fmaxf(mx, fabsf(v));
             }
           }
-          // ---------- the two threads of the row agree on the power-of-two scale ----------
-          if (act) maxb[(xb * 2 + cg) * 128 + row] = mx;
-          named_bar_sync(1 + quad, 64);
-          mx = fmaxf(mx, maxb[(xb * 2 + (cg ^ 1)) * 128 + row]);
+          // ---------- the threads of the row agree on the power-of-two scale ----------
+          if (HALF) {
+            maxb[(xb * 4 + t4) * 64 + row] = mx;
+            named_bar_sync(1 + quad, 64);
+            mx = fmaxf(fmaxf(mx, maxb[(xb * 4 + (t4 ^ 1)) * 64 + row]),
+                       fmaxf(maxb[(xb * 4 + (t4 ^ 2)) * 64 + row], maxb[(xb * 4 + (t4 ^ 3)) * 64 + row]));
+          } else {
+            maxb[(xb * 2 + cg) * 128 + row] = mx;
+            named_bar_sync(1 + quad, 64);
+            mx = fmaxf(mx, maxb[(xb * 2 + (cg ^ 1)) * 128 + row]);
+          }
           xb ^= 1;
           if (k == 1) TCWB_TRACE(3); else TCWB_TRACE(8);
           const int er = row_exp_w(mx);
@@ -420,8 +488,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           // ---------- pass 2: gate cotangents, dg, direct term, A-operand chunks ----------
           float* dg_k = dg_tile + ((int64_t)t * NL + k) * (kDgSlots * 64 * kTileRows);
 #pragma unroll
-          for (int c = 0; c < 4; ++c, ++gc) {
-            const int j0 = c * 16 + cg * 8;
+          for (int c = 0; c < NCHK; ++c, ++gc) {
+            const int j0 = c * 16 + cg * 8;                                      // accumulator column
+            const int ju = HALF ? c * 32 + lh * 16 + cg * 8 : c * 16 + cg * 8;  // hidden unit
             float cr[8], cu[8], cn[8], cnh[8], chp[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -433,7 +502,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             uint32_t dirv[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const int i = j0 + q;
+              const int i = ju + q;
               const float r = cr[q], u = cu[q], n = cn[q], nhh = cnh[q], hp = chp[q];
               const float dhv = (q & 1) ? dh2[c * 4 + q / 2].y : dh2[c * 4 + q / 2].x;
               const float dnp = dhv * (1.f - u) * (1.f - n * n);
@@ -441,56 +510,56 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
               const float drp = dnp * nhh * r * (1.f - r);
               const float dnh = dnp * r;
               dirv[q] = __float_as_uint(dhv * u);
-              if (act) {
-                dg_k[(0 * 64 + i) * kTileRows] = drp;
-                dg_k[(1 * 64 + i) * kTileRows] = dup;
-                dg_k[(2 * 64 + i) * kTileRows] = dnp;
-                dg_k[(3 * 64 + i) * kTileRows] = dnh;
-              }
+              dg_k[(0 * 64 + i) * kTileRows] = drp;
+              dg_k[(1 * 64 + i) * kTileRows] = dup;
+              dg_k[(2 * 64 + i) * kTileRows] = dnp;
+              dg_k[(3 * 64 + i) * kTileRows] = dnh;
               dr_[q] = drp * rs; du_[q] = dup * rs; dn_[q] = dnp * rs; dnh_[q] = dnh * rs;
             }
-            tmem_st8(tl + DIR_COL + (uint32_t)k * 64 + j0, dirv);
+            tmem_st8(tl + DIR_COL + (uint32_t)k * BW + j0, dirv);
             const uint32_t slot = gc & 1;
             if (gc >= 2) mbar_wait(&bars->empty[slot], ((gc >> 1) - 1) & 1);
             uint8_t* ahi = a_ring + slot * SLOT_BYTES;
-            if (act) {
+            {
+              // M = 128: one K = 64 tile, 16-byte group 2 g + cg of gate g.  M = 64: two K = 64 tiles of 64 rows (gates r | u, then
+              // n | n_hh), group 4 (g & 1) + t4 of tile g >> 1
+              const uint32_t o0 = HALF ? sw128(row, t4) : sw128(row, 0 + cg);
+              const uint32_t o1 = HALF ? sw128(row, 4 + t4) : sw128(row, 2 + cg);
+              const uint32_t o2 = HALF ? 8192u + sw128(row, t4) : sw128(row, 4 + cg);
+              const uint32_t o3 = HALF ? 8192u + sw128(row, 4 + t4) : sw128(row, 6 + cg);
               uint4 hi, lo;
               split8(dr_, hi, lo);
-              *reinterpret_cast<uint4*>(ahi + sw128(row, 0 + cg)) = hi;
-              *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 0 + cg)) = lo;
+              *reinterpret_cast<uint4*>(ahi + o0) = hi;
+              *reinterpret_cast<uint4*>(ahi + kATileBytes + o0) = lo;
               split8(du_, hi, lo);
-              *reinterpret_cast<uint4*>(ahi + sw128(row, 2 + cg)) = hi;
-              *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 2 + cg)) = lo;
+              *reinterpret_cast<uint4*>(ahi + o1) = hi;
+              *reinterpret_cast<uint4*>(ahi + kATileBytes + o1) = lo;
               split8(dn_, hi, lo);
-              *reinterpret_cast<uint4*>(ahi + sw128(row, 4 + cg)) = hi;
-              *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 4 + cg)) = lo;
+              *reinterpret_cast<uint4*>(ahi + o2) = hi;
+              *reinterpret_cast<uint4*>(ahi + kATileBytes + o2) = lo;
               split8(dnh_, hi, lo);
-              *reinterpret_cast<uint4*>(ahi + sw128(row, 6 + cg)) = hi;
-              *reinterpret_cast<uint4*>(ahi + kATileBytes + sw128(row, 6 + cg)) = lo;
+              *reinterpret_cast<uint4*>(ahi + o3) = hi;
+              *reinterpret_cast<uint4*>(ahi + kATileBytes + o3) = lo;
             }
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(&bars->full[slot]);
             if (warp == (int)(gc & 7)) {
               mbar_wait(&bars->full[slot], (gc >> 1) & 1);
+              if (t > 0) mbar_wait(&bars->wy, k == 1 ? 0u : 1u);  // Y holds W_hh_l1^T in the layer-1 phase (even completions
+                                                                  // of wy), W_hh_l0^T in the layer-0 phase (odd)
+              if (!pro_ok) {  // first use of a prologue-copied tile (W_ih_l1^T, W_z) by this warp
+                mbar_wait(&bars->pro, 0);
+                pro_ok = true;
+              }
               tc_fence_after();
-              if (lane == 0) {
+              if (elect_one_sync()) {
                 const uint32_t sb = a0 + slot * SLOT_BYTES;
-                if (t > 0) {
-                  // Y holds W_hh_l1^T in the layer-1 phase (even completions of wy), W_hh_l0^T in the layer-0 phase (odd)
-                  mbar_wait(&bars->wy, k == 1 ? 0u : 1u);
-                  tc_fence_after();
-                  issue(tmem + (uint32_t)(k * 2 + ((t & 1) ^ 1)) * 64, sb, wy, c, true, c == 0);
-                }
-                if (!pro_ok) {  // first use of a prologue-copied tile (W_ih_l1^T, W_z) by this lane
-                  mbar_wait(&bars->pro, 0);
-                  tc_fence_after();
-                  pro_ok = true;
-                }
+                if (t > 0) issue(tmem + (uint32_t)(k * 2 + ((t & 1) ^ 1)) * BW, sb, wy, c, true, c == 0);
                 if (k == 1) issue(tmem + IN0_COL, sb, w1, c, false, c == 0);
                 else issue_dz(sb, c);
                 umma_commit(&bars->empty[slot]);
-                if (k == 1 && c == 3) umma_commit(&bars->in0);
+                if (k == 1 && c == NCHK - 1) umma_commit(&bars->in0);
               }
               __syncwarp();
             }
