@@ -47,7 +47,7 @@ struct TcwBwdSmem {
   static constexpr int OFF_MAX = OFF_WREST + (NREST > 0 ? NREST : 1) * 64 * 4;  // float [2 buffers][2 cg][128]
   static constexpr int OFF_BAR = (OFF_MAX + 2 * 2 * 128 * 4 + 15) / 16 * 16;
   struct Bars {
-    uint64_t full[2], empty[2], in0, wy, pro, outd;
+    uint64_t full[2], empty[2], in0, wy, pro, outd, dzr;
     uint32_t tmem_base;
   };
   static constexpr size_t bytes = OFF_BAR + sizeof(Bars) + 1024;
@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
     mbar_init(&bars->wy, 1);
     mbar_init(&bars->pro, 1);
     mbar_init(&bars->outd, 1);
+    mbar_init(&bars->dzr, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&bars->tmem_base, TMEM_COLS);
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
     const bool wr0 = lh == 0;                         // per-row values are computed by every lane half, stored by the first
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     uint8_t* a_ring = smem + L::OFF_A;
-    uint32_t ph_in0 = 0, ph_outd = 0, xb = 0;
+    uint32_t ph_in0 = 0, ph_outd = 0, ph_dzr = 0, xb = 0;
 
     for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int64_t tile = item / SUBS;
@@ -290,16 +291,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
         if (cg == 0) load_half(std::integral_constant<int, 0>{}); else load_half(std::integral_constant<int, 1>{});
 #pragma unroll
         for (int r = 0; r < NREST; ++r) rest_gm[r] = ct[(S + KMU + r) * kTileRows];
-        // ---- Y <- W_hh_l1^T for this step's layer-1 phase (its carried products are issued for t >= 1 only): every MMA
-        // issued so far has completed once the last chunk's commit has (in-order tensor pipe)
-        if (tid == 0 && t >= 1) {
-          if (gc >= 1) mbar_wait(&bars->empty[(gc - 1) & 1], ((gc - 1) >> 1) & 1);
-          load_y(2);
-        }
+        const uint32_t gc_top = gc;  // gc_top - 1 = the last layer-0 chunk of step t + 1
         // ---- cotangent of z_{t+1}: d z through the state columns of W_ih_l0 was accumulated on the tensor pipe by the layer-0
-        // chunks of step t + 1 (16 TMEM columns): all of them have completed once the last chunk's commit has
+        // chunks of step t + 1 (16 TMEM columns).  Each chunk issues its d z MMAs AHEAD of its carried-dh product and the last one
+        // commits them to `dzr`: this wait does not include the 36 - 54 MMAs of the carried product behind them
         if (!first) {
-          mbar_wait(&bars->empty[(gc - 1) & 1], ((gc - 1) >> 1) & 1);
+          mbar_wait(&bars->dzr, ph_dzr);
+          ph_dzr ^= 1;
           tc_fence_after();
           uint32_t zv[16];
           tmem_ld16_nowait(tl + DZ_COL, zv);
@@ -379,6 +377,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
           tc_fence_before();
           TCWB_TRACE(11);
           mbar_arrive(&bars->full[slot]);
+          // ---- Y <- W_hh_l1^T for this step's layer-1 phase (its carried products are issued for t >= 1 only): every MMA of step
+          // t + 1 has completed once its last chunk's commit has (in-order tensor pipe) -- long ago by now, so this does not stall
+          if (tid == 0 && t >= 1) {
+            if (gc_top >= 1) mbar_wait(&bars->empty[(gc_top - 1) & 1], ((gc_top - 1) >> 1) & 1);
+            load_y(2);
+          }
           if (warp == (int)(gc & 7)) {
             mbar_wait(&bars->full[slot], (gc >> 1) & 1);
             tc_fence_after();
@@ -418,8 +422,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             ph_in0 ^= 1;
             tc_fence_after();
             TCWB_TRACE(6);
-            // every MMA of the layer-1 phase has completed (the in0 commit follows its last chunk): Y <- W_hh_l0^T
-            if (tid == 0 && t >= 1) load_y(0);
           }
           // ---------- pass 1: dh of this thread's 8 NCHK units, row maximum ----------
           float2 dh2[NCHK * 4];  // dh of the q-th unit of chunk c lives in dh2[c * 4 + q / 2].{x, y}
@@ -480,6 +482,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             mx = fmaxf(mx, maxb[(xb * 2 + (cg ^ 1)) * 128 + row]);
           }
           xb ^= 1;
+          if (k == 0 && tid == 0 && t >= 1) {
+            // Y <- W_hh_l0^T once the carried products of the layer-1 phase (issued BEHIND the dh_in0 products that `in0` covers)
+            // have finished reading W_hh_l1^T
+            mbar_wait(&bars->empty[(gc - 1) & 1], ((gc - 1) >> 1) & 1);
+            load_y(0);
+          }
           if (k == 1) TCWB_TRACE(3); else TCWB_TRACE(8);
           const int er = row_exp_w(mx);
           const float rs = exp2i(er);
@@ -546,20 +554,27 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             mbar_arrive(&bars->full[slot]);
             if (warp == (int)(gc & 7)) {
               mbar_wait(&bars->full[slot], (gc >> 1) & 1);
-              if (t > 0) mbar_wait(&bars->wy, k == 1 ? 0u : 1u);  // Y holds W_hh_l1^T in the layer-1 phase (even completions
-                                                                  // of wy), W_hh_l0^T in the layer-0 phase (odd)
               if (!pro_ok) {  // first use of a prologue-copied tile (W_ih_l1^T, W_z) by this warp
                 mbar_wait(&bars->pro, 0);
                 pro_ok = true;
               }
               tc_fence_after();
+              const uint32_t sb = a0 + slot * SLOT_BYTES;
+              // the product the NEXT phase waits for goes first and gets its own commit: dh_in0 (layer 1 -> `in0`), d z_t (layer 0
+              // -> `dzr`); the carried dh, read one step later, follows
               if (elect_one_sync()) {
-                const uint32_t sb = a0 + slot * SLOT_BYTES;
-                if (t > 0) issue(tmem + (uint32_t)(k * 2 + ((t & 1) ^ 1)) * BW, sb, wy, c, true, c == 0);
                 if (k == 1) issue(tmem + IN0_COL, sb, w1, c, false, c == 0);
                 else issue_dz(sb, c);
+                if (c == NCHK - 1) umma_commit(k == 1 ? &bars->in0 : &bars->dzr);
+              }
+              __syncwarp();
+              if (t > 0) {
+                mbar_wait(&bars->wy, k == 1 ? 0u : 1u);  // Y holds W_hh_l1^T in the layer-1 phase (even completions of wy),
+                tc_fence_after();                        // W_hh_l0^T in the layer-0 phase (odd)
+              }
+              if (elect_one_sync()) {
+                if (t > 0) issue(tmem + (uint32_t)(k * 2 + ((t & 1) ^ 1)) * BW, sb, wy, c, true, c == 0);
                 umma_commit(&bars->empty[slot]);
-                if (k == 1 && c == NCHK - 1) umma_commit(&bars->in0);
               }
               __syncwarp();
             }
@@ -573,6 +588,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
       }
       // grad_x0 = d z_0 + g_paths[:, 0]; the state-column part of d z_0 sits in TMEM behind the last chunk's MMAs
       {
+        mbar_wait(&bars->dzr, ph_dzr);
+        ph_dzr ^= 1;
         mbar_wait(&bars->empty[(gc - 1) & 1], ((gc - 1) >> 1) & 1);
         tc_fence_after();
         uint32_t zv[16];
