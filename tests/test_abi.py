@@ -227,10 +227,10 @@ def test_auto_family_selection_table(lib):
              1024: (T8, T8), 1184: (T8, T8), 2048: (T8, T8), 3071: (T8, T8), 3072: (TC, TC), 65536: (TC, TC)}
     for B, (fw, bw) in table.items():
         assert (fam(B, 0), fam(B, 1)) == (fw, bw), f"B={B}: {(fam(B, 0), fam(B, 1))}"
-    # wide state (BASELINE config 5, S = 10): the wide tensor-core family from 1 536 trajectories per GPU (N = 1, 2, 4 of the
-    # strong-scaled run), the register-resident wide family below (N = 8: measured crossover B ~ 1 250, profiles/r2_config5.md)
+    # wide state (BASELINE config 5, S = 10): the wide tensor-core family from 1 024 trajectories per GPU (every shard size of the
+    # strong-scaled run, N = 1 .. 8), the register-resident wide family below (measured crossover B ~ 900, profiles/r2_config5.md)
     assert fam(8192, 0, S=10) == TC and fam(8192, 1, S=10) == TC and fam(4096, 1, S=10) == TC and fam(2048, 0, S=10) == TC
-    assert fam(1536, 1, S=10) == TC and fam(1535, 0, S=10) == FS and fam(1024, 1, S=10) == FS
+    assert fam(1536, 1, S=10) == TC and fam(1024, 0, S=10) == TC and fam(1023, 1, S=10) == FS and fam(768, 0, S=10) == FS
     assert fam(8192, 0, S=10, NL=1) == FS and fam(8192, 0, S=12) == FS    # outside the wide tensor-core shapes (NL = 2, S <= 10)
     assert fam(8192, 0, H=128) == G and fam(128, 1, NL=3) == G          # outside the register-resident shapes
     assert fam(8192, 0, Cd=64) == T8                                      # no tcgen05 K0 for this context width: no TC recurrence

@@ -93,8 +93,9 @@ bool tc_rec_possible(const visde_dims* d) {
 
 // wide-state tensor-core recurrence (path_tcw.cu): 4 < S <= 10, two layers.  Its alternative is the one-trajectory-per-CTA FAST-S
 // family (no batch-tiled family for wide states), so it pays off earlier than the narrow one: measured at S = 10, T = 100
-// (profiles/r2_config5.md) 1 024 trajectories 3.46 ms vs 2.81 ms FAST-S, 1 536: 3.77 vs 4.26, 2 048: 4.03 vs 5.40
-constexpr int64_t kTcwRecMinBatch = 1536;
+// (profiles/r2_config5.md, 64-row tiles with four threads per row) 768 trajectories 2.56 ms vs 2.38 ms FAST-S, 1 024: 2.68 vs 2.80,
+// 1 536: 2.99 vs 4.26, 2 048: 3.27 vs 5.40
+constexpr int64_t kTcwRecMinBatch = 1024;
 bool tcw_rec_possible(const visde_dims* d) {
   const int fam = d->variant & 0xff;
   return (fam == VISDE_VARIANT_TC || (fam == VISDE_VARIANT_AUTO && d->B >= kTcwRecMinBatch)) && d->H == 64 && d->NL == 2 &&

@@ -482,12 +482,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
             mx = fmaxf(mx, maxb[(xb * 2 + (cg ^ 1)) * 128 + row]);
           }
           xb ^= 1;
-          if (k == 0 && tid == 0 && t >= 1) {
-            // Y <- W_hh_l0^T once the carried products of the layer-1 phase (issued BEHIND the dh_in0 products that `in0` covers)
-            // have finished reading W_hh_l1^T
-            mbar_wait(&bars->empty[(gc - 1) & 1], ((gc - 1) >> 1) & 1);
-            load_y(0);
-          }
           if (k == 1) TCWB_TRACE(3); else TCWB_TRACE(8);
           const int er = row_exp_w(mx);
           const float rs = exp2i(er);
@@ -525,6 +519,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) path_bwd_tcw_kernel(PathParams
               dr_[q] = drp * rs; du_[q] = dup * rs; dn_[q] = dnp * rs; dnh_[q] = dnh * rs;
             }
             tmem_st8(tl + DIR_COL + (uint32_t)k * BW + j0, dirv);
+            if (k == 0 && c == 0 && tid == 0 && t >= 1) {
+              // Y <- W_hh_l0^T once the carried products of the layer-1 phase (issued BEHIND the dh_in0 products that `in0` covers)
+              // have finished reading W_hh_l1^T: about a microsecond after `in0`, i.e. by now, so this wait does not stall
+              mbar_wait(&bars->empty[(gc - 1) & 1], ((gc - 1) >> 1) & 1);
+              load_y(0);
+            }
             const uint32_t slot = gc & 1;
             if (gc >= 2) mbar_wait(&bars->empty[slot], ((gc >> 1) - 1) & 1);
             uint8_t* ahi = a_ring + slot * SLOT_BYTES;
