@@ -52,6 +52,7 @@ def test_floored_diagonal_gradient_rule():
 def test_state_space_matches_oracle():
     from viforsdes_b200.state_space import StateSpace
 
+    torch.manual_seed(5)
     z = torch.randn(3, 7, 4, dtype=torch.float64) * 15
     z[0, 0, 1] = 30.0  # beyond softplus' threshold
     for pos in ([], [1, 3], [0, 1, 2, 3]):
@@ -59,7 +60,8 @@ def test_state_space_matches_oracle():
         zz = z.clone().requires_grad_(True)
         zr = z.clone().requires_grad_(True)
         x, xr = sp.to_state(zz), O.to_state(zr, pos)
-        assert torch.equal(x, xr)
+        # the vectorised and the gathered-column softplus of torch's CPU backend differ in the last bit for some arguments
+        assert torch.allclose(x, xr, rtol=4e-16, atol=0)
         lj = sp.log_jacobian(zz[:, 1:]).sum(-1)
         assert torch.allclose(lj, O.log_jacobian(zr, pos), atol=1e-12)
         (x.sum() + lj.sum()).backward()
