@@ -59,8 +59,9 @@ class Lorenz96:
         return (ahead - behind2) * behind - x + sde_parameters[..., 0:1]
 
     def diffusion(self, x: Tensor, sde_parameters: Tensor) -> Tensor:
-        eye = torch.eye(self.state_dim, dtype=x.dtype, device=x.device)
-        return sde_parameters[..., 1].reshape(-1, 1, 1) * eye
+        # sigma I written as diag_embed: the same values as ``sigma[..., None, None] * eye`` (the oracle's form), but its autograd
+        # backward reads the S diagonal entries of the cotangent instead of multiplying and reducing the whole [.., S, S] block
+        return torch.diag_embed(sde_parameters[..., 1:2].expand(*x.shape[:-1], self.state_dim))
 
 
 @dataclass
