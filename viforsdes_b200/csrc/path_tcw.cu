@@ -284,13 +284,9 @@ __device__ __forceinline__ void issue_gemm_w(uint32_t dcol, uint32_t a_hi, uint3
   for (int j = 0; j < 4; ++j) {
     const uint64_t dah = umma_desc(a_hi + j * 32, 16, 1024, 2), dal = umma_desc(a_lo + j * 32, 16, 1024, 2);
     const uint64_t dbh = umma_desc(b_hi + j * 32, 16, 1024, 2), dbl = umma_desc(b_lo + j * 32, 16, 1024, 2);
-#ifdef VISDE_TCW_EXP1  // timing experiment only (wrong numerics): one pass instead of three
-    umma_f16(dcol, dah, dbh, idesc, (accumulate || j > 0) ? 1u : 0u);
-#else
     umma_f16(dcol, dal, dbh, idesc, (accumulate || j > 0) ? 1u : 0u);
     umma_f16(dcol, dah, dbl, idesc, 1u);
     umma_f16(dcol, dah, dbh, idesc, 1u);
-#endif
   }
 }
 
