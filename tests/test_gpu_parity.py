@@ -460,3 +460,14 @@ def test_tc_family_large_batch_properties():
     ref = O.sample_paths(w64, p.x0[sl].double(), p.context[sl].double(), p.theta[sl].double(), p.eps[sl].double(), p.dt)
     for a, r, nm in zip(o1, ref, ("paths", "means", "chol")):
         assert normwise(a[sl], r) < 1e-4, f"{nm} vs fp64 oracle: {normwise(a[sl], r)}"
+
+
+def test_wide_tensor_core_recurrence_128_row_form_and_tile_loop():
+    """149 tiles: more than SMs / 2, so the wide family runs its 128-row form (MMA M = 128, two threads per row) instead of the 64-row
+    one every smaller case takes, and more than 148, so one CTA walks two tiles (barrier phases carried across tiles); ragged last tile."""
+    from viforsdes_b200 import _lib, ops
+
+    p = O.make_problem("l96", 148 * 128 + 37, 3, context_dim=128, hidden_dim=64, num_layers=2, state_dim=10)
+    r32, r64 = oracle_refs(p)
+    ops.set_variant(_lib.VARIANT_TC)
+    check_iteration(run_cuda_fwd_bwd(p), r32, r64, tag="tc/l96s10_b18981_m128/")
