@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(SMAX <= 4 ? kElboMaxThreads : kElboThreads) el
 // memory (slot tau + 1 of the chunk; the last slot carries over to the next chunk of the trajectory).  The first version
 // re-solved transition tau - 1 in thread tau: twice the triangular solves and twice the factor-block reads.
 template <int SMAX>
-__global__ void __launch_bounds__(SMAX <= 4 ? kElboMaxThreads : kElboThreads) elbo_bwd_kernel(ElboParams p) {
+__global__ void __launch_bounds__(SMAX <= 4 ? kElboMaxThreads : kElboThreads, SMAX <= 4 ? 1 : (SMAX <= 10 ? 3 : 2)) elbo_bwd_kernel(ElboParams p) {
   constexpr int NTMAX = SMAX <= 4 ? kElboMaxThreads : kElboThreads;
   __shared__ float red[kElboMaxThreads / 32];
   __shared__ float nxt[2][NTMAX + 1][SMAX];  // [0]: cotangent of z_next (generative term), [1]: of x_next (SDE term)
