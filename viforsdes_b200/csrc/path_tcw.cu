@@ -436,7 +436,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
 
   {
     const int quad = warp & 3, cg = warp >> 2;
-    constexpr bool act = true;
     const int lh = HALF ? lane >> 4 : 0;              // M = 64: unit half = TMEM lane half of this thread
     const int row = quad * LPQ + (lane & (LPQ - 1));  // row of the CTA's A tile / accumulators
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
@@ -450,7 +449,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
       const int64_t tile = item / SUBS;
       const int grow = (int)(item % SUBS) * MT + row;  // row of the 128-row tile of the global layouts
       const int64_t b_raw = tile * kTileRows + grow;
-      const bool ok = act && b_raw < p.B;
+      const bool ok = b_raw < p.B;
       const int64_t b = b_raw < p.B ? b_raw : p.B - 1;
       const bool writer = cg == 0 && lh == 0;  // pad rows write too: the tiled records of pad rows are never read as data
       // X holds W_ih_l1 at every tile start.  The first tile's copy was issued in the prologue; a later tile re-issues it so
@@ -463,10 +462,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           const uint32_t off = sw128(row, (u0 >> 3) + c);
-          if (act) {
-            *reinterpret_cast<uint4*>(a_tiles + (2 * k) * kATileBytes + off) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(a_tiles + (2 * k + 1) * kATileBytes + off) = make_uint4(0, 0, 0, 0);
-          }
+          *reinterpret_cast<uint4*>(a_tiles + (2 * k) * kATileBytes + off) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(a_tiles + (2 * k + 1) * kATileBytes + off) = make_uint4(0, 0, 0, 0);
         }
       fence_proxy_async();
       mbar_arrive(&bars->init);
@@ -493,7 +490,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
 #pragma unroll
         for (int j = 0; j < UPT; ++j) hprev[k][j] = 0.f;
       const float* gi_p = p.gi_ctx + tile * T * (int64_t)(192 * kTileRows) + (int64_t)u0 * kTileRows + grow;
-      float* st_p = p.stash && act ? p.stash + tile * T * (int64_t)(2 * kStashSlots * 64 * kTileRows) + (int64_t)u0 * kTileRows + grow
+      float* st_p = p.stash ? p.stash + tile * T * (int64_t)(2 * kStashSlots * 64 * kTileRows) + (int64_t)u0 * kTileRows + grow
                                    : nullptr;
       const float* eps_p = p.epst + tile * T * (int64_t)(S * kTileRows) + grow;
       float* ot_p = p.otile + tile * T * (int64_t)(OF * kTileRows) + grow;
@@ -570,10 +567,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
           uint4 hi, lo;
           split8(hx, hi, lo);
           const uint32_t off = sw128(row, j0 >> 3);
-          if (act) {
-            *reinterpret_cast<uint4*>(a_tiles + off) = hi;
-            *reinterpret_cast<uint4*>(a_tiles + kATileBytes + off) = lo;
-          }
+          *reinterpret_cast<uint4*>(a_tiles + off) = hi;
+          *reinterpret_cast<uint4*>(a_tiles + kATileBytes + off) = lo;
         }
         fence_proxy_async();
         tc_fence_before();
@@ -646,10 +641,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) path_fwd_tcw_kernel(PathParams
           uint4 hi, lo;
           split8(hx, hi, lo);
           const uint32_t off = sw128(row, j0 >> 3);
-          if (act) {
-            *reinterpret_cast<uint4*>(a_tiles + 2 * kATileBytes + off) = hi;
-            *reinterpret_cast<uint4*>(a_tiles + 3 * kATileBytes + off) = lo;
-          }
+          *reinterpret_cast<uint4*>(a_tiles + 2 * kATileBytes + off) = hi;
+          *reinterpret_cast<uint4*>(a_tiles + 3 * kATileBytes + off) = lo;
         }
         fence_proxy_async();
         tc_fence_before();
@@ -818,7 +811,7 @@ int launch_tcw_tile_multi(const float* const* src, const int64_t* bstride, const
   }
   a.nsrc = nsrc;
   a.FD = FD;
-  a.steps = fmax >= 96 ? 2 : (192 / fmax > 16 ? 16 : 192 / fmax);
+  a.steps = fmax >= 96 ? 1 : (192 / fmax > 16 ? 16 : 192 / fmax);
   a.B = B;
   a.T = T;
   a.dst = dst;
